@@ -1,0 +1,98 @@
+/*
+ * usaug.h -- C ABI of libusaug.so: the B200 (sm_100a) hot path of the physics-inspired
+ * ultrasound augmentation chain (probe-pressure deformation + TGC + remap, random-walk
+ * confidence map, SNR change + reverberation).
+ *
+ * Reference interface replaced: NONE IS VISIBLE.  The mounted reference is
+ * /root/reference/README.md:1-2 (title + "Realistic and Physics based Ultrasound
+ * Augmentation"); it ships no code, so there is no reference FFI to cite line by line.
+ * The boundary below is the one SURVEY.md section 8(b) defines for this path (API UNPINNED by
+ * the reference); each entry point names the SURVEY.md Appendix-A clause it implements.
+ *
+ * Contract for every function:
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - returns 0 (USAUG_OK) or a negative USAUG_E_* code; never throws.
+ *   - never allocates, frees or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *   - every pointer is a DEVICE pointer owned by the caller and must stay valid until the
+ *     stream has executed the work; scratch memory comes from the caller (`ws`, sized by the
+ *     matching *_workspace_bytes query, 256-byte aligned).
+ *   - re-entrant; one call may be in flight per stream.
+ *   - layouts: image float32 [B,H,W] contiguous (NCHW with C=1), label uint8 [B,H,W],
+ *     bone = non-zero.  Rows = depth (probe at row 0), columns = scanlines.
+ *   - there is NO CPU fallback: without a CUDA device the calls return USAUG_E_CUDA.
+ */
+#ifndef USAUG_H_
+#define USAUG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USAUG_VERSION 10100 /* 1.1.0 */
+
+enum {
+  USAUG_OK = 0,
+  USAUG_E_INVALID_ARG = -1,
+  USAUG_E_CUDA = -2,
+  USAUG_E_WORKSPACE_TOO_SMALL = -3
+};
+
+/* preconditioner of the confidence-map PCG */
+enum { USAUG_PRECOND_JACOBI = 0, USAUG_PRECOND_LINE = 1 };
+
+/* flags of usaug_confmap_pcg */
+enum {
+  USAUG_CM_FP64_VECTORS = 1, /* keep the CG vectors in fp64 (default: fp32 vectors + fp64 refinement) */
+  USAUG_CM_ZERO_GUESS = 2    /* start from x0 = 0 instead of the linear depth ramp */
+};
+
+int usaug_version(void);
+/* thread-local message of the last failing call on this thread ("" if none) */
+const char* usaug_last_error(void);
+
+/* ---- K1: bone-surface scan + fused TGC + deformation + remap ---------
+ * d[B]      axial probe displacement in pixels (clamped on device to |d| <= 0.5*min s_hat)
+ * tgc[B,K]  K >= 1 control gains at depths k(H-1)/(K-1)
+ * taps[2R+1] smoothing taps of the bone-surface profile (host-computed, identical to the oracle's)
+ * out_img/out_lab must not alias the inputs.  Requires 1 <= W <= 4096.
+ */
+size_t usaug_warp_workspace_bytes(int B, int H, int W);
+int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, float* out_img, uint8_t* out_lab,
+                           int B, int H, int W, const float* d, const float* tgc, int K,
+                           const float* taps, int R, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K2: confidence map, matrix-free PCG on the 8-neighbour random-walk Laplacian (A.3) ----
+ * cm[B,H,W] out (row 0 = 1, row H-1 = 0).  Stops per image when the TRUE residual satisfies
+ * ||b - A x||_2 <= rtol*||b||_2 or after maxiter inner iterations.
+ * iters[B] (nullable) inner iterations used; relres[B] (nullable) true relative residual reached.
+ * Requires H >= 3.
+ */
+size_t usaug_confmap_workspace_bytes(int B, int H, int W, int precond, int flags);
+int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int W, float alpha, float beta,
+                      float gamma, double rtol, int maxiter, int precond, int flags, int* iters,
+                      double* relres, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K3: SNR change + reverberation, fused (A.4, A.5) --------------------------------------
+ * cm nullable (NULL = no SNR change).  a_snr[B], rho[B], nghost[B] per-sample parameters;
+ * feather_taps[2R+1] Gaussian taps of the bone-mask feathering.  out must not alias img.
+ */
+size_t usaug_snr_reverb_workspace_bytes(int B, int H, int W);
+int usaug_snr_reverb(const float* img, const float* cm, const uint8_t* lab, float* out, int B,
+                     int H, int W, const float* a_snr, const float* rho, const int* nghost,
+                     const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- bone bounding box of a label batch (A.1 step 2 / A.5 "bone-surface row") --------------
+ * box[B,4] = {y_top, y_bottom, x_left, x_right}; y_top = -1 when the image has no bone.
+ */
+size_t usaug_bone_box_workspace_bytes(int B, int H, int W);
+int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box, void* ws, size_t ws_bytes,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USAUG_H_ */

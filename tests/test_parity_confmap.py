@@ -1,0 +1,79 @@
+"""K2 parity: CUDA matrix-free PCG confidence map vs the oracle's direct fp64 solve (A.3).
+
+Tolerance (stated, residual-derived): max|C_gpu - C_oracle| <= 5e4 * rtol + 1e-6
+(amplification K <= 2.9e4 measured at beta = 90, Appendix B).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import confmap as ocm
+from tests import util
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-8
+
+
+def gpu_cm(dev, img, **kw):
+    from ultrasoundaugmentation_b200 import ops
+    cm, it, rr = ops.confidence_map(util.cuda(img, dev), return_info=True, **kw)
+    torch.cuda.synchronize()
+    return cm.cpu().numpy(), it.cpu().numpy(), rr.cpu().numpy()
+
+
+@pytest.mark.parametrize("H,W", [(33, 17), (64, 64), (50, 3)])
+@pytest.mark.parametrize("fp64", [False, True])
+def test_constant_image_is_linear_ramp(cuda_device, H, W, fp64):
+    """KAT independent of any implementation: constant image => C[y,x] = 1 - y/(H-1) exactly."""
+    img = np.full((2, H, W), 0.3, np.float32)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=1e-10, fp64_vectors=fp64, zero_guess=True)
+    ramp = (1.0 - np.arange(H) / (H - 1.0))[None, :, None]
+    assert np.abs(cm - ramp).max() <= 2e-6
+    assert (rr <= 1e-10).all() and (it > 0).all()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 48), (3, 96, 80), (2, 128, 128), (1, 67, 131), (2, 3, 40), (1, 40, 1)])
+@pytest.mark.parametrize("precond", ["line", "jacobi"])
+def test_cm_parity_small(cuda_device, B, H, W, precond):
+    img, _ = util.synth_batch(B, H, W)
+    ref = ocm.confidence_map_batch(img)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, precond=precond, maxiter=60000)
+    assert (rr <= RTOL).all(), rr
+    assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
+    assert np.all(cm[:, 0] == 1.0) and np.all(cm[:, -1] == 0.0)
+    assert cm.min() >= -1e-6 and cm.max() <= 1.0 + 1e-6
+
+
+@pytest.mark.parametrize("fp64", [False, True])
+def test_cm_parity_256(cuda_device, fp64):
+    img, _ = util.synth_batch(2, 256, 256)
+    ref = ocm.confidence_map_batch(img)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, fp64_vectors=fp64)
+    assert (rr <= RTOL).all(), rr
+    assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
+
+
+def test_cm_batch_independence_and_determinism(cuda_device):
+    """An image's map does not depend on its batch mates; repeated runs are bitwise identical."""
+    img, _ = util.synth_batch(5, 96, 64)
+    a, ita, _ = gpu_cm(cuda_device, img, rtol=1e-7)
+    b, itb, _ = gpu_cm(cuda_device, img, rtol=1e-7)
+    assert np.array_equal(a, b) and np.array_equal(ita, itb)
+    c, itc, _ = gpu_cm(cuda_device, img[2:3], rtol=1e-7)
+    assert np.array_equal(c[0], a[2]) and itc[0] == ita[2]
+    d, _, _ = gpu_cm(cuda_device, img, rtol=1e-7, max_wave=2)
+    assert np.array_equal(d, a)
+
+
+def test_cm_maxiter_reports_nonconvergence(cuda_device):
+    img, _ = util.synth_batch(1, 128, 128)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=1e-12, maxiter=5)
+    assert it[0] == 5 and rr[0] > 1e-12 and np.isfinite(cm).all()
+
+
+def test_cm_monotone_for_constant_columns(cuda_device):
+    """Discrete maximum principle on a depth-only image: monotone non-increasing in depth."""
+    H, W = 64, 32
+    img = np.tile(np.linspace(0.2, 0.9, H, dtype=np.float32)[None, :, None], (1, 1, W))
+    cm, _, _ = gpu_cm(cuda_device, img, rtol=1e-9)
+    assert (np.diff(cm[0], axis=0) <= 1e-6).all()

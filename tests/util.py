@@ -1,0 +1,43 @@
+"""Shared helpers of the parity tests (oracle = checker, CUDA path = thing under test)."""
+import numpy as np
+import torch
+
+from oracle import deform as odeform
+from oracle import synth as osynth
+
+REL_TOL = 1e-5          # north_star: image transforms within 1e-5 relative error
+REL_DEN_FLOOR = 1e-3    # denominator max(|ref|, 1e-3)
+
+
+def rel_err(got: np.ndarray, ref: np.ndarray) -> float:
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), REL_DEN_FLOOR)))
+
+
+def tol_cm(rtol: float) -> float:
+    """max|dC| <= 5e4 * rtol + 1e-6 (measured K <= 2.9e4 at beta=90)."""
+    return 5e4 * rtol + 1e-6
+
+
+def synth_batch(B, H, W, seed0=1234):
+    return osynth.make_batch(B, H, W, seed0)
+
+
+def sample_params(B, H, K=8, seed=7):
+    rng = np.random.default_rng(seed)
+    return dict(
+        d=rng.uniform(-0.05 * H, 0.15 * H, B).astype(np.float32),
+        tgc=rng.uniform(0.6, 1.4, (B, K)).astype(np.float32),
+        a_snr=rng.uniform(0.7, 1.4, B).astype(np.float32),
+        rho=rng.uniform(0.3, 0.7, B).astype(np.float32),
+        n_ghost=rng.integers(1, 3, B).astype(np.int32),
+    )
+
+
+def cuda(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def warp_taps(W, sigma_rel=0.02):
+    return odeform.gaussian_taps(sigma_rel * W)

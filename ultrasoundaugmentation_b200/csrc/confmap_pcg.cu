@@ -1,0 +1,641 @@
+// K2: ultrasound confidence map -- random-walk potentials on the
+// 8-neighbour image graph, solved per image with a matrix-free preconditioned conjugate gradient.
+//
+//   setup   : min/max normalise, depth attenuation, edge differences, weights
+//             w = exp(-beta*(dn + pen)) + 1e-6  (4 planes: S, E, SE, SW), column-line LDL^T factors.
+//   solve   : ONE persistent cooperative kernel for the whole batch.  Every image carries its own
+//             state machine (RESID -> PRECOND -> INNER* -> FOLD -> RESID ... -> FINAL -> DONE):
+//             an inner PCG in the vector type T (fp32 by default) wrapped in fp64 iterative
+//             refinement (x64 += e; r = b - A x64 evaluated in fp64), because a pure-fp32 CG
+//             stagnates at a true relative residual of ~1e-5 on these badly scaled systems.
+//             A step of the kernel is   slot 1 (stencil tasks)  | grid sync |
+//                                       slot 2 (column sweeps)  | grid sync.
+//             Dot products: fp64 per-lane accumulation -> warp butterfly -> one slot per task ->
+//             the LAST arriving task of an image sums the slots in index order (deterministic;
+//             no floating-point atomics) and advances that image's state.
+//   precond : column-line tridiagonal (vertical couplings + full diagonal), applied as
+//             z = L^-T D^-1 L^-1 r with one down and one up sweep per column, thread per column.
+#include <cooperative_groups.h>
+
+#include <type_traits>
+
+#include "kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace usaug {
+
+constexpr int kChunks = 32;        // per-image partial reductions in the setup kernels
+constexpr float kEps = 2.220446e-16f;
+constexpr float kFloor = 1e-6f;
+constexpr float kSqrt2 = 1.41421356237309515f;
+constexpr int kStripCols = 30;     // productive columns per warp in stencil tasks (2 halo lanes)
+constexpr int kRowBlock = 32;      // rows per stencil task
+
+enum Mode : int { M_RESID = 0, M_PRECOND = 1, M_INNER = 2, M_FOLD = 3, M_FINAL = 4, M_DONE = 5 };
+
+struct ImgState {
+  int mode, iters, first, outer;
+  double rz, alpha, beta, bb, rr_true, rr_prev, rr_target, rr_rec;
+  unsigned cnt1, cnt2;
+};
+
+// ---------------------------------------------------------------------------------------------
+// setup kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void cm_depth_kernel(float* __restrict__ depth, int H, float alpha) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y < H) depth[y] = (float)(1.0 - exp(-(double)alpha * (double)y / (double)max(H - 1, 1)));
+}
+
+__device__ __forceinline__ void block_minmax(float& mn, float& mx) {
+  __shared__ float s_mn[8], s_mx[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mn = warp_min(mn); mx = warp_max(mx);
+  __syncthreads();
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  mn = s_mn[0]; mx = s_mx[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+}
+
+__global__ void __launch_bounds__(256) cm_minmax_kernel(const float* __restrict__ img, int N,
+                                                        float* __restrict__ mm) {
+  const int b = blockIdx.y, c = blockIdx.x;
+  const float* I = img + (size_t)b * N;
+  const int lo = (int)((long long)N * c / kChunks), hi = (int)((long long)N * (c + 1) / kChunks);
+  float mn = 3.0e38f, mx = -3.0e38f;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) { const float v = I[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  block_minmax(mn, mx);
+  if (threadIdx.x == 0) { mm[((size_t)b * kChunks + c) * 2] = mn; mm[((size_t)b * kChunks + c) * 2 + 1] = mx; }
+}
+
+__device__ __forceinline__ void read_mm(const float* __restrict__ mm, int b, float& mn, float& den) {
+  float lo = 3.0e38f, hi = -3.0e38f;
+#pragma unroll 8
+  for (int c = 0; c < kChunks; ++c) {
+    lo = fminf(lo, mm[((size_t)b * kChunks + c) * 2]);
+    hi = fmaxf(hi, mm[((size_t)b * kChunks + c) * 2 + 1]);
+  }
+  mn = lo;
+  den = __fadd_rn(__fsub_rn(hi, lo), kEps);
+}
+
+// attenuated, normalised intensity a = ((I - mn) / den) * depth[y]   (A.3 steps 1-2)
+__device__ __forceinline__ float atten(const float* __restrict__ I, const float* __restrict__ depth,
+                                       int y, int x, int W, float mn, float den) {
+  return __fmul_rn(__fdiv_rn(__fsub_rn(I[(size_t)y * W + x], mn), den), depth[y]);
+}
+
+__global__ void __launch_bounds__(256) cm_delta_kernel(const float* __restrict__ img, int H, int W,
+                                                       const float* __restrict__ depth,
+                                                       const float* __restrict__ mm1,
+                                                       float* __restrict__ mm2) {
+  const int b = blockIdx.y, c = blockIdx.x, N = H * W;
+  const float* I = img + (size_t)b * N;
+  float mn1, den1;
+  read_mm(mm1, b, mn1, den1);
+  const int lo = (int)((long long)N * c / kChunks), hi = (int)((long long)N * (c + 1) / kChunks);
+  float mn = 3.0e38f, mx = -3.0e38f;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    const int y = i / W, x = i - y * W;
+    const float a0 = atten(I, depth, y, x, W, mn1, den1);
+    if (x < W - 1) { const float d = fabsf(__fsub_rn(a0, atten(I, depth, y, x + 1, W, mn1, den1))); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+    if (y < H - 1) {
+      { const float d = fabsf(__fsub_rn(a0, atten(I, depth, y + 1, x, W, mn1, den1))); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+      if (x < W - 1) { const float d = fabsf(__fsub_rn(a0, atten(I, depth, y + 1, x + 1, W, mn1, den1))); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+      if (x > 0) { const float d = fabsf(__fsub_rn(a0, atten(I, depth, y + 1, x - 1, W, mn1, den1))); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+    }
+  }
+  block_minmax(mn, mx);
+  if (threadIdx.x == 0) { mm2[((size_t)b * kChunks + c) * 2] = mn; mm2[((size_t)b * kChunks + c) * 2 + 1] = mx; }
+}
+
+__device__ __forceinline__ float edge_w(float a0, float a1, float mn, float den, float beta, float pen) {
+  const float d = fabsf(__fsub_rn(a0, a1));
+  const float dn = __fdiv_rn(__fsub_rn(d, mn), den);
+  const float arg = -__fmul_rn(beta, __fadd_rn(dn, pen));
+  return __fadd_rn(expf(arg), kFloor);
+}
+
+__global__ void __launch_bounds__(256) cm_weights_kernel(
+    const float* __restrict__ img, int H, int W, const float* __restrict__ depth,
+    const float* __restrict__ mm1, const float* __restrict__ mm2, float beta, float gamma,
+    float* __restrict__ wS, float* __restrict__ wE, float* __restrict__ wSE, float* __restrict__ wSW) {
+  const int b = blockIdx.y, N = H * W;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const float* I = img + (size_t)b * N;
+  float mn1, den1, mn2, den2;
+  read_mm(mm1, b, mn1, den1);
+  read_mm(mm2, b, mn2, den2);
+  const float pen_d = __fmul_rn(kSqrt2, gamma);
+  const int y = i / W, x = i - y * W;
+  const float a0 = atten(I, depth, y, x, W, mn1, den1);
+  float s = 0.f, e = 0.f, se = 0.f, sw = 0.f;
+  if (x < W - 1) e = edge_w(a0, atten(I, depth, y, x + 1, W, mn1, den1), mn2, den2, beta, gamma);
+  if (y < H - 1) {
+    s = edge_w(a0, atten(I, depth, y + 1, x, W, mn1, den1), mn2, den2, beta, 0.0f);
+    if (x < W - 1) se = edge_w(a0, atten(I, depth, y + 1, x + 1, W, mn1, den1), mn2, den2, beta, pen_d);
+    if (x > 0) sw = edge_w(a0, atten(I, depth, y + 1, x - 1, W, mn1, den1), mn2, den2, beta, pen_d);
+  }
+  const size_t o = (size_t)b * N + i;
+  wS[o] = s; wE[o] = e; wSE[o] = se; wSW[o] = sw;
+}
+
+// Column-line factorisation T = L D L^T (T = vertical couplings + full diagonal of L_UU):
+//   piv[y] = diag[y] - wS[y-1]^2 / piv[y-1],  ip = 1/piv,  c[y] = wS[y] * ip[y].
+// Jacobi: ip = 1/diag, c = 0.  Also writes the initial guess into x64 (seed rows 1 / 0) and the
+// per-block partial of ||b||^2.
+__global__ void __launch_bounds__(128) cm_factor_kernel(
+    int H, int W, const float* __restrict__ wS, const float* __restrict__ wE,
+    const float* __restrict__ wSE, const float* __restrict__ wSW, int precond, int zero_guess,
+    float* __restrict__ ip, float* __restrict__ c, double* __restrict__ x64,
+    double* __restrict__ bbpart) {
+  __shared__ double s_bb[4];
+  const int b = blockIdx.y;
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const size_t base = (size_t)b * H * W;
+  double bb = 0.0;
+  if (x < W) {
+    const float* S = wS + base; const float* E = wE + base;
+    const float* SE = wSE + base; const float* SW = wSW + base;
+    {
+      double bv = (double)S[x];
+      if (x > 0) bv += (double)SE[x - 1];
+      if (x < W - 1) bv += (double)SW[x + 1];
+      bb = bv * bv;
+    }
+    x64[base + x] = 1.0;
+    x64[base + (size_t)(H - 1) * W + x] = 0.0;
+    ip[base + x] = 0.f; c[base + x] = 0.f;
+    ip[base + (size_t)(H - 1) * W + x] = 0.f; c[base + (size_t)(H - 1) * W + x] = 0.f;
+    double ip_prev = 0.0;   // row 0 is a seed: not part of T
+    float s_prev = S[x];
+    for (int y = 1; y <= H - 2; ++y) {
+      const size_t o = (size_t)y * W + x;
+      const float s = S[o];
+      double dg = (double)s + (double)s_prev + (double)E[o] + (double)SE[o] + (double)SW[o];
+      if (x > 0) dg += (double)E[o - 1] + (double)SE[o - W - 1];
+      if (x < W - 1) dg += (double)SW[o - W + 1];
+      double piv = dg;
+      if (precond == USAUG_PRECOND_LINE && y > 1) piv -= (double)s_prev * (double)s_prev * ip_prev;
+      const double ipv = 1.0 / piv;
+      ip[base + o] = (float)ipv;
+      c[base + o] = (precond == USAUG_PRECOND_LINE && y < H - 2) ? (float)((double)s * ipv) : 0.0f;
+      x64[base + o] = zero_guess ? 0.0 : 1.0 - (double)y / (double)(H - 1);
+      // keep the recurrence consistent with the ROUNDED factors the sweeps will use
+      ip_prev = (double)(float)ipv;
+      s_prev = s;
+    }
+  }
+  bb = warp_sum(bb);
+  if ((threadIdx.x & 31) == 0) s_bb[threadIdx.x >> 5] = bb;
+  __syncthreads();
+  if (threadIdx.x == 0) bbpart[(size_t)b * gridDim.x + blockIdx.x] = s_bb[0] + s_bb[1] + s_bb[2] + s_bb[3];
+}
+
+__global__ void cm_init_state_kernel(int B, int nblk, const double* __restrict__ bbpart,
+                                     ImgState* __restrict__ st, unsigned* __restrict__ done) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *done = 0u;
+  if (b >= B) return;
+  double bb = 0.0;
+  for (int i = 0; i < nblk; ++i) bb += bbpart[(size_t)b * nblk + i];
+  ImgState s;
+  s.mode = M_RESID; s.iters = 0; s.first = 1; s.outer = 0;
+  s.rz = 0; s.alpha = 0; s.beta = 0; s.bb = bb; s.rr_true = 0; s.rr_prev = 1e300; s.rr_target = 0; s.rr_rec = 0;
+  s.cnt1 = 0; s.cnt2 = 0;
+  st[b] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent PCG kernel
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct PcgArgs {
+  int B, H, W, maxiter;
+  double rtol2;      // rtol^2
+  double inner_red2; // squared residual reduction asked of one inner solve (0 => run to rtol)
+  const float *wS, *wE, *wSE, *wSW, *ip, *c;
+  double* x64;
+  T *e, *r, *p, *q, *z;   // q doubles as h (forward-eliminated residual) inside slot 2
+  ImgState* st;
+  double* part;      // [B][pmax][2]
+  unsigned* done;
+  float* cm;
+  int* iters_out;
+  double* relres_out;
+  int nstrip1, nrb, nstrip2, pmax, max_steps;
+};
+
+template <typename T>
+__device__ __forceinline__ T p_new(T z, T p, T beta, bool first) {
+  return first ? z : (T)fma(beta, p, z);
+}
+
+// arrival of one task of image b; returns true in all lanes of the last task to arrive
+__device__ __forceinline__ bool arrive_last(unsigned* cnt, unsigned ntasks, int lane) {
+  unsigned t = 0;
+  __syncwarp();
+  if (lane == 0) { __threadfence(); t = atomicAdd(cnt, 1u); }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  const bool last = (t == ntasks - 1);
+  if (last) __threadfence();
+  return last;
+}
+
+__device__ __forceinline__ void reduce_parts(const double* part, int n, int lane, double& s0, double& s1) {
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = lane; i < n; i += 32) { a0 += __ldcg(part + 2 * i); a1 += __ldcg(part + 2 * i + 1); }
+  s0 = warp_sum(a0); s1 = warp_sum(a1);
+}
+
+// ---- slot 1: q = A p_new (INNER) or r = b - A x64 (RESID) on a 30-column x kRowBlock-row tile ---
+template <typename T, bool RESID>
+__device__ __forceinline__ double stencil_task(const PcgArgs<T>& a, int b, int strip, int rbk, int lane,
+                                               T beta, bool first) {
+  using A = typename std::conditional<RESID, double, T>::type;
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W;
+  const int x = strip * kStripCols + lane - 1;
+  const bool valid = (x >= 0) && (x < W);
+  const bool own = valid && lane >= 1 && lane <= kStripCols;
+  const int ya = 1 + rbk * kRowBlock, yb = min(ya + kRowBlock, H - 1);
+  const float* __restrict__ S = a.wS + base; const float* __restrict__ E = a.wE + base;
+  const float* __restrict__ SE = a.wSE + base; const float* __restrict__ SW = a.wSW + base;
+  const double* X = a.x64 + base;
+  const T* Z = a.z + base; const T* P = a.p + base;
+  T* __restrict__ Q = a.q + base; T* __restrict__ Rv = a.r + base;
+
+  auto val = [&](int yy) -> A {
+    if (!valid) return (A)0;
+    const size_t o = (size_t)yy * W + x;
+    if (RESID) return (A)X[o];
+    if (yy == 0 || yy == H - 1) return (A)0;
+    return (A)p_new<T>(Z[o], first ? (T)0 : P[o], beta, first);
+  };
+  const unsigned full = 0xffffffffu;
+  A Pm = val(ya - 1), Pc = val(ya);
+  A PmL = __shfl_up_sync(full, Pm, 1), PmR = __shfl_down_sync(full, Pm, 1);
+  A PcL = __shfl_up_sync(full, Pc, 1), PcR = __shfl_down_sync(full, Pc, 1);
+  const size_t om = (size_t)(ya - 1) * W + x;
+  float wSm = valid ? S[om] : 0.f;
+  float wSEmL = __shfl_up_sync(full, valid ? SE[om] : 0.f, 1);
+  float wSWmR = __shfl_down_sync(full, valid ? SW[om] : 0.f, 1);
+  double acc = 0.0;
+#pragma unroll 2
+  for (int y = ya; y < yb; ++y) {
+    const size_t o = (size_t)y * W + x;
+    const A Pn = val(y + 1);
+    const float s = valid ? S[o] : 0.f, e = valid ? E[o] : 0.f;
+    const float se = valid ? SE[o] : 0.f, sw = valid ? SW[o] : 0.f;
+    const A PnL = __shfl_up_sync(full, Pn, 1), PnR = __shfl_down_sync(full, Pn, 1);
+    const float eL = __shfl_up_sync(full, e, 1);
+    A q = (A)s * (Pc - Pn);
+    q += (A)wSm * (Pc - Pm);
+    q += (A)e * (Pc - PcR);
+    q += (A)eL * (Pc - PcL);
+    q += (A)se * (Pc - PnR);
+    q += (A)sw * (Pc - PnL);
+    q += (A)wSEmL * (Pc - PmL);
+    q += (A)wSWmR * (Pc - PmR);
+    if (own) {
+      if (RESID) { const double rr = -(double)q; Rv[o] = (T)rr; acc += rr * rr; }
+      else { Q[o] = (T)q; acc += (double)Pc * (double)q; }
+    }
+    Pm = Pc; PmL = PcL; PmR = PcR;
+    Pc = Pn; PcL = PnL; PcR = PnR;
+    wSm = s;
+    wSEmL = __shfl_up_sync(full, se, 1);
+    wSWmR = __shfl_down_sync(full, sw, 1);
+  }
+  return warp_sum(acc);
+}
+
+// ---- slot 2 bodies: one lane = one column, rows 1..H-2 ------------------------------------------
+constexpr int kU = 4;   // rows loaded ahead per lane in the sweeps
+
+// INNER: p = z + beta p; e += alpha p; r -= alpha q; h = L^-1 r (stored over q); then z = L^-T D^-1 h
+template <typename T>
+__device__ __forceinline__ void sweep_inner(const PcgArgs<T>& a, int b, int x, bool valid, T alpha, T beta,
+                                            bool first, double& rr_out, double& rz_out) {
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W + x;
+  const float* __restrict__ IP = a.ip + base; const float* __restrict__ C = a.c + base;
+  T* __restrict__ Z = a.z + base; T* __restrict__ P = a.p + base; T* __restrict__ E = a.e + base;
+  T* __restrict__ R = a.r + base; T* __restrict__ Q = a.q + base;
+  double rr = 0.0, rz = 0.0;
+  if (valid) {
+    T hprev = (T)0; float cprev = 0.f;
+    for (int y0 = 1; y0 <= H - 2; y0 += kU) {
+      T zv[kU], pv[kU], ev[kU], rv[kU], qv[kU]; float iv[kU], cv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int y = y0 + u;
+        if (y <= H - 2) {
+          const size_t o = (size_t)y * W;
+          zv[u] = Z[o]; pv[u] = first ? (T)0 : P[o]; ev[u] = E[o]; rv[u] = R[o]; qv[u] = Q[o];
+          iv[u] = IP[o]; cv[u] = C[o];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int y = y0 + u;
+        if (y <= H - 2) {
+          const size_t o = (size_t)y * W;
+          const T pn = p_new<T>(zv[u], pv[u], beta, first);
+          P[o] = pn;
+          E[o] = (T)fma(alpha, pn, ev[u]);
+          const T rn = (T)fma(-alpha, qv[u], rv[u]);
+          R[o] = rn;
+          rr += (double)rn * (double)rn;
+          const T h = (T)fma((T)cprev, hprev, rn);
+          Q[o] = h;
+          rz += (double)iv[u] * ((double)h * (double)h);
+          hprev = h; cprev = cv[u];
+        }
+      }
+    }
+    T znext = (T)0;
+    for (int y0 = H - 2; y0 >= 1; y0 -= kU) {
+      T hv[kU]; float iv[kU], cv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int y = y0 - u;
+        if (y >= 1) { const size_t o = (size_t)y * W; hv[u] = Q[o]; iv[u] = IP[o]; cv[u] = C[o]; }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int y = y0 - u;
+        if (y >= 1) {
+          const size_t o = (size_t)y * W;
+          const T zz = (T)fma((T)cv[u], znext, (T)iv[u] * hv[u]);
+          Z[o] = zz; znext = zz;
+        }
+      }
+    }
+  }
+  rr_out = warp_sum(rr); rz_out = warp_sum(rz);
+}
+
+// PRECOND: z = M^-1 r for a fresh residual, e = 0
+template <typename T>
+__device__ __forceinline__ double sweep_precond(const PcgArgs<T>& a, int b, int x, bool valid) {
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W + x;
+  const float* __restrict__ IP = a.ip + base; const float* __restrict__ C = a.c + base;
+  T* __restrict__ Z = a.z + base; T* __restrict__ E = a.e + base;
+  const T* __restrict__ R = a.r + base; T* __restrict__ Q = a.q + base;
+  double rz = 0.0;
+  if (valid) {
+    T hprev = (T)0; float cprev = 0.f;
+#pragma unroll 4
+    for (int y = 1; y <= H - 2; ++y) {
+      const size_t o = (size_t)y * W;
+      const T h = (T)fma((T)cprev, hprev, R[o]);
+      Q[o] = h; E[o] = (T)0;
+      rz += (double)IP[o] * ((double)h * (double)h);
+      hprev = h; cprev = C[o];
+    }
+    T znext = (T)0;
+#pragma unroll 4
+    for (int y = H - 2; y >= 1; --y) {
+      const size_t o = (size_t)y * W;
+      const T zz = (T)fma((T)C[o], znext, (T)IP[o] * Q[o]);
+      Z[o] = zz; znext = zz;
+    }
+  }
+  return warp_sum(rz);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int nw = gridDim.x * wpb;
+  const int B = a.B, H = a.H, W = a.W;
+  const int per1 = a.nstrip1 * a.nrb;
+  const int tot1 = per1 * B, tot2 = a.nstrip2 * B;
+
+  for (int step = 0; step < a.max_steps; ++step) {
+    // ------------------------------ slot 1: stencil tasks --------------------------------------
+    for (int t = gw; t < tot1; t += nw) {
+      const int b = t % B, ti = t / B;
+      ImgState* st = a.st + b;
+      const int mode = __ldcg(&st->mode);
+      if (mode != M_INNER && mode != M_RESID) continue;
+      const int strip = ti % a.nstrip1, rbk = ti / a.nstrip1;
+      double s;
+      if (mode == M_INNER) {
+        const bool first = __ldcg(&st->first) != 0;
+        const T beta = (T)__ldcg(&st->beta);
+        s = stencil_task<T, false>(a, b, strip, rbk, lane, beta, first);
+      } else {
+        s = stencil_task<T, true>(a, b, strip, rbk, lane, (T)0, true);
+      }
+      double* part = a.part + (size_t)b * a.pmax * 2;
+      if (lane == 0) { part[2 * ti] = s; part[2 * ti + 1] = 0.0; }
+      if (arrive_last(&st->cnt1, (unsigned)per1, lane)) {
+        double s0, s1;
+        reduce_parts(part, per1, lane, s0, s1);
+        if (lane == 0) {
+          st->cnt1 = 0;
+          if (mode == M_INNER) {
+            if (s0 > 0.0) st->alpha = __ldcg(&st->rz) / s0;
+            else { st->alpha = 0.0; st->rr_target = 1e300; }   // breakdown: leave the inner solve
+          } else {
+            const double bb = __ldcg(&st->bb), prev = __ldcg(&st->rr_prev);
+            const int it = __ldcg(&st->iters), outer = __ldcg(&st->outer);
+            st->rr_true = s0;
+            const bool conv = s0 <= a.rtol2 * bb;
+            const bool stalled = outer > 0 && s0 > 0.25 * prev;
+            if (conv || stalled || it >= a.maxiter) st->mode = M_FINAL;
+            else {
+              st->mode = M_PRECOND;
+              st->rr_prev = s0;
+              st->rr_target = fmax(0.49 * a.rtol2 * bb, a.inner_red2 * s0);
+            }
+          }
+        }
+      }
+    }
+    grid.sync();
+    // ------------------------------ slot 2: column sweeps --------------------------------------
+    for (int t = gw; t < tot2; t += nw) {
+      const int b = t % B, strip = t / B;
+      ImgState* st = a.st + b;
+      const int mode = __ldcg(&st->mode);
+      if (mode == M_DONE || mode == M_RESID) continue;
+      const int x = strip * 32 + lane;
+      const bool valid = x < W;
+      const size_t base = (size_t)b * H * W + x;
+      double s0 = 0.0, s1 = 0.0;
+      if (mode == M_INNER) {
+        const bool first = __ldcg(&st->first) != 0;
+        sweep_inner<T>(a, b, x, valid, (T)__ldcg(&st->alpha), (T)__ldcg(&st->beta), first, s0, s1);
+      } else if (mode == M_PRECOND) {
+        s1 = sweep_precond<T>(a, b, x, valid);
+      } else if (mode == M_FOLD) {
+        if (valid) {
+#pragma unroll 4
+          for (int y = 1; y <= H - 2; ++y) { const size_t o = base + (size_t)y * W; a.x64[o] += (double)a.e[o]; }
+        }
+      } else {  // M_FINAL
+        if (valid) {
+#pragma unroll 4
+          for (int y = 0; y < H; ++y) { const size_t o = base + (size_t)y * W; a.cm[o] = (float)a.x64[o]; }
+        }
+      }
+      double* part = a.part + (size_t)b * a.pmax * 2;
+      if (lane == 0) { part[2 * strip] = s0; part[2 * strip + 1] = s1; }
+      if (arrive_last(&st->cnt2, (unsigned)a.nstrip2, lane)) {
+        reduce_parts(part, a.nstrip2, lane, s0, s1);
+        if (lane == 0) {
+          st->cnt2 = 0;
+          if (mode == M_INNER) {
+            const double rz_old = __ldcg(&st->rz);
+            const int it = __ldcg(&st->iters) + 1;
+            st->iters = it; st->rr_rec = s0; st->rz = s1; st->first = 0;
+            st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
+            if (s0 <= __ldcg(&st->rr_target) || it >= a.maxiter || !(s1 > 0.0)) st->mode = M_FOLD;
+          } else if (mode == M_PRECOND) {
+            st->rz = s1; st->first = 1; st->beta = 0.0;
+            st->mode = (s1 > 0.0) ? M_INNER : M_FINAL;
+          } else if (mode == M_FOLD) {
+            st->mode = M_RESID; st->outer = __ldcg(&st->outer) + 1;
+          } else {
+            st->mode = M_DONE;
+            const double bb = __ldcg(&st->bb);
+            if (a.iters_out) a.iters_out[b] = __ldcg(&st->iters);
+            if (a.relres_out) a.relres_out[b] = (bb > 0.0) ? sqrt(__ldcg(&st->rr_true) / bb) : 0.0;
+            __threadfence();
+            atomicAdd(a.done, 1u);
+          }
+        }
+      }
+    }
+    grid.sync();
+    if (__ldcg(a.done) >= (unsigned)B) break;
+  }
+}
+
+struct CmLayout {
+  float *depth, *mm1, *mm2, *wS, *wE, *wSE, *wSW, *ip, *c;
+  double *x64, *bbpart, *part;
+  void *e, *r, *p, *q, *z;
+  ImgState* st;
+  unsigned* done;
+  int nblk, nstrip1, nrb, nstrip2, pmax;
+  size_t bytes;
+};
+
+static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
+  CmLayout L;
+  const size_t N = (size_t)B * H * W;
+  const size_t tsz = (flags & USAUG_CM_FP64_VECTORS) ? 8 : 4;
+  L.nblk = (W + 127) / 128;
+  L.nstrip1 = (W + kStripCols - 1) / kStripCols;
+  L.nrb = (H - 2 + kRowBlock - 1) / kRowBlock;
+  L.nstrip2 = (W + 31) / 32;
+  L.pmax = L.nstrip1 * L.nrb > L.nstrip2 ? L.nstrip1 * L.nrb : L.nstrip2;
+  Carver cv(ws);
+  L.depth = cv.take<float>(H);
+  L.mm1 = cv.take<float>((size_t)B * kChunks * 2);
+  L.mm2 = cv.take<float>((size_t)B * kChunks * 2);
+  L.wS = cv.take<float>(N); L.wE = cv.take<float>(N); L.wSE = cv.take<float>(N); L.wSW = cv.take<float>(N);
+  L.ip = cv.take<float>(N); L.c = cv.take<float>(N);
+  L.x64 = cv.take<double>(N);
+  L.e = cv.take<char>(N * tsz); L.r = cv.take<char>(N * tsz); L.p = cv.take<char>(N * tsz);
+  L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz);
+  L.bbpart = cv.take<double>((size_t)B * L.nblk);
+  L.part = cv.take<double>((size_t)B * L.pmax * 2);
+  L.st = cv.take<ImgState>(B);
+  L.done = cv.take<unsigned>(1);
+  L.bytes = cv.off;
+  return L;
+}
+
+template <typename T>
+static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double rtol, int maxiter,
+                      int* iters, double* relres, cudaStream_t stream) {
+  PcgArgs<T> a;
+  a.B = B; a.H = H; a.W = W; a.maxiter = maxiter;
+  a.rtol2 = rtol * rtol;
+  const double inner_red = std::is_same<T, float>::value ? 1e-4 : 0.0;
+  a.inner_red2 = inner_red * inner_red;
+  a.wS = L.wS; a.wE = L.wE; a.wSE = L.wSE; a.wSW = L.wSW; a.ip = L.ip; a.c = L.c;
+  a.x64 = L.x64;
+  a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z;
+  a.st = L.st; a.part = L.part; a.done = L.done; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
+  a.nstrip1 = L.nstrip1; a.nrb = L.nrb; a.nstrip2 = L.nstrip2; a.pmax = L.pmax;
+  // every inner iteration is one step; each refinement round adds <= 3 steps and needs >= 1 iteration
+  a.max_steps = 4 * maxiter + 16;
+
+  int dev = 0, sms = 0, per_sm = 0;
+  USAUG_CUDA(cudaGetDevice(&dev));
+  USAUG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_persistent_kernel<T>, 256, 0));
+  if (per_sm < 1) { set_error("pcg_persistent_kernel cannot be resident"); return USAUG_E_CUDA; }
+  // enough warps for every column task, never more blocks than can be co-resident
+  const int want_warps = L.nstrip2 * B > L.nstrip1 * L.nrb * B / 4 ? L.nstrip2 * B : L.nstrip1 * L.nrb * B / 4;
+  int blocks = (want_warps + 7) / 8;
+  const int cap = sms * (per_sm > 4 ? 4 : per_sm);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  void* params[] = {(void*)&a};
+  USAUG_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_persistent_kernel<T>, dim3(blocks), dim3(256),
+                                         params, 0, stream));
+  return USAUG_OK;
+}
+
+}  // namespace usaug
+
+using namespace usaug;
+
+extern "C" size_t usaug_confmap_workspace_bytes(int B, int H, int W, int precond, int flags) {
+  (void)precond;
+  if (B <= 0 || H < 3 || W <= 0) return 0;
+  return cm_layout(nullptr, B, H, W, flags).bytes;
+}
+
+extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int W, float alpha,
+                                 float beta, float gamma, double rtol, int maxiter, int precond,
+                                 int flags, int* iters, double* relres, void* ws, size_t ws_bytes,
+                                 void* stream_) {
+  if (!img || !cm || !ws) { set_error("usaug_confmap_pcg: null pointer"); return USAUG_E_INVALID_ARG; }
+  if (B <= 0 || H < 3 || W <= 0 || (long long)H * W > (1ll << 30)) {
+    set_error("usaug_confmap_pcg: bad shape B=%d H=%d W=%d (need H>=3)", B, H, W); return USAUG_E_INVALID_ARG;
+  }
+  if (!(rtol > 0.0) || maxiter < 0 || (precond != USAUG_PRECOND_JACOBI && precond != USAUG_PRECOND_LINE)) {
+    set_error("usaug_confmap_pcg: bad solver options rtol=%g maxiter=%d precond=%d", rtol, maxiter, precond);
+    return USAUG_E_INVALID_ARG;
+  }
+  const size_t need = usaug_confmap_workspace_bytes(B, H, W, precond, flags);
+  if (ws_bytes < need) { set_error("usaug_confmap_pcg: workspace %zu < %zu", ws_bytes, need); return USAUG_E_WORKSPACE_TOO_SMALL; }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CmLayout L = cm_layout(ws, B, H, W, flags);
+  const int N = H * W;
+
+  cm_depth_kernel<<<(H + 127) / 128, 128, 0, stream>>>(L.depth, H, alpha);
+  USAUG_CHECK_LAUNCH("cm_depth_kernel");
+  cm_minmax_kernel<<<dim3(kChunks, B), 256, 0, stream>>>(img, N, L.mm1);
+  USAUG_CHECK_LAUNCH("cm_minmax_kernel");
+  cm_delta_kernel<<<dim3(kChunks, B), 256, 0, stream>>>(img, H, W, L.depth, L.mm1, L.mm2);
+  USAUG_CHECK_LAUNCH("cm_delta_kernel");
+  cm_weights_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(img, H, W, L.depth, L.mm1, L.mm2, beta,
+                                                                 gamma, L.wS, L.wE, L.wSE, L.wSW);
+  USAUG_CHECK_LAUNCH("cm_weights_kernel");
+  cm_factor_kernel<<<dim3(L.nblk, B), 128, 0, stream>>>(H, W, L.wS, L.wE, L.wSE, L.wSW, precond,
+                                                        (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.ip, L.c,
+                                                        L.x64, L.bbpart);
+  USAUG_CHECK_LAUNCH("cm_factor_kernel");
+  cm_init_state_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, L.nblk, L.bbpart, L.st, L.done);
+  USAUG_CHECK_LAUNCH("cm_init_state_kernel");
+  if (flags & USAUG_CM_FP64_VECTORS)
+    return launch_pcg<double>(L, cm, B, H, W, rtol, maxiter, iters, relres, stream);
+  return launch_pcg<float>(L, cm, B, H, W, rtol, maxiter, iters, relres, stream);
+}

@@ -1,0 +1,316 @@
+// K1: bone-surface scan -> profile smoothing -> fused TGC + probe-pressure deformation + remap.
+// Implements SURVEY.md Appendix A.1 (steps 1-5) and A.2.  The coordinate path uses explicitly
+// rounded fp32 intrinsics (no FMA contraction) so nearest-neighbour label picks are bit-exact
+// against the oracle (oracle/deform.py).
+#include "kernels.cuh"
+
+namespace usaug {
+
+// ---------------------------------------------------------------------------------------------
+// Surface scan: every label byte is read exactly once, fully parallel (no early-exit chains).
+// Block = 256 threads = 8 warps; a block covers 32*VEC columns x kScanRows rows; lane owns VEC
+// adjacent columns, warps interleave rows.  Per-column first/last bone row inside the tile is
+// merged through shared memory, then at most one atomicMin pair per column and tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanRows = 64;
+
+template <int VEC>
+__global__ void __launch_bounds__(256) surface_scan_kernel(const uint8_t* __restrict__ lab, int H,
+                                                           int W, int* __restrict__ surf) {
+  __shared__ int s_first[8][32 * VEC];
+  __shared__ int s_last[8][32 * VEC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int x0 = (blockIdx.x * 32 + lane) * VEC;
+  const int y0 = blockIdx.y * kScanRows;
+  const uint8_t* L = lab + (size_t)b * H * W;
+  int first[VEC], last[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { first[v] = kNone; last[v] = -1; }
+  if (x0 < W) {
+    uint32_t vals[kScanRows / 8];
+#pragma unroll
+    for (int i = 0; i < kScanRows / 8; ++i) {
+      const int y = y0 + warp + 8 * i;
+      uint32_t w = 0;
+      if (y < H) {
+        if (VEC == 4) {
+          w = *reinterpret_cast<const uint32_t*>(L + (size_t)y * W + x0);
+        } else {
+          w = L[(size_t)y * W + x0];
+        }
+      }
+      vals[i] = w;
+    }
+#pragma unroll
+    for (int i = 0; i < kScanRows / 8; ++i) {
+      const int y = y0 + warp + 8 * i;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if ((vals[i] >> (8 * v)) & 0xffu) {
+          first[v] = min(first[v], y);
+          last[v] = max(last[v], y);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    s_first[warp][lane * VEC + v] = first[v];
+    s_last[warp][lane * VEC + v] = last[v];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    int f = kNone, l = -1;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      f = min(f, s_first[w][c]);
+      l = max(l, s_last[w][c]);
+    }
+    const int x = blockIdx.x * 32 * VEC + c;
+    if (l >= 0 && x < W) {
+      int* dst = surf + ((size_t)b * W + x) * 2;
+      atomicMin(dst, f);
+      atomicMin(dst + 1, H - 1 - l);
+    }
+  }
+}
+
+size_t surface_scan_bytes(int B, int W) { return align_up((size_t)B * W * 2 * sizeof(int)); }
+
+int launch_surface_scan(const uint8_t* lab, int B, int H, int W, int* surf, cudaStream_t stream) {
+  USAUG_CUDA(cudaMemsetAsync(surf, 0x7f, (size_t)B * W * 2 * sizeof(int), stream));
+  const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0);
+  if (vec) {
+    dim3 grid((W + 127) / 128, (H + kScanRows - 1) / kScanRows, B);
+    surface_scan_kernel<4><<<grid, 256, 0, stream>>>(lab, H, W, surf);
+  } else {
+    dim3 grid((W + 31) / 32, (H + kScanRows - 1) / kScanRows, B);
+    surface_scan_kernel<1><<<grid, 256, 0, stream>>>(lab, H, W, surf);
+  }
+  USAUG_CHECK_LAUNCH("surface_scan_kernel");
+  return USAUG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Profile kernel: one block per image.  Hole fill (nearest bone column, ties -> lower x),
+// order-pinned smoothing, displacement clamp.  info[b] = {d_eff, y_top(as int bits)}.
+// ---------------------------------------------------------------------------------------------
+struct WarpInfo {
+  float d_eff;
+  int y_top;
+};
+
+__global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ surf, int H, int W,
+                                                      const float* __restrict__ d,
+                                                      const float* __restrict__ taps, int R,
+                                                      float* __restrict__ s_hat,
+                                                      WarpInfo* __restrict__ info) {
+  extern __shared__ int sm[];
+  int* s_first = sm;                                  // [W] first bone row or -1
+  float* s_fill = reinterpret_cast<float*>(sm + W);   // [W] hole-filled profile as fp32
+  __shared__ int s_red_i[8];
+  __shared__ float s_red_f[8];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  int ytop = kNone;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int f = surf[((size_t)b * W + x) * 2];
+    s_first[x] = (f == kNone) ? -1 : f;
+    ytop = min(ytop, f);
+  }
+  ytop = warp_min_i(ytop);
+  if (lane == 0) s_red_i[warp] = ytop;
+  __syncthreads();
+  ytop = kNone;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) ytop = min(ytop, s_red_i[w]);
+  const bool has_bone = (ytop != kNone);
+
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    int s = H - 1;
+    if (has_bone) {
+      s = s_first[x];
+      for (int j = 1; s < 0; ++j) {            // outward search; left first => ties to lower x
+        if (x - j >= 0 && s_first[x - j] >= 0) s = s_first[x - j];
+        else if (x + j < W && s_first[x + j] >= 0) s = s_first[x + j];
+      }
+    }
+    s_fill[x] = (float)s;
+  }
+  __syncthreads();
+
+  float mn = 3.0e38f;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    float acc = 0.0f;
+    for (int k = -R; k <= R; ++k) {
+      const int xi = min(max(x + k, 0), W - 1);
+      acc = __fadd_rn(acc, __fmul_rn(taps[k + R], s_fill[xi]));
+    }
+    s_hat[(size_t)b * W + x] = acc;
+    mn = fminf(mn, acc);
+  }
+  mn = warp_min(mn);
+  if (lane == 0) s_red_f[warp] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s_red_f[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fminf(m, s_red_f[w]);
+    const float lim = __fmul_rn(0.5f, m);
+    WarpInfo wi;
+    wi.d_eff = fminf(fmaxf(d[b], -lim), lim);
+    wi.y_top = has_bone ? ytop : -1;
+    info[b] = wi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused warp: thread = one scanline (column), block = 128 scanlines x kWarpRows output rows.
+// Per output pixel: 2 image taps + 1 label tap gathered along the scanline, TGC gain, clip.
+// 10 algorithmic bytes per pixel (4+1 in, 4+1 out).
+// ---------------------------------------------------------------------------------------------
+constexpr int kWarpRows = 16;
+
+__global__ void __launch_bounds__(128) fused_warp_kernel(
+    const float* __restrict__ img, const uint8_t* __restrict__ lab, float* __restrict__ out_img,
+    uint8_t* __restrict__ out_lab, int H, int W, const float* __restrict__ s_hat,
+    const WarpInfo* __restrict__ info, const float* __restrict__ tgc, int K, float gscale) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= W) return;
+  const size_t base = (size_t)b * H * W;
+  const float* I = img + base;
+  const uint8_t* L = lab + base;
+  const float de = info[b].d_eff;
+  const float den = __fsub_rn(s_hat[(size_t)b * W + x], de);
+  const float* g = tgc + (size_t)b * K;
+  const int ya = blockIdx.y * kWarpRows;
+
+#pragma unroll 8
+  for (int r = 0; r < kWarpRows; ++r) {
+    const int y = ya + r;
+    if (y >= H) break;
+    const float yf = (float)y;
+    const float t = (yf < den) ? __fdiv_rn(yf, den) : 1.0f;
+    const float ys = __fadd_rn(yf, __fmul_rn(de, t));
+    const float y0f = floorf(ys);
+    const float fr = ys - y0f;
+    const int i0 = (int)y0f, i1 = i0 + 1;
+    const float v0 = (i0 >= 0 && i0 < H) ? I[(size_t)i0 * W + x] : 0.0f;
+    const float v1 = (i1 >= 0 && i1 < H) ? I[(size_t)i1 * W + x] : 0.0f;
+    const int yn = (int)floorf(__fadd_rn(ys, 0.5f));
+    const uint8_t lv = (yn >= 0 && yn < H) ? L[(size_t)yn * W + x] : (uint8_t)0;
+
+    float gain;
+    if (K == 1) {
+      gain = g[0];
+    } else {
+      const float u = __fmul_rn(yf, gscale);
+      const int k0 = min((int)floorf(u), K - 2);
+      const float fg = u - (float)k0;
+      const float g0 = g[k0], g1 = g[k0 + 1];
+      gain = g0 + fg * (g1 - g0);
+    }
+    const float v = (1.0f - fr) * v0 + fr * v1;
+    out_img[base + (size_t)y * W + x] = fminf(fmaxf(gain * v, 0.0f), 1.0f);
+    out_lab[base + (size_t)y * W + x] = lv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bone box: reduces the surface scan to {y_top, y_bottom, x_left, x_right} per image.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bone_box_kernel(const int* __restrict__ surf, int H, int W,
+                                                       int* __restrict__ box) {
+  __shared__ int s_red[4][8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int yt = kNone, yb = -1, xl = kNone, xr = -1;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int f = surf[((size_t)b * W + x) * 2];
+    if (f != kNone) {
+      const int l = H - 1 - surf[((size_t)b * W + x) * 2 + 1];
+      yt = min(yt, f); yb = max(yb, l); xl = min(xl, x); xr = max(xr, x);
+    }
+  }
+  yt = warp_min_i(yt); yb = warp_max_i(yb); xl = warp_min_i(xl); xr = warp_max_i(xr);
+  if (lane == 0) { s_red[0][warp] = yt; s_red[1][warp] = yb; s_red[2][warp] = xl; s_red[3][warp] = xr; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      yt = min(yt, s_red[0][w]); yb = max(yb, s_red[1][w]);
+      xl = min(xl, s_red[2][w]); xr = max(xr, s_red[3][w]);
+    }
+    int* o = box + (size_t)b * 4;
+    if (yt == kNone) { o[0] = -1; o[1] = -1; o[2] = -1; o[3] = -1; }
+    else { o[0] = yt; o[1] = yb; o[2] = xl; o[3] = xr; }
+  }
+}
+
+}  // namespace usaug
+
+using namespace usaug;
+
+extern "C" size_t usaug_warp_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return surface_scan_bytes(B, W) + align_up((size_t)B * W * sizeof(float)) +
+         align_up((size_t)B * sizeof(WarpInfo));
+}
+
+extern "C" int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, float* out_img,
+                                      uint8_t* out_lab, int B, int H, int W, const float* d,
+                                      const float* tgc, int K, const float* taps, int R, void* ws,
+                                      size_t ws_bytes, void* stream_) {
+  if (!img || !lab || !out_img || !out_lab || !d || !tgc || !taps || !ws) {
+    set_error("usaug_fused_tgc_deform: null pointer"); return USAUG_E_INVALID_ARG;
+  }
+  if (B <= 0 || H <= 0 || W <= 0 || W > 4096 || K < 1 || R < 0) {
+    set_error("usaug_fused_tgc_deform: bad shape B=%d H=%d W=%d K=%d R=%d (need 1<=W<=4096)", B, H, W, K, R);
+    return USAUG_E_INVALID_ARG;
+  }
+  if (img == out_img || lab == out_lab) {
+    set_error("usaug_fused_tgc_deform: outputs must not alias inputs"); return USAUG_E_INVALID_ARG;
+  }
+  if (ws_bytes < usaug_warp_workspace_bytes(B, H, W)) {
+    set_error("usaug_fused_tgc_deform: workspace %zu < %zu", ws_bytes, usaug_warp_workspace_bytes(B, H, W));
+    return USAUG_E_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Carver cv(ws);
+  int* surf = cv.take<int>((size_t)B * W * 2);
+  float* s_hat = cv.take<float>((size_t)B * W);
+  WarpInfo* info = cv.take<WarpInfo>(B);
+
+  int rc = launch_surface_scan(lab, B, H, W, surf, stream);
+  if (rc) return rc;
+  profile_kernel<<<B, 256, (size_t)W * 8, stream>>>(surf, H, W, d, taps, R, s_hat, info);
+  USAUG_CHECK_LAUNCH("profile_kernel");
+  const float gscale = (H > 1 && K > 1) ? (float)((double)(K - 1) / (double)(H - 1)) : 0.0f;
+  dim3 grid((W + 127) / 128, (H + kWarpRows - 1) / kWarpRows, B);
+  fused_warp_kernel<<<grid, 128, 0, stream>>>(img, lab, out_img, out_lab, H, W, s_hat, info, tgc,
+                                              (H > 1) ? K : 1, gscale);
+  USAUG_CHECK_LAUNCH("fused_warp_kernel");
+  return USAUG_OK;
+}
+
+extern "C" size_t usaug_bone_box_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return surface_scan_bytes(B, W);
+}
+
+extern "C" int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box, void* ws,
+                              size_t ws_bytes, void* stream_) {
+  if (!lab || !box || !ws) { set_error("usaug_bone_box: null pointer"); return USAUG_E_INVALID_ARG; }
+  if (B <= 0 || H <= 0 || W <= 0) { set_error("usaug_bone_box: bad shape"); return USAUG_E_INVALID_ARG; }
+  if (ws_bytes < usaug_bone_box_workspace_bytes(B, H, W)) {
+    set_error("usaug_bone_box: workspace too small"); return USAUG_E_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int* surf = static_cast<int*>(ws);
+  int rc = launch_surface_scan(lab, B, H, W, surf, stream);
+  if (rc) return rc;
+  bone_box_kernel<<<B, 256, 0, stream>>>(surf, H, W, box);
+  USAUG_CHECK_LAUNCH("bone_box_kernel");
+  return USAUG_OK;
+}

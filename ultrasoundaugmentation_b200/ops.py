@@ -1,0 +1,174 @@
+"""Functional layer: torch CUDA tensors in, torch CUDA tensors out, all compute in libusaug.so.
+
+Every function enqueues on the CURRENT torch stream and never synchronises.  CPU tensors are
+rejected (there is no CPU fallback); batches are [B,H,W] here -- the transform classes handle
+the [H,W] / [1,H,W] / [B,1,H,W] conveniences.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _ffi
+
+
+def gaussian_taps(sigma: float, radius: int | None = None) -> torch.Tensor:
+    """exp(-k^2/2 sigma^2) normalised in fp64, rounded to fp32."""
+    if radius is None:
+        radius = int(math.ceil(3.0 * float(sigma)))
+    radius = max(int(radius), 0)
+    k = np.arange(-radius, radius + 1, dtype=np.float64)
+    t = (k == 0).astype(np.float64) if sigma <= 0 else np.exp(-(k * k) / (2.0 * float(sigma) ** 2))
+    t /= t.sum()
+    return torch.from_numpy(t.astype(np.float32))
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _dev_param(v, B: int, device, dtype, name: str, width: int | None = None) -> torch.Tensor:
+    t = torch.as_tensor(v, dtype=dtype)
+    if t.dim() == 0:
+        t = t.expand(B) if width is None else t.expand(B, width)
+    want = (B,) if width is None else (B, width)
+    if tuple(t.shape) != want:
+        raise ValueError(f"{name} must have shape {want}, got {tuple(t.shape)}")
+    return t.contiguous().to(device, non_blocking=True)
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _check_pair(image, label):
+    image = _need_cuda(image, "image", torch.float32)
+    label = _need_cuda(label, "label", torch.uint8)
+    if image.dim() != 3 or image.shape != label.shape or image.device != label.device:
+        raise ValueError(f"image/label must both be [B,H,W] on one device, got {tuple(image.shape)} / {tuple(label.shape)}")
+    return image, label
+
+
+def fused_tgc_deform(image, label, d, tgc, taps):
+    """K1 (A.1 + A.2).  image f32 [B,H,W], label u8 [B,H,W], d [B], tgc [B,K], taps [2R+1]."""
+    lib = _ffi.load()
+    image, label = _check_pair(image, label)
+    B, H, W = image.shape
+    dev = image.device
+    tgc_t = torch.as_tensor(tgc, dtype=torch.float32)
+    if tgc_t.dim() == 1:
+        tgc_t = tgc_t.unsqueeze(0).expand(B, -1)
+    K = int(tgc_t.shape[1])
+    with torch.cuda.device(dev):
+        d_t = _dev_param(d, B, dev, torch.float32, "d")
+        tgc_t = _dev_param(tgc_t, B, dev, torch.float32, "tgc", K)
+        taps_t = torch.as_tensor(taps, dtype=torch.float32).contiguous().to(dev, non_blocking=True)
+        if taps_t.numel() % 2 != 1:
+            raise ValueError("taps must have odd length 2R+1")
+        R = (taps_t.numel() - 1) // 2
+        out_img = torch.empty_like(image)
+        out_lab = torch.empty_like(label)
+        nbytes = lib.usaug_warp_workspace_bytes(B, H, W)
+        ws = _ws(nbytes, dev)
+        rc = lib.usaug_fused_tgc_deform(image.data_ptr(), label.data_ptr(), out_img.data_ptr(),
+                                        out_lab.data_ptr(), B, H, W, d_t.data_ptr(), tgc_t.data_ptr(),
+                                        K, taps_t.data_ptr(), R, ws.data_ptr(), ws.numel(),
+                                        _stream_ptr(dev))
+        _ffi.check(rc, "usaug_fused_tgc_deform")
+    return out_img, out_lab
+
+
+def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-6, maxiter=10000,
+                   precond="line", fp64_vectors=False, zero_guess=False, max_wave=None,
+                   return_info=False):
+    """K2 (A.3).  image f32 [B,H,W] -> cm f32 [B,H,W] (+ iters int32 [B], true relres f64 [B]).
+
+    The batch is solved in waves of at most ``max_wave`` images (workspace ~56 B/pixel/image
+    with fp32 vectors); default keeps the workspace under ~16 GiB.
+    """
+    lib = _ffi.load()
+    image = _need_cuda(image, "image", torch.float32)
+    if image.dim() != 3:
+        raise ValueError(f"image must be [B,H,W], got {tuple(image.shape)}")
+    B, H, W = image.shape
+    if H < 3:
+        raise ValueError("confidence map needs H >= 3")
+    dev = image.device
+    pc = {"jacobi": _ffi.PRECOND_JACOBI, "line": _ffi.PRECOND_LINE}[precond]
+    flags = (_ffi.CM_FP64_VECTORS if fp64_vectors else 0) | (_ffi.CM_ZERO_GUESS if zero_guess else 0)
+    with torch.cuda.device(dev):
+        per_img = lib.usaug_confmap_workspace_bytes(1, H, W, pc, flags)
+        if max_wave is None:
+            max_wave = max(1, min(B, (16 << 30) // max(per_img, 1)))
+        max_wave = max(1, min(int(max_wave), B))
+        cm = torch.empty_like(image)
+        iters = torch.full((B,), -1, dtype=torch.int32, device=dev)
+        relres = torch.full((B,), float("nan"), dtype=torch.float64, device=dev)
+        ws = _ws(lib.usaug_confmap_workspace_bytes(max_wave, H, W, pc, flags), dev)
+        for lo in range(0, B, max_wave):
+            n = min(max_wave, B - lo)
+            rc = lib.usaug_confmap_pcg(image[lo:lo + n].data_ptr(), cm[lo:lo + n].data_ptr(), n, H, W,
+                                       float(alpha), float(beta), float(gamma), float(rtol),
+                                       int(maxiter), pc, flags, iters[lo:lo + n].data_ptr(),
+                                       relres[lo:lo + n].data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _stream_ptr(dev))
+            _ffi.check(rc, "usaug_confmap_pcg")
+    if return_info:
+        return cm, iters, relres
+    return cm
+
+
+def snr_reverb(image, cm, label, a_snr, rho, n_ghost, feather_taps):
+    """K3 (A.4 + A.5).  cm may be None (reverb only); n_ghost = 0 disables the ghosts."""
+    lib = _ffi.load()
+    image, label = _check_pair(image, label)
+    B, H, W = image.shape
+    dev = image.device
+    if cm is not None:
+        cm = _need_cuda(cm, "cm", torch.float32)
+        if cm.shape != image.shape:
+            raise ValueError("cm must have the image's shape")
+    with torch.cuda.device(dev):
+        a_t = _dev_param(a_snr, B, dev, torch.float32, "a_snr")
+        r_t = _dev_param(rho, B, dev, torch.float32, "rho")
+        n_t = _dev_param(n_ghost, B, dev, torch.int32, "n_ghost")
+        taps_t = torch.as_tensor(feather_taps, dtype=torch.float32).contiguous().to(dev, non_blocking=True)
+        if taps_t.numel() % 2 != 1:
+            raise ValueError("feather_taps must have odd length 2R+1")
+        R = (taps_t.numel() - 1) // 2
+        out = torch.empty_like(image)
+        ws = _ws(lib.usaug_snr_reverb_workspace_bytes(B, H, W), dev)
+        rc = lib.usaug_snr_reverb(image.data_ptr(), 0 if cm is None else cm.data_ptr(), label.data_ptr(),
+                                  out.data_ptr(), B, H, W, a_t.data_ptr(), r_t.data_ptr(), n_t.data_ptr(),
+                                  taps_t.data_ptr(), R, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _ffi.check(rc, "usaug_snr_reverb")
+    return out
+
+
+def bone_box(label):
+    """[B,4] int32 {y_top, y_bottom, x_left, x_right}; y_top = -1 for an image without bone."""
+    lib = _ffi.load()
+    label = _need_cuda(label, "label", torch.uint8)
+    if label.dim() != 3:
+        raise ValueError("label must be [B,H,W]")
+    B, H, W = label.shape
+    dev = label.device
+    with torch.cuda.device(dev):
+        box = torch.empty((B, 4), dtype=torch.int32, device=dev)
+        ws = _ws(lib.usaug_bone_box_workspace_bytes(B, H, W), dev)
+        rc = lib.usaug_bone_box(label.data_ptr(), B, H, W, box.data_ptr(), ws.data_ptr(), ws.numel(),
+                                _stream_ptr(dev))
+        _ffi.check(rc, "usaug_bone_box")
+    return box

@@ -1,0 +1,293 @@
+"""Per-transform callables with a parameter-sampling API (the dataloader-facing boundary).
+
+The reference mount (/root/reference/README.md:1-2) defines no API, so this follows the
+de-facto PyTorch transform protocol that SURVEY.md section 8(b) pins:
+
+    t = ProbePressureDeformation(...)            # constructed once, picklable (config only)
+    params = t.get_params(batch_size, generator=None, sample_index=None, image_size=(H, W))
+    image_out, label_out = t(image, label, params=None)
+
+image: float32 in [0,1], label: uint8 (bone = non-zero); shapes [H,W], [1,H,W], [B,H,W] or
+[B,1,H,W]; CUDA tensors only (TypeError / ValueError otherwise -- there is no CPU fallback).
+Outputs are new tensors on the same device, enqueued on the current stream, no host sync.
+Physics: SURVEY.md Appendix A.1-A.5; kernels: csrc/*.cu through the C ABI in include/usaug.h.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .params import uniforms
+
+__all__ = ["ProbePressureDeformation", "TimeGainCompensation", "ConfidenceSNR", "Reverberation",
+           "PhysicsChain"]
+
+
+def _to_bhw(image: torch.Tensor, label: torch.Tensor):
+    if not isinstance(image, torch.Tensor) or not isinstance(label, torch.Tensor):
+        raise TypeError("image and label must be torch tensors")
+    if image.shape != label.shape:
+        raise ValueError(f"image {tuple(image.shape)} and label {tuple(label.shape)} differ in shape")
+    shp = tuple(image.shape)
+    if image.dim() == 2:
+        v = (1,) + shp
+    elif image.dim() == 3:
+        v = shp
+    elif image.dim() == 4 and shp[1] == 1:
+        v = (shp[0], shp[2], shp[3])
+    else:
+        raise ValueError(f"expected [H,W], [1,H,W], [B,H,W] or [B,1,H,W], got {shp}")
+    return image.reshape(v), label.reshape(v), shp
+
+
+def _as_tensor_dict(d: dict) -> dict:
+    return {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v)))
+            for k, v in d.items()}
+
+
+class _Transform:
+    """Common machinery: application probability p, seed, RNG stream id."""
+
+    _stream = 0
+
+    def __init__(self, p: float = 1.0, seed: int = 0):
+        if not 0.0 <= p <= 1.0:
+            raise ValueError("p must be in [0,1]")
+        self.p = float(p)
+        self.seed = int(seed)
+
+    def _draw(self, B, n, generator, sample_index):
+        # column 0 decides application; columns 1.. are the transform's own draws
+        u = uniforms(B, n + 1, seed=self.seed, stream=self._stream, generator=generator,
+                     sample_index=sample_index)
+        return u[:, 0] < self.p, u[:, 1:]
+
+    def get_params(self, batch_size, generator=None, sample_index=None, image_size=None) -> dict:
+        raise NotImplementedError
+
+    def __call__(self, image, label, params: Optional[dict] = None, sample_index=None):
+        chain = PhysicsChain([self])
+        return chain(image, label, params=params, sample_index=sample_index)
+
+
+class ProbePressureDeformation(_Transform):
+    """A.1: axial displacement field along scanlines, scaled by depth and the bone surface.
+
+    d ~ U(d_range) * H pixels (positive = more pressure; clamped on device to half the
+    shallowest smoothed bone depth).  sigma_rel*W is the Gaussian sigma of the surface profile.
+    """
+
+    _stream = 1
+
+    def __init__(self, d_range: Sequence[float] = (-0.05, 0.15), sigma_rel: float = 0.02,
+                 p: float = 1.0, seed: int = 0):
+        super().__init__(p, seed)
+        self.d_range = (float(d_range[0]), float(d_range[1]))
+        self.sigma_rel = float(sigma_rel)
+
+    def taps(self, W: int) -> torch.Tensor:
+        return ops.gaussian_taps(self.sigma_rel * W)
+
+    def get_params(self, batch_size, generator=None, sample_index=None, image_size=None):
+        if image_size is None:
+            raise ValueError("ProbePressureDeformation.get_params needs image_size=(H, W)")
+        H = int(image_size[0])
+        apply, u = self._draw(batch_size, 1, generator, sample_index)
+        lo, hi = self.d_range
+        d = (lo + (hi - lo) * u[:, 0]) * H
+        d = np.where(apply, d, 0.0).astype(np.float32)
+        return _as_tensor_dict({"d": d})
+
+
+class TimeGainCompensation(_Transform):
+    """A.2 TGC: K control gains ~ U(gain_range), linear in output depth."""
+
+    _stream = 2
+
+    def __init__(self, num_gains: int = 8, gain_range: Sequence[float] = (0.6, 1.4), p: float = 1.0,
+                 seed: int = 0):
+        super().__init__(p, seed)
+        if num_gains < 1:
+            raise ValueError("num_gains must be >= 1")
+        self.num_gains = int(num_gains)
+        self.gain_range = (float(gain_range[0]), float(gain_range[1]))
+
+    def get_params(self, batch_size, generator=None, sample_index=None, image_size=None):
+        apply, u = self._draw(batch_size, self.num_gains, generator, sample_index)
+        lo, hi = self.gain_range
+        g = lo + (hi - lo) * u
+        g = np.where(apply[:, None], g, 1.0).astype(np.float32)
+        return _as_tensor_dict({"tgc": g})
+
+
+class ConfidenceSNR(_Transform):
+    """A.3 + A.4: confidence map of the (deformed) image, then I + (a-1) * C * I, clipped."""
+
+    _stream = 3
+
+    def __init__(self, a_range: Sequence[float] = (0.7, 1.4), alpha: float = 2.0, beta: float = 90.0,
+                 gamma: float = 0.05, rtol: float = 1e-6, maxiter: int = 20000, precond: str = "line",
+                 fp64_vectors: bool = False, max_wave: Optional[int] = None, p: float = 1.0,
+                 seed: int = 0):
+        super().__init__(p, seed)
+        if precond not in ("line", "jacobi"):
+            raise ValueError("precond must be 'line' or 'jacobi'")
+        self.a_range = (float(a_range[0]), float(a_range[1]))
+        self.alpha, self.beta, self.gamma = float(alpha), float(beta), float(gamma)
+        self.rtol, self.maxiter, self.precond = float(rtol), int(maxiter), precond
+        self.fp64_vectors = bool(fp64_vectors)
+        self.max_wave = max_wave
+        self.last_info = None      # (iters, relres) device tensors of the most recent call
+
+    def get_params(self, batch_size, generator=None, sample_index=None, image_size=None):
+        apply, u = self._draw(batch_size, 1, generator, sample_index)
+        lo, hi = self.a_range
+        a = np.where(apply, lo + (hi - lo) * u[:, 0], 1.0).astype(np.float32)
+        return _as_tensor_dict({"a_snr": a})
+
+    def confidence_map(self, image_bhw: torch.Tensor) -> torch.Tensor:
+        cm, it, rr = ops.confidence_map(image_bhw, self.alpha, self.beta, self.gamma, self.rtol,
+                                        self.maxiter, self.precond, self.fp64_vectors,
+                                        max_wave=self.max_wave, return_info=True)
+        self.last_info = (it, rr)
+        return cm
+
+    def __getstate__(self):
+        s = dict(self.__dict__)
+        s["last_info"] = None
+        return s
+
+
+class Reverberation(_Transform):
+    """A.5: ghosts of the bone region at multiples of the bone-surface depth, attenuated by rho^k."""
+
+    _stream = 4
+
+    def __init__(self, rho_range: Sequence[float] = (0.3, 0.7), max_ghosts: int = 2,
+                 sigma_feather: float = 2.0, p: float = 1.0, seed: int = 0):
+        super().__init__(p, seed)
+        if max_ghosts < 1:
+            raise ValueError("max_ghosts must be >= 1")
+        if math.ceil(3.0 * sigma_feather) > 32:
+            raise ValueError("sigma_feather too large (tap radius must be <= 32)")
+        self.rho_range = (float(rho_range[0]), float(rho_range[1]))
+        self.max_ghosts = int(max_ghosts)
+        self.sigma_feather = float(sigma_feather)
+
+    def taps(self) -> torch.Tensor:
+        return ops.gaussian_taps(self.sigma_feather)
+
+    def get_params(self, batch_size, generator=None, sample_index=None, image_size=None):
+        apply, u = self._draw(batch_size, 2, generator, sample_index)
+        lo, hi = self.rho_range
+        rho = (lo + (hi - lo) * u[:, 0]).astype(np.float32)
+        n = np.minimum(1 + np.floor(u[:, 1] * self.max_ghosts), self.max_ghosts).astype(np.int32)
+        n = np.where(apply, n, 0).astype(np.int32)
+        return _as_tensor_dict({"rho": rho, "n_ghost": n})
+
+
+class PhysicsChain:
+    """deformation (+TGC, one fused launch) -> confidence-map SNR -> reverberation (one fused launch).
+
+    Accepts any subset of the four transforms (at most one of each); the physical order is fixed
+    (SURVEY.md Appendix A "Chain order").
+    """
+
+    def __init__(self, transforms: Sequence[_Transform]):
+        self.deform = self.tgc = self.snr = self.reverb = None
+        for t in transforms:
+            if isinstance(t, ProbePressureDeformation):
+                slot = "deform"
+            elif isinstance(t, TimeGainCompensation):
+                slot = "tgc"
+            elif isinstance(t, ConfidenceSNR):
+                slot = "snr"
+            elif isinstance(t, Reverberation):
+                slot = "reverb"
+            else:
+                raise TypeError(f"unsupported transform {type(t).__name__}")
+            if getattr(self, slot) is not None:
+                raise ValueError(f"duplicate {slot} transform")
+            setattr(self, slot, t)
+        self.transforms = [t for t in (self.deform, self.tgc, self.snr, self.reverb) if t is not None]
+        if not self.transforms:
+            raise ValueError("empty chain")
+
+    @classmethod
+    def full(cls, seed: int = 0, **snr_kwargs) -> "PhysicsChain":
+        return cls([ProbePressureDeformation(seed=seed), TimeGainCompensation(seed=seed),
+                    ConfidenceSNR(seed=seed, **snr_kwargs), Reverberation(seed=seed)])
+
+    def get_params(self, batch_size, generator=None, sample_index=None, image_size=None) -> dict:
+        out = {}
+        for t in self.transforms:
+            out.update(t.get_params(batch_size, generator, sample_index, image_size))
+        return out
+
+    # ---- device path --------------------------------------------------------------------------
+    def __call__(self, image, label, params: Optional[dict] = None, sample_index=None):
+        img, lab, shp = _to_bhw(image, label)
+        if not img.is_cuda or not lab.is_cuda:
+            raise ValueError("PhysicsChain needs CUDA tensors (no CPU fallback exists); "
+                             "use augment_host() for host buffers")
+        if img.dtype != torch.float32:
+            raise TypeError(f"image must be float32, got {img.dtype}")
+        if lab.dtype != torch.uint8:
+            raise TypeError(f"label must be uint8, got {lab.dtype}")
+        B, H, W = img.shape
+        if params is None:
+            params = self.get_params(B, None, sample_index, (H, W))
+        out_img, out_lab = self._run(img.contiguous(), lab.contiguous(), params)
+        return out_img.reshape(shp), out_lab.reshape(shp)
+
+    def _run(self, img, lab, params):
+        B, H, W = img.shape
+        if self.deform is not None or self.tgc is not None:
+            d = params["d"] if self.deform is not None else torch.zeros(B)
+            tgc = params["tgc"] if self.tgc is not None else torch.ones(B, 1)
+            taps = self.deform.taps(W) if self.deform is not None else ops.gaussian_taps(0.0, 0)
+            img, lab = ops.fused_tgc_deform(img, lab, d, tgc, taps)
+        cm = None
+        if self.snr is not None:
+            cm = self.snr.confidence_map(img)
+        if self.snr is not None or self.reverb is not None:
+            a = params["a_snr"] if self.snr is not None else torch.ones(B)
+            if self.reverb is not None:
+                rho, n, taps = params["rho"], params["n_ghost"], self.reverb.taps()
+            else:
+                rho, n, taps = torch.zeros(B), torch.zeros(B, dtype=torch.int32), ops.gaussian_taps(0.0, 0)
+            img = ops.snr_reverb(img, cm, lab, a, rho, n, taps)
+        return img, lab
+
+    # ---- host path: pinned host buffers in, pinned host buffers out ---------------------------
+    def augment_host(self, image: torch.Tensor, label: torch.Tensor, params: Optional[dict] = None,
+                     sample_index=None, device=None, out: Optional[tuple] = None):
+        """Host tensors -> H2D -> chain on the GPU -> D2H.  Not a CPU fallback: compute is CUDA.
+
+        Everything is enqueued on the current stream of `device`; the call returns after the
+        stream has finished so the host buffers are valid.
+        """
+        if image.is_cuda or label.is_cuda:
+            raise ValueError("augment_host takes host tensors; call the chain directly for CUDA tensors")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        img, lab, shp = _to_bhw(image, label)
+        B, H, W = img.shape
+        if params is None:
+            params = self.get_params(B, None, sample_index, (H, W))
+        with torch.cuda.device(device):
+            d_img = img.contiguous().to(device, non_blocking=True)
+            d_lab = lab.contiguous().to(device, non_blocking=True)
+            o_img, o_lab = self._run(d_img, d_lab, params)
+            if out is None:
+                h_img = torch.empty((B, H, W), dtype=torch.float32, pin_memory=True)
+                h_lab = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
+            else:
+                h_img, h_lab = out[0].reshape(B, H, W), out[1].reshape(B, H, W)
+            h_img.copy_(o_img, non_blocking=True)
+            h_lab.copy_(o_lab, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+        return h_img.reshape(shp), h_lab.reshape(shp)
