@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Headline benchmark: augmented images/sec at 512x512 (BASELINE.json `metric`).
+
+Workload = BASELINE.json configs[4], the configuration the metric is quoted on: the FULL chain
+(probe-pressure deformation + TGC + remap -> confidence map PCG -> SNR -> reverb) with per-sample
+random parameters on synthetic 512x512 B-mode images, sharded over N GPUs with no collective on
+the data path.  Every GPU owns 512 images per step (weak scaling), so N = 8 is exactly configs[4]'s
+batch of 4096 and N = 1 is its per-GPU share.
+
+    python bench.py --gpus N --steps K --warmup W            # N>1: launched by torch.distributed.run
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the chain over the whole (sharded) batch.  Timed with CUDA events,
+barrier + synchronize on both sides, max over ranks.  Rank 0 prints ONE JSON line.
+The reference mount holds no code (README.md only), so the reference arm times the self-written
+CPU oracle (`oracle/`, kind "port") on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "augmented images/sec at 512x512 (full chain)"
+UNIT = "images/s"
+H = W = 512
+PER_GPU_BATCH = 512             # configs[4]: 4096 images over 8 GPUs
+WAVE = 256                      # images per PCG launch (workspace ~3.5 GiB)
+PCG_BYTES_PER_UNKNOWN_ITER = 64  # SURVEY.md 8(d) algorithmic-bytes model
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--per-gpu-batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
+    ap.add_argument("--rtol", type=float, default=1e-8)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores (one image per task, BLAS threads pinned to 1)
+# ------------------------------------------------------------------------------------------------
+def _cpu_warm(_):
+    for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[v] = "1"
+    import numpy as np
+    from oracle import chain as ochain, deform as odeform, synth as osynth
+    img, lab = osynth.make_bmode(24, 24, 1)
+    ochain.full_chain(img, lab, 1.0, np.ones(2, np.float32), 1.1, 0.5, 1, odeform.gaussian_taps(1.0),
+                      odeform.gaussian_taps(1.0))
+    return os.getpid()
+
+
+def _cpu_one(args):
+    idx, p = args
+    from oracle import chain as ochain, deform as odeform, synth as osynth
+    img, lab = osynth.make_bmode(H, W, 1234 + idx)
+    t0 = time.perf_counter()
+    ochain.full_chain(img, lab, p["d"], p["tgc"], p["a_snr"], p["rho"], p["n_ghost"],
+                      odeform.gaussian_taps(0.02 * W), odeform.gaussian_taps(2.0))
+    return time.perf_counter() - t0
+
+
+def cpu_oracle_rate(n_images: int, cores: int, first: int = 0):
+    """images/s of the oracle full chain (`oracle/`, the checker) on `cores` host processes."""
+    import multiprocessing as mp
+
+    import ultrasoundaugmentation_b200 as us
+    ch = us.PhysicsChain.full(seed=2021)
+    idx = [first + i for i in range(n_images)]
+    prm = {k: v.numpy() for k, v in ch.get_params(n_images, sample_index=idx, image_size=(H, W)).items()}
+    tasks = [(idx[i], {k: v[i] for k, v in prm.items()}) for i in range(n_images)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_warm, range(cores), chunksize=1)     # imports + first-touch outside the timed region
+        t0 = time.perf_counter()
+        per = pool.map(_cpu_one, tasks, chunksize=1)
+        wall = time.perf_counter() - t0
+    return n_images / wall, wall, sum(per) / len(per)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = a.cpu_sample or cores
+    rates = []
+    for s in range(a.warmup + a.steps):
+        # warm-up steps import numpy/scipy and page in the workers; keep them short
+        r, wall, per = cpu_oracle_rate(n if s >= a.warmup else min(n, cores), cores, first=s * n)
+        if s >= a.warmup:
+            rates.append((r, wall))
+    total_wall = sum(w for _, w in rates)
+    value = a.steps * n / total_wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total_wall / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "configs[4]: full chain 512x512 (bounded sample per step)",
+                   "sample_images_per_step": n, "solver": "scipy.sparse.linalg.splu (direct, fp64)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} images/step of the same synthetic 512x512 workload, oracle full chain, "
+                                   f"multiprocessing.Pool({cores}), 1 BLAS thread each"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import ultrasoundaugmentation_b200 as us
+    from ultrasoundaugmentation_b200 import _ffi, sharding, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and a.gpus > 1:
+        # convenience: re-launch under torch.distributed.run exactly as the driver would
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs CUDA devices (there is no CPU fallback); use --impl reference for the CPU arm")
+    _ffi.load()                                       # fail loudly if libusaug.so is missing
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    a.batch = a.per_gpu_batch * world             # total images per step over all GPUs
+    lo, hi = sharding.shard_bounds(a.batch, rank, world)
+    nloc = hi - lo
+    img, lab = synth.make_batch(nloc, H, W, seed=1234 + rank, device=dev)
+    chain = us.PhysicsChain.full(seed=2021, rtol=a.rtol, max_wave=WAVE)
+    idx = torch.arange(lo, hi).numpy()
+
+    def params_for(step):
+        return chain.get_params(nloc, sample_index=idx + step * a.batch, image_size=(H, W))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for s in range(a.warmup):
+        chain(img, lab, params_for(s))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    chain.snr.timing = []
+    iters_log = []
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(a.steps):
+        chain(img, lab, params_for(a.warmup + s))
+        iters_log.append(chain.snr.last_info[0])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    timing, chain.snr.timing = chain.snr.timing, None
+    value = a.batch * a.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel (pcg_persistent_kernel), measured live -------------------
+    iters_all = torch.cat(iters_log).to(torch.float64)          # [steps * nloc]
+    unknowns = (H - 2) * W
+    launches = len(timing)
+    pcg_ms = sum(t0.elapsed_time(t1) for t0, t1, _, _ in timing)
+    alg_bytes = float(iters_all.sum().item()) * PCG_BYTES_PER_UNKNOWN_ITER * unknowns
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.loads((ROOT / "profiles" / "pcg_traffic.json").read_text()).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "pcg_persistent_kernel<float>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "launches": launches, "avg_launch_ms": pcg_ms / max(launches, 1),
+                "algorithmic_bytes_per_launch": alg_bytes / max(launches, 1),
+                "model": "64 B/unknown/iteration x 261120 unknowns x sum of per-image iterations (SURVEY.md 8(d))",
+                "share_of_step": pcg_ms / (e0.elapsed_time(e1))}
+
+    # ---- end to end through the public API with HOST buffers ---------------------------------------
+    h_img = img.cpu().pin_memory()
+    h_lab = lab.cpu().pin_memory()
+    o_img = torch.empty_like(h_img).pin_memory()
+    o_lab = torch.empty_like(h_lab).pin_memory()
+    chunk = WAVE
+
+    def host_step(step):
+        p = params_for(step)
+        for c0 in range(0, nloc, chunk):
+            c1 = min(c0 + chunk, nloc)
+            pc = {k: v[c0:c1] for k, v in p.items()}
+            chain.augment_host(h_img[c0:c1], h_lab[c0:c1], pc, device=dev, out=(o_img[c0:c1], o_lab[c0:c1]))
+
+    e2e = None
+    if a.e2e_steps > 0:
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(a.e2e_steps):
+            host_step(1000 + s)
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        wall = max_over_ranks(wall * 1e3) / 1e3
+        bytes_in = nloc * H * W * 5
+        e2e = {"value": a.batch * a.e2e_steps / wall, "unit": UNIT, "h2d_bytes_per_step": bytes_in * world,
+               "d2h_bytes_per_step": bytes_in * world, "steps": a.e2e_steps,
+               "note": "PhysicsChain.augment_host on pinned host tensors, H2D + D2H inside the timed region"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = a.cpu_sample or cores
+        r, wall, per = cpu_oracle_rate(n, cores)
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} images of the same synthetic 512x512 full-chain workload, oracle (NumPy + SciPy splu), "
+                         f"Pool({cores}), wall {wall:.1f} s, {per:.2f} s/image/core"}
+
+    if rank == 0:
+        waves = (nloc + WAVE - 1) // WAVE
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp64 dot products + fp64 residual refinement)", "data": "synthetic",
+            "config": {"workload": "configs[4]: full chain (deform+TGC+remap, confidence-map PCG, SNR, reverb), "
+                                   f"{a.per_gpu_batch} images of {H}x{W} per GPU per step, {world} GPU(s) = batch {a.batch} "
+                                   "(8 GPUs = configs[4]'s 4096)",
+                       "per_gpu_batch": nloc, "pcg_rtol": a.rtol, "pcg_precond": "column-line",
+                       "pcg_iters_mean": float(iters_all.mean().item()), "pcg_iters_max": float(iters_all.max().item()),
+                       "pcg_wave": WAVE, "l2_policy": f"inputs larger than L2 ({nloc * H * W * 5 / 2**20:.0f} MiB per GPU)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": a.steps * (3 + 3 + 7 * waves),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

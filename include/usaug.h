@@ -47,7 +47,8 @@ enum { USAUG_PRECOND_JACOBI = 0, USAUG_PRECOND_LINE = 1 };
 /* flags of usaug_confmap_pcg */
 enum {
   USAUG_CM_FP64_VECTORS = 1, /* keep the CG vectors in fp64 (default: fp32 vectors + fp64 refinement) */
-  USAUG_CM_ZERO_GUESS = 2    /* start from x0 = 0 instead of the linear depth ramp */
+  USAUG_CM_ZERO_GUESS = 2,   /* start from x0 = 0 instead of the linear depth ramp */
+  USAUG_CM_DEBUG_TIMING = 4  /* development: the kernel prints per-slot wall times of a few steps */
 };
 
 int usaug_version(void);
@@ -75,6 +76,11 @@ size_t usaug_confmap_workspace_bytes(int B, int H, int W, int precond, int flags
 int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int W, float alpha, float beta,
                       float gamma, double rtol, int maxiter, int precond, int flags, int* iters,
                       double* relres, void* ws, size_t ws_bytes, void* stream);
+
+/* Measurement hook (not part of the data path): when set (non-NULL cudaEvent_t handles), the
+ * next usaug_confmap_pcg calls made by THIS thread record `start`/`stop` on the launching stream
+ * immediately around the persistent PCG kernel.  Pass NULL, NULL to clear. */
+void usaug_confmap_set_timing_events(void* start_event, void* stop_event);
 
 /* ---- K3: SNR change + reverberation, fused (A.4, A.5) --------------------------------------
  * cm nullable (NULL = no SNR change).  a_snr[B], rho[B], nghost[B] per-sample parameters;

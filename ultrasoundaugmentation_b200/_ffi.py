@@ -32,6 +32,7 @@ SYMBOLS = {
     "usaug_confmap_pcg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
                                   c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
+    "usaug_confmap_set_timing_events": (None, [c_void_p, c_void_p]),
     "usaug_snr_reverb_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "usaug_snr_reverb": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,

@@ -30,7 +30,7 @@ constexpr float kEps = 2.220446e-16f;
 constexpr float kFloor = 1e-6f;
 constexpr float kSqrt2 = 1.41421356237309515f;
 constexpr int kStripCols = 30;     // productive columns per warp in stencil tasks (2 halo lanes)
-constexpr int kRowBlock = 32;      // rows per stencil task
+constexpr int kRowBlock = 64;      // rows per stencil task
 
 enum Mode : int { M_RESID = 0, M_PRECOND = 1, M_INNER = 2, M_FOLD = 3, M_FINAL = 4, M_DONE = 5 };
 
@@ -228,6 +228,8 @@ struct PcgArgs {
   int* iters_out;
   double* relres_out;
   int nstrip1, nrb, nstrip2, pmax, max_steps;
+  int vec4, nstrip4; // vectorised stencil (fp32 vectors, W % 4 == 0): 128-column strips
+  int debug;         // USAUG_CM_DEBUG_TIMING: block 0 prints per-slot wall times of a few steps
 };
 
 template <typename T>
@@ -253,10 +255,18 @@ __device__ __forceinline__ void reduce_parts(const double* part, int n, int lane
 }
 
 // ---- slot 1: q = A p_new (INNER) or r = b - A x64 (RESID) on a 30-column x kRowBlock-row tile ---
+// Warp-marching stencil: lane = column (lanes 0 / 31 are halo columns), rows march down through
+// registers; horizontal neighbours come from warp shuffles, so every plane is read once with fully
+// coalesced 128-byte rows.  Loads run kQ rows ahead of the arithmetic in a rolling register queue
+// (each slot is refilled right after it is consumed) to keep ~kQ*6 lines per warp in flight.
+template <typename A, typename T>
+struct StRow { A v; T z, p; float s, e, se, sw; };
+
 template <typename T, bool RESID>
 __device__ __forceinline__ double stencil_task(const PcgArgs<T>& a, int b, int strip, int rbk, int lane,
                                                T beta, bool first) {
   using A = typename std::conditional<RESID, double, T>::type;
+  constexpr int kQ = RESID ? 4 : 8;
   const int H = a.H, W = a.W;
   const size_t base = (size_t)b * H * W;
   const int x = strip * kStripCols + lane - 1;
@@ -269,58 +279,213 @@ __device__ __forceinline__ double stencil_task(const PcgArgs<T>& a, int b, int s
   const T* Z = a.z + base; const T* P = a.p + base;
   T* __restrict__ Q = a.q + base; T* __restrict__ Rv = a.r + base;
 
-  auto val = [&](int yy) -> A {
-    if (!valid) return (A)0;
-    const size_t o = (size_t)yy * W + x;
-    if (RESID) return (A)X[o];
-    if (yy == 0 || yy == H - 1) return (A)0;
-    return (A)p_new<T>(Z[o], first ? (T)0 : P[o], beta, first);
+  // loads only -- no arithmetic on the loaded values here, or the in-order warp would wait for
+  // the loads it has just issued and the queue would collapse to a depth of one row
+  auto ldrow = [&](int yy) -> StRow<A, T> {
+    StRow<A, T> r; r.v = (A)0; r.z = r.p = (T)0; r.s = r.e = r.se = r.sw = 0.f;
+    if (valid && yy <= yb) {
+      const size_t o = (size_t)yy * W + x;
+      if (RESID) r.v = (A)X[o];
+      else if (yy != 0 && yy != H - 1) { r.z = Z[o]; if (!first) r.p = P[o]; }
+      r.s = S[o]; r.e = E[o]; r.se = SE[o]; r.sw = SW[o];
+    }
+    return r;
+  };
+  auto value = [&](const StRow<A, T>& r) -> A {
+    if (RESID) return r.v;
+    return (A)p_new<T>(r.z, r.p, beta, first);      // seed rows and invalid lanes hold z = p = 0
   };
   const unsigned full = 0xffffffffu;
-  A Pm = val(ya - 1), Pc = val(ya);
+  StRow<A, T> m = ldrow(ya - 1), c = ldrow(ya);
+  StRow<A, T> qu[kQ];
+#pragma unroll
+  for (int u = 0; u < kQ; ++u) qu[u] = ldrow(ya + 1 + u);
+  A Pm = value(m), Pc = value(c);
   A PmL = __shfl_up_sync(full, Pm, 1), PmR = __shfl_down_sync(full, Pm, 1);
   A PcL = __shfl_up_sync(full, Pc, 1), PcR = __shfl_down_sync(full, Pc, 1);
-  const size_t om = (size_t)(ya - 1) * W + x;
-  float wSm = valid ? S[om] : 0.f;
-  float wSEmL = __shfl_up_sync(full, valid ? SE[om] : 0.f, 1);
-  float wSWmR = __shfl_down_sync(full, valid ? SW[om] : 0.f, 1);
+  float wSEmL = __shfl_up_sync(full, m.se, 1), wSWmR = __shfl_down_sync(full, m.sw, 1);
+  float mS = m.s;
   double acc = 0.0;
-#pragma unroll 2
-  for (int y = ya; y < yb; ++y) {
-    const size_t o = (size_t)y * W + x;
-    const A Pn = val(y + 1);
-    const float s = valid ? S[o] : 0.f, e = valid ? E[o] : 0.f;
-    const float se = valid ? SE[o] : 0.f, sw = valid ? SW[o] : 0.f;
-    const A PnL = __shfl_up_sync(full, Pn, 1), PnR = __shfl_down_sync(full, Pn, 1);
-    const float eL = __shfl_up_sync(full, e, 1);
-    A q = (A)s * (Pc - Pn);
-    q += (A)wSm * (Pc - Pm);
-    q += (A)e * (Pc - PcR);
-    q += (A)eL * (Pc - PcL);
-    q += (A)se * (Pc - PnR);
-    q += (A)sw * (Pc - PnL);
-    q += (A)wSEmL * (Pc - PmL);
-    q += (A)wSWmR * (Pc - PmR);
-    if (own) {
-      if (RESID) { const double rr = -(double)q; Rv[o] = (T)rr; acc += rr * rr; }
-      else { Q[o] = (T)q; acc += (double)Pc * (double)q; }
+  for (int y0 = ya; y0 < yb; y0 += kQ) {
+#pragma unroll
+    for (int u = 0; u < kQ; ++u) {
+      const int y = y0 + u;
+      if (y < yb) {
+        const StRow<A, T> n = qu[u];
+        qu[u] = ldrow(y + 1 + kQ);                    // refill first: the new loads go out before we block on n
+        const A Pn = value(n);
+        const A PnL = __shfl_up_sync(full, Pn, 1), PnR = __shfl_down_sync(full, Pn, 1);
+        const float eL = __shfl_up_sync(full, c.e, 1);
+        A q = (A)c.s * (Pc - Pn);
+        q += (A)mS * (Pc - Pm);
+        q += (A)c.e * (Pc - PcR);
+        q += (A)eL * (Pc - PcL);
+        q += (A)c.se * (Pc - PnR);
+        q += (A)c.sw * (Pc - PnL);
+        q += (A)wSEmL * (Pc - PmL);
+        q += (A)wSWmR * (Pc - PmR);
+        if (own) {
+          const size_t o = (size_t)y * W + x;
+          if (RESID) { const double rr = -(double)q; Rv[o] = (T)rr; acc += rr * rr; }
+          else { Q[o] = (T)q; acc += (double)Pc * (double)q; }
+        }
+        wSEmL = __shfl_up_sync(full, c.se, 1);
+        wSWmR = __shfl_down_sync(full, c.sw, 1);
+        mS = c.s;
+        Pm = Pc; PmL = PcL; PmR = PcR;
+        Pc = Pn; PcL = PnL; PcR = PnR;
+        c = n;
+      }
     }
-    Pm = Pc; PmL = PcL; PmR = PcR;
-    Pc = Pn; PcL = PnL; PcR = PnR;
-    wSm = s;
-    wSEmL = __shfl_up_sync(full, se, 1);
-    wSWmR = __shfl_down_sync(full, sw, 1);
   }
   return warp_sum(acc);
 }
 
-// ---- slot 2 bodies: one lane = one column, rows 1..H-2 ------------------------------------------
-constexpr int kU = 4;   // rows loaded ahead per lane in the sweeps
+// ---- slot 1, vectorised (fp32 vectors, W % 4 == 0): lane = 4 adjacent columns, warp = 128-column strip.
+// Global -> shared staging with cp.async (LDGSTS): every lane copies ITS OWN 16-byte pieces of the next
+// kRing rows into a private ring in shared memory (zero-fill predication instead of branches), so no
+// barrier is ever needed -- cp.async.wait_group orders a lane against its own copies only -- and the
+// bytes in flight are bounded by shared memory (~21 KB per warp), not by registers.
+// Horizontal neighbours inside the lane are registers, across lanes two shuffles per row, across strips
+// one 4-byte halo copy on lane 0 / lane 31.
+constexpr int kStrip4 = 128;
+constexpr int kRing = 6;
 
-// INNER: p = z + beta p; e += alpha p; r -= alpha q; h = L^-1 r (stored over q); then z = L^-T D^-1 h
+struct RingRow {            // one staged image row of a 128-column strip (3584 bytes)
+  float4 z[32], p[32], s[32], e[32], se[32], sw[32];
+  float hz[32], hp[32], hw1[32], hw2[32];   // lane 0: (z, p, wE, wSE) at column x0-1; lane 31: (z, p, wSW, -) at x0+128
+};
+constexpr size_t kRingBytesPerWarp = sizeof(RingRow) * kRing;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ double stencil_task_v4(const PcgArgs<float>& a, RingRow* ring, int b, int strip, int rbk,
+                                                  int lane, float beta, bool first) {
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W;
+  const int x0 = strip * kStrip4, x = x0 + 4 * lane;
+  const bool valid = x < W;
+  const int hx = (lane == 0) ? x0 - 1 : x0 + kStrip4;
+  const bool hvalid = (lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < W);
+  const int ya = 1 + rbk * kRowBlock, yb = min(ya + kRowBlock, H - 1);
+  const float* __restrict__ S = a.wS + base; const float* __restrict__ E = a.wE + base;
+  const float* __restrict__ SE = a.wSE + base; const float* __restrict__ SW = a.wSW + base;
+  const float* Z = a.z + base; const float* P = a.p + base;
+  float* __restrict__ Q = a.q + base;
+  const float* __restrict__ HW1 = (lane == 0) ? E : SW;
+  const int xs = valid ? x : 0, hxs = hvalid ? hx : 0;      // keep predicated-off addresses in bounds
+
+  // stage row yy into ring slot (yy - (ya-1)) % kRing; always commits a group so the count stays in step
+  auto issue = [&](int yy) {
+    RingRow* r = ring + ((yy - (ya - 1)) % kRing);
+    const bool in = yy <= yb;
+    const bool interior = in && (yy != 0) && (yy != H - 1);
+    const size_t o = (size_t)(in ? yy : 0) * W;
+    cp_async16(&r->z[lane], Z + o + xs, interior && valid);
+    cp_async16(&r->p[lane], P + o + xs, interior && valid && !first);
+    cp_async16(&r->s[lane], S + o + xs, in && valid);
+    cp_async16(&r->e[lane], E + o + xs, in && valid);
+    cp_async16(&r->se[lane], SE + o + xs, in && valid);
+    cp_async16(&r->sw[lane], SW + o + xs, in && valid);
+    cp_async4(&r->hz[lane], Z + o + hxs, interior && hvalid);
+    cp_async4(&r->hp[lane], P + o + hxs, interior && hvalid && !first);
+    cp_async4(&r->hw1[lane], HW1 + o + hxs, in && hvalid);
+    cp_async4(&r->hw2[lane], SE + o + hxs, in && hvalid && lane == 0);
+    cp_async_commit();
+  };
+  const unsigned full = 0xffffffffu;
+  struct WRow { float4 s, e, se, sw; float hw1, hw2; };
+  // v[0] = left neighbour column, v[1..4] = own columns, v[5] = right neighbour column
+  auto fetch = [&](int yy, float (&v)[6], WRow& w) {
+    const RingRow* r = ring + ((yy - (ya - 1)) % kRing);
+    const float4 z = r->z[lane], p = r->p[lane];
+    w.s = r->s[lane]; w.e = r->e[lane]; w.se = r->se[lane]; w.sw = r->sw[lane];
+    w.hw1 = r->hw1[lane]; w.hw2 = r->hw2[lane];
+    v[1] = p_new<float>(z.x, p.x, beta, first); v[2] = p_new<float>(z.y, p.y, beta, first);
+    v[3] = p_new<float>(z.z, p.z, beta, first); v[4] = p_new<float>(z.w, p.w, beta, first);
+    const float h = p_new<float>(r->hz[lane], r->hp[lane], beta, first);
+    const float l = __shfl_up_sync(full, v[4], 1), rt = __shfl_down_sync(full, v[1], 1);
+    v[0] = (lane == 0) ? h : l;
+    v[5] = (lane == 31) ? h : rt;
+  };
+
+#pragma unroll
+  for (int u = 0; u < kRing; ++u) issue(ya - 1 + u);
+  float pm[6], pc[6], pn[6];
+  WRow m, c, n;
+  cp_async_wait<kRing - 2>();            // rows ya-1 and ya have landed
+  fetch(ya - 1, pm, m);
+  fetch(ya, pc, c);
+  issue(ya - 1 + kRing);
+  issue(ya + kRing);
+  double acc = 0.0;
+#pragma unroll 2
+  for (int y = ya; y < yb; ++y) {
+    cp_async_wait<kRing - 1>();          // row y+1 has landed (kRing-1 younger groups may still fly)
+    fetch(y + 1, pn, n);
+    // edge weights shared with the neighbouring lanes / strips
+    const float eL_s = __shfl_up_sync(full, c.e.w, 1);
+    const float semL_s = __shfl_up_sync(full, m.se.w, 1);
+    const float swmR_s = __shfl_down_sync(full, m.sw.x, 1);
+    const float eL = (lane == 0) ? c.hw1 : eL_s;          // wE[y, x-1]
+    const float semL = (lane == 0) ? m.hw2 : semL_s;      // wSE[y-1, x-1]
+    const float swmR = (lane == 31) ? m.hw1 : swmR_s;     // wSW[y-1, x+4]
+    const float S_[4] = {c.s.x, c.s.y, c.s.z, c.s.w};
+    const float Sm[4] = {m.s.x, m.s.y, m.s.z, m.s.w};
+    const float E5[5] = {eL, c.e.x, c.e.y, c.e.z, c.e.w};
+    const float SE_[4] = {c.se.x, c.se.y, c.se.z, c.se.w};
+    const float SW_[4] = {c.sw.x, c.sw.y, c.sw.z, c.sw.w};
+    const float SEm[4] = {semL, m.se.x, m.se.y, m.se.z};
+    const float SWm[4] = {m.sw.y, m.sw.z, m.sw.w, swmR};
+    float q[4], dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float pcj = pc[j + 1];
+      float t = S_[j] * (pcj - pn[j + 1]);
+      t = fmaf(Sm[j], pcj - pm[j + 1], t);
+      t = fmaf(E5[j + 1], pcj - pc[j + 2], t);
+      t = fmaf(E5[j], pcj - pc[j], t);
+      t = fmaf(SE_[j], pcj - pn[j + 2], t);
+      t = fmaf(SW_[j], pcj - pn[j], t);
+      t = fmaf(SEm[j], pcj - pm[j], t);
+      t = fmaf(SWm[j], pcj - pm[j + 2], t);
+      q[j] = t;
+      dot = fmaf(pcj, t, dot);
+    }
+    if (valid) {
+      *reinterpret_cast<float4*>(Q + (size_t)y * W + x) = make_float4(q[0], q[1], q[2], q[3]);
+      acc += (double)dot;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { pm[j] = pc[j]; pc[j] = pn[j]; }
+    m = c; c = n;
+    issue(y + 1 + kRing);                // refill the slot row y+1 was read from (its values are consumed)
+  }
+  cp_async_wait<0>();                    // drain before the ring is reused by the next task
+  return warp_sum(acc);
+}
+
+// ---- slot 2 bodies: one lane = one column, rows 1..H-2 ------------------------------------------
+// INNER: p = z + beta p; e += alpha p; r -= alpha q; h = L^-1 r (stored over q); then z = L^-T D^-1 h.
+// The recurrences are sequential in y, so parallelism is one lane per column; bandwidth comes from
+// rolling register prefetch queues (kD rows x 7 planes down, kUp rows x 3 planes up per lane).
 template <typename T>
 __device__ __forceinline__ void sweep_inner(const PcgArgs<T>& a, int b, int x, bool valid, T alpha, T beta,
                                             bool first, double& rr_out, double& rz_out) {
+  constexpr int kD = sizeof(T) == 4 ? 8 : 4;
+  constexpr int kUp = sizeof(T) == 4 ? 16 : 8;
   const int H = a.H, W = a.W;
   const size_t base = (size_t)b * H * W + x;
   const float* __restrict__ IP = a.ip + base; const float* __restrict__ C = a.c + base;
@@ -328,51 +493,57 @@ __device__ __forceinline__ void sweep_inner(const PcgArgs<T>& a, int b, int x, b
   T* __restrict__ R = a.r + base; T* __restrict__ Q = a.q + base;
   double rr = 0.0, rz = 0.0;
   if (valid) {
-    T hprev = (T)0; float cprev = 0.f;
-    for (int y0 = 1; y0 <= H - 2; y0 += kU) {
-      T zv[kU], pv[kU], ev[kU], rv[kU], qv[kU]; float iv[kU], cv[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int y = y0 + u;
+    {
+      T zv[kD], pv[kD], ev[kD], rv[kD], qv[kD]; float iv[kD], cv[kD];
+      auto ld = [&](int u, int y) {
         if (y <= H - 2) {
           const size_t o = (size_t)y * W;
           zv[u] = Z[o]; pv[u] = first ? (T)0 : P[o]; ev[u] = E[o]; rv[u] = R[o]; qv[u] = Q[o];
           iv[u] = IP[o]; cv[u] = C[o];
         }
-      }
+      };
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int y = y0 + u;
-        if (y <= H - 2) {
-          const size_t o = (size_t)y * W;
-          const T pn = p_new<T>(zv[u], pv[u], beta, first);
-          P[o] = pn;
-          E[o] = (T)fma(alpha, pn, ev[u]);
-          const T rn = (T)fma(-alpha, qv[u], rv[u]);
-          R[o] = rn;
-          rr += (double)rn * (double)rn;
-          const T h = (T)fma((T)cprev, hprev, rn);
-          Q[o] = h;
-          rz += (double)iv[u] * ((double)h * (double)h);
-          hprev = h; cprev = cv[u];
+      for (int u = 0; u < kD; ++u) ld(u, 1 + u);
+      T hprev = (T)0; float cprev = 0.f;
+      for (int y0 = 1; y0 <= H - 2; y0 += kD) {
+#pragma unroll
+        for (int u = 0; u < kD; ++u) {
+          const int y = y0 + u;
+          if (y <= H - 2) {
+            const size_t o = (size_t)y * W;
+            const T pn = p_new<T>(zv[u], pv[u], beta, first);
+            P[o] = pn;
+            E[o] = (T)fma(alpha, pn, ev[u]);
+            const T rn = (T)fma(-alpha, qv[u], rv[u]);
+            R[o] = rn;
+            rr += (double)rn * (double)rn;
+            const T h = (T)fma((T)cprev, hprev, rn);
+            Q[o] = h;
+            rz += (double)iv[u] * ((double)h * (double)h);
+            hprev = h; cprev = cv[u];
+            ld(u, y + kD);
+          }
         }
       }
     }
-    T znext = (T)0;
-    for (int y0 = H - 2; y0 >= 1; y0 -= kU) {
-      T hv[kU]; float iv[kU], cv[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int y = y0 - u;
+    {
+      T hv[kUp]; float iv[kUp], cv[kUp];
+      auto ld = [&](int u, int y) {
         if (y >= 1) { const size_t o = (size_t)y * W; hv[u] = Q[o]; iv[u] = IP[o]; cv[u] = C[o]; }
-      }
+      };
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int y = y0 - u;
-        if (y >= 1) {
-          const size_t o = (size_t)y * W;
-          const T zz = (T)fma((T)cv[u], znext, (T)iv[u] * hv[u]);
-          Z[o] = zz; znext = zz;
+      for (int u = 0; u < kUp; ++u) ld(u, H - 2 - u);
+      T znext = (T)0;
+      for (int y0 = H - 2; y0 >= 1; y0 -= kUp) {
+#pragma unroll
+        for (int u = 0; u < kUp; ++u) {
+          const int y = y0 - u;
+          if (y >= 1) {
+            const size_t o = (size_t)y * W;
+            const T zz = (T)fma((T)cv[u], znext, (T)iv[u] * hv[u]);
+            Z[o] = zz; znext = zz;
+            ld(u, y - kUp);
+          }
         }
       }
     }
@@ -413,27 +584,42 @@ __device__ __forceinline__ double sweep_precond(const PcgArgs<T>& a, int b, int 
 template <typename T>
 __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a) {
   cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  RingRow* ring = reinterpret_cast<RingRow*>(smem_raw) + (size_t)(threadIdx.x >> 5) * kRing;
   const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
   const int nw = gridDim.x * wpb;
   const int B = a.B, H = a.H, W = a.W;
-  const int per1 = a.nstrip1 * a.nrb;
-  const int tot1 = per1 * B, tot2 = a.nstrip2 * B;
+  const int per_rs = a.nstrip1 * a.nrb;                       // RESID: scalar 30-column strips
+  const int per_in = a.vec4 ? a.nstrip4 * a.nrb : per_rs;     // INNER: 128-column strips when vectorised
+  const int tot1 = (per_in > per_rs ? per_in : per_rs) * B, tot2 = a.nstrip2 * B;
 
+  auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
   for (int step = 0; step < a.max_steps; ++step) {
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    const bool dbg = a.debug && blockIdx.x == 0 && threadIdx.x == 0 && step >= 10 && step < 14;
+    if (dbg) t0 = now();
     // ------------------------------ slot 1: stencil tasks --------------------------------------
     for (int t = gw; t < tot1; t += nw) {
       const int b = t % B, ti = t / B;
       ImgState* st = a.st + b;
       const int mode = __ldcg(&st->mode);
       if (mode != M_INNER && mode != M_RESID) continue;
-      const int strip = ti % a.nstrip1, rbk = ti / a.nstrip1;
+      const int per1 = (mode == M_INNER) ? per_in : per_rs;
+      if (ti >= per1) continue;
+      const int nstr = (mode == M_INNER && a.vec4) ? a.nstrip4 : a.nstrip1;
+      const int strip = ti % nstr, rbk = ti / nstr;
       double s;
       if (mode == M_INNER) {
         const bool first = __ldcg(&st->first) != 0;
         const T beta = (T)__ldcg(&st->beta);
-        s = stencil_task<T, false>(a, b, strip, rbk, lane, beta, first);
+        if constexpr (std::is_same<T, float>::value) {
+          if (a.vec4) s = stencil_task_v4(a, ring, b, strip, rbk, lane, beta, first);
+          else s = stencil_task<T, false>(a, b, strip, rbk, lane, beta, first);
+        } else {
+          s = stencil_task<T, false>(a, b, strip, rbk, lane, beta, first);
+        }
       } else {
         s = stencil_task<T, true>(a, b, strip, rbk, lane, (T)0, true);
       }
@@ -463,7 +649,9 @@ __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a)
         }
       }
     }
+    if (dbg) t1 = now();
     grid.sync();
+    if (dbg) t2 = now();
     // ------------------------------ slot 2: column sweeps --------------------------------------
     for (int t = gw; t < tot2; t += nw) {
       const int b = t % B, strip = t / B;
@@ -518,7 +706,10 @@ __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a)
         }
       }
     }
+    if (dbg) t3 = now();
     grid.sync();
+    if (dbg) printf("[pcg dbg] step %d: slot1 %llu ns (block 0), sync wait %llu ns, slot2 %llu ns, sync wait %llu ns\n",
+                    step, t1 - t0, t2 - t1, t3 - t2, now() - t3);
     if (__ldcg(a.done) >= (unsigned)B) break;
   }
 }
@@ -559,6 +750,11 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   return L;
 }
 
+// Optional measurement hook: a (start, stop) cudaEvent_t pair recorded on the launching stream
+// immediately around the persistent kernel (bench.py's roofline uses it).  Thread-local.
+static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+static thread_local int g_debug = 0;
+
 template <typename T>
 static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double rtol, int maxiter,
                       int* iters, double* relres, cudaStream_t stream) {
@@ -572,29 +768,43 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z;
   a.st = L.st; a.part = L.part; a.done = L.done; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
   a.nstrip1 = L.nstrip1; a.nrb = L.nrb; a.nstrip2 = L.nstrip2; a.pmax = L.pmax;
+  a.vec4 = (std::is_same<T, float>::value && W % 4 == 0) ? 1 : 0;
+  a.nstrip4 = (W + kStrip4 - 1) / kStrip4;
   // every inner iteration is one step; each refinement round adds <= 3 steps and needs >= 1 iteration
   a.max_steps = 4 * maxiter + 16;
+  a.debug = g_debug;
 
   int dev = 0, sms = 0, per_sm = 0;
+  const size_t smem = a.vec4 ? kRingBytesPerWarp * 8 : 0;
   USAUG_CUDA(cudaGetDevice(&dev));
   USAUG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_persistent_kernel<T>, 256, 0));
+  if (smem > 48 * 1024)
+    USAUG_CUDA(cudaFuncSetAttribute(pcg_persistent_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_persistent_kernel<T>, 256, smem));
   if (per_sm < 1) { set_error("pcg_persistent_kernel cannot be resident"); return USAUG_E_CUDA; }
   // enough warps for every column task, never more blocks than can be co-resident
-  const int want_warps = L.nstrip2 * B > L.nstrip1 * L.nrb * B / 4 ? L.nstrip2 * B : L.nstrip1 * L.nrb * B / 4;
+  const int tasks1 = (a.vec4 ? a.nstrip4 : L.nstrip1) * L.nrb * B;
+  const int want_warps = L.nstrip2 * B > tasks1 ? L.nstrip2 * B : tasks1;
   int blocks = (want_warps + 7) / 8;
   const int cap = sms * (per_sm > 4 ? 4 : per_sm);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   void* params[] = {(void*)&a};
+  if (g_ev_start) USAUG_CUDA(cudaEventRecord(g_ev_start, stream));
   USAUG_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_persistent_kernel<T>, dim3(blocks), dim3(256),
-                                         params, 0, stream));
+                                         params, smem, stream));
+  if (g_ev_stop) USAUG_CUDA(cudaEventRecord(g_ev_stop, stream));
   return USAUG_OK;
 }
 
 }  // namespace usaug
 
 using namespace usaug;
+
+extern "C" void usaug_confmap_set_timing_events(void* start_event, void* stop_event) {
+  g_ev_start = static_cast<cudaEvent_t>(start_event);
+  g_ev_stop = static_cast<cudaEvent_t>(stop_event);
+}
 
 extern "C" size_t usaug_confmap_workspace_bytes(int B, int H, int W, int precond, int flags) {
   (void)precond;
@@ -619,6 +829,7 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CmLayout L = cm_layout(ws, B, H, W, flags);
   const int N = H * W;
+  g_debug = (flags & USAUG_CM_DEBUG_TIMING) ? 1 : 0;
 
   cm_depth_kernel<<<(H + 127) / 128, 128, 0, stream>>>(L.depth, H, alpha);
   USAUG_CHECK_LAUNCH("cm_depth_kernel");

@@ -90,13 +90,15 @@ def fused_tgc_deform(image, label, d, tgc, taps):
     return out_img, out_lab
 
 
-def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-6, maxiter=10000,
+def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=20000,
                    precond="line", fp64_vectors=False, zero_guess=False, max_wave=None,
-                   return_info=False):
+                   return_info=False, timing: list | None = None, debug_timing=False):
     """K2 (A.3).  image f32 [B,H,W] -> cm f32 [B,H,W] (+ iters int32 [B], true relres f64 [B]).
 
     The batch is solved in waves of at most ``max_wave`` images (workspace ~56 B/pixel/image
-    with fp32 vectors); default keeps the workspace under ~16 GiB.
+    with fp32 vectors); default keeps the workspace under ~16 GiB.  ``timing`` (measurement
+    only): a list that receives one (start_event, stop_event, lo, n) tuple per wave, recorded on
+    the launching stream right around the persistent PCG kernel.
     """
     lib = _ffi.load()
     image = _need_cuda(image, "image", torch.float32)
@@ -108,6 +110,7 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-6, maxiter=1
     dev = image.device
     pc = {"jacobi": _ffi.PRECOND_JACOBI, "line": _ffi.PRECOND_LINE}[precond]
     flags = (_ffi.CM_FP64_VECTORS if fp64_vectors else 0) | (_ffi.CM_ZERO_GUESS if zero_guess else 0)
+    flags |= 4 if debug_timing else 0
     with torch.cuda.device(dev):
         per_img = lib.usaug_confmap_workspace_bytes(1, H, W, pc, flags)
         if max_wave is None:
@@ -119,11 +122,18 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-6, maxiter=1
         ws = _ws(lib.usaug_confmap_workspace_bytes(max_wave, H, W, pc, flags), dev)
         for lo in range(0, B, max_wave):
             n = min(max_wave, B - lo)
+            if timing is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record(); ev[1].record()        # materialise the underlying cudaEvent_t handles
+                lib.usaug_confmap_set_timing_events(ev[0].cuda_event, ev[1].cuda_event)
+                timing.append((ev[0], ev[1], lo, n))
             rc = lib.usaug_confmap_pcg(image[lo:lo + n].data_ptr(), cm[lo:lo + n].data_ptr(), n, H, W,
                                        float(alpha), float(beta), float(gamma), float(rtol),
                                        int(maxiter), pc, flags, iters[lo:lo + n].data_ptr(),
                                        relres[lo:lo + n].data_ptr(), ws.data_ptr(), ws.numel(),
                                        _stream_ptr(dev))
+            if timing is not None:
+                lib.usaug_confmap_set_timing_events(None, None)
             _ffi.check(rc, "usaug_confmap_pcg")
     if return_info:
         return cm, iters, relres

@@ -130,7 +130,7 @@ class ConfidenceSNR(_Transform):
     _stream = 3
 
     def __init__(self, a_range: Sequence[float] = (0.7, 1.4), alpha: float = 2.0, beta: float = 90.0,
-                 gamma: float = 0.05, rtol: float = 1e-6, maxiter: int = 20000, precond: str = "line",
+                 gamma: float = 0.05, rtol: float = 1e-8, maxiter: int = 20000, precond: str = "line",
                  fp64_vectors: bool = False, max_wave: Optional[int] = None, p: float = 1.0,
                  seed: int = 0):
         super().__init__(p, seed)
@@ -142,6 +142,7 @@ class ConfidenceSNR(_Transform):
         self.fp64_vectors = bool(fp64_vectors)
         self.max_wave = max_wave
         self.last_info = None      # (iters, relres) device tensors of the most recent call
+        self.timing = None         # measurement only: list receiving per-wave PCG kernel events
 
     def get_params(self, batch_size, generator=None, sample_index=None, image_size=None):
         apply, u = self._draw(batch_size, 1, generator, sample_index)
@@ -152,13 +153,14 @@ class ConfidenceSNR(_Transform):
     def confidence_map(self, image_bhw: torch.Tensor) -> torch.Tensor:
         cm, it, rr = ops.confidence_map(image_bhw, self.alpha, self.beta, self.gamma, self.rtol,
                                         self.maxiter, self.precond, self.fp64_vectors,
-                                        max_wave=self.max_wave, return_info=True)
+                                        max_wave=self.max_wave, return_info=True, timing=self.timing)
         self.last_info = (it, rr)
         return cm
 
     def __getstate__(self):
         s = dict(self.__dict__)
         s["last_info"] = None
+        s["timing"] = None
         return s
 
 
