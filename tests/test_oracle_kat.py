@@ -1,0 +1,123 @@
+"""Known-answer tests that pin the SELF-WRITTEN oracle: every expected value here is
+closed-form or comes from an independent library, not from the oracle itself."""
+import numpy as np
+import pytest
+from scipy.ndimage import map_coordinates
+
+from oracle import confmap as ocm, deform as odeform, snr_reverb as osr, synth as osynth
+from tests import util
+
+f32 = np.float32
+
+
+def test_identity_warp_is_bit_exact():
+    img, lab = osynth.make_bmode(64, 48)
+    o, l, info = odeform.fused_tgc_deform(img, lab, 0.0, np.ones(8, f32), util.warp_taps(48))
+    assert np.array_equal(o, img) and np.array_equal(l, lab)
+
+
+def test_tgc_unit_gains_identity_and_constant_gain():
+    img, lab = osynth.make_bmode(40, 32)
+    o, _, _ = odeform.fused_tgc_deform(img, lab, 0.0, np.full(4, 0.5, f32), util.warp_taps(32))
+    assert np.allclose(o, 0.5 * img, rtol=1e-6, atol=0)
+    g = odeform.tgc_gain(33, np.array([1.0, 2.0, 4.0], f32))
+    assert g[0] == 1.0 and g[16] == 2.0 and g[32] == 4.0 and np.isclose(g[8], 1.5) and np.isclose(g[24], 3.0)
+
+
+def test_bilinear_matches_scipy_map_coordinates():
+    img, lab = osynth.make_bmode(96, 64)
+    o, _, info = odeform.fused_tgc_deform(img, lab, 7.3, np.ones(2, f32), util.warp_taps(64))
+    ys = info["y_src"].astype(np.float64)
+    xs = np.broadcast_to(np.arange(64)[None, :], ys.shape).astype(np.float64)
+    # grid-constant = zero padding that takes part in the interpolation (A.2: "samples outside read as 0")
+    ref = map_coordinates(img.astype(np.float64), [ys, xs], order=1, mode="grid-constant", cval=0.0)
+    assert np.abs(ref - o).max() <= 2e-7
+
+
+def test_horizontal_line_phantom_moves_as_the_forward_model_says():
+    """A bright line at depth Y above the bone lands at Y - d*min(Y/s_hat, 1) (+-1 px)."""
+    H, W, Y, d = 128, 64, 30, 8.0
+    img = np.zeros((H, W), f32); img[Y] = 1.0
+    lab = np.zeros((H, W), np.uint8); lab[80:84] = 1
+    o, l, info = odeform.fused_tgc_deform(img, lab, d, np.ones(2, f32), util.warp_taps(W))
+    assert info["d_eff"] == f32(d) and np.allclose(info["s_hat"], 80.0, atol=1e-3)
+    expect = Y - d * min(Y / 80.0, 1.0)
+    assert abs(np.argmax(o[:, W // 2]) - expect) <= 1.0
+    assert np.flatnonzero(l[:, 3])[0] == 80 - int(d)            # bone moves rigidly with the full d
+
+
+def test_bone_surface_hole_fill_and_no_bone():
+    lab = np.zeros((10, 9), np.uint8)
+    lab[4, 2] = 1; lab[7, 6] = 1
+    s, y_top, has = odeform.bone_surface(lab)
+    assert has and y_top == 4
+    assert s.tolist() == [4, 4, 4, 4, 4, 7, 7, 7, 7]           # x=4 is equidistant: tie -> lower x (col 2)
+    s, y_top, has = odeform.bone_surface(np.zeros((10, 9), np.uint8))
+    assert (not has) and y_top == -1 and (s == 9).all()
+
+
+def test_displacement_clamp():
+    s_hat = np.full(16, 20.0, f32)
+    assert odeform.clamp_displacement(100.0, s_hat) == f32(10.0)
+    assert odeform.clamp_displacement(-100.0, s_hat) == f32(-10.0)
+    assert odeform.clamp_displacement(3.0, s_hat) == f32(3.0)
+
+
+@pytest.mark.parametrize("H,W", [(33, 17), (64, 64), (9, 3)])
+def test_constant_image_confidence_map_is_linear_ramp(H, W):
+    C = ocm.confidence_map(np.full((H, W), 0.37, f32))
+    assert np.abs(C - (1.0 - np.arange(H) / (H - 1.0))[:, None]).max() < 1e-12
+
+
+def test_constant_image_has_three_distinct_weights():
+    wS, wE, wSE, wSW = ocm.edge_weights(np.full((8, 8), 0.5, f32), beta=90.0, gamma=0.05)
+    assert np.allclose(np.unique(wS[:-1]), [1.000001], rtol=1e-6)
+    assert np.allclose(np.unique(wE[:, :-1]), [np.exp(-4.5) + 1e-6], rtol=1e-5)
+    assert np.allclose(np.unique(wSE[:-1, :-1]), [np.exp(-90 * np.sqrt(2) * 0.05) + 1e-6], rtol=1e-5)
+    assert np.array_equal(wSE[:-1, :-1], wSW[:-1, 1:])
+
+
+def test_confidence_map_boundaries_range_residual():
+    img, _ = osynth.make_bmode(64, 48)
+    C, info = ocm.confidence_map(img, return_info=True)
+    assert (C[0] == 1).all() and (C[-1] == 0).all()
+    assert C.min() >= -1e-12 and C.max() <= 1 + 1e-12
+    assert info["relres"] < 1e-12
+    A = info["A"]
+    assert abs(A - A.T).max() < 1e-15 and (A.diagonal() > 0).all()
+
+
+def test_pcg_reference_agrees_with_direct_solve():
+    img, _ = osynth.make_bmode(48, 40)
+    C, info = ocm.confidence_map(img, return_info=True)
+    for pc in ("jacobi", "line"):
+        x, it, _ = ocm.pcg_reference(info["A"], info["b"], pc, W=40, rtol=1e-10)
+        assert np.abs(x.reshape(46, 40) - C[1:-1]).max() < 1e-5
+
+
+def test_snr_and_reverb_identities():
+    img, lab = osynth.make_bmode(64, 48)
+    cm = np.random.default_rng(0).uniform(0, 1, img.shape).astype(f32)
+    taps = odeform.gaussian_taps(2.0)
+    assert np.array_equal(osr.snr_apply(img, cm, 1.0), img)
+    assert np.array_equal(osr.reverb(img, np.zeros_like(lab), 0.5, 2, taps), img)     # empty mask
+    assert np.array_equal(osr.reverb(img, lab, 0.0, 2, taps), np.clip(img, 0, 1))      # rho = 0
+    assert np.array_equal(osr.reverb(img, lab, 0.5, 0, taps), img)                     # no ghosts
+    out = osr.reverb(img, lab, 0.5, 1, taps)
+    _, y_top, _ = odeform.bone_surface(lab)
+    assert np.array_equal(out[:y_top], img[:y_top])          # nothing above the first ghost row
+    assert (out >= img - 1e-7).all() and out.max() <= 1.0
+
+
+def test_feather_mask_mass_and_support():
+    lab = np.zeros((40, 40), np.uint8); lab[20, 20] = 1
+    taps = odeform.gaussian_taps(2.0)
+    m = osr.feather_mask(lab, taps)
+    assert np.isclose(m.sum(), 1.0, atol=1e-5) and np.isclose(m[20, 20], taps[6] ** 2, rtol=1e-5)
+    assert m[:13].sum() == 0 and m[:, 27:].sum() == 0
+
+
+def test_synth_is_seeded_and_in_range():
+    a, la = osynth.make_bmode(64, 64, 5); b, lb = osynth.make_bmode(64, 64, 5); c, _ = osynth.make_bmode(64, 64, 6)
+    assert np.array_equal(a, b) and np.array_equal(la, lb) and not np.array_equal(a, c)
+    assert a.min() >= 0 and a.max() == 1.0 and la.sum() > 0 and set(np.unique(la)) == {0, 1}
