@@ -250,13 +250,15 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (pcg_ms / 1e3) / 1e9 if pcg_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.loads((ROOT / "profiles" / "pcg_traffic.json").read_text()).get("dram_bytes_per_launch")
-    except (OSError, ValueError):
+    traffic, traffic_src = None, None
+    try:   # ncu dram__bytes per unknown per iteration (one --set full capture), scaled to this run's launches
+        tj = json.loads((ROOT / "profiles" / "pcg_traffic.json").read_text())
+        traffic = tj["dram_bytes_per_unknown_iteration"] * float(iters_all.sum().item()) * unknowns / max(launches, 1)
+        traffic_src = tj.get("source")
+    except (OSError, ValueError, KeyError):
         pass
     roofline = {"bound": "hbm", "kernel": "pcg_persistent_kernel<float>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "launches": launches, "avg_launch_ms": pcg_ms / max(launches, 1),
                 "algorithmic_bytes_per_launch": alg_bytes / max(launches, 1),
