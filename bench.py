@@ -34,7 +34,7 @@ METRIC = "augmented images/sec at 512x512 (full chain)"
 UNIT = "images/s"
 H = W = 512
 PER_GPU_BATCH = 512             # configs[4]: 4096 images over 8 GPUs
-WAVE = 256                      # images per PCG launch (workspace ~3.5 GiB)
+WAVE = 512                      # images per PCG launch (workspace ~7.7 GiB of the 180 GB)
 PCG_BYTES_PER_UNKNOWN_ITER = 64  # SURVEY.md 8(d) algorithmic-bytes model
 
 
@@ -257,7 +257,7 @@ def run_ours(a):
         traffic_src = tj.get("source")
     except (OSError, ValueError, KeyError):
         pass
-    roofline = {"bound": "hbm", "kernel": "pcg_persistent_kernel<float>", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "pcg_fused_kernel<8> (persistent cooperative PCG)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "launches": launches, "avg_launch_ms": pcg_ms / max(launches, 1),

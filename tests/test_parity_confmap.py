@@ -44,11 +44,12 @@ def test_cm_parity_small(cuda_device, B, H, W, precond):
     assert cm.min() >= -1e-6 and cm.max() <= 1.0 + 1e-6
 
 
-@pytest.mark.parametrize("fp64", [False, True])
-def test_cm_parity_256(cuda_device, fp64):
+@pytest.mark.parametrize("variant", ["fused", "legacy", "fp64"])
+def test_cm_parity_256(cuda_device, variant):
     img, _ = util.synth_batch(2, 256, 256)
     ref = ocm.confidence_map_batch(img)
-    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, fp64_vectors=fp64)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, fp64_vectors=(variant == "fp64"),
+                        legacy_kernel=(variant == "legacy"))
     assert (rr <= RTOL).all(), rr
     assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
 
@@ -63,6 +64,16 @@ def test_cm_batch_independence_and_determinism(cuda_device):
     assert np.array_equal(c[0], a[2]) and itc[0] == ita[2]
     d, _, _ = gpu_cm(cuda_device, img, rtol=1e-7, max_wave=2)
     assert np.array_equal(d, a)
+
+
+def test_cm_fused_and_legacy_kernels_agree(cuda_device):
+    """The fused fp32 kernel (W % 4 == 0) and the two-slot kernel solve the same systems."""
+    img, _ = util.synth_batch(3, 96, 132)
+    a, ita, rra = gpu_cm(cuda_device, img, rtol=1e-9)
+    b, itb, rrb = gpu_cm(cuda_device, img, rtol=1e-9, legacy_kernel=True)
+    assert (rra <= 1e-9).all() and (rrb <= 1e-9).all()
+    assert np.abs(a - b).max() <= 2 * util.tol_cm(1e-9)
+    assert np.abs(ita.astype(int) - itb.astype(int)).max() <= 0.1 * itb.max() + 5
 
 
 def test_cm_maxiter_reports_nonconvergence(cuda_device):

@@ -38,6 +38,11 @@ struct ImgState {
   int mode, iters, first, outer;
   double rz, alpha, beta, bb, rr_true, rr_prev, rr_target, rr_rec;
   unsigned cnt1, cnt2;
+  // fused kernel: (first interval in which the mode may run) << 32 | mode.  Phases have different
+  // task counts, so a mode published by the last arriver must not be picked up by tasks of the
+  // same image that are still to come in the SAME interval.
+  unsigned long long fword;
+  int pcur, pad_;     // which of the two p planes holds the current search direction
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -206,7 +211,7 @@ __global__ void cm_init_state_kernel(int B, int nblk, const double* __restrict__
   ImgState s;
   s.mode = M_RESID; s.iters = 0; s.first = 1; s.outer = 0;
   s.rz = 0; s.alpha = 0; s.beta = 0; s.bb = bb; s.rr_true = 0; s.rr_prev = 1e300; s.rr_target = 0; s.rr_rec = 0;
-  s.cnt1 = 0; s.cnt2 = 0;
+  s.cnt1 = 0; s.cnt2 = 0; s.fword = 0ull; s.pcur = 0; s.pad_ = 0;
   st[b] = s;
 }
 
@@ -221,6 +226,7 @@ struct PcgArgs {
   const float *wS, *wE, *wSE, *wSW, *ip, *c;
   double* x64;
   T *e, *r, *p, *q, *z;   // q doubles as h (forward-eliminated residual) inside slot 2
+  T *p2;                  // fused kernel: second search-direction plane (ping-pong); z holds h there
   ImgState* st;
   double* part;      // [B][pmax][2]
   unsigned* done;
@@ -714,10 +720,350 @@ __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a)
   }
 }
 
+// =============================================================================================
+// Fused fp32 kernel (W % 4 == 0): the production path.
+//   One grid-sync interval = one PHASE per image (images may be in different phases):
+//     F_UP    z = L^-T D^-1 h on the fly (never stored), p = z + beta p, q = A p, partial p.q
+//             -- the up sweep of iteration k fused with the stencil of iteration k+1
+//     F_DOWN  e += alpha p; r -= alpha q; h = L^-1 r (stored over q); partial r.r and r.z = sum ip h^2
+//   19 plane touches per unknown and iteration (UP: read h, ip, c, p, 4 weights, write p, q;
+//   DOWN: read p, e, r, q, c, ip, write e, r, h) instead of 22, and no z plane.
+//   Task = (image, 128-column strip), lane = 4 adjacent columns, rows staged through a private
+//   cp.async ring in shared memory (see stencil_task_v4); the column recurrences are 4-way
+//   independent per lane.  Strip halo columns: lane 0 / lane 31 carry one extra scalar recurrence;
+//   their six scalars per row are fetched by ONE cp.async.4 instruction (lanes 0-5 left, 16-21 right).
+// =============================================================================================
+enum FMode : int { F_RESID = 0, F_PRECOND = 1, F_UP = 2, F_DOWN = 3, F_FOLD = 4, F_FINAL = 5, F_DONE = 6 };
+
+struct RingU {   // one staged row of a 128-column strip for F_UP (4608 bytes)
+  float4 h[32], ip[32], c[32], p[32], s[32], e[32], se[32], sw[32];
+  // 16-byte chunks that contain the strip's halo columns (cp.async.cg = L2, never a stale L1 line):
+  // [0..5] columns x0-4..x0-1 of h, ip, c, p, wE, wSE (.w is the left neighbour column);
+  // [16..20] columns x0+128..x0+131 of h, ip, c, p, wSW (.x is the right neighbour column)
+  float4 halo[32];
+};
+struct RingD {   // one staged row for F_DOWN / F_PRECOND (3072 bytes)
+  float4 p[32], e[32], r[32], q[32], c[32], ip[32];
+};
+constexpr int kRingRowsPerCta = 48;                                   // 48 x 4608 B = 216 KB per CTA
+constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
+
+__device__ __forceinline__ float hsel(const float4& v, int lane) { return lane == 31 ? v.x : v.w; }
+
+template <int R>
+__device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+                                          float beta, bool first, int pcur) {
+  RingU* ring = reinterpret_cast<RingU*>(ringmem);
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W;
+  const int x0 = strip * kStrip4, x = x0 + 4 * lane;
+  const bool valid = x < W;
+  const int xs = valid ? x : 0;
+  const float* __restrict__ S = a.wS + base; const float* __restrict__ E = a.wE + base;
+  const float* __restrict__ SE = a.wSE + base; const float* __restrict__ SW = a.wSW + base;
+  const float* __restrict__ IP = a.ip + base; const float* __restrict__ C = a.c + base;
+  // reads: h (z plane), p_old (pin); writes: p_new (pout), q.  Nothing is updated in place, because the
+  // halo columns of this strip belong to a neighbouring strip whose warp runs asynchronously.
+  const float* __restrict__ Hb = a.z + base;
+  const float* __restrict__ Pin = (pcur ? a.p2 : a.p) + base;
+  float* __restrict__ P = (pcur ? a.p : a.p2) + base;
+  float* __restrict__ Q = a.q + base;
+  // halo fetch role of this lane: k = which plane, left (lanes 0-5) or right (lanes 16-20) chunk
+  const int k = lane & 15;
+  const bool isL = lane < 16;
+  const int hx = isL ? x0 - 4 : x0 + kStrip4;
+  const bool hcol = isL ? (x0 > 0) : (x0 + kStrip4 < W);
+  const bool hrole = hcol && (k <= 4 || (k == 5 && isL));
+  const float* hsrc = (k == 0) ? Hb : (k == 1) ? IP : (k == 2) ? C : (k == 3) ? Pin : (k == 4) ? (isL ? E : SW) : SE;
+  const int hxs = hrole ? hx : 0;
+
+  auto issue = [&](int y) {                       // stage row y (rows are visited bottom -> top)
+    RingU* r = ring + ((H - 2 - y) % R);
+    const bool in = y >= 0;
+    const bool interior = y >= 1;
+    const size_t o = (size_t)(in ? y : 0) * W;
+    cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
+    cp_async16(&r->ip[lane], IP + o + xs, interior && valid);
+    cp_async16(&r->c[lane], C + o + xs, interior && valid);
+    cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
+    cp_async16(&r->s[lane], S + o + xs, in && valid);
+    cp_async16(&r->e[lane], E + o + xs, interior && valid);
+    cp_async16(&r->se[lane], SE + o + xs, in && valid);
+    cp_async16(&r->sw[lane], SW + o + xs, in && valid);
+    cp_async16(&r->halo[lane], hsrc + o + hxs, in && hrole && (k >= 4 || interior) && !(k == 3 && first));
+    cp_async_commit();
+  };
+  const unsigned full = 0xffffffffu;
+  struct WRow { float4 s, e, se, sw; float hw1, hw2; };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float zn[4] = {0.f, 0.f, 0.f, 0.f}, zhn = 0.f;            // z of the row below (own columns, halo column)
+  float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pu[6];
+  WRow wc, wu;
+  wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
+  const int hoff = (lane == 31) ? 16 : 0;
+
+#pragma unroll
+  for (int u = 0; u < R; ++u) issue(H - 2 - u);
+  double acc = 0.0;
+#pragma unroll 1
+  for (int y = H - 2; y >= 0; --y) {
+    cp_async_wait<R - 1>();
+    {
+      const RingU* r = ring + ((H - 2 - y) % R);
+      const float4 h = r->h[lane], ip = r->ip[lane], c = r->c[lane], p = r->p[lane];
+      wu.s = r->s[lane]; wu.e = r->e[lane]; wu.se = r->se[lane]; wu.sw = r->sw[lane];
+      // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
+      const float hh = hsel(r->halo[hoff + 0], lane), hip = hsel(r->halo[hoff + 1], lane);
+      const float hc = hsel(r->halo[hoff + 2], lane), hp = hsel(r->halo[hoff + 3], lane);
+      wu.hw1 = hsel(r->halo[hoff + 4], lane); wu.hw2 = hsel(r->halo[hoff + 5], lane);
+      float z[4];
+      z[0] = fmaf(c.x, zn[0], ip.x * h.x); z[1] = fmaf(c.y, zn[1], ip.y * h.y);
+      z[2] = fmaf(c.z, zn[2], ip.z * h.z); z[3] = fmaf(c.w, zn[3], ip.w * h.w);
+      const float zh = fmaf(hc, zhn, hip * hh);
+      pu[1] = fmaf(beta, p.x, z[0]); pu[2] = fmaf(beta, p.y, z[1]);
+      pu[3] = fmaf(beta, p.z, z[2]); pu[4] = fmaf(beta, p.w, z[3]);
+      const float ph = fmaf(beta, hp, zh);
+      const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
+      pu[0] = (lane == 0) ? ph : l;
+      pu[5] = (lane == 31) ? ph : rt;
+      zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
+      if (valid && y >= 1) *reinterpret_cast<float4*>(P + (size_t)y * W + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
+    }
+    const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
+    if (yc <= H - 2) {
+      const float eL_s = __shfl_up_sync(full, wc.e.w, 1);
+      const float seL_s = __shfl_up_sync(full, wu.se.w, 1);
+      const float swR_s = __shfl_down_sync(full, wu.sw.x, 1);
+      const float eL = (lane == 0) ? wc.hw1 : eL_s;           // wE[c, x-1]
+      const float seL = (lane == 0) ? wu.hw2 : seL_s;         // wSE[u, x-1]
+      const float swR = (lane == 31) ? wu.hw1 : swR_s;        // wSW[u, x+4]
+      const float Sc[4] = {wc.s.x, wc.s.y, wc.s.z, wc.s.w};
+      const float Su[4] = {wu.s.x, wu.s.y, wu.s.z, wu.s.w};
+      const float E5[5] = {eL, wc.e.x, wc.e.y, wc.e.z, wc.e.w};
+      const float SEc[4] = {wc.se.x, wc.se.y, wc.se.z, wc.se.w};
+      const float SWc[4] = {wc.sw.x, wc.sw.y, wc.sw.z, wc.sw.w};
+      const float SEu[4] = {seL, wu.se.x, wu.se.y, wu.se.z};
+      const float SWu[4] = {wu.sw.y, wu.sw.z, wu.sw.w, swR};
+      float q[4], dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pcj = pc[j + 1];
+        float t = Sc[j] * (pcj - pl[j + 1]);
+        t = fmaf(Su[j], pcj - pu[j + 1], t);
+        t = fmaf(E5[j + 1], pcj - pc[j + 2], t);
+        t = fmaf(E5[j], pcj - pc[j], t);
+        t = fmaf(SEc[j], pcj - pl[j + 2], t);
+        t = fmaf(SWc[j], pcj - pl[j], t);
+        t = fmaf(SEu[j], pcj - pu[j], t);
+        t = fmaf(SWu[j], pcj - pu[j + 2], t);
+        q[j] = t;
+        dot = fmaf(pcj, t, dot);
+      }
+      if (valid) {
+        *reinterpret_cast<float4*>(Q + (size_t)yc * W + x) = make_float4(q[0], q[1], q[2], q[3]);
+        acc += (double)dot;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[j]; }
+    wc = wu;
+    issue(y - R);
+  }
+  cp_async_wait<0>();
+  return warp_sum(acc);
+}
+
+// F_DOWN (INIT = false) and F_PRECOND (INIT = true: fresh residual, e = 0, no update)
+template <int RD, bool INIT>
+__device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+                                          float alpha, int pcur, double& rr_out, double& rz_out) {
+  RingD* ring = reinterpret_cast<RingD*>(ringmem);
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W;
+  const int x = strip * kStrip4 + 4 * lane;
+  const bool valid = x < W;
+  const int xs = valid ? x : 0;
+  const float* __restrict__ IP = a.ip + base; const float* __restrict__ C = a.c + base;
+  const float* __restrict__ P = (pcur ? a.p2 : a.p) + base;
+  float* __restrict__ Ev = a.e + base; float* __restrict__ Rv = a.r + base;
+  const float* __restrict__ Q = a.q + base;
+  float* __restrict__ Hb = a.z + base;          // h = L^-1 r goes to the z plane (read by the next F_UP)
+  auto issue = [&](int y) {
+    RingD* r = ring + ((y - 1) % RD);
+    const bool in = (y <= H - 2) && valid;
+    const size_t o = (size_t)(y <= H - 2 ? y : 0) * W + xs;
+    if (!INIT) {
+      cp_async16(&r->p[lane], P + o, in);
+      cp_async16(&r->e[lane], Ev + o, in);
+      cp_async16(&r->q[lane], Q + o, in);
+    }
+    cp_async16(&r->r[lane], Rv + o, in);
+    cp_async16(&r->c[lane], C + o, in);
+    cp_async16(&r->ip[lane], IP + o, in);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int u = 0; u < RD; ++u) issue(1 + u);
+  float hp[4] = {0.f, 0.f, 0.f, 0.f}, cp[4] = {0.f, 0.f, 0.f, 0.f};
+  double rr = 0.0, rz = 0.0;
+#pragma unroll 1
+  for (int y = 1; y <= H - 2; ++y) {
+    cp_async_wait<RD - 1>();
+    const RingD* r = ring + ((y - 1) % RD);
+    const float4 rv = r->r[lane], cv = r->c[lane], iv = r->ip[lane];
+    float rn[4] = {rv.x, rv.y, rv.z, rv.w};
+    if (!INIT) {
+      const float4 pv = r->p[lane], ev = r->e[lane], qv = r->q[lane];
+      const float4 en = make_float4(fmaf(alpha, pv.x, ev.x), fmaf(alpha, pv.y, ev.y), fmaf(alpha, pv.z, ev.z),
+                                    fmaf(alpha, pv.w, ev.w));
+      rn[0] = fmaf(-alpha, qv.x, rv.x); rn[1] = fmaf(-alpha, qv.y, rv.y);
+      rn[2] = fmaf(-alpha, qv.z, rv.z); rn[3] = fmaf(-alpha, qv.w, rv.w);
+      if (valid) {
+        *reinterpret_cast<float4*>(Ev + (size_t)y * W + x) = en;
+        *reinterpret_cast<float4*>(Rv + (size_t)y * W + x) = make_float4(rn[0], rn[1], rn[2], rn[3]);
+      }
+    } else if (valid) {
+      *reinterpret_cast<float4*>(Ev + (size_t)y * W + x) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = fmaf(cp[j], hp[j], rn[j]);
+    if (valid) *reinterpret_cast<float4*>(Hb + (size_t)y * W + x) = make_float4(h[0], h[1], h[2], h[3]);
+    const float srr = fmaf(rn[0], rn[0], fmaf(rn[1], rn[1], fmaf(rn[2], rn[2], rn[3] * rn[3])));
+    const float srz = fmaf(iv.x * h[0], h[0], fmaf(iv.y * h[1], h[1], fmaf(iv.z * h[2], h[2], iv.w * h[3] * h[3])));
+    rr += (double)srr; rz += (double)srz;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hp[j] = h[j];
+    cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
+    issue(y + RD);
+  }
+  cp_async_wait<0>();
+  rr_out = warp_sum(rr); rz_out = warp_sum(rz);
+}
+
+template <int AW>   // AW = active warps per CTA (8 or 4): fewer active warps own deeper rings
+__global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> a) {
+  constexpr int R = kRingRowsPerCta / AW;                         // F_UP ring depth   (6 / 12)
+  constexpr int RD = (int)(sizeof(RingU) * R / sizeof(RingD));    // F_DOWN ring depth (8 / 16)
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool active = warp < AW;
+  unsigned char* ringmem = smem_raw + (size_t)warp * sizeof(RingU) * R;
+  // warp-major task order: consecutive tasks land on different SMs, so a small batch still spreads
+  // over the whole GPU (one or two busy warps per SM, each with a deep ring)
+  const int gw = warp * gridDim.x + blockIdx.x, nw = gridDim.x * AW;
+  const int B = a.B, H = a.H, W = a.W;
+  const int per_rs = a.nstrip1 * a.nrb, per_col = a.nstrip4;
+  const int tot = (per_rs > per_col ? per_rs : per_col) * B;
+  auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+
+  for (int step = 0; step < a.max_steps; ++step) {
+    unsigned long long t0 = 0;
+    const bool dbg = a.debug && blockIdx.x == 0 && threadIdx.x == 0 && step >= 20 && step < 24;
+    if (dbg) t0 = now();
+    if (active) {
+      for (int t = gw; t < tot; t += nw) {
+        const int b = t % B, ti = t / B;
+        ImgState* st = a.st + b;
+        const unsigned long long fw = __ldcg(&st->fword);
+        const int mode = (int)(fw & 0xffffffffull);
+        if (mode == F_DONE || (int)(fw >> 32) > step) continue;   // done, or published during this interval
+        const int per = (mode == F_RESID) ? per_rs : per_col;
+        if (ti >= per) continue;
+        const unsigned long long next_from = (unsigned long long)(step + 1) << 32;
+        double s0 = 0.0, s1 = 0.0;
+        if (mode == F_UP) {
+          s0 = up_task<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+        } else if (mode == F_DOWN) {
+          down_task<RD, false>(a, ringmem, b, ti, lane, (float)__ldcg(&st->alpha), __ldcg(&st->pcur), s0, s1);
+        } else if (mode == F_PRECOND) {
+          down_task<RD, true>(a, ringmem, b, ti, lane, 0.f, 0, s0, s1);
+        } else if (mode == F_RESID) {
+          s0 = stencil_task<float, true>(a, b, ti % a.nstrip1, ti / a.nstrip1, lane, 0.f, true);
+        } else {
+          const int x = ti * kStrip4 + 4 * lane;
+          if (x < W) {
+            const size_t base = (size_t)b * H * W + x;
+            if (mode == F_FOLD) {
+#pragma unroll 4
+              for (int y = 1; y <= H - 2; ++y) {
+                const size_t o = base + (size_t)y * W;
+                const float4 e = *reinterpret_cast<const float4*>(a.e + o);
+                double2* xp = reinterpret_cast<double2*>(a.x64 + o);
+                double2 v0 = xp[0], v1 = xp[1];
+                v0.x += (double)e.x; v0.y += (double)e.y; v1.x += (double)e.z; v1.y += (double)e.w;
+                xp[0] = v0; xp[1] = v1;
+              }
+            } else {   // F_FINAL
+#pragma unroll 4
+              for (int y = 0; y < H; ++y) {
+                const size_t o = base + (size_t)y * W;
+                const double2* xp = reinterpret_cast<const double2*>(a.x64 + o);
+                const double2 v0 = xp[0], v1 = xp[1];
+                *reinterpret_cast<float4*>(a.cm + o) = make_float4((float)v0.x, (float)v0.y, (float)v1.x, (float)v1.y);
+              }
+            }
+          }
+        }
+        double* part = a.part + (size_t)b * a.pmax * 2;
+        if (lane == 0) { part[2 * ti] = s0; part[2 * ti + 1] = s1; }
+        if (arrive_last(&st->cnt1, (unsigned)per, lane)) {
+          reduce_parts(part, per, lane, s0, s1);
+          if (lane == 0) {
+            st->cnt1 = 0;
+            if (mode == F_UP) {
+              if (s0 > 0.0) st->alpha = __ldcg(&st->rz) / s0;
+              else { st->alpha = 0.0; st->rr_target = 1e300; }
+              st->pcur = __ldcg(&st->pcur) ^ 1;          // F_UP wrote the other plane
+              st->fword = next_from | F_DOWN;
+            } else if (mode == F_DOWN) {
+              const double rz_old = __ldcg(&st->rz);
+              const int it = __ldcg(&st->iters) + 1;
+              st->iters = it; st->rr_rec = s0; st->rz = s1; st->first = 0;
+              st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
+              st->fword = next_from | ((s0 <= __ldcg(&st->rr_target) || it >= a.maxiter || !(s1 > 0.0)) ? F_FOLD : F_UP);
+            } else if (mode == F_PRECOND) {
+              st->rz = s1; st->first = 1; st->beta = 0.0;
+              st->fword = next_from | ((s1 > 0.0) ? F_UP : F_FINAL);
+            } else if (mode == F_RESID) {
+              const double bb = __ldcg(&st->bb), prev = __ldcg(&st->rr_prev);
+              const int it = __ldcg(&st->iters), outer = __ldcg(&st->outer);
+              st->rr_true = s0;
+              const bool conv = s0 <= a.rtol2 * bb;
+              const bool stalled = outer > 0 && s0 > 0.25 * prev;
+              if (conv || stalled || it >= a.maxiter) st->fword = next_from | F_FINAL;
+              else {
+                st->fword = next_from | F_PRECOND;
+                st->rr_prev = s0;
+                st->rr_target = fmax(0.49 * a.rtol2 * bb, a.inner_red2 * s0);
+              }
+            } else if (mode == F_FOLD) {
+              st->fword = next_from | F_RESID; st->outer = __ldcg(&st->outer) + 1;
+            } else {   // F_FINAL
+              st->fword = next_from | F_DONE;
+              const double bb = __ldcg(&st->bb);
+              if (a.iters_out) a.iters_out[b] = __ldcg(&st->iters);
+              if (a.relres_out) a.relres_out[b] = (bb > 0.0) ? sqrt(__ldcg(&st->rr_true) / bb) : 0.0;
+              __threadfence();
+              atomicAdd(a.done, 1u);
+            }
+          }
+        }
+      }
+    }
+    unsigned long long t1 = 0;
+    if (dbg) t1 = now();
+    grid.sync();
+    if (dbg) printf("[pcg fused dbg] step %d: phase %llu ns (block 0 thread 0), sync wait %llu ns\n", step, t1 - t0, now() - t1);
+    if (__ldcg(a.done) >= (unsigned)B) break;
+  }
+}
+
 struct CmLayout {
   float *depth, *mm1, *mm2, *wS, *wE, *wSE, *wSW, *ip, *c;
   double *x64, *bbpart, *part;
-  void *e, *r, *p, *q, *z;
+  void *e, *r, *p, *q, *z, *p2;
   ImgState* st;
   unsigned* done;
   int nblk, nstrip1, nrb, nstrip2, pmax;
@@ -741,7 +1087,7 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.ip = cv.take<float>(N); L.c = cv.take<float>(N);
   L.x64 = cv.take<double>(N);
   L.e = cv.take<char>(N * tsz); L.r = cv.take<char>(N * tsz); L.p = cv.take<char>(N * tsz);
-  L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz);
+  L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz); L.p2 = cv.take<char>(N * tsz);
   L.bbpart = cv.take<double>((size_t)B * L.nblk);
   L.part = cv.take<double>((size_t)B * L.pmax * 2);
   L.st = cv.take<ImgState>(B);
@@ -755,6 +1101,39 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
 static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 static thread_local int g_debug = 0;
 
+static thread_local int g_legacy = 0;   // USAUG_CM_LEGACY_KERNEL: force the two-slot kernel (A/B testing)
+
+template <int AW>
+static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t stream) {
+  int per_sm = 0;
+  USAUG_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<AW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+  USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel<AW>, 256, kFusedSmem));
+  if (per_sm < 1) { set_error("pcg_fused_kernel cannot be resident"); return USAUG_E_CUDA; }
+  const int tasks = a.nstrip4 * a.B;
+  int blocks = tasks;
+  if (blocks > blocks_cap_sms) blocks = blocks_cap_sms;
+  if (blocks < 1) blocks = 1;
+  void* params[] = {(void*)&a};
+  if (g_ev_start) USAUG_CUDA(cudaEventRecord(g_ev_start, stream));
+  USAUG_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel<AW>, dim3(blocks), dim3(256), params,
+                                         kFusedSmem, stream));
+  if (g_ev_stop) USAUG_CUDA(cudaEventRecord(g_ev_stop, stream));
+  return USAUG_OK;
+}
+
+static int launch_fused(PcgArgs<float>& a, const CmLayout& L, int B, cudaStream_t stream) {
+  (void)L;
+  int dev = 0, sms = 0;
+  USAUG_CUDA(cudaGetDevice(&dev));
+  USAUG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // every inner iteration is two phases; a refinement round adds four
+  a.max_steps = 6 * a.maxiter + 64;   // worst case: a refinement round (5 phases) after every iteration
+  const int tasks = a.nstrip4 * B;
+  // few tasks: 4 active warps per CTA with rings twice as deep keep enough bytes in flight
+  if (tasks >= 6 * sms) return launch_fused_aw<8>(a, sms, stream);
+  return launch_fused_aw<4>(a, sms, stream);
+}
+
 template <typename T>
 static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double rtol, int maxiter,
                       int* iters, double* relres, cudaStream_t stream) {
@@ -765,7 +1144,7 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.inner_red2 = inner_red * inner_red;
   a.wS = L.wS; a.wE = L.wE; a.wSE = L.wSE; a.wSW = L.wSW; a.ip = L.ip; a.c = L.c;
   a.x64 = L.x64;
-  a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z;
+  a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z; a.p2 = (T*)L.p2;
   a.st = L.st; a.part = L.part; a.done = L.done; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
   a.nstrip1 = L.nstrip1; a.nrb = L.nrb; a.nstrip2 = L.nstrip2; a.pmax = L.pmax;
   a.vec4 = (std::is_same<T, float>::value && W % 4 == 0) ? 1 : 0;
@@ -774,6 +1153,9 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.max_steps = 4 * maxiter + 16;
   a.debug = g_debug;
 
+  if constexpr (std::is_same<T, float>::value) {
+    if (a.vec4 && !g_legacy) return launch_fused(a, L, B, stream);
+  }
   int dev = 0, sms = 0, per_sm = 0;
   const size_t smem = a.vec4 ? kRingBytesPerWarp * 8 : 0;
   USAUG_CUDA(cudaGetDevice(&dev));
@@ -830,6 +1212,7 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   CmLayout L = cm_layout(ws, B, H, W, flags);
   const int N = H * W;
   g_debug = (flags & USAUG_CM_DEBUG_TIMING) ? 1 : 0;
+  g_legacy = (flags & USAUG_CM_LEGACY_KERNEL) ? 1 : 0;
 
   cm_depth_kernel<<<(H + 127) / 128, 128, 0, stream>>>(L.depth, H, alpha);
   USAUG_CHECK_LAUNCH("cm_depth_kernel");
