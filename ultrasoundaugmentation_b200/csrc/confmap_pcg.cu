@@ -149,6 +149,13 @@ __global__ void __launch_bounds__(256) cm_weights_kernel(
   wS[o] = s; wE[o] = e; wSE[o] = se; wSW[o] = sw;
 }
 
+__device__ __forceinline__ uint32_t bf16_bits(float v) {      // round to nearest even, finite inputs
+  const uint32_t u = __float_as_uint(v);
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
 // Column-line factorisation T = L D L^T (T = vertical couplings + full diagonal of L_UU):
 //   piv[y] = diag[y] - wS[y-1]^2 / piv[y-1],  ip = 1/piv,  c[y] = wS[y] * ip[y].
 // Jacobi: ip = 1/diag, c = 0.  Also writes the initial guess into x64 (seed rows 1 / 0) and the
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(256) cm_weights_kernel(
 __global__ void __launch_bounds__(128) cm_factor_kernel(
     int H, int W, const float* __restrict__ wS, const float* __restrict__ wE,
     const float* __restrict__ wSE, const float* __restrict__ wSW, int precond, int zero_guess,
-    float* __restrict__ ip, float* __restrict__ c, double* __restrict__ x64,
+    float* __restrict__ ip, float* __restrict__ c, uint32_t* __restrict__ ipc, double* __restrict__ x64,
     double* __restrict__ bbpart) {
   __shared__ double s_bb[4];
   const int b = blockIdx.y;
@@ -174,8 +181,9 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
     }
     x64[base + x] = 1.0;
     x64[base + (size_t)(H - 1) * W + x] = 0.0;
-    ip[base + x] = 0.f; c[base + x] = 0.f;
+    ip[base + x] = 0.f; c[base + x] = 0.f; ipc[base + x] = 0u;
     ip[base + (size_t)(H - 1) * W + x] = 0.f; c[base + (size_t)(H - 1) * W + x] = 0.f;
+    ipc[base + (size_t)(H - 1) * W + x] = 0u;
     double ip_prev = 0.0;   // row 0 is a seed: not part of T
     float s_prev = S[x];
     for (int y = 1; y <= H - 2; ++y) {
@@ -187,8 +195,13 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
       double piv = dg;
       if (precond == USAUG_PRECOND_LINE && y > 1) piv -= (double)s_prev * (double)s_prev * ip_prev;
       const double ipv = 1.0 / piv;
-      ip[base + o] = (float)ipv;
-      c[base + o] = (precond == USAUG_PRECOND_LINE && y < H - 2) ? (float)((double)s * ipv) : 0.0f;
+      const float ipf = (float)ipv;
+      const float cf = (precond == USAUG_PRECOND_LINE && y < H - 2) ? (float)((double)s * ipv) : 0.0f;
+      ip[base + o] = ipf;
+      c[base + o] = cf;
+      // fused kernel: both factors as bf16 in one word (low = ip, high = c).  M = L D L^T stays SPD for
+      // any positive ip and any c, and the iteration count is unchanged.
+      ipc[base + o] = bf16_bits(ipf) | (bf16_bits(cf) << 16);
       x64[base + o] = zero_guess ? 0.0 : 1.0 - (double)y / (double)(H - 1);
       // keep the recurrence consistent with the ROUNDED factors the sweeps will use
       ip_prev = (double)(float)ipv;
@@ -224,6 +237,7 @@ struct PcgArgs {
   double rtol2;      // rtol^2
   double inner_red2; // squared residual reduction asked of one inner solve (0 => run to rtol)
   const float *wS, *wE, *wSE, *wSW, *ip, *c;
+  const uint32_t* ipc;   // fused kernel: bf16 ip (low half) | bf16 c (high half)
   double* x64;
   T *e, *r, *p, *q, *z;   // q doubles as h (forward-eliminated residual) inside slot 2
   T *p2;                  // fused kernel: second search-direction plane (ping-pong); z holds h there
@@ -735,17 +749,19 @@ __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a)
 // =============================================================================================
 enum FMode : int { F_RESID = 0, F_PRECOND = 1, F_UP = 2, F_DOWN = 3, F_FOLD = 4, F_FINAL = 5, F_DONE = 6 };
 
-struct RingU {   // one staged row of a 128-column strip for F_UP (4608 bytes)
-  float4 h[32], ip[32], c[32], p[32], s[32], e[32], se[32], sw[32];
+struct RingU {   // one staged row of a 128-column strip for F_UP (4096 bytes)
+  float4 h[32], p[32], s[32], e[32], se[32], sw[32];
+  uint4 ipc[32];
   // 16-byte chunks that contain the strip's halo columns (cp.async.cg = L2, never a stale L1 line):
-  // [0..5] columns x0-4..x0-1 of h, ip, c, p, wE, wSE (.w is the left neighbour column);
-  // [16..20] columns x0+128..x0+131 of h, ip, c, p, wSW (.x is the right neighbour column)
+  // [0..4] columns x0-4..x0-1 of h, ipc, p, wE, wSE (.w is the left neighbour column);
+  // [16..19] columns x0+128..x0+131 of h, ipc, p, wSW (.x is the right neighbour column)
   float4 halo[32];
 };
-struct RingD {   // one staged row for F_DOWN / F_PRECOND (3072 bytes)
-  float4 p[32], e[32], r[32], q[32], c[32], ip[32];
+struct RingD {   // one staged row for F_DOWN / F_PRECOND (2560 bytes)
+  float4 p[32], e[32], r[32], q[32];
+  uint4 ipc[32];
 };
-constexpr int kRingRowsPerCta = 48;                                   // 48 x 4608 B = 216 KB per CTA
+constexpr int kRingRowsPerCta = 48;                                   // 48 x 4096 B = 192 KB per CTA
 constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
 
 __device__ __forceinline__ float hsel(const float4& v, int lane) { return lane == 31 ? v.x : v.w; }
@@ -761,20 +777,21 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   const int xs = valid ? x : 0;
   const float* __restrict__ S = a.wS + base; const float* __restrict__ E = a.wE + base;
   const float* __restrict__ SE = a.wSE + base; const float* __restrict__ SW = a.wSW + base;
-  const float* __restrict__ IP = a.ip + base; const float* __restrict__ C = a.c + base;
+  const uint32_t* __restrict__ IPC = a.ipc + base;
   // reads: h (z plane), p_old (pin); writes: p_new (pout), q.  Nothing is updated in place, because the
   // halo columns of this strip belong to a neighbouring strip whose warp runs asynchronously.
   const float* __restrict__ Hb = a.z + base;
   const float* __restrict__ Pin = (pcur ? a.p2 : a.p) + base;
   float* __restrict__ P = (pcur ? a.p : a.p2) + base;
   float* __restrict__ Q = a.q + base;
-  // halo fetch role of this lane: k = which plane, left (lanes 0-5) or right (lanes 16-20) chunk
+  // halo fetch role of this lane: k = which plane, left (lanes 0-4) or right (lanes 16-19) chunk
   const int k = lane & 15;
   const bool isL = lane < 16;
   const int hx = isL ? x0 - 4 : x0 + kStrip4;
   const bool hcol = isL ? (x0 > 0) : (x0 + kStrip4 < W);
-  const bool hrole = hcol && (k <= 4 || (k == 5 && isL));
-  const float* hsrc = (k == 0) ? Hb : (k == 1) ? IP : (k == 2) ? C : (k == 3) ? Pin : (k == 4) ? (isL ? E : SW) : SE;
+  const bool hrole = hcol && (k <= 3 || (k == 4 && isL));
+  const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin
+                      : (k == 3) ? (isL ? E : SW) : SE;
   const int hxs = hrole ? hx : 0;
 
   auto issue = [&](int y) {                       // stage row y (rows are visited bottom -> top)
@@ -783,14 +800,13 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
     const bool interior = y >= 1;
     const size_t o = (size_t)(in ? y : 0) * W;
     cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
-    cp_async16(&r->ip[lane], IP + o + xs, interior && valid);
-    cp_async16(&r->c[lane], C + o + xs, interior && valid);
+    cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
     cp_async16(&r->s[lane], S + o + xs, in && valid);
     cp_async16(&r->e[lane], E + o + xs, interior && valid);
     cp_async16(&r->se[lane], SE + o + xs, in && valid);
     cp_async16(&r->sw[lane], SW + o + xs, in && valid);
-    cp_async16(&r->halo[lane], hsrc + o + hxs, in && hrole && (k >= 4 || interior) && !(k == 3 && first));
+    cp_async16(&r->halo[lane], hsrc + o + hxs, in && hrole && (k >= 3 || interior) && !(k == 2 && first));
     cp_async_commit();
   };
   const unsigned full = 0xffffffffu;
@@ -805,21 +821,23 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(H - 2 - u);
   double acc = 0.0;
-#pragma unroll 1
+#pragma unroll 2
   for (int y = H - 2; y >= 0; --y) {
     cp_async_wait<R - 1>();
     {
       const RingU* r = ring + ((H - 2 - y) % R);
-      const float4 h = r->h[lane], ip = r->ip[lane], c = r->c[lane], p = r->p[lane];
+      const float4 h = r->h[lane], p = r->p[lane];
+      const uint4 f = r->ipc[lane];
       wu.s = r->s[lane]; wu.e = r->e[lane]; wu.se = r->se[lane]; wu.sw = r->sw[lane];
       // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
-      const float hh = hsel(r->halo[hoff + 0], lane), hip = hsel(r->halo[hoff + 1], lane);
-      const float hc = hsel(r->halo[hoff + 2], lane), hp = hsel(r->halo[hoff + 3], lane);
-      wu.hw1 = hsel(r->halo[hoff + 4], lane); wu.hw2 = hsel(r->halo[hoff + 5], lane);
+      const float hh = hsel(r->halo[hoff + 0], lane);
+      const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
+      const float hp = hsel(r->halo[hoff + 2], lane);
+      wu.hw1 = hsel(r->halo[hoff + 3], lane); wu.hw2 = hsel(r->halo[hoff + 4], lane);
       float z[4];
-      z[0] = fmaf(c.x, zn[0], ip.x * h.x); z[1] = fmaf(c.y, zn[1], ip.y * h.y);
-      z[2] = fmaf(c.z, zn[2], ip.z * h.z); z[3] = fmaf(c.w, zn[3], ip.w * h.w);
-      const float zh = fmaf(hc, zhn, hip * hh);
+      z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
+      z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
+      const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
       pu[1] = fmaf(beta, p.x, z[0]); pu[2] = fmaf(beta, p.y, z[1]);
       pu[3] = fmaf(beta, p.z, z[2]); pu[4] = fmaf(beta, p.w, z[3]);
       const float ph = fmaf(beta, hp, zh);
@@ -883,7 +901,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   const int x = strip * kStrip4 + 4 * lane;
   const bool valid = x < W;
   const int xs = valid ? x : 0;
-  const float* __restrict__ IP = a.ip + base; const float* __restrict__ C = a.c + base;
+  const uint32_t* __restrict__ IPC = a.ipc + base;
   const float* __restrict__ P = (pcur ? a.p2 : a.p) + base;
   float* __restrict__ Ev = a.e + base; float* __restrict__ Rv = a.r + base;
   const float* __restrict__ Q = a.q + base;
@@ -898,19 +916,21 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
       cp_async16(&r->q[lane], Q + o, in);
     }
     cp_async16(&r->r[lane], Rv + o, in);
-    cp_async16(&r->c[lane], C + o, in);
-    cp_async16(&r->ip[lane], IP + o, in);
+    cp_async16(&r->ipc[lane], IPC + o, in);
     cp_async_commit();
   };
 #pragma unroll
   for (int u = 0; u < RD; ++u) issue(1 + u);
   float hp[4] = {0.f, 0.f, 0.f, 0.f}, cp[4] = {0.f, 0.f, 0.f, 0.f};
   double rr = 0.0, rz = 0.0;
-#pragma unroll 1
+#pragma unroll 2
   for (int y = 1; y <= H - 2; ++y) {
     cp_async_wait<RD - 1>();
     const RingD* r = ring + ((y - 1) % RD);
-    const float4 rv = r->r[lane], cv = r->c[lane], iv = r->ip[lane];
+    const float4 rv = r->r[lane];
+    const uint4 f = r->ipc[lane];
+    const float4 cv = make_float4(bf16_hi(f.x), bf16_hi(f.y), bf16_hi(f.z), bf16_hi(f.w));
+    const float4 iv = make_float4(bf16_lo(f.x), bf16_lo(f.y), bf16_lo(f.z), bf16_lo(f.w));
     float rn[4] = {rv.x, rv.y, rv.z, rv.w};
     if (!INIT) {
       const float4 pv = r->p[lane], ev = r->e[lane], qv = r->q[lane];
@@ -1062,6 +1082,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
 
 struct CmLayout {
   float *depth, *mm1, *mm2, *wS, *wE, *wSE, *wSW, *ip, *c;
+  uint32_t* ipc;
   double *x64, *bbpart, *part;
   void *e, *r, *p, *q, *z, *p2;
   ImgState* st;
@@ -1084,7 +1105,7 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.mm1 = cv.take<float>((size_t)B * kChunks * 2);
   L.mm2 = cv.take<float>((size_t)B * kChunks * 2);
   L.wS = cv.take<float>(N); L.wE = cv.take<float>(N); L.wSE = cv.take<float>(N); L.wSW = cv.take<float>(N);
-  L.ip = cv.take<float>(N); L.c = cv.take<float>(N);
+  L.ip = cv.take<float>(N); L.c = cv.take<float>(N); L.ipc = cv.take<uint32_t>(N);
   L.x64 = cv.take<double>(N);
   L.e = cv.take<char>(N * tsz); L.r = cv.take<char>(N * tsz); L.p = cv.take<char>(N * tsz);
   L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz); L.p2 = cv.take<char>(N * tsz);
@@ -1142,7 +1163,7 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.rtol2 = rtol * rtol;
   const double inner_red = std::is_same<T, float>::value ? 1e-4 : 0.0;
   a.inner_red2 = inner_red * inner_red;
-  a.wS = L.wS; a.wE = L.wE; a.wSE = L.wSE; a.wSW = L.wSW; a.ip = L.ip; a.c = L.c;
+  a.wS = L.wS; a.wE = L.wE; a.wSE = L.wSE; a.wSW = L.wSW; a.ip = L.ip; a.c = L.c; a.ipc = L.ipc;
   a.x64 = L.x64;
   a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z; a.p2 = (T*)L.p2;
   a.st = L.st; a.part = L.part; a.done = L.done; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
@@ -1225,7 +1246,7 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   USAUG_CHECK_LAUNCH("cm_weights_kernel");
   cm_factor_kernel<<<dim3(L.nblk, B), 128, 0, stream>>>(H, W, L.wS, L.wE, L.wSE, L.wSW, precond,
                                                         (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.ip, L.c,
-                                                        L.x64, L.bbpart);
+                                                        L.ipc, L.x64, L.bbpart);
   USAUG_CHECK_LAUNCH("cm_factor_kernel");
   cm_init_state_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, L.nblk, L.bbpart, L.st, L.done);
   USAUG_CHECK_LAUNCH("cm_init_state_kernel");

@@ -4,12 +4,13 @@
 
 namespace usaug {
 
-// "no bone seen" marker produced by cudaMemsetAsync(.., 0x7f, ..)
+// "no bone seen" marker for first-row values
 constexpr int kNone = 0x7f7f7f7f;
 
-// surf[B][W][2]: {first bone row, H-1-last bone row}, both kNone when the column has no bone.
-// Enqueues memset + scan on `stream`.
+// surf[B][scan_tiles(H)][W][2]: per 64-row tile {first bone row or kNone, last bone row or -1}.
+// One scan kernel on `stream` (no memset, no atomics); consumers reduce over the tiles.
 int launch_surface_scan(const uint8_t* lab, int B, int H, int W, int* surf, cudaStream_t stream);
-size_t surface_scan_bytes(int B, int W);
+int scan_tiles(int H);
+size_t surface_scan_bytes(int B, int H, int W);
 
 }  // namespace usaug

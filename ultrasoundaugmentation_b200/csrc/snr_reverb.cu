@@ -8,6 +8,7 @@
 namespace usaug {
 
 constexpr int kSrRows = 16;
+constexpr int kSrCols = 128;
 constexpr int kMaxTaps = 65;   // R <= 32
 
 __device__ __forceinline__ float snr_px(float I, float c, float k) {
@@ -15,18 +16,26 @@ __device__ __forceinline__ float snr_px(float I, float c, float k) {
   return fminf(fmaxf(I + (k * c) * I, 0.0f), 1.0f);
 }
 
-__global__ void __launch_bounds__(128) snr_reverb_kernel(
+// Block = 128 scanlines x 16 output rows, thread = scanline.  The ghost term only exists where the
+// shifted bone box (+R) meets the tile; there the feathered mask of the 16 x 128 source tile is built
+// SEPARABLY in shared memory (row pass over 16+2R label rows, then column pass: 2*(2R+1) MACs per
+// pixel instead of (2R+1)^2), in the oracle's order (rows first, increasing tap index).
+__global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
     const float* __restrict__ img, const float* __restrict__ cm, const uint8_t* __restrict__ lab,
     float* __restrict__ out, int H, int W, const float* __restrict__ a_snr,
     const float* __restrict__ rho, const int* __restrict__ nghost, const int* __restrict__ box,
     const float* __restrict__ taps_g, int R) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ float taps[kMaxTaps];
+  const int TR = kSrRows + 2 * R;              // label / row-pass rows
+  const int TC = kSrCols + 2 * R;              // label columns
+  float* rowp = reinterpret_cast<float*>(sm_raw);                               // [TR][kSrCols]
+  uint8_t* labs = sm_raw + (size_t)TR * kSrCols * sizeof(float);               // [TR][TC]
   for (int i = threadIdx.x; i < 2 * R + 1; i += blockDim.x) taps[i] = taps_g[i];
-  __syncthreads();
 
   const int b = blockIdx.z;
-  const int x = blockIdx.x * 128 + threadIdx.x;
-  if (x >= W) return;
+  const int x0 = blockIdx.x * kSrCols, x = x0 + threadIdx.x;
+  const bool xin = x < W;
   const size_t base = (size_t)b * H * W;
   const float* I = img + base;
   const float* C = cm ? cm + base : nullptr;
@@ -36,49 +45,64 @@ __global__ void __launch_bounds__(128) snr_reverb_kernel(
   const int n = nghost[b];
   const float rh = rho[b];
   const bool ghosts = (ytop >= 1) && (n >= 1);
-  const bool x_in = ghosts && (x >= xl - R) && (x <= xr + R);
   const int ya = blockIdx.y * kSrRows;
 
-#pragma unroll 4
+  float v[kSrRows], acc[kSrRows];
+#pragma unroll
   for (int r = 0; r < kSrRows; ++r) {
     const int y = ya + r;
-    if (y >= H) break;
-    const size_t o = (size_t)y * W + x;
-    float v = I[o];
-    if (C) v = snr_px(v, C[o], ks);
-    if (ghosts) {
-      float acc = v;
-      if (x_in) {
-        float coef = 1.0f;
-        for (int k = 1; k <= n; ++k) {
-          coef *= rh;
-          const int ys = y - k * ytop;
-          if (ys < 0) break;
-          if (ys < ytop - R || ys > ybot + R) continue;
-          // feathered mask at (ys, x): rows then columns, increasing tap index
-          float m = 0.0f;
-          for (int j = -R; j <= R; ++j) {
-            const int yy = ys + j;
-            if (yy < 0 || yy >= H) continue;
-            const uint8_t* Lr = L + (size_t)yy * W;
-            float row = 0.0f;
-            for (int i = -R; i <= R; ++i) {
-              const int xx = x + i;
-              if (xx >= 0 && xx < W && Lr[xx]) row += taps[i + R];
-            }
-            m += taps[j + R] * row;
-          }
-          if (m > 0.0f) {
-            const size_t so = (size_t)ys * W + x;
-            float sv = I[so];
-            if (C) sv = snr_px(sv, C[so], ks);
-            acc += coef * (m * sv);
-          }
+    float t = 0.f;
+    if (xin && y < H) {
+      t = I[(size_t)y * W + x];
+      if (C) t = snr_px(t, C[(size_t)y * W + x], ks);
+    }
+    v[r] = t; acc[r] = t;
+  }
+  __syncthreads();   // taps visible
+
+  if (ghosts) {
+    float coef = 1.0f;
+    for (int k = 1; k <= n; ++k) {
+      coef *= rh;
+      const int ys0 = ya - k * ytop;                      // source row of output row ya
+      if (ys0 + kSrRows - 1 < 0) break;                   // whole tile above the first ghost row
+      // block-uniform cull: source tile (+R) against the bone box
+      if (ys0 > ybot + R || ys0 + kSrRows - 1 < ytop - R || x0 > xr + R || x0 + kSrCols - 1 < xl - R) continue;
+      __syncthreads();                                    // previous ghost done with the tiles
+      for (int i = threadIdx.x; i < TR * TC; i += blockDim.x) {
+        const int rr = i / TC, cc = i - rr * TC;
+        const int yy = ys0 - R + rr, xx = x0 - R + cc;
+        labs[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (uint8_t)(L[(size_t)yy * W + xx] != 0) : (uint8_t)0;
+      }
+      __syncthreads();
+      for (int rr = 0; rr < TR; ++rr) {                   // row pass: thread = column
+        const uint8_t* lr = labs + rr * TC + threadIdx.x;
+        float s = 0.0f;
+        for (int i = 0; i <= 2 * R; ++i) s += lr[i] ? taps[i] : 0.0f;
+        rowp[rr * kSrCols + threadIdx.x] = s;
+      }
+      // column pass needs only this thread's own column of rowp: no barrier required
+#pragma unroll
+      for (int r = 0; r < kSrRows; ++r) {
+        const int ys = ys0 + r;
+        if (ys < 0 || ya + r >= H || !xin) continue;
+        float m = 0.0f;
+        for (int j = 0; j <= 2 * R; ++j) m += taps[j] * rowp[(r + j) * kSrCols + threadIdx.x];
+        if (m > 0.0f) {
+          const size_t so = (size_t)ys * W + x;
+          float sv = I[so];
+          if (C) sv = snr_px(sv, C[so], ks);
+          acc[r] += coef * (m * sv);
         }
       }
-      v = fminf(fmaxf(acc, 0.0f), 1.0f);
     }
-    out[base + o] = v;
+  }
+  if (xin) {
+#pragma unroll
+    for (int r = 0; r < kSrRows; ++r) {
+      const int y = ya + r;
+      if (y < H) out[base + (size_t)y * W + x] = ghosts ? fminf(fmaxf(acc[r], 0.0f), 1.0f) : v[r];
+    }
   }
 }
 
@@ -88,7 +112,7 @@ using namespace usaug;
 
 extern "C" size_t usaug_snr_reverb_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return surface_scan_bytes(B, W) + align_up((size_t)B * 4 * sizeof(int));
+  return surface_scan_bytes(B, H, W) + align_up((size_t)B * 4 * sizeof(int));
 }
 
 extern "C" int usaug_snr_reverb(const float* img, const float* cm, const uint8_t* lab, float* out,
@@ -108,13 +132,16 @@ extern "C" int usaug_snr_reverb(const float* img, const float* cm, const uint8_t
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Carver cv(ws);
-  int* surf = cv.take<int>((size_t)B * W * 2);
+  int* surf = cv.take<int>((size_t)B * scan_tiles(H) * W * 2);
   int* box = cv.take<int>((size_t)B * 4);
-  int rc = usaug_bone_box(lab, B, H, W, box, surf, surface_scan_bytes(B, W), stream_);
+  int rc = usaug_bone_box(lab, B, H, W, box, surf, surface_scan_bytes(B, H, W), stream_);
   if (rc) return rc;
-  dim3 grid((W + 127) / 128, (H + kSrRows - 1) / kSrRows, B);
-  snr_reverb_kernel<<<grid, 128, 0, stream>>>(img, cm, lab, out, H, W, a_snr, rho, nghost, box,
-                                              feather_taps, R);
+  dim3 grid((W + kSrCols - 1) / kSrCols, (H + kSrRows - 1) / kSrRows, B);
+  const size_t smem = (size_t)(kSrRows + 2 * R) * kSrCols * sizeof(float) + (size_t)(kSrRows + 2 * R) * (kSrCols + 2 * R);
+  if (smem > 48 * 1024)
+    USAUG_CUDA(cudaFuncSetAttribute(snr_reverb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  snr_reverb_kernel<<<grid, kSrCols, smem, stream>>>(img, cm, lab, out, H, W, a_snr, rho, nghost, box,
+                                                     feather_taps, R);
   USAUG_CHECK_LAUNCH("snr_reverb_kernel");
   return USAUG_OK;
 }

@@ -10,7 +10,7 @@ namespace usaug {
 // Surface scan: every label byte is read exactly once, fully parallel (no early-exit chains).
 // Block = 256 threads = 8 warps; a block covers 32*VEC columns x kScanRows rows; lane owns VEC
 // adjacent columns, warps interleave rows.  Per-column first/last bone row inside the tile is
-// merged through shared memory, then at most one atomicMin pair per column and tile.
+// merged through shared memory and written as one partial per (tile, column): no memset, no atomics.
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanRows = 64;
 
@@ -68,18 +68,30 @@ __global__ void __launch_bounds__(256) surface_scan_kernel(const uint8_t* __rest
       l = max(l, s_last[w][c]);
     }
     const int x = blockIdx.x * 32 * VEC + c;
-    if (l >= 0 && x < W) {
-      int* dst = surf + ((size_t)b * W + x) * 2;
-      atomicMin(dst, f);
-      atomicMin(dst + 1, H - 1 - l);
+    if (x < W) {   // one partial per (image, row tile, column): no memset, no atomics
+      int* dst = surf + (((size_t)b * gridDim.y + blockIdx.y) * W + x) * 2;
+      dst[0] = f;
+      dst[1] = (l >= 0) ? l : -1;
     }
   }
 }
 
-size_t surface_scan_bytes(int B, int W) { return align_up((size_t)B * W * 2 * sizeof(int)); }
+// first / last bone row of column x from the per-tile partials
+__device__ __forceinline__ void column_extent(const int* __restrict__ surf, int b, int ntile, int W, int x,
+                                              int& first, int& last) {
+  int f = kNone, l = -1;
+  for (int t = 0; t < ntile; ++t) {
+    const int* p = surf + (((size_t)b * ntile + t) * W + x) * 2;
+    f = min(f, p[0]);
+    l = max(l, p[1]);
+  }
+  first = f; last = l;
+}
+
+int scan_tiles(int H) { return (H + kScanRows - 1) / kScanRows; }
+size_t surface_scan_bytes(int B, int H, int W) { return align_up((size_t)B * scan_tiles(H) * W * 2 * sizeof(int)); }
 
 int launch_surface_scan(const uint8_t* lab, int B, int H, int W, int* surf, cudaStream_t stream) {
-  USAUG_CUDA(cudaMemsetAsync(surf, 0x7f, (size_t)B * W * 2 * sizeof(int), stream));
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0);
   if (vec) {
     dim3 grid((W + 127) / 128, (H + kScanRows - 1) / kScanRows, B);
@@ -101,7 +113,7 @@ struct WarpInfo {
   int y_top;
 };
 
-__global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ surf, int H, int W,
+__global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ surf, int ntile, int H, int W,
                                                       const float* __restrict__ d,
                                                       const float* __restrict__ taps, int R,
                                                       float* __restrict__ s_hat,
@@ -116,7 +128,8 @@ __global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ su
 
   int ytop = kNone;
   for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const int f = surf[((size_t)b * W + x) * 2];
+    int f, l;
+    column_extent(surf, b, ntile, W, x, f, l);
     s_first[x] = (f == kNone) ? -1 : f;
     ytop = min(ytop, f);
   }
@@ -177,32 +190,13 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
     const float* __restrict__ img, const uint8_t* __restrict__ lab, float* __restrict__ out_img,
     uint8_t* __restrict__ out_lab, int H, int W, const float* __restrict__ s_hat,
     const WarpInfo* __restrict__ info, const float* __restrict__ tgc, int K, float gscale) {
+  __shared__ float s_gain[kWarpRows];
   const int b = blockIdx.z;
   const int x = blockIdx.x * 128 + threadIdx.x;
-  if (x >= W) return;
-  const size_t base = (size_t)b * H * W;
-  const float* I = img + base;
-  const uint8_t* L = lab + base;
-  const float de = info[b].d_eff;
-  const float den = __fsub_rn(s_hat[(size_t)b * W + x], de);
-  const float* g = tgc + (size_t)b * K;
   const int ya = blockIdx.y * kWarpRows;
-
-#pragma unroll 8
-  for (int r = 0; r < kWarpRows; ++r) {
-    const int y = ya + r;
-    if (y >= H) break;
-    const float yf = (float)y;
-    const float t = (yf < den) ? __fdiv_rn(yf, den) : 1.0f;
-    const float ys = __fadd_rn(yf, __fmul_rn(de, t));
-    const float y0f = floorf(ys);
-    const float fr = ys - y0f;
-    const int i0 = (int)y0f, i1 = i0 + 1;
-    const float v0 = (i0 >= 0 && i0 < H) ? I[(size_t)i0 * W + x] : 0.0f;
-    const float v1 = (i1 >= 0 && i1 < H) ? I[(size_t)i1 * W + x] : 0.0f;
-    const int yn = (int)floorf(__fadd_rn(ys, 0.5f));
-    const uint8_t lv = (yn >= 0 && yn < H) ? L[(size_t)yn * W + x] : (uint8_t)0;
-
+  if (threadIdx.x < kWarpRows) {          // TGC gain is a function of the output row only
+    const float* g = tgc + (size_t)b * K;
+    const float yf = (float)(ya + threadIdx.x);
     float gain;
     if (K == 1) {
       gain = g[0];
@@ -213,24 +207,65 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
       const float g0 = g[k0], g1 = g[k0 + 1];
       gain = g0 + fg * (g1 - g0);
     }
-    const float v = (1.0f - fr) * v0 + fr * v1;
-    out_img[base + (size_t)y * W + x] = fminf(fmaxf(gain * v, 0.0f), 1.0f);
-    out_lab[base + (size_t)y * W + x] = lv;
+    s_gain[threadIdx.x] = gain;
+  }
+  __syncthreads();
+  if (x >= W) return;
+  const size_t base = (size_t)b * H * W;
+  const float* __restrict__ I = img + base + x;          // column pointers; in-image offsets fit 32 bits
+  const uint8_t* __restrict__ L = lab + base + x;
+  float* __restrict__ OI = out_img + base + x;
+  uint8_t* __restrict__ OL = out_lab + base + x;
+  const float de = info[b].d_eff;
+  const float den = __fsub_rn(s_hat[(size_t)b * W + x], de);
+  const unsigned uH = (unsigned)H;
+
+  // Phase 1: source coordinates of all 16 rows (the IEEE divide has a slow-path call that would
+  // otherwise fence the loads of one row from the next).  Phase 2: all gathers back-to-back.
+  int i0[kWarpRows], yn[kWarpRows];
+  float fr[kWarpRows];
+#pragma unroll
+  for (int r = 0; r < kWarpRows; ++r) {
+    const float yf = (float)(ya + r);
+    float t = 1.0f;
+    if (yf < den) t = __fdiv_rn(yf, den);                 // rows at / below the bone surface skip the divide
+    const float ys = __fadd_rn(yf, __fmul_rn(de, t));
+    i0[r] = __float2int_rd(ys);
+    fr[r] = ys - (float)i0[r];
+    yn[r] = __float2int_rd(__fadd_rn(ys, 0.5f));
+  }
+  float v0[kWarpRows], v1[kWarpRows];
+  uint8_t lv[kWarpRows];
+#pragma unroll
+  for (int r = 0; r < kWarpRows; ++r) {
+    const bool in = ya + r < H;
+    v0[r] = (in && (unsigned)i0[r] < uH) ? I[i0[r] * W] : 0.0f;
+    v1[r] = (in && (unsigned)(i0[r] + 1) < uH) ? I[(i0[r] + 1) * W] : 0.0f;
+    lv[r] = (in && (unsigned)yn[r] < uH) ? L[yn[r] * W] : (uint8_t)0;
+  }
+#pragma unroll
+  for (int r = 0; r < kWarpRows; ++r) {
+    const int y = ya + r;
+    if (y < H) {
+      const float v = (1.0f - fr[r]) * v0[r] + fr[r] * v1[r];
+      OI[y * W] = fminf(fmaxf(s_gain[r] * v, 0.0f), 1.0f);
+      OL[y * W] = lv[r];
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Bone box: reduces the surface scan to {y_top, y_bottom, x_left, x_right} per image.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bone_box_kernel(const int* __restrict__ surf, int H, int W,
+__global__ void __launch_bounds__(256) bone_box_kernel(const int* __restrict__ surf, int ntile, int H, int W,
                                                        int* __restrict__ box) {
   __shared__ int s_red[4][8];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int yt = kNone, yb = -1, xl = kNone, xr = -1;
   for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const int f = surf[((size_t)b * W + x) * 2];
+    int f, l;
+    column_extent(surf, b, ntile, W, x, f, l);
     if (f != kNone) {
-      const int l = H - 1 - surf[((size_t)b * W + x) * 2 + 1];
       yt = min(yt, f); yb = max(yb, l); xl = min(xl, x); xr = max(xr, x);
     }
   }
@@ -254,7 +289,7 @@ using namespace usaug;
 
 extern "C" size_t usaug_warp_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return surface_scan_bytes(B, W) + align_up((size_t)B * W * sizeof(float)) +
+  return surface_scan_bytes(B, H, W) + align_up((size_t)B * W * sizeof(float)) +
          align_up((size_t)B * sizeof(WarpInfo));
 }
 
@@ -278,13 +313,13 @@ extern "C" int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, floa
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Carver cv(ws);
-  int* surf = cv.take<int>((size_t)B * W * 2);
+  int* surf = cv.take<int>((size_t)B * scan_tiles(H) * W * 2);
   float* s_hat = cv.take<float>((size_t)B * W);
   WarpInfo* info = cv.take<WarpInfo>(B);
 
   int rc = launch_surface_scan(lab, B, H, W, surf, stream);
   if (rc) return rc;
-  profile_kernel<<<B, 256, (size_t)W * 8, stream>>>(surf, H, W, d, taps, R, s_hat, info);
+  profile_kernel<<<B, 256, (size_t)W * 8, stream>>>(surf, scan_tiles(H), H, W, d, taps, R, s_hat, info);
   USAUG_CHECK_LAUNCH("profile_kernel");
   const float gscale = (H > 1 && K > 1) ? (float)((double)(K - 1) / (double)(H - 1)) : 0.0f;
   dim3 grid((W + 127) / 128, (H + kWarpRows - 1) / kWarpRows, B);
@@ -296,7 +331,7 @@ extern "C" int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, floa
 
 extern "C" size_t usaug_bone_box_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return surface_scan_bytes(B, W);
+  return surface_scan_bytes(B, H, W);
 }
 
 extern "C" int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box, void* ws,
@@ -310,7 +345,7 @@ extern "C" int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box,
   int* surf = static_cast<int*>(ws);
   int rc = launch_surface_scan(lab, B, H, W, surf, stream);
   if (rc) return rc;
-  bone_box_kernel<<<B, 256, 0, stream>>>(surf, H, W, box);
+  bone_box_kernel<<<B, 256, 0, stream>>>(surf, scan_tiles(H), H, W, box);
   USAUG_CHECK_LAUNCH("bone_box_kernel");
   return USAUG_OK;
 }
