@@ -49,7 +49,8 @@ enum {
   USAUG_CM_FP64_VECTORS = 1, /* keep the CG vectors in fp64 (default: fp32 vectors + fp64 refinement) */
   USAUG_CM_ZERO_GUESS = 2,   /* start from x0 = 0 instead of the linear depth ramp */
   USAUG_CM_DEBUG_TIMING = 4, /* development: the kernel prints per-slot wall times of a few steps */
-  USAUG_CM_LEGACY_KERNEL = 8 /* A/B testing: use the two-slot kernel even where the fused fp32 kernel applies */
+  USAUG_CM_LEGACY_KERNEL = 8, /* A/B testing: use the two-slot kernel even where the fused fp32 kernel applies */
+  USAUG_CM_CONTINUE = 16      /* experimental: residual replacement every 2 decades, keep the search direction */
 };
 
 int usaug_version(void);

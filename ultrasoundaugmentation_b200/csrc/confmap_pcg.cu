@@ -117,35 +117,54 @@ __global__ void __launch_bounds__(256) cm_delta_kernel(const float* __restrict__
   if (threadIdx.x == 0) { mm2[((size_t)b * kChunks + c) * 2] = mn; mm2[((size_t)b * kChunks + c) * 2 + 1] = mx; }
 }
 
-__device__ __forceinline__ float edge_w(float a0, float a1, float mn, float den, float beta, float pen) {
-  const float d = fabsf(__fsub_rn(a0, a1));
-  const float dn = __fdiv_rn(__fsub_rn(d, mn), den);
-  const float arg = -__fmul_rn(beta, __fadd_rn(dn, pen));
-  return __fadd_rn(expf(arg), kFloor);
+// Edge weight w = exp(-beta * ((|a0 - a1| - mn) / den + pen)) + 1e-6  (A.3 steps 3-5), evaluated as
+//   ex2(k1 * |a0 - a1| + k0) + 1e-6,   k1 = -beta*log2(e)/den,   k0 = beta*log2(e)*(mn/den - pen)
+// with per-image constants (k1, k0 per edge type) formed in fp64.  ONE function for every kernel (weight
+// planes, line factors, fp64 residual, and the fused UP phase that recomputes the weights from the `a`
+// plane instead of reading four planes), so the matrix is bit-identical wherever it is applied.
+// Relative deviation from the oracle's exp(): <= ~5e-6 where w > 1e-6 matters (|arg| <= 20).
+__device__ __forceinline__ float edge_w_fast(float a0, float a1, float k1, float k0) {
+  float e;
+  const float arg = fmaf(fabsf(__fsub_rn(a0, a1)), k1, k0);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+  return __fadd_rn(e, kFloor);
+}
+
+// wk[b] = {k1, k0_vertical, k0_horizontal, k0_diagonal}
+__global__ void cm_wconst_kernel(int B, const float* __restrict__ mm2, float beta, float gamma,
+                                 float4* __restrict__ wk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float mn2, den2;
+  read_mm(mm2, b, mn2, den2);
+  const double L2E = 1.4426950408889634074, bd = (double)beta, dn = (double)den2, m = (double)mn2 / dn;
+  const double pen_h = (double)gamma, pen_d = (double)__fmul_rn(kSqrt2, gamma);
+  wk[b] = make_float4((float)(-bd * L2E / dn), (float)(bd * L2E * m), (float)(bd * L2E * (m - pen_h)),
+                      (float)(bd * L2E * (m - pen_d)));
 }
 
 __global__ void __launch_bounds__(256) cm_weights_kernel(
     const float* __restrict__ img, int H, int W, const float* __restrict__ depth,
-    const float* __restrict__ mm1, const float* __restrict__ mm2, float beta, float gamma,
+    const float* __restrict__ mm1, const float4* __restrict__ wk, float* __restrict__ aplane,
     float* __restrict__ wS, float* __restrict__ wE, float* __restrict__ wSE, float* __restrict__ wSW) {
   const int b = blockIdx.y, N = H * W;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= N) return;
   const float* I = img + (size_t)b * N;
-  float mn1, den1, mn2, den2;
+  float mn1, den1;
   read_mm(mm1, b, mn1, den1);
-  read_mm(mm2, b, mn2, den2);
-  const float pen_d = __fmul_rn(kSqrt2, gamma);
+  const float4 k = wk[b];
   const int y = i / W, x = i - y * W;
   const float a0 = atten(I, depth, y, x, W, mn1, den1);
   float s = 0.f, e = 0.f, se = 0.f, sw = 0.f;
-  if (x < W - 1) e = edge_w(a0, atten(I, depth, y, x + 1, W, mn1, den1), mn2, den2, beta, gamma);
+  if (x < W - 1) e = edge_w_fast(a0, atten(I, depth, y, x + 1, W, mn1, den1), k.x, k.z);
   if (y < H - 1) {
-    s = edge_w(a0, atten(I, depth, y + 1, x, W, mn1, den1), mn2, den2, beta, 0.0f);
-    if (x < W - 1) se = edge_w(a0, atten(I, depth, y + 1, x + 1, W, mn1, den1), mn2, den2, beta, pen_d);
-    if (x > 0) sw = edge_w(a0, atten(I, depth, y + 1, x - 1, W, mn1, den1), mn2, den2, beta, pen_d);
+    s = edge_w_fast(a0, atten(I, depth, y + 1, x, W, mn1, den1), k.x, k.y);
+    if (x < W - 1) se = edge_w_fast(a0, atten(I, depth, y + 1, x + 1, W, mn1, den1), k.x, k.w);
+    if (x > 0) sw = edge_w_fast(a0, atten(I, depth, y + 1, x - 1, W, mn1, den1), k.x, k.w);
   }
   const size_t o = (size_t)b * N + i;
+  aplane[o] = a0;
   wS[o] = s; wE[o] = e; wSE[o] = se; wSW[o] = sw;
 }
 
@@ -238,6 +257,8 @@ struct PcgArgs {
   double inner_red2; // squared residual reduction asked of one inner solve (0 => run to rtol)
   const float *wS, *wE, *wSE, *wSW, *ip, *c;
   const uint32_t* ipc;   // fused kernel: bf16 ip (low half) | bf16 c (high half)
+  const float* aplane;   // attenuated normalised intensity a (A.3 step 2); fused UP recomputes weights from it
+  const float4* wk;      // per image {k1, k0_vertical, k0_horizontal, k0_diagonal} of edge_w_fast
   double* x64;
   T *e, *r, *p, *q, *z;   // q doubles as h (forward-eliminated residual) inside slot 2
   T *p2;                  // fused kernel: second search-direction plane (ping-pong); z holds h there
@@ -249,6 +270,7 @@ struct PcgArgs {
   double* relres_out;
   int nstrip1, nrb, nstrip2, pmax, max_steps;
   int vec4, nstrip4; // vectorised stencil (fp32 vectors, W % 4 == 0): 128-column strips
+  int restart;       // experimental (USAUG_CM_CONTINUE): keep p across refinement rounds, replace r every 2 decades
   int debug;         // USAUG_CM_DEBUG_TIMING: block 0 prints per-slot wall times of a few steps
 };
 
@@ -749,7 +771,24 @@ __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a)
 // =============================================================================================
 enum FMode : int { F_RESID = 0, F_PRECOND = 1, F_UP = 2, F_DOWN = 3, F_FOLD = 4, F_FINAL = 5, F_DONE = 6 };
 
-struct RingU {   // one staged row of a 128-column strip for F_UP (4096 bytes)
+struct RingU {   // one staged row of a 128-column strip for F_UP (2560 bytes)
+  float4 h[32], p[32], a[32];
+  uint4 ipc[32];
+  // 16-byte chunks that contain the strip's halo columns (cp.async.cg = L2, never a stale L1 line):
+  // [0..3] columns x0-4..x0-1 of h, ipc, p, a (.w is the left neighbour column);
+  // [16..19] columns x0+128..x0+131 of the same planes (.x is the right neighbour column)
+  float4 halo[32];
+};
+struct RingD {   // one staged row for F_DOWN / F_PRECOND (2560 bytes)
+  float4 p[32], e[32], r[32], q[32];
+  uint4 ipc[32];
+};
+constexpr int kRingRowsPerCta = 80;                                   // 80 x 2560 B = 200 KB per CTA
+constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
+
+__device__ __forceinline__ float hsel(const float4& v, int lane) { return lane == 31 ? v.x : v.w; }
+
+struct RingUP {   // one staged row of a 128-column strip for F_UP, weight planes read from memory (4096 bytes)
   float4 h[32], p[32], s[32], e[32], se[32], sw[32];
   uint4 ipc[32];
   // 16-byte chunks that contain the strip's halo columns (cp.async.cg = L2, never a stale L1 line):
@@ -757,19 +796,154 @@ struct RingU {   // one staged row of a 128-column strip for F_UP (4096 bytes)
   // [16..19] columns x0+128..x0+131 of h, ipc, p, wSW (.x is the right neighbour column)
   float4 halo[32];
 };
-struct RingD {   // one staged row for F_DOWN / F_PRECOND (2560 bytes)
-  float4 p[32], e[32], r[32], q[32];
-  uint4 ipc[32];
-};
-constexpr int kRingRowsPerCta = 48;                                   // 48 x 4096 B = 192 KB per CTA
-constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
 
-__device__ __forceinline__ float hsel(const float4& v, int lane) { return lane == 31 ? v.x : v.w; }
+// Edge weights of one image row for the 4 columns of a lane (plus the three that belong to its
+// neighbours' columns), recomputed from the `a` plane.
+struct WRow {
+  float s[4], e[4], se[4], sw[4];
+  float eL;    // wE [row, x-1]
+  float seL;   // wSE[row, x-1]
+  float swR;   // wSW[row, x+4]
+};
 
 template <int R>
 __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
                                           float beta, bool first, int pcur) {
   RingU* ring = reinterpret_cast<RingU*>(ringmem);
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W;
+  const int x0 = strip * kStrip4, x = x0 + 4 * lane;
+  const bool valid = x < W;
+  const bool hasL = valid && x > 0, hasR = valid && (x + 4 < W);
+  const int xs = valid ? x : 0;
+  const uint32_t* __restrict__ IPC = a.ipc + base;
+  const float* __restrict__ Ap = a.aplane + base;
+  const float4 wk = a.wk[b];
+  // reads: h (z plane), p_old (pin); writes: p_new (pout), q.  Nothing is updated in place, because the
+  // halo columns of this strip belong to a neighbouring strip whose warp runs asynchronously.
+  const float* __restrict__ Hb = a.z + base;
+  const float* __restrict__ Pin = (pcur ? a.p2 : a.p) + base;
+  float* __restrict__ P = (pcur ? a.p : a.p2) + base;
+  float* __restrict__ Q = a.q + base;
+  // halo fetch role of this lane: k = which plane, left (lanes 0-3) or right (lanes 16-19) chunk
+  const int k = lane & 15;
+  const bool isL = lane < 16;
+  const int hx = isL ? x0 - 4 : x0 + kStrip4;
+  const bool hcol = isL ? (x0 > 0) : (x0 + kStrip4 < W);
+  const bool hrole = hcol && k <= 3;
+  const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin : Ap;
+  const int hxs = hrole ? hx : 0;
+
+  auto issue = [&](int y) {                       // stage row y (rows are visited bottom -> top, H-1 .. 0)
+    RingU* r = ring + ((H - 1 - y) % R);
+    const bool in = y >= 0;
+    const bool interior = y >= 1 && y <= H - 2;
+    const size_t o = (size_t)(in ? y : 0) * W;
+    cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
+    cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
+    cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
+    cp_async16(&r->a[lane], Ap + o + xs, in && valid);
+    cp_async16(&r->halo[lane], hsrc + o + hxs, in && hrole && (k == 3 || interior) && !(k == 2 && first));
+    cp_async_commit();
+  };
+  const unsigned full = 0xffffffffu;
+  float zn[4] = {0.f, 0.f, 0.f, 0.f}, zhn = 0.f;            // z of the row below (own columns, halo column)
+  float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pu[6];
+  float ab[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, au[6];     // a of the row below / of this row, columns x-1..x+4
+  WRow wc, wu;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wc.s[j] = wc.e[j] = wc.se[j] = wc.sw[j] = 0.f;
+  wc.eL = wc.seL = wc.swR = 0.f;
+  const int hoff = (lane == 31) ? 16 : 0;
+
+#pragma unroll
+  for (int u = 0; u < R; ++u) issue(H - 1 - u);
+  double acc = 0.0;
+#pragma unroll 2
+  for (int y = H - 1; y >= 0; --y) {
+    cp_async_wait<R - 1>();
+    {
+      const RingU* r = ring + ((H - 1 - y) % R);
+      const float4 h = r->h[lane], p = r->p[lane], av = r->a[lane];
+      const uint4 f = r->ipc[lane];
+      // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
+      const float hh = hsel(r->halo[hoff + 0], lane);
+      const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
+      const float hp = hsel(r->halo[hoff + 2], lane);
+      const float ha = hsel(r->halo[hoff + 3], lane);
+      float z[4];
+      z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
+      z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
+      const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
+      pu[1] = fmaf(beta, p.x, z[0]); pu[2] = fmaf(beta, p.y, z[1]);
+      pu[3] = fmaf(beta, p.z, z[2]); pu[4] = fmaf(beta, p.w, z[3]);
+      const float ph = fmaf(beta, hp, zh);
+      const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
+      pu[0] = (lane == 0) ? ph : l;
+      pu[5] = (lane == 31) ? ph : rt;
+      zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
+      if (valid && y >= 1 && y <= H - 2)
+        *reinterpret_cast<float4*>(P + (size_t)y * W + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
+      au[1] = av.x; au[2] = av.y; au[3] = av.z; au[4] = av.w;
+      const float al = __shfl_up_sync(full, av.w, 1), ar = __shfl_down_sync(full, av.x, 1);
+      au[0] = (lane == 0) ? ha : al;
+      au[5] = (lane == 31) ? ha : ar;
+    }
+    // weights of row y (edges inside the row and down to row y+1), masked where the edge does not exist
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      wu.s[j] = valid ? edge_w_fast(au[j + 1], ab[j + 1], wk.x, wk.y) : 0.f;
+      wu.e[j] = valid ? edge_w_fast(au[j + 1], au[j + 2], wk.x, wk.z) : 0.f;
+      wu.se[j] = valid ? edge_w_fast(au[j + 1], ab[j + 2], wk.x, wk.w) : 0.f;
+      wu.sw[j] = valid ? edge_w_fast(au[j + 1], ab[j], wk.x, wk.w) : 0.f;
+    }
+    wu.eL = hasL ? edge_w_fast(au[0], au[1], wk.x, wk.z) : 0.f;
+    wu.seL = hasL ? edge_w_fast(au[0], ab[1], wk.x, wk.w) : 0.f;
+    wu.swR = hasR ? edge_w_fast(au[5], ab[4], wk.x, wk.w) : 0.f;
+    if (!hasR) { wu.e[3] = 0.f; wu.se[3] = 0.f; }
+    if (!hasL) wu.sw[0] = 0.f;
+
+    const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
+    if (yc <= H - 2) {
+      const float E5[5] = {wc.eL, wc.e[0], wc.e[1], wc.e[2], wc.e[3]};
+      const float SEu[4] = {wu.seL, wu.se[0], wu.se[1], wu.se[2]};
+      const float SWu[4] = {wu.sw[1], wu.sw[2], wu.sw[3], wu.swR};
+      float q[4], dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pcj = pc[j + 1];
+        float t = wc.s[j] * (pcj - pl[j + 1]);
+        t = fmaf(wu.s[j], pcj - pu[j + 1], t);
+        t = fmaf(E5[j + 1], pcj - pc[j + 2], t);
+        t = fmaf(E5[j], pcj - pc[j], t);
+        t = fmaf(wc.se[j], pcj - pl[j + 2], t);
+        t = fmaf(wc.sw[j], pcj - pl[j], t);
+        t = fmaf(SEu[j], pcj - pu[j], t);
+        t = fmaf(SWu[j], pcj - pu[j + 2], t);
+        q[j] = t;
+        dot = fmaf(pcj, t, dot);
+      }
+      if (valid) {
+        *reinterpret_cast<float4*>(Q + (size_t)yc * W + x) = make_float4(q[0], q[1], q[2], q[3]);
+        acc += (double)dot;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[j]; ab[j] = au[j]; }
+    wc = wu;
+    issue(y - R);
+  }
+  cp_async_wait<0>();
+  return warp_sum(acc);
+}
+
+// Variant of F_UP that READS the four weight planes (9 plane touches instead of 6, but ~25 % fewer
+// instructions per row): used when there are too few tasks to be bandwidth-bound, where the single-warp
+// instruction latency of a strip, not HBM, sets the pace.
+template <int R>
+__device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+                                          float beta, bool first, int pcur) {
+  RingUP* ring = reinterpret_cast<RingUP*>(ringmem);
   const int H = a.H, W = a.W;
   const size_t base = (size_t)b * H * W;
   const int x0 = strip * kStrip4, x = x0 + 4 * lane;
@@ -795,7 +969,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   const int hxs = hrole ? hx : 0;
 
   auto issue = [&](int y) {                       // stage row y (rows are visited bottom -> top)
-    RingU* r = ring + ((H - 2 - y) % R);
+    RingUP* r = ring + ((H - 2 - y) % R);
     const bool in = y >= 0;
     const bool interior = y >= 1;
     const size_t o = (size_t)(in ? y : 0) * W;
@@ -810,11 +984,11 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
     cp_async_commit();
   };
   const unsigned full = 0xffffffffu;
-  struct WRow { float4 s, e, se, sw; float hw1, hw2; };
+  struct WRowP { float4 s, e, se, sw; float hw1, hw2; };
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float zn[4] = {0.f, 0.f, 0.f, 0.f}, zhn = 0.f;            // z of the row below (own columns, halo column)
   float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pu[6];
-  WRow wc, wu;
+  WRowP wc, wu;
   wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
 
@@ -825,7 +999,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   for (int y = H - 2; y >= 0; --y) {
     cp_async_wait<R - 1>();
     {
-      const RingU* r = ring + ((H - 2 - y) % R);
+      const RingUP* r = ring + ((H - 2 - y) % R);
       const float4 h = r->h[lane], p = r->p[lane];
       const uint4 f = r->ipc[lane];
       wu.s = r->s[lane]; wu.e = r->e[lane]; wu.se = r->se[lane]; wu.sw = r->sw[lane];
@@ -961,15 +1135,18 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   rr_out = warp_sum(rr); rz_out = warp_sum(rz);
 }
 
-template <int AW>   // AW = active warps per CTA (8 or 4): fewer active warps own deeper rings
+// AW = active warps per CTA (8 or 4): fewer active warps own deeper rings.
+// RECOMP = F_UP recomputes the edge weights from the `a` plane (bandwidth-bound regime) or reads them.
+template <int AW, bool RECOMP>
 __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> a) {
-  constexpr int R = kRingRowsPerCta / AW;                         // F_UP ring depth   (6 / 12)
-  constexpr int RD = (int)(sizeof(RingU) * R / sizeof(RingD));    // F_DOWN ring depth (8 / 16)
+  constexpr size_t kWarpRing = kFusedSmem / AW;                   // ring bytes per active warp
+  constexpr int R = (int)(kWarpRing / (RECOMP ? sizeof(RingU) : sizeof(RingUP)));   // F_UP ring depth in rows
+  constexpr int RD = (int)(kWarpRing / sizeof(RingD));                              // F_DOWN ring depth
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool active = warp < AW;
-  unsigned char* ringmem = smem_raw + (size_t)warp * sizeof(RingU) * R;
+  unsigned char* ringmem = smem_raw + (size_t)warp * kWarpRing;
   // warp-major task order: consecutive tasks land on different SMs, so a small batch still spreads
   // over the whole GPU (one or two busy warps per SM, each with a deep ring)
   const int gw = warp * gridDim.x + blockIdx.x, nw = gridDim.x * AW;
@@ -994,7 +1171,10 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
         const unsigned long long next_from = (unsigned long long)(step + 1) << 32;
         double s0 = 0.0, s1 = 0.0;
         if (mode == F_UP) {
-          s0 = up_task<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+          if constexpr (RECOMP)
+            s0 = up_task<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+          else
+            s0 = up_task_planes<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
         } else if (mode == F_DOWN) {
           down_task<RD, false>(a, ringmem, b, ti, lane, (float)__ldcg(&st->alpha), __ldcg(&st->pcur), s0, s1);
         } else if (mode == F_PRECOND) {
@@ -1044,7 +1224,11 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
               st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
               st->fword = next_from | ((s0 <= __ldcg(&st->rr_target) || it >= a.maxiter || !(s1 > 0.0)) ? F_FOLD : F_UP);
             } else if (mode == F_PRECOND) {
-              st->rz = s1; st->first = 1; st->beta = 0.0;
+              // First round: start CG (p = z).  Later rounds: RESIDUAL REPLACEMENT -- r was refreshed with the
+              // true fp64 residual, the search direction p is kept, so CG continues instead of restarting.
+              const double rz_old = __ldcg(&st->rz);
+              const bool cont = __ldcg(&st->outer) > 0 && rz_old > 0.0 && a.restart;   // restart field = CONTINUE flag
+              st->rz = s1; st->first = cont ? 0 : 1; st->beta = cont ? s1 / rz_old : 0.0;
               st->fword = next_from | ((s1 > 0.0) ? F_UP : F_FINAL);
             } else if (mode == F_RESID) {
               const double bb = __ldcg(&st->bb), prev = __ldcg(&st->rr_prev);
@@ -1081,8 +1265,9 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
 }
 
 struct CmLayout {
-  float *depth, *mm1, *mm2, *wS, *wE, *wSE, *wSW, *ip, *c;
+  float *depth, *mm1, *mm2, *wS, *wE, *wSE, *wSW, *ip, *c, *aplane;
   uint32_t* ipc;
+  float4* wk;
   double *x64, *bbpart, *part;
   void *e, *r, *p, *q, *z, *p2;
   ImgState* st;
@@ -1106,6 +1291,7 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.mm2 = cv.take<float>((size_t)B * kChunks * 2);
   L.wS = cv.take<float>(N); L.wE = cv.take<float>(N); L.wSE = cv.take<float>(N); L.wSW = cv.take<float>(N);
   L.ip = cv.take<float>(N); L.c = cv.take<float>(N); L.ipc = cv.take<uint32_t>(N);
+  L.aplane = cv.take<float>(N); L.wk = cv.take<float4>(B);
   L.x64 = cv.take<double>(N);
   L.e = cv.take<char>(N * tsz); L.r = cv.take<char>(N * tsz); L.p = cv.take<char>(N * tsz);
   L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz); L.p2 = cv.take<char>(N * tsz);
@@ -1122,13 +1308,14 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
 static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 static thread_local int g_debug = 0;
 
+static thread_local int g_restart = 0;
 static thread_local int g_legacy = 0;   // USAUG_CM_LEGACY_KERNEL: force the two-slot kernel (A/B testing)
 
-template <int AW>
+template <int AW, bool RECOMP>
 static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t stream) {
   int per_sm = 0;
-  USAUG_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<AW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
-  USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel<AW>, 256, kFusedSmem));
+  USAUG_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<AW, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+  USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel<AW, RECOMP>, 256, kFusedSmem));
   if (per_sm < 1) { set_error("pcg_fused_kernel cannot be resident"); return USAUG_E_CUDA; }
   const int tasks = a.nstrip4 * a.B;
   int blocks = tasks;
@@ -1136,7 +1323,7 @@ static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t s
   if (blocks < 1) blocks = 1;
   void* params[] = {(void*)&a};
   if (g_ev_start) USAUG_CUDA(cudaEventRecord(g_ev_start, stream));
-  USAUG_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel<AW>, dim3(blocks), dim3(256), params,
+  USAUG_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel<AW, RECOMP>, dim3(blocks), dim3(256), params,
                                          kFusedSmem, stream));
   if (g_ev_stop) USAUG_CUDA(cudaEventRecord(g_ev_stop, stream));
   return USAUG_OK;
@@ -1151,8 +1338,8 @@ static int launch_fused(PcgArgs<float>& a, const CmLayout& L, int B, cudaStream_
   a.max_steps = 6 * a.maxiter + 64;   // worst case: a refinement round (5 phases) after every iteration
   const int tasks = a.nstrip4 * B;
   // few tasks: 4 active warps per CTA with rings twice as deep keep enough bytes in flight
-  if (tasks >= 6 * sms) return launch_fused_aw<8>(a, sms, stream);
-  return launch_fused_aw<4>(a, sms, stream);
+  if (tasks >= 6 * sms) return launch_fused_aw<8, true>(a, sms, stream);
+  return launch_fused_aw<4, false>(a, sms, stream);
 }
 
 template <typename T>
@@ -1161,9 +1348,9 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   PcgArgs<T> a;
   a.B = B; a.H = H; a.W = W; a.maxiter = maxiter;
   a.rtol2 = rtol * rtol;
-  const double inner_red = std::is_same<T, float>::value ? 1e-4 : 0.0;
+  const double inner_red = std::is_same<T, float>::value ? (g_restart ? 1e-2 : 1e-4) : 0.0;
   a.inner_red2 = inner_red * inner_red;
-  a.wS = L.wS; a.wE = L.wE; a.wSE = L.wSE; a.wSW = L.wSW; a.ip = L.ip; a.c = L.c; a.ipc = L.ipc;
+  a.wS = L.wS; a.wE = L.wE; a.wSE = L.wSE; a.wSW = L.wSW; a.ip = L.ip; a.c = L.c; a.ipc = L.ipc; a.aplane = L.aplane; a.wk = L.wk;
   a.x64 = L.x64;
   a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z; a.p2 = (T*)L.p2;
   a.st = L.st; a.part = L.part; a.done = L.done; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
@@ -1173,6 +1360,7 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   // every inner iteration is one step; each refinement round adds <= 3 steps and needs >= 1 iteration
   a.max_steps = 4 * maxiter + 16;
   a.debug = g_debug;
+  a.restart = g_restart;
 
   if constexpr (std::is_same<T, float>::value) {
     if (a.vec4 && !g_legacy) return launch_fused(a, L, B, stream);
@@ -1234,6 +1422,7 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   const int N = H * W;
   g_debug = (flags & USAUG_CM_DEBUG_TIMING) ? 1 : 0;
   g_legacy = (flags & USAUG_CM_LEGACY_KERNEL) ? 1 : 0;
+  g_restart = (flags & USAUG_CM_CONTINUE) ? 1 : 0;
 
   cm_depth_kernel<<<(H + 127) / 128, 128, 0, stream>>>(L.depth, H, alpha);
   USAUG_CHECK_LAUNCH("cm_depth_kernel");
@@ -1241,8 +1430,10 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   USAUG_CHECK_LAUNCH("cm_minmax_kernel");
   cm_delta_kernel<<<dim3(kChunks, B), 256, 0, stream>>>(img, H, W, L.depth, L.mm1, L.mm2);
   USAUG_CHECK_LAUNCH("cm_delta_kernel");
-  cm_weights_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(img, H, W, L.depth, L.mm1, L.mm2, beta,
-                                                                 gamma, L.wS, L.wE, L.wSE, L.wSW);
+  cm_wconst_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, L.mm2, beta, gamma, L.wk);
+  USAUG_CHECK_LAUNCH("cm_wconst_kernel");
+  cm_weights_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(img, H, W, L.depth, L.mm1, L.wk, L.aplane,
+                                                                 L.wS, L.wE, L.wSE, L.wSW);
   USAUG_CHECK_LAUNCH("cm_weights_kernel");
   cm_factor_kernel<<<dim3(L.nblk, B), 128, 0, stream>>>(H, W, L.wS, L.wE, L.wSE, L.wSW, precond,
                                                         (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.ip, L.c,
