@@ -5,7 +5,7 @@ import numpy as np, torch
 from oracle import synth as osynth
 from ultrasoundaugmentation_b200 import ops
 dev = torch.device("cuda", 0)
-for (B, H, W) in [(1, 96, 64), (1, 110, 64), (1, 130, 64), (1, 200, 64), (2, 96, 64)]:
+for (B, H, W) in [(1, 64, 128), (1, 64, 256), (2, 64, 256)]:
     img, _ = osynth.make_batch(B, H, W)
     t = torch.from_numpy(img).to(dev)
     for mi in (0, 1, 2, 3, 20):

@@ -16,6 +16,8 @@
 //   precond : column-line tridiagonal (vertical couplings + full diagonal), applied as
 //             z = L^-T D^-1 L^-1 r with one down and one up sweep per column, thread per column.
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <cuda/std/type_traits>
 
 #include <type_traits>
 
@@ -269,6 +271,9 @@ struct PcgArgs {
   int* iters_out;
   double* relres_out;
   int nstrip1, nrb, nstrip2, pmax, max_steps;
+  unsigned long long *qslots, *qhead, *qtail;   // fused kernel: ready queue of (image, strip) tasks
+  unsigned qcap;
+  int wpb;           // fused kernel: worker warps per block actually used (<= AW)
   int vec4, nstrip4; // vectorised stencil (fp32 vectors, W % 4 == 0): 128-column strips
   int restart;       // experimental (USAUG_CM_CONTINUE): keep p across refinement rounds, replace r every 2 decades
   int debug;         // USAUG_CM_DEBUG_TIMING: block 0 prints per-slot wall times of a few steps
@@ -305,15 +310,16 @@ template <typename A, typename T>
 struct StRow { A v; T z, p; float s, e, se, sw; };
 
 template <typename T, bool RESID>
-__device__ __forceinline__ double stencil_task(const PcgArgs<T>& a, int b, int strip, int rbk, int lane,
+__device__ __forceinline__ double stencil_task(const PcgArgs<T>& a, int b, int xbase, int ncols, int rbk, int lane,
                                                T beta, bool first) {
+  // productive columns xbase .. xbase+ncols-1 (ncols <= 30) on lanes 1..ncols; lanes 0 and ncols+1 are halo
   using A = typename std::conditional<RESID, double, T>::type;
   constexpr int kQ = RESID ? 4 : 8;
   const int H = a.H, W = a.W;
   const size_t base = (size_t)b * H * W;
-  const int x = strip * kStripCols + lane - 1;
-  const bool valid = (x >= 0) && (x < W);
-  const bool own = valid && lane >= 1 && lane <= kStripCols;
+  const int x = xbase + lane - 1;
+  const bool valid = (x >= 0) && (x < W) && lane <= ncols + 1;
+  const bool own = valid && lane >= 1 && lane <= ncols;
   const int ya = 1 + rbk * kRowBlock, yb = min(ya + kRowBlock, H - 1);
   const float* __restrict__ S = a.wS + base; const float* __restrict__ E = a.wE + base;
   const float* __restrict__ SE = a.wSE + base; const float* __restrict__ SW = a.wSW + base;
@@ -327,7 +333,7 @@ __device__ __forceinline__ double stencil_task(const PcgArgs<T>& a, int b, int s
     StRow<A, T> r; r.v = (A)0; r.z = r.p = (T)0; r.s = r.e = r.se = r.sw = 0.f;
     if (valid && yy <= yb) {
       const size_t o = (size_t)yy * W + x;
-      if (RESID) r.v = (A)X[o];
+      if (RESID) r.v = (A)__ldcg(X + o);      // x64 may have been folded by another SM: read at L2
       else if (yy != 0 && yy != H - 1) { r.z = Z[o]; if (!first) r.p = P[o]; }
       r.s = S[o]; r.e = E[o]; r.se = SE[o]; r.sw = SW[o];
     }
@@ -658,12 +664,12 @@ __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a)
         const T beta = (T)__ldcg(&st->beta);
         if constexpr (std::is_same<T, float>::value) {
           if (a.vec4) s = stencil_task_v4(a, ring, b, strip, rbk, lane, beta, first);
-          else s = stencil_task<T, false>(a, b, strip, rbk, lane, beta, first);
+          else s = stencil_task<T, false>(a, b, strip * kStripCols, kStripCols, rbk, lane, beta, first);
         } else {
-          s = stencil_task<T, false>(a, b, strip, rbk, lane, beta, first);
+          s = stencil_task<T, false>(a, b, strip * kStripCols, kStripCols, rbk, lane, beta, first);
         }
       } else {
-        s = stencil_task<T, true>(a, b, strip, rbk, lane, (T)0, true);
+        s = stencil_task<T, true>(a, b, strip * kStripCols, kStripCols, rbk, lane, (T)0, true);
       }
       double* part = a.part + (size_t)b * a.pmax * 2;
       if (lane == 0) { part[2 * ti] = s; part[2 * ti + 1] = 0.0; }
@@ -862,6 +868,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
 #pragma unroll 2
   for (int y = H - 1; y >= 0; --y) {
     cp_async_wait<R - 1>();
+    __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
     {
       const RingU* r = ring + ((H - 1 - y) % R);
       const float4 h = r->h[lane], p = r->p[lane], av = r->a[lane];
@@ -889,6 +896,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
       au[0] = (lane == 0) ? ha : al;
       au[5] = (lane == 31) ? ha : ar;
     }
+    __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
     // weights of row y (edges inside the row and down to row y+1), masked where the edge does not exist
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -998,6 +1006,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
 #pragma unroll 2
   for (int y = H - 2; y >= 0; --y) {
     cp_async_wait<R - 1>();
+    if (!(a.debug & 4)) __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
     {
       const RingUP* r = ring + ((H - 2 - y) % R);
       const float4 h = r->h[lane], p = r->p[lane];
@@ -1021,6 +1030,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
       zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
       if (valid && y >= 1) *reinterpret_cast<float4*>(P + (size_t)y * W + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
     }
+    if (!(a.debug & 4)) __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
     const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
     if (yc <= H - 2) {
       const float eL_s = __shfl_up_sync(full, wc.e.w, 1);
@@ -1135,6 +1145,64 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   rr_out = warp_sum(rr); rz_out = warp_sum(rz);
 }
 
+// ---- ready queue (multi-producer / multi-consumer ticket ring in global memory) -------------------
+// Only the strips of ONE image have to meet between phases, so the fused kernel has no grid-wide
+// barrier: the last-arriving strip of an image publishes the image's next phase as nstrip4 new
+// tasks, and any idle warp pops the next task.  Work-conserving: no SM waits for a slower SM.
+constexpr unsigned kPoison = 0xffffffffu;
+
+// pushes n entries: payload0, payload0+stride, ...  (one lane; one reservation, one release fence)
+__device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, unsigned payload0, unsigned stride, unsigned n) {
+  const unsigned long long k0 = atomicAdd(a.qtail, (unsigned long long)n);
+  __threadfence();                                          // release: state written before the stamps
+  for (unsigned i = 0; i < n; ++i) {
+    const unsigned long long k = k0 + i;
+    volatile unsigned long long* slot = a.qslots + (k % a.qcap);
+    *slot = ((k + 1ull) << 32) | (unsigned long long)(payload0 + i * stride);
+  }
+}
+
+__device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {        // whole warp
+  unsigned payload = 0;
+  if (lane == 0) {
+    const unsigned long long k = atomicAdd(a.qhead, 1ull);
+    volatile unsigned long long* slot = a.qslots + (k % a.qcap);
+    const unsigned stamp = (unsigned)(k + 1ull);
+    unsigned long long v;
+    unsigned ns = 32;
+    const unsigned nsmax = (a.debug & 8) ? 8192u : 512u;
+    while ((unsigned)((v = *slot) >> 32) != stamp) { __nanosleep(ns); if (ns < nsmax) ns *= 2; }
+    __threadfence();                                        // acquire
+    payload = (unsigned)(v & 0xffffffffull);
+  }
+  return __shfl_sync(0xffffffffu, payload, 0);
+}
+
+// slots 0..T-1 hold the first phase (RESID) of every image, image index fastest
+__global__ void cm_init_queue_kernel(unsigned long long* __restrict__ slots, unsigned cap, int B, int nstrip4,
+                                     unsigned long long* __restrict__ head, unsigned long long* __restrict__ tail) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned T = (unsigned)(B * nstrip4);
+  if (i == 0) { *head = 0ull; *tail = (unsigned long long)T; }
+  if (i >= cap) return;
+  unsigned long long v = 0ull;
+  if (i < T) {
+    const unsigned b = i % (unsigned)B, ti = i / (unsigned)B;
+    v = ((unsigned long long)(i + 1u) << 32) | (unsigned long long)(b * (unsigned)nstrip4 + ti);
+  }
+  slots[i] = v;
+}
+
+// fp64 residual r = b - A x64 over one 128-column strip (rare: once per refinement round)
+__device__ __forceinline__ double resid_strip(const PcgArgs<float>& a, int b, int strip, int lane) {
+  const int x0 = strip * kStrip4, xe = min(x0 + kStrip4, a.W);
+  double s = 0.0;
+  for (int xb = x0; xb < xe; xb += kStripCols)
+    for (int rbk = 0; rbk < a.nrb; ++rbk)
+      s += stencil_task<float, true>(a, b, xb, min(kStripCols, xe - xb), rbk, lane, 0.f, true);
+  return s;
+}
+
 // AW = active warps per CTA (8 or 4): fewer active warps own deeper rings.
 // RECOMP = F_UP recomputes the edge weights from the `a` plane (bandwidth-bound regime) or reads them.
 template <int AW, bool RECOMP>
@@ -1142,126 +1210,133 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
   constexpr size_t kWarpRing = kFusedSmem / AW;                   // ring bytes per active warp
   constexpr int R = (int)(kWarpRing / (RECOMP ? sizeof(RingU) : sizeof(RingUP)));   // F_UP ring depth in rows
   constexpr int RD = (int)(kWarpRing / sizeof(RingD));                              // F_DOWN ring depth
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool active = warp < AW;
+  if (warp >= AW || warp >= a.wpb) return;                        // no block-wide barrier anywhere below
+  if (a.debug == 2 && (blockIdx.x != 0 || warp != 0)) return;     // debug: a single worker runs every task
   unsigned char* ringmem = smem_raw + (size_t)warp * kWarpRing;
-  // warp-major task order: consecutive tasks land on different SMs, so a small batch still spreads
-  // over the whole GPU (one or two busy warps per SM, each with a deep ring)
-  const int gw = warp * gridDim.x + blockIdx.x, nw = gridDim.x * AW;
   const int B = a.B, H = a.H, W = a.W;
-  const int per_rs = a.nstrip1 * a.nrb, per_col = a.nstrip4;
-  const int tot = (per_rs > per_col ? per_rs : per_col) * B;
-  auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  const int per = a.nstrip4;
+  const unsigned nworkers = (a.debug == 2) ? 1u : gridDim.x * (unsigned)a.wpb;
 
-  for (int step = 0; step < a.max_steps; ++step) {
-    unsigned long long t0 = 0;
-    const bool dbg = a.debug && blockIdx.x == 0 && threadIdx.x == 0 && step >= 20 && step < 24;
-    if (dbg) t0 = now();
-    if (active) {
-      for (int t = gw; t < tot; t += nw) {
-        const int b = t % B, ti = t / B;
-        ImgState* st = a.st + b;
-        const unsigned long long fw = __ldcg(&st->fword);
-        const int mode = (int)(fw & 0xffffffffull);
-        if (mode == F_DONE || (int)(fw >> 32) > step) continue;   // done, or published during this interval
-        const int per = (mode == F_RESID) ? per_rs : per_col;
-        if (ti >= per) continue;
-        const unsigned long long next_from = (unsigned long long)(step + 1) << 32;
-        double s0 = 0.0, s1 = 0.0;
-        if (mode == F_UP) {
-          if constexpr (RECOMP)
-            s0 = up_task<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
-          else
-            s0 = up_task_planes<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
-        } else if (mode == F_DOWN) {
-          down_task<RD, false>(a, ringmem, b, ti, lane, (float)__ldcg(&st->alpha), __ldcg(&st->pcur), s0, s1);
-        } else if (mode == F_PRECOND) {
-          down_task<RD, true>(a, ringmem, b, ti, lane, 0.f, 0, s0, s1);
-        } else if (mode == F_RESID) {
-          s0 = stencil_task<float, true>(a, b, ti % a.nstrip1, ti / a.nstrip1, lane, 0.f, true);
-        } else {
-          const int x = ti * kStrip4 + 4 * lane;
-          if (x < W) {
-            const size_t base = (size_t)b * H * W + x;
-            if (mode == F_FOLD) {
+  auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  unsigned long long t_wait = 0, t_mode[7] = {0, 0, 0, 0, 0, 0, 0}, t_arr = 0;
+  unsigned n_mode[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (;;) {
+    const unsigned long long tq0 = a.debug ? now() : 0ull;
+    const unsigned payload = q_pop(a, lane);
+    const unsigned long long tq1 = a.debug ? now() : 0ull;
+    t_wait += tq1 - tq0;
+    if (payload == kPoison) break;
+    const int b = (int)(payload / (unsigned)per), ti = (int)(payload % (unsigned)per);
+    ImgState* st = a.st + b;
+    const int mode = (int)(__ldcg(&st->fword) & 0xffffffffull);
+    double s0 = 0.0, s1 = 0.0;
+    if (mode == F_UP) {
+      if constexpr (RECOMP)
+        s0 = up_task<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+      else
+        s0 = up_task_planes<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+    } else if (mode == F_DOWN) {
+      down_task<RD, false>(a, ringmem, b, ti, lane, (float)__ldcg(&st->alpha), __ldcg(&st->pcur), s0, s1);
+    } else if (mode == F_PRECOND) {
+      down_task<RD, true>(a, ringmem, b, ti, lane, 0.f, 0, s0, s1);
+    } else if (mode == F_RESID) {
+      s0 = resid_strip(a, b, ti, lane);
+    } else {
+      const int x = ti * kStrip4 + 4 * lane;
+      if (x < W) {
+        const size_t base = (size_t)b * H * W + x;
+        if (mode == F_FOLD) {
 #pragma unroll 4
-              for (int y = 1; y <= H - 2; ++y) {
-                const size_t o = base + (size_t)y * W;
-                const float4 e = *reinterpret_cast<const float4*>(a.e + o);
-                double2* xp = reinterpret_cast<double2*>(a.x64 + o);
-                double2 v0 = xp[0], v1 = xp[1];
-                v0.x += (double)e.x; v0.y += (double)e.y; v1.x += (double)e.z; v1.y += (double)e.w;
-                xp[0] = v0; xp[1] = v1;
-              }
-            } else {   // F_FINAL
-#pragma unroll 4
-              for (int y = 0; y < H; ++y) {
-                const size_t o = base + (size_t)y * W;
-                const double2* xp = reinterpret_cast<const double2*>(a.x64 + o);
-                const double2 v0 = xp[0], v1 = xp[1];
-                *reinterpret_cast<float4*>(a.cm + o) = make_float4((float)v0.x, (float)v0.y, (float)v1.x, (float)v1.y);
-              }
-            }
+          for (int y = 1; y <= H - 2; ++y) {
+            const size_t o = base + (size_t)y * W;
+            const float4 e = __ldcg(reinterpret_cast<const float4*>(a.e + o));
+            double2* xp = reinterpret_cast<double2*>(a.x64 + o);
+            double2 v0 = __ldcg(xp), v1 = __ldcg(xp + 1);
+            v0.x += (double)e.x; v0.y += (double)e.y; v1.x += (double)e.z; v1.y += (double)e.w;
+            xp[0] = v0; xp[1] = v1;
           }
-        }
-        double* part = a.part + (size_t)b * a.pmax * 2;
-        if (lane == 0) { part[2 * ti] = s0; part[2 * ti + 1] = s1; }
-        if (arrive_last(&st->cnt1, (unsigned)per, lane)) {
-          reduce_parts(part, per, lane, s0, s1);
-          if (lane == 0) {
-            st->cnt1 = 0;
-            if (mode == F_UP) {
-              if (s0 > 0.0) st->alpha = __ldcg(&st->rz) / s0;
-              else { st->alpha = 0.0; st->rr_target = 1e300; }
-              st->pcur = __ldcg(&st->pcur) ^ 1;          // F_UP wrote the other plane
-              st->fword = next_from | F_DOWN;
-            } else if (mode == F_DOWN) {
-              const double rz_old = __ldcg(&st->rz);
-              const int it = __ldcg(&st->iters) + 1;
-              st->iters = it; st->rr_rec = s0; st->rz = s1; st->first = 0;
-              st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
-              st->fword = next_from | ((s0 <= __ldcg(&st->rr_target) || it >= a.maxiter || !(s1 > 0.0)) ? F_FOLD : F_UP);
-            } else if (mode == F_PRECOND) {
-              // First round: start CG (p = z).  Later rounds: RESIDUAL REPLACEMENT -- r was refreshed with the
-              // true fp64 residual, the search direction p is kept, so CG continues instead of restarting.
-              const double rz_old = __ldcg(&st->rz);
-              const bool cont = __ldcg(&st->outer) > 0 && rz_old > 0.0 && a.restart;   // restart field = CONTINUE flag
-              st->rz = s1; st->first = cont ? 0 : 1; st->beta = cont ? s1 / rz_old : 0.0;
-              st->fword = next_from | ((s1 > 0.0) ? F_UP : F_FINAL);
-            } else if (mode == F_RESID) {
-              const double bb = __ldcg(&st->bb), prev = __ldcg(&st->rr_prev);
-              const int it = __ldcg(&st->iters), outer = __ldcg(&st->outer);
-              st->rr_true = s0;
-              const bool conv = s0 <= a.rtol2 * bb;
-              const bool stalled = outer > 0 && s0 > 0.25 * prev;
-              if (conv || stalled || it >= a.maxiter) st->fword = next_from | F_FINAL;
-              else {
-                st->fword = next_from | F_PRECOND;
-                st->rr_prev = s0;
-                st->rr_target = fmax(0.49 * a.rtol2 * bb, a.inner_red2 * s0);
-              }
-            } else if (mode == F_FOLD) {
-              st->fword = next_from | F_RESID; st->outer = __ldcg(&st->outer) + 1;
-            } else {   // F_FINAL
-              st->fword = next_from | F_DONE;
-              const double bb = __ldcg(&st->bb);
-              if (a.iters_out) a.iters_out[b] = __ldcg(&st->iters);
-              if (a.relres_out) a.relres_out[b] = (bb > 0.0) ? sqrt(__ldcg(&st->rr_true) / bb) : 0.0;
-              __threadfence();
-              atomicAdd(a.done, 1u);
-            }
+        } else {   // F_FINAL
+#pragma unroll 4
+          for (int y = 0; y < H; ++y) {
+            const size_t o = base + (size_t)y * W;
+            const double2* xp = reinterpret_cast<const double2*>(a.x64 + o);
+            const double2 v0 = __ldcg(xp), v1 = __ldcg(xp + 1);
+            *reinterpret_cast<float4*>(a.cm + o) = make_float4((float)v0.x, (float)v0.y, (float)v1.x, (float)v1.y);
           }
         }
       }
     }
-    unsigned long long t1 = 0;
-    if (dbg) t1 = now();
-    grid.sync();
-    if (dbg) printf("[pcg fused dbg] step %d: phase %llu ns (block 0 thread 0), sync wait %llu ns\n", step, t1 - t0, now() - t1);
-    if (__ldcg(a.done) >= (unsigned)B) break;
+    const unsigned long long tq2 = a.debug ? now() : 0ull;
+    if (a.debug) { t_mode[mode] += tq2 - tq1; n_mode[mode]++; }
+    // ---- arrival: every lane publishes its own stores, then lane 0 takes a ticket -------------------
+    double* part = a.part + (size_t)b * a.pmax * 2;
+    if (lane == 0) { part[2 * ti] = s0; part[2 * ti + 1] = s1; }
+    __threadfence();
+    __syncwarp();
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(&st->cnt1, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (a.debug) t_arr += now() - tq2;
+    if (tk != (unsigned)per - 1) continue;
+    // ---- last strip of this image and phase: reduce, advance the state, publish the next phase ------
+    __threadfence();
+    reduce_parts(part, per, lane, s0, s1);
+    if (lane != 0) continue;
+    st->cnt1 = 0;
+    int next = F_DONE;
+    if (mode == F_UP) {
+      if (s0 > 0.0) st->alpha = __ldcg(&st->rz) / s0;
+      else { st->alpha = 0.0; st->rr_target = 1e300; }          // breakdown: leave the inner solve
+      st->pcur = __ldcg(&st->pcur) ^ 1;                           // F_UP wrote the other p plane
+      next = F_DOWN;
+    } else if (mode == F_DOWN) {
+      const double rz_old = __ldcg(&st->rz);
+      const int it = __ldcg(&st->iters) + 1;
+      st->iters = it; st->rr_rec = s0; st->rz = s1; st->first = 0;
+      st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
+      next = (s0 <= __ldcg(&st->rr_target) || it >= a.maxiter || !(s1 > 0.0)) ? F_FOLD : F_UP;
+    } else if (mode == F_PRECOND) {
+      // First round: start CG (p = z).  USAUG_CM_CONTINUE (experimental, rejected: more iterations): keep p.
+      const double rz_old = __ldcg(&st->rz);
+      const bool cont = __ldcg(&st->outer) > 0 && rz_old > 0.0 && a.restart;
+      st->rz = s1; st->first = cont ? 0 : 1; st->beta = cont ? s1 / rz_old : 0.0;
+      next = (s1 > 0.0) ? F_UP : F_FINAL;
+    } else if (mode == F_RESID) {
+      const double bb = __ldcg(&st->bb), prev = __ldcg(&st->rr_prev);
+      const int it = __ldcg(&st->iters), outer = __ldcg(&st->outer);
+      st->rr_true = s0;
+      const bool conv = s0 <= a.rtol2 * bb;
+      const bool stalled = outer > 0 && s0 > 0.25 * prev;
+      if (conv || stalled || it >= a.maxiter) next = F_FINAL;
+      else {
+        next = F_PRECOND;
+        st->rr_prev = s0;
+        st->rr_target = fmax(0.49 * a.rtol2 * bb, a.inner_red2 * s0);
+      }
+    } else if (mode == F_FOLD) {
+      next = F_RESID; st->outer = __ldcg(&st->outer) + 1;
+    } else {   // F_FINAL
+      const double bb = __ldcg(&st->bb);
+      if (a.iters_out) a.iters_out[b] = __ldcg(&st->iters);
+      if (a.relres_out) a.relres_out[b] = (bb > 0.0) ? sqrt(__ldcg(&st->rr_true) / bb) : 0.0;
+      next = F_DONE;
+    }
+    st->fword = (unsigned long long)next;
+    if (next == F_DONE) {
+      __threadfence();
+      if (atomicAdd(a.done, 1u) == (unsigned)B - 1u) q_push_n(a, kPoison, 0u, nworkers);   // release every worker
+    } else {
+      q_push_n(a, (unsigned)(b * per), 1u, (unsigned)per);
+    }
   }
+  if ((a.debug & 1) && lane == 0 && warp == 0 && (blockIdx.x % 74) == 0)
+    printf("[pcg queue dbg] block %d: wait %.1f us | UP %u x %.1f us | DOWN %u x %.1f us | PRECOND %u x %.1f | RESID %u x %.1f | arrive %.1f us total\n",
+           blockIdx.x, t_wait * 1e-3, n_mode[F_UP], n_mode[F_UP] ? t_mode[F_UP] * 1e-3 / n_mode[F_UP] : 0.0, n_mode[F_DOWN],
+           n_mode[F_DOWN] ? t_mode[F_DOWN] * 1e-3 / n_mode[F_DOWN] : 0.0, n_mode[F_PRECOND],
+           n_mode[F_PRECOND] ? t_mode[F_PRECOND] * 1e-3 / n_mode[F_PRECOND] : 0.0, n_mode[F_RESID],
+           n_mode[F_RESID] ? t_mode[F_RESID] * 1e-3 / n_mode[F_RESID] : 0.0, t_arr * 1e-3);
 }
 
 struct CmLayout {
@@ -1272,6 +1347,8 @@ struct CmLayout {
   void *e, *r, *p, *q, *z, *p2;
   ImgState* st;
   unsigned* done;
+  unsigned long long *qslots, *qhead, *qtail;
+  unsigned qcap;
   int nblk, nstrip1, nrb, nstrip2, pmax;
   size_t bytes;
 };
@@ -1299,6 +1376,10 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.part = cv.take<double>((size_t)B * L.pmax * 2);
   L.st = cv.take<ImgState>(B);
   L.done = cv.take<unsigned>(1);
+  // ready queue: every image has at most nstrip4 ready tasks at a time; plus one poison per worker warp
+  L.qcap = (unsigned)(2 * ((W + kStrip4 - 1) / kStrip4) * B + 8192);
+  L.qslots = cv.take<unsigned long long>(L.qcap);
+  L.qhead = cv.take<unsigned long long>(1); L.qtail = cv.take<unsigned long long>(1);
   L.bytes = cv.off;
   return L;
 }
@@ -1321,8 +1402,15 @@ static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t s
   int blocks = tasks;
   if (blocks > blocks_cap_sms) blocks = blocks_cap_sms;
   if (blocks < 1) blocks = 1;
+  // no more workers than tasks that can be ready at once: an idle worker only polls the queue
+  a.wpb = (tasks + blocks - 1) / blocks;
+  if (a.wpb > AW) a.wpb = AW;
+  if (getenv("USAUG_DEBUG_WPB")) a.wpb = atoi(getenv("USAUG_DEBUG_WPB"));
+  cm_init_queue_kernel<<<(a.qcap + 255) / 256, 256, 0, stream>>>(a.qslots, a.qcap, a.B, a.nstrip4, a.qhead, a.qtail);
+  USAUG_CHECK_LAUNCH("cm_init_queue_kernel");
   void* params[] = {(void*)&a};
   if (g_ev_start) USAUG_CUDA(cudaEventRecord(g_ev_start, stream));
+  // cooperative launch only for its co-residency guarantee: workers spin on the ready queue
   USAUG_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel<AW, RECOMP>, dim3(blocks), dim3(256), params,
                                          kFusedSmem, stream));
   if (g_ev_stop) USAUG_CUDA(cudaEventRecord(g_ev_stop, stream));
@@ -1353,7 +1441,8 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.wS = L.wS; a.wE = L.wE; a.wSE = L.wSE; a.wSW = L.wSW; a.ip = L.ip; a.c = L.c; a.ipc = L.ipc; a.aplane = L.aplane; a.wk = L.wk;
   a.x64 = L.x64;
   a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z; a.p2 = (T*)L.p2;
-  a.st = L.st; a.part = L.part; a.done = L.done; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
+  a.st = L.st; a.part = L.part; a.done = L.done;
+  a.qslots = L.qslots; a.qhead = L.qhead; a.qtail = L.qtail; a.qcap = L.qcap; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
   a.nstrip1 = L.nstrip1; a.nrb = L.nrb; a.nstrip2 = L.nstrip2; a.pmax = L.pmax;
   a.vec4 = (std::is_same<T, float>::value && W % 4 == 0) ? 1 : 0;
   a.nstrip4 = (W + kStrip4 - 1) / kStrip4;
@@ -1421,6 +1510,8 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   CmLayout L = cm_layout(ws, B, H, W, flags);
   const int N = H * W;
   g_debug = (flags & USAUG_CM_DEBUG_TIMING) ? 1 : 0;
+  if (getenv("USAUG_DEBUG_SINGLE")) g_debug = 2;
+  if (getenv("USAUG_DEBUG_BITS")) g_debug = atoi(getenv("USAUG_DEBUG_BITS"));
   g_legacy = (flags & USAUG_CM_LEGACY_KERNEL) ? 1 : 0;
   g_restart = (flags & USAUG_CM_CONTINUE) ? 1 : 0;
 
