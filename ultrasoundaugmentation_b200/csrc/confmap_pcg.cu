@@ -1006,7 +1006,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
 #pragma unroll 2
   for (int y = H - 2; y >= 0; --y) {
     cp_async_wait<R - 1>();
-    if (!(a.debug & 4)) __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
+    __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
     {
       const RingUP* r = ring + ((H - 2 - y) % R);
       const float4 h = r->h[lane], p = r->p[lane];
@@ -1030,7 +1030,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
       zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
       if (valid && y >= 1) *reinterpret_cast<float4*>(P + (size_t)y * W + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
     }
-    if (!(a.debug & 4)) __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
+    __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
     const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
     if (yc <= H - 2) {
       const float eL_s = __shfl_up_sync(full, wc.e.w, 1);
@@ -1163,19 +1163,18 @@ __device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, unsigned paylo
 }
 
 __device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {        // whole warp
-  unsigned payload = 0;
-  if (lane == 0) {
-    const unsigned long long k = atomicAdd(a.qhead, 1ull);
-    volatile unsigned long long* slot = a.qslots + (k % a.qcap);
-    const unsigned stamp = (unsigned)(k + 1ull);
-    unsigned long long v;
-    unsigned ns = 32;
-    const unsigned nsmax = (a.debug & 8) ? 8192u : 512u;
-    while ((unsigned)((v = *slot) >> 32) != stamp) { __nanosleep(ns); if (ns < nsmax) ns *= 2; }
-    __threadfence();                                        // acquire
-    payload = (unsigned)(v & 0xffffffffull);
-  }
-  return __shfl_sync(0xffffffffu, payload, 0);
+  // lane 0 takes the ticket; then ALL lanes poll the slot together (a warp with 31 lanes parked at a
+  // convergence barrier while one lane spins was measured to slow the other warps of the SM ~4x)
+  unsigned long long k = 0;
+  if (lane == 0) k = atomicAdd(a.qhead, 1ull);
+  k = __shfl_sync(0xffffffffu, k, 0);
+  volatile unsigned long long* slot = a.qslots + (k % a.qcap);
+  const unsigned stamp = (unsigned)(k + 1ull);
+  unsigned long long v;
+  unsigned ns = 32;
+  while ((unsigned)((v = *slot) >> 32) != stamp) { __nanosleep(ns); if (ns < 512) ns *= 2; }
+  __threadfence();                                          // acquire
+  return (unsigned)(v & 0xffffffffull);
 }
 
 // slots 0..T-1 hold the first phase (RESID) of every image, image index fastest
@@ -1426,6 +1425,10 @@ static int launch_fused(PcgArgs<float>& a, const CmLayout& L, int B, cudaStream_
   a.max_steps = 6 * a.maxiter + 64;   // worst case: a refinement round (5 phases) after every iteration
   const int tasks = a.nstrip4 * B;
   // few tasks: 4 active warps per CTA with rings twice as deep keep enough bytes in flight
+  if (const char* v = getenv("USAUG_DEBUG_VARIANT")) {          // development: force a kernel instance
+    if (v[0] == 'r') return launch_fused_aw<8, true>(a, sms, stream);
+    if (v[0] == 'p') return launch_fused_aw<4, false>(a, sms, stream);
+  }
   if (tasks >= 6 * sms) return launch_fused_aw<8, true>(a, sms, stream);
   return launch_fused_aw<4, false>(a, sms, stream);
 }
@@ -1510,8 +1513,7 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   CmLayout L = cm_layout(ws, B, H, W, flags);
   const int N = H * W;
   g_debug = (flags & USAUG_CM_DEBUG_TIMING) ? 1 : 0;
-  if (getenv("USAUG_DEBUG_SINGLE")) g_debug = 2;
-  if (getenv("USAUG_DEBUG_BITS")) g_debug = atoi(getenv("USAUG_DEBUG_BITS"));
+  if (getenv("USAUG_DEBUG_SINGLE")) g_debug = 2;   // development: one worker warp runs every task
   g_legacy = (flags & USAUG_CM_LEGACY_KERNEL) ? 1 : 0;
   g_restart = (flags & USAUG_CM_CONTINUE) ? 1 : 0;
 
