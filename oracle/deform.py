@@ -18,7 +18,7 @@ def gaussian_taps(sigma: float, radius: int | None = None) -> np.ndarray:
         radius = int(np.ceil(3.0 * float(sigma)))
     radius = max(int(radius), 0)
     k = np.arange(-radius, radius + 1, dtype=np.float64)
-    if sigma <= 0:
+    if sigma < 1e-6:                      # degenerate sigma: identity tap
         t = (k == 0).astype(np.float64)
     else:
         t = np.exp(-(k * k) / (2.0 * float(sigma) ** 2))

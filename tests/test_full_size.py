@@ -1,0 +1,69 @@
+"""BASELINE.json's full-size configurations on the GPU: size-independent properties (the oracle is too
+slow for whole batches at these sizes) plus one oracle-checked image per configuration."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import confmap as ocm
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config3_confmap_batch64_512(cuda_device):
+    """configs[2]: confidence-map PCG, batch 64 of 512x512."""
+    from ultrasoundaugmentation_b200 import ops, synth
+    img, _ = synth.make_batch(64, 512, 512, seed=77, device=cuda_device)
+    cm, it, rr = ops.confidence_map(img, rtol=1e-8, return_info=True)
+    cm2, it2, _ = ops.confidence_map(img, rtol=1e-8, return_info=True)
+    torch.cuda.synchronize()
+    assert torch.equal(cm, cm2) and torch.equal(it, it2)                 # bitwise repeatable despite dynamic scheduling
+    assert (rr <= 1e-8).all() and (it > 0).all() and (it < 20000).all()
+    assert (cm[:, 0] == 1).all() and (cm[:, -1] == 0).all()
+    assert cm.min() >= -1e-5 and cm.max() <= 1 + 1e-5
+    assert (cm[:, 1:64].mean(dim=(1, 2)) > cm[:, -64:-1].mean(dim=(1, 2))).all()    # confidence decays with depth
+    ref = ocm.confidence_map(img[5].cpu().numpy())                        # one image against the direct solve
+    assert np.abs(cm[5].cpu().numpy() - ref).max() <= util.tol_cm(1e-8)
+    solo, it_solo, _ = ops.confidence_map(img[5:6], rtol=1e-8, return_info=True)
+    assert torch.equal(solo[0], cm[5]) and it_solo[0] == it[5]            # independent of batch mates
+
+
+def test_config4_full_chain_32x1024(cuda_device):
+    """configs[3]: full chain with per-sample random parameters, 1024x1024, batch 32."""
+    import ultrasoundaugmentation_b200 as us
+    from ultrasoundaugmentation_b200 import ops, synth
+    B, H, W = 32, 1024, 1024
+    img, lab = synth.make_batch(B, H, W, seed=5, device=cuda_device)
+    chain = us.PhysicsChain.full(seed=9, rtol=1e-8)
+    params = chain.get_params(B, image_size=(H, W))
+    oi, ol = chain(img, lab, params)
+    it, rr = chain.snr.last_info
+    oi2, ol2 = chain(img, lab, params)
+    torch.cuda.synchronize()
+    assert torch.equal(oi, oi2) and torch.equal(ol, ol2)
+    assert (rr <= 1e-8).all()
+    assert oi.min() >= 0 and oi.max() <= 1 and torch.isfinite(oi).all()
+    assert set(torch.unique(ol).tolist()) <= {0, 1}
+    k1_i, k1_l = ops.fused_tgc_deform(img, lab, params["d"], params["tgc"], chain.deform.taps(W))
+    assert torch.equal(ol, k1_l)                                          # SNR / reverb never touch the label
+    assert (oi - k1_i).abs().max() > 1e-3                                 # ... but they do change the image
+    # bone keeps its area to within the deformation's stretch (no label mass invented or lost wholesale)
+    a0, a1 = lab.sum(dim=(1, 2)).float(), ol.sum(dim=(1, 2)).float()
+    assert ((a1 / a0) > 0.7).all() and ((a1 / a0) < 1.4).all()
+
+
+def test_config5_shard_of_dataloader_sweep(cuda_device):
+    """configs[4]: 512x512 full chain; a 64-image shard of the 4096 batch equals the same rows of a 128-image run."""
+    import ultrasoundaugmentation_b200 as us
+    from ultrasoundaugmentation_b200 import sharding, synth
+    H = W = 512
+    img, lab = synth.make_batch(128, H, W, seed=11, device=cuda_device)
+    chain = us.PhysicsChain.full(seed=2021, rtol=1e-8)
+    idx = np.arange(4096 - 128, 4096)                                     # global sample indices of this block
+    p_all = chain.get_params(128, sample_index=idx, image_size=(H, W))
+    oi, ol = chain(img, lab, p_all)
+    lo, hi = sharding.shard_bounds(128, 1, 2)
+    p_half = chain.get_params(hi - lo, sample_index=idx[lo:hi], image_size=(H, W))
+    hi_i, hi_l = chain(img[lo:hi], lab[lo:hi], p_half)
+    torch.cuda.synchronize()
+    assert torch.equal(hi_i, oi[lo:hi]) and torch.equal(hi_l, ol[lo:hi])

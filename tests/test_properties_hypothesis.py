@@ -1,0 +1,75 @@
+"""Hypothesis-driven fuzzing of shapes and parameters against the oracle (GPU): labels bit-exact and a
+subset of the input values, images in range and within tolerance, determinism."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle import deform as odeform, snr_reverb as osr, synth as osynth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+SETTINGS = dict(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+
+
+@settings(**SETTINGS)
+@given(H=st.integers(3, 70), W=st.integers(1, 150), d=st.floats(-40, 40), K=st.integers(1, 9),
+       seed=st.integers(0, 10_000), sigma=st.floats(0.0, 4.0))
+def test_warp_fuzz(cuda_device, H, W, d, K, seed, sigma):
+    from ultrasoundaugmentation_b200 import ops
+    rng = np.random.default_rng(seed)
+    img = rng.random((1, H, W), dtype=np.float32)
+    lab = (rng.random((1, H, W)) < 0.15).astype(np.uint8) * rng.integers(1, 255, (1, H, W)).astype(np.uint8)
+    if seed % 3 == 0:
+        _, l2 = osynth.make_bmode(H, max(W, 2)); lab = l2[None, :, :W].copy()
+    tgc = rng.uniform(0.5, 1.5, (1, K)).astype(np.float32)
+    taps = odeform.gaussian_taps(sigma)
+    dd = np.array([d], np.float32)
+    ref_i, ref_l = odeform.fused_tgc_deform_batch(img, lab, dd, tgc, taps)
+    gi, gl = ops.fused_tgc_deform(util.cuda(img, cuda_device), util.cuda(lab, cuda_device), torch.from_numpy(dd),
+                                  torch.from_numpy(tgc), torch.from_numpy(taps))
+    gi2, gl2 = ops.fused_tgc_deform(util.cuda(img, cuda_device), util.cuda(lab, cuda_device), torch.from_numpy(dd),
+                                    torch.from_numpy(tgc), torch.from_numpy(taps))
+    assert torch.equal(gi, gi2) and torch.equal(gl, gl2)
+    gl, gi = gl.cpu().numpy(), gi.cpu().numpy()
+    assert np.array_equal(gl, ref_l)
+    assert util.rel_err(gi, ref_i) <= util.REL_TOL
+    assert gi.min() >= 0 and gi.max() <= 1
+    assert set(np.unique(gl)) <= set(np.unique(lab)) | {0}
+
+
+@settings(**SETTINGS)
+@given(H=st.integers(3, 60), W=st.integers(1, 140), seed=st.integers(0, 10_000), n=st.integers(0, 4),
+       rho=st.floats(0.0, 0.9), a=st.floats(0.5, 1.6), sigma=st.floats(0.3, 3.0), with_cm=st.booleans())
+def test_snr_reverb_fuzz(cuda_device, H, W, seed, n, rho, a, sigma, with_cm):
+    from ultrasoundaugmentation_b200 import ops
+    rng = np.random.default_rng(seed)
+    img = rng.random((1, H, W), dtype=np.float32)
+    lab = np.zeros((1, H, W), np.uint8)
+    y0 = int(rng.integers(0, H)); y1 = int(rng.integers(y0, H)) + 1
+    x0 = int(rng.integers(0, W)); x1 = int(rng.integers(x0, W)) + 1
+    if seed % 4:
+        lab[0, y0:y1, x0:x1] = 1
+    cm = rng.random((1, H, W), dtype=np.float32) if with_cm else None
+    taps = odeform.gaussian_taps(sigma)
+    av, rv, nv = np.array([a], np.float32), np.array([rho], np.float32), np.array([n], np.int32)
+    ref = osr.snr_reverb_batch(img, cm, lab, av, rv, nv, taps)
+    got = ops.snr_reverb(util.cuda(img, cuda_device), None if cm is None else util.cuda(cm, cuda_device),
+                         util.cuda(lab, cuda_device), torch.from_numpy(av), torch.from_numpy(rv), torch.from_numpy(nv),
+                         torch.from_numpy(taps)).cpu().numpy()
+    assert util.rel_err(got, ref) <= util.REL_TOL
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(H=st.integers(3, 48), W=st.integers(1, 140), seed=st.integers(0, 10_000), B=st.integers(1, 3))
+def test_confmap_fuzz(cuda_device, H, W, seed, B):
+    from oracle import confmap as ocm
+    from ultrasoundaugmentation_b200 import ops
+    rng = np.random.default_rng(seed)
+    img = rng.random((B, H, W), dtype=np.float32)
+    if seed % 2:
+        img = np.stack([osynth.make_bmode(H, W, seed + b)[0] for b in range(B)])
+    ref = ocm.confidence_map_batch(img)
+    cm, it, rr = ops.confidence_map(util.cuda(img, cuda_device), rtol=1e-9, maxiter=100000, return_info=True)
+    assert (rr.cpu().numpy() <= 1e-9).all()
+    assert np.abs(cm.cpu().numpy() - ref).max() <= util.tol_cm(1e-9) + 2e-5

@@ -44,7 +44,8 @@ struct ImgState {
   // task counts, so a mode published by the last arriver must not be picked up by tasks of the
   // same image that are still to come in the SAME interval.
   unsigned long long fword;
-  int pcur, pad_;     // which of the two p planes holds the current search direction
+  int pcur, poor;     // pcur: which p plane holds the current search direction; poor: consecutive weak refinement rounds
+  double inner2;      // squared residual reduction asked of the next inner solve (adapts to the fp32 drift floor)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -245,8 +246,33 @@ __global__ void cm_init_state_kernel(int B, int nblk, const double* __restrict__
   ImgState s;
   s.mode = M_RESID; s.iters = 0; s.first = 1; s.outer = 0;
   s.rz = 0; s.alpha = 0; s.beta = 0; s.bb = bb; s.rr_true = 0; s.rr_prev = 1e300; s.rr_target = 0; s.rr_rec = 0;
-  s.cnt1 = 0; s.cnt2 = 0; s.fword = 0ull; s.pcur = 0; s.pad_ = 0;
+  s.cnt1 = 0; s.cnt2 = 0; s.fword = 0ull; s.pcur = 0; s.poor = 0; s.inner2 = 0.0;
   st[b] = s;
+}
+
+// Decision after a true-residual evaluation (both PCG kernels).  Returns true when the image is finished.
+// Refinement rounds adapt: a round that truly gained less than it was asked for (fp32 drift floor) makes
+// the next round ask for less; only two consecutive rounds with < 2x gain count as stagnation.
+__device__ __forceinline__ bool after_true_residual(ImgState* st, double s0, double rtol2, double inner_red2, int maxiter) {
+  const double bb = __ldcg(&st->bb), prev = __ldcg(&st->rr_prev);
+  const int it = __ldcg(&st->iters), outer = __ldcg(&st->outer);
+  st->rr_true = s0;
+  if (s0 <= rtol2 * bb || it >= maxiter) return true;
+  double ask = (outer == 0) ? inner_red2 : __ldcg(&st->inner2);
+  int poor = 0;
+  if (outer > 0 && inner_red2 > 0.0) {
+    const double achieved = s0 / prev;                      // true squared reduction of the last round
+    poor = (achieved > 0.25) ? __ldcg(&st->poor) + 1 : 0;
+    if (poor >= 2) return true;
+    ask = fmin(1e-2, fmax(inner_red2, 10.0 * achieved));     // ask ~3x less (in norm) than was achieved
+  } else if (outer > 0 && s0 > 0.25 * prev) {
+    return true;                                            // fp64 vectors: no refinement to adapt
+  }
+  st->poor = poor;
+  st->inner2 = ask;
+  st->rr_prev = s0;
+  st->rr_target = fmax(0.49 * rtol2 * bb, ask * s0);
+  return false;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -682,17 +708,7 @@ __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a)
             if (s0 > 0.0) st->alpha = __ldcg(&st->rz) / s0;
             else { st->alpha = 0.0; st->rr_target = 1e300; }   // breakdown: leave the inner solve
           } else {
-            const double bb = __ldcg(&st->bb), prev = __ldcg(&st->rr_prev);
-            const int it = __ldcg(&st->iters), outer = __ldcg(&st->outer);
-            st->rr_true = s0;
-            const bool conv = s0 <= a.rtol2 * bb;
-            const bool stalled = outer > 0 && s0 > 0.25 * prev;
-            if (conv || stalled || it >= a.maxiter) st->mode = M_FINAL;
-            else {
-              st->mode = M_PRECOND;
-              st->rr_prev = s0;
-              st->rr_target = fmax(0.49 * a.rtol2 * bb, a.inner_red2 * s0);
-            }
+            st->mode = after_true_residual(st, s0, a.rtol2, a.inner_red2, a.maxiter) ? M_FINAL : M_PRECOND;
           }
         }
       }
@@ -1303,17 +1319,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       st->rz = s1; st->first = cont ? 0 : 1; st->beta = cont ? s1 / rz_old : 0.0;
       next = (s1 > 0.0) ? F_UP : F_FINAL;
     } else if (mode == F_RESID) {
-      const double bb = __ldcg(&st->bb), prev = __ldcg(&st->rr_prev);
-      const int it = __ldcg(&st->iters), outer = __ldcg(&st->outer);
-      st->rr_true = s0;
-      const bool conv = s0 <= a.rtol2 * bb;
-      const bool stalled = outer > 0 && s0 > 0.25 * prev;
-      if (conv || stalled || it >= a.maxiter) next = F_FINAL;
-      else {
-        next = F_PRECOND;
-        st->rr_prev = s0;
-        st->rr_target = fmax(0.49 * a.rtol2 * bb, a.inner_red2 * s0);
-      }
+      next = after_true_residual(st, s0, a.rtol2, a.inner_red2, a.maxiter) ? F_FINAL : F_PRECOND;
     } else if (mode == F_FOLD) {
       next = F_RESID; st->outer = __ldcg(&st->outer) + 1;
     } else {   // F_FINAL

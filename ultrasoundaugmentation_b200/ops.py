@@ -20,7 +20,7 @@ def gaussian_taps(sigma: float, radius: int | None = None) -> torch.Tensor:
         radius = int(math.ceil(3.0 * float(sigma)))
     radius = max(int(radius), 0)
     k = np.arange(-radius, radius + 1, dtype=np.float64)
-    t = (k == 0).astype(np.float64) if sigma <= 0 else np.exp(-(k * k) / (2.0 * float(sigma) ** 2))
+    t = (k == 0).astype(np.float64) if sigma < 1e-6 else np.exp(-(k * k) / (2.0 * float(sigma) ** 2))
     t /= t.sum()
     return torch.from_numpy(t.astype(np.float32))
 
