@@ -236,6 +236,27 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
   }
   float v0[kWarpRows], v1[kWarpRows];
   uint8_t lv[kWarpRows];
+  // Block-uniform fast path: 0 <= y_src <= y + |d|, so a tile whose last row + |d| + 2 stays inside
+  // the image needs no bounds checks at all (every tile except the bottom few).
+  const bool interior = (float)(ya + kWarpRows + 1) + fabsf(de) < (float)(H - 1);
+  if (interior) {
+#pragma unroll
+    for (int r = 0; r < kWarpRows; ++r) {
+      const float* p0 = I + i0[r] * W;
+      v0[r] = p0[0];
+      v1[r] = p0[W];
+      lv[r] = L[yn[r] * W];
+    }
+    float* po = OI + ya * W;
+    uint8_t* pl = OL + ya * W;
+#pragma unroll
+    for (int r = 0; r < kWarpRows; ++r) {
+      const float v = fmaf(fr[r], v1[r] - v0[r], v0[r]);
+      po[r * W] = fminf(fmaxf(s_gain[r] * v, 0.0f), 1.0f);
+      pl[r * W] = lv[r];
+    }
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < kWarpRows; ++r) {
     const bool in = ya + r < H;
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
   for (int r = 0; r < kWarpRows; ++r) {
     const int y = ya + r;
     if (y < H) {
-      const float v = (1.0f - fr[r]) * v0[r] + fr[r] * v1[r];
+      const float v = fmaf(fr[r], v1[r] - v0[r], v0[r]);
       OI[y * W] = fminf(fmaxf(s_gain[r] * v, 0.0f), 1.0f);
       OL[y * W] = lv[r];
     }
