@@ -22,6 +22,7 @@
 #include <type_traits>
 
 #include "kernels.cuh"
+#include "confmap_coarse.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -47,7 +48,8 @@ struct ImgState {
   int pcur, poor;     // pcur: which p plane holds the current search direction; poor: consecutive weak refinement rounds
   double inner2;      // squared residual reduction asked of the next inner solve (adapts to the fp32 drift floor)
   double alpha_prev;  // fused kernel: step length of the iteration whose e-update is still pending
-  int epend, pad2_;   // fused kernel: 1 = e += alpha_prev * p_prev has been deferred to the next DOWN / FOLD
+  int epend, fresh;   // epend: 1 = e += alpha_prev * p_prev is deferred to the next DOWN / FOLD; fresh: COARSE follows a PRECOND
+  double rz_line;     // line part of r.z of the current iteration (the COARSE task adds rc.zc)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -248,7 +250,7 @@ __global__ void cm_init_state_kernel(int B, int nblk, const double* __restrict__
   ImgState s;
   s.mode = M_RESID; s.iters = 0; s.first = 1; s.outer = 0;
   s.rz = 0; s.alpha = 0; s.beta = 0; s.bb = bb; s.rr_true = 0; s.rr_prev = 1e300; s.rr_target = 0; s.rr_rec = 0;
-  s.cnt1 = 0; s.cnt2 = 0; s.fword = 0ull; s.pcur = 0; s.poor = 0; s.inner2 = 0.0; s.alpha_prev = 0.0; s.epend = 0; s.pad2_ = 0;
+  s.cnt1 = 0; s.cnt2 = 0; s.fword = 0ull; s.pcur = 0; s.poor = 0; s.inner2 = 0.0; s.alpha_prev = 0.0; s.epend = 0; s.fresh = 0; s.rz_line = 0.0;
   st[b] = s;
 }
 
@@ -302,6 +304,9 @@ struct PcgArgs {
   unsigned long long *qslots, *qhead, *qtail;   // fused kernel: ready queue of (image, strip) tasks
   unsigned qcap;
   int wpb;           // fused kernel: worker warps per block actually used (<= AW)
+  CoarseGeom cg;     // coarse-grid correction geometry (cg.by == 0: disabled)
+  float *rc, *zc;    // [B][nc] restricted residual / coarse correction
+  const float *Lr, *Ur;   // [B][nc][kd1] banded Cholesky factor of Ac, row- and column-oriented
   int vec4, nstrip4; // vectorised stencil (fp32 vectors, W % 4 == 0): 128-column strips
   int restart;       // experimental (USAUG_CM_CONTINUE): keep p across refinement rounds, replace r every 2 decades
   int debug;         // USAUG_CM_DEBUG_TIMING: block 0 prints per-slot wall times of a few steps
@@ -793,7 +798,7 @@ __global__ void __launch_bounds__(256) pcg_persistent_kernel(const PcgArgs<T> a)
 //   independent per lane.  Strip halo columns: lane 0 / lane 31 carry one extra scalar recurrence;
 //   their six scalars per row are fetched by ONE cp.async.4 instruction (lanes 0-5 left, 16-21 right).
 // =============================================================================================
-enum FMode : int { F_RESID = 0, F_PRECOND = 1, F_UP = 2, F_DOWN = 3, F_FOLD = 4, F_FINAL = 5, F_DONE = 6 };
+enum FMode : int { F_RESID = 0, F_PRECOND = 1, F_UP = 2, F_DOWN = 3, F_FOLD = 4, F_FINAL = 5, F_DONE = 6, F_COARSE = 7 };
 
 struct RingU {   // one staged row of a 128-column strip for F_UP (2560 bytes)
   float4 h[32], p[32], a[32];
@@ -819,6 +824,44 @@ struct RingUP {   // one staged row of a 128-column strip for F_UP, weight plane
   // [0..4] columns x0-4..x0-1 of h, ipc, p, wE, wSE (.w is the left neighbour column);
   // [16..19] columns x0+128..x0+131 of h, ipc, p, wSW (.x is the right neighbour column)
   float4 halo[32];
+};
+
+// Prolongation P zc inside F_UP: the coarse value of this lane's aggregate column (and of the strip's halo
+// column on lanes 0 / 31), fetched one aggregate row ahead of use while the sweep marches upward.
+struct CoarseZ {
+  const float* zc;      // this image's coarse correction, nullptr = disabled
+  int sh, nbx, jown, jhalo, icur;
+  float cur, curh, nxt, nxth;
+  bool own, halo;
+  __device__ __forceinline__ void init(const PcgArgs<float>& a, int b, int x, int x0, int lane, bool valid, int W) {
+    zc = a.cg.by ? a.zc + (size_t)b * a.cg.nc : nullptr;
+    sh = a.cg.by_shift; nbx = a.cg.nbx; icur = -1;
+    own = valid; jown = valid ? (x >> a.cg.bx_shift) : 0;
+    const int hx = (lane == 0) ? x0 - 1 : x0 + kStrip4;
+    halo = (lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < W);
+    jhalo = halo ? (hx >> a.cg.bx_shift) : 0;
+    cur = curh = nxt = nxth = 0.f;
+  }
+  // returns the additive terms for row y (0 outside the unknown rows)
+  __device__ __forceinline__ void at_row(int y, int H, float& add, float& addh) {
+    add = 0.f; addh = 0.f;
+    if (zc == nullptr || y < 1 || y > H - 2) return;
+    const int I = (y - 1) >> sh;
+    if (I != icur) {
+      if (icur < 0) {
+        cur = own ? __ldcg(zc + I * nbx + jown) : 0.f;
+        curh = halo ? __ldcg(zc + I * nbx + jhalo) : 0.f;
+      } else {
+        cur = nxt; curh = nxth;
+      }
+      icur = I;
+      if (I > 0) {
+        nxt = own ? __ldcg(zc + (I - 1) * nbx + jown) : 0.f;
+        nxth = halo ? __ldcg(zc + (I - 1) * nbx + jhalo) : 0.f;
+      }
+    }
+    add = cur; addh = curh;
+  }
 };
 
 // Edge weights of one image row for the 4 columns of a lane (plus the three that belong to its
@@ -879,6 +922,8 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   for (int j = 0; j < 4; ++j) wc.s[j] = wc.e[j] = wc.se[j] = wc.sw[j] = 0.f;
   wc.eL = wc.seL = wc.swR = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
+  CoarseZ cz;
+  cz.init(a, b, x, x0, lane, valid, W);
 
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(H - 1 - u);
@@ -896,13 +941,15 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
       const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
       const float hp = hsel(r->halo[hoff + 2], lane);
       const float ha = hsel(r->halo[hoff + 3], lane);
-      float z[4];
+      float z[4];     // line part of z (the recurrence runs on it alone); the coarse part is added on top
       z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
       z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
       const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
-      pu[1] = fmaf(beta, p.x, z[0]); pu[2] = fmaf(beta, p.y, z[1]);
-      pu[3] = fmaf(beta, p.z, z[2]); pu[4] = fmaf(beta, p.w, z[3]);
-      const float ph = fmaf(beta, hp, zh);
+      float zadd, zaddh;
+      cz.at_row(y, H, zadd, zaddh);
+      pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
+      pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
+      const float ph = fmaf(beta, hp, zh + zaddh);
       const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
       pu[0] = (lane == 0) ? ph : l;
       pu[5] = (lane == 31) ? ph : rt;
@@ -1017,6 +1064,8 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   WRowP wc, wu;
   wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
+  CoarseZ cz;
+  cz.init(a, b, x, x0, lane, valid, W);
 
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(H - 2 - u);
@@ -1035,13 +1084,15 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
       const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
       const float hp = hsel(r->halo[hoff + 2], lane);
       wu.hw1 = hsel(r->halo[hoff + 3], lane); wu.hw2 = hsel(r->halo[hoff + 4], lane);
-      float z[4];
+      float z[4];     // line part of z (the recurrence runs on it alone); the coarse part is added on top
       z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
       z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
       const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
-      pu[1] = fmaf(beta, p.x, z[0]); pu[2] = fmaf(beta, p.y, z[1]);
-      pu[3] = fmaf(beta, p.z, z[2]); pu[4] = fmaf(beta, p.w, z[3]);
-      const float ph = fmaf(beta, hp, zh);
+      float zadd, zaddh;
+      cz.at_row(y, H, zadd, zaddh);
+      pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
+      pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
+      const float ph = fmaf(beta, hp, zh + zaddh);
       const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
       pu[0] = (lane == 0) ? ph : l;
       pu[5] = (lane == 31) ? ph : rt;
@@ -1131,6 +1182,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
 #pragma unroll
   for (int u = 0; u < RD; ++u) issue(1 + u);
   float hp[4] = {0.f, 0.f, 0.f, 0.f}, cp[4] = {0.f, 0.f, 0.f, 0.f};
+  float racc = 0.f;
   double rr = 0.0, rz = 0.0;
 #pragma unroll 2
   for (int y = 1; y <= H - 2; ++y) {
@@ -1162,6 +1214,17 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
     const float srr = fmaf(rn[0], rn[0], fmaf(rn[1], rn[1], fmaf(rn[2], rn[2], rn[3] * rn[3])));
     const float srz = fmaf(iv.x * h[0], h[0], fmaf(iv.y * h[1], h[1], fmaf(iv.z * h[2], h[2], iv.w * h[3] * h[3])));
     rr += (double)srr; rz += (double)srz;
+    if (a.cg.by) {                               // restriction rc = P^T r: sum of the new residual over each aggregate
+      racc += (rn[0] + rn[1]) + (rn[2] + rn[3]);
+      if ((y & (a.cg.by - 1)) == 0 || y == H - 2) {          // (y-1) is the last row of its aggregate row
+        float v = racc;                                      // 8 (or 16) lanes share one aggregate column
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (a.cg.bx_shift == 6) v += __shfl_xor_sync(0xffffffffu, v, 8);
+        if ((lane & ((1 << (a.cg.bx_shift - 2)) - 1)) == 0 && valid)
+          a.rc[(size_t)b * a.cg.nc + (size_t)((y - 1) >> a.cg.by_shift) * a.cg.nbx + (x >> a.cg.bx_shift)] = v;
+        racc = 0.f;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) hp[j] = h[j];
     cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
@@ -1169,6 +1232,107 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   }
   cp_async_wait<0>();
   rr_out = warp_sum(rr); rz_out = warp_sum(rz);
+}
+
+// F_COARSE: one warp solves Ac zc = rc for one image and returns rc . zc.
+// Two triangular sweeps in saxpy form with a ROTATING REGISTER WINDOW: lane l holds the vector element
+// j == l (mod 32) of the 32-wide window that starts at the current row, so a step is
+//   broadcast the head element (one shuffle)  ->  every lane: w -= F[i][d] * head  (one FMA)
+// and the dependent chain per row is shuffle + FMA (~30 cycles) instead of a shared-memory round trip.
+// Needs band width kd <= 31.  The factor rows are pre-scaled (F[i][d] = L[.]/L[i,i], F[i][0] = 1/L[i,i])
+// and staged in shared memory by cp.async tiles; the vector lives in shared memory only as input/output.
+__device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane) {
+  const CoarseGeom g = a.cg;
+  const int n = g.nc, kd1 = g.kd1;
+  float* ysb = reinterpret_cast<float*>(ringmem);                // 32 zeros | vector [n] | zeros up to kCoarseMaxN + 64
+  float* ys = ysb + 32;
+  float* tiles = ysb + kCoarseMaxN + 96;                         // 2 x [kCoarseTileRows][32]
+  const float* rc = a.rc + (size_t)b * n;
+  float* zc = a.zc + (size_t)b * n;
+  const float* U = a.Ur + (size_t)b * n * kd1;
+  const float* L = a.Lr + (size_t)b * n * kd1;
+  const unsigned full = 0xffffffffu;
+  const int ntile = (n + kCoarseTileRows - 1) / kCoarseTileRows;
+  auto issue_tile = [&](const float* F, int t, float* buf) {
+    if (t >= 0 && t < ntile) {
+      const int r0 = t * kCoarseTileRows, rows = min(kCoarseTileRows, n - r0);
+      const int chunks = rows * kd1 / 4;
+      for (int c = lane; c < chunks; c += 32) cp_async16(buf + 4 * c, F + (size_t)r0 * kd1 + 4 * c, true);
+    }
+    cp_async_commit();
+  };
+  ysb[lane] = 0.f;
+  for (int i = lane; i < n + 64; i += 32) ys[i] = (i < n) ? __ldcg(rc + i) : 0.f;
+  __syncwarp();
+  // ---- forward: L y = rc, column-oriented (row i of Ur = scaled column i of L) -----------------------
+  issue_tile(U, 0, tiles);
+  float w = ys[lane];                                            // window [0, 32)
+  for (int t = 0; t < ntile; ++t) {
+    issue_tile(U, t + 1, tiles + ((t + 1) & 1) * kCoarseTileRows * kd1);
+    cp_async_wait<1>();
+    __syncwarp();
+    const float* T = tiles + (t & 1) * kCoarseTileRows * kd1;
+    const int i0 = t * kCoarseTileRows, i1 = min(i0 + kCoarseTileRows, n);
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+      // branch-free step: uniform-address loads, a select, and a same-value store by all lanes
+      const float* row = T + (i - i0) * 32;
+      const int hl = i & 31;
+      const int d = (lane - hl) & 31;                            // this lane holds element i + d
+      const float f = (d == 0) ? 0.f : row[d];                   // rows are zero padded beyond the band
+      const float nxt = ys[i + 32];                              // element entering the window
+      const float r0 = row[0];
+      const float head = __shfl_sync(full, w, hl);               // element i, fully updated
+      w = fmaf(-f, head, w);
+      w = (d == 0) ? nxt : w;                                    // retire element i, admit element i + 32
+      ys[i] = head * r0;
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  // ---- backward: L^T x = y, row-oriented (row i of Lr = scaled row i of L) -----------------------------
+  // after the forward sweep ys[i] = y_i / 1 ... (already divided by L[i,i]); the backward recurrence is
+  //   x_i = (y_i - sum_{k>i} L[k,i] x_k) / L[i,i]  with y_i here meaning the forward result times L[i,i]^-1 ... see below
+  issue_tile(L, ntile - 1, tiles);
+  // window (n-32, n-1]: lane l holds element j == l (mod 32)
+  {
+    const int j = (n - 1) - (((n - 1) - lane) & 31);
+    w = (j >= 0) ? ys[j] : 0.f;
+  }
+  for (int k = 0; k < ntile; ++k) {
+    const int t = ntile - 1 - k;
+    issue_tile(L, t - 1, tiles + ((k + 1) & 1) * kCoarseTileRows * kd1);
+    cp_async_wait<1>();
+    __syncwarp();
+    const float* T = tiles + (k & 1) * kCoarseTileRows * kd1;
+    const int i0 = t * kCoarseTileRows, i1 = min(i0 + kCoarseTileRows, n);
+#pragma unroll 4
+    for (int i = i1 - 1; i >= i0; --i) {
+      const float* row = T + (i - i0) * 32;
+      const int hl = i & 31;
+      const int d = (hl - lane) & 31;                            // this lane holds element i - d
+      const float f = (d == 0) ? 0.f : row[d];
+      const float nxt = ysb[i];                                  // = ys[i - 32] (zero below 0): element entering the window
+      const float r0 = row[0];
+      const float head = __shfl_sync(full, w, hl);               // element i with all later rows eliminated
+      const float xi = head * r0;                                // x_i = head / L[i,i]
+      w = fmaf(-f, xi, w);
+      w = (d == 0) ? nxt : w;                                    // retire element i, admit element i - 32
+      ys[i] = xi;
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  double acc = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const float v = ys[i];
+    zc[i] = v;
+    acc += (double)v * (double)__ldcg(rc + i);
+  }
+  __syncwarp();
+  return warp_sum(acc);
 }
 
 // ---- ready queue (multi-producer / multi-consumer ticket ring in global memory) -------------------
@@ -1245,8 +1409,8 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
   const unsigned nworkers = (a.debug == 2) ? 1u : gridDim.x * (unsigned)a.wpb;
 
   auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-  unsigned long long t_wait = 0, t_mode[7] = {0, 0, 0, 0, 0, 0, 0}, t_arr = 0;
-  unsigned n_mode[7] = {0, 0, 0, 0, 0, 0, 0};
+  unsigned long long t_wait = 0, t_mode[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_arr = 0;
+  unsigned n_mode[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (;;) {
     const unsigned long long tq0 = a.debug ? now() : 0ull;
     const unsigned payload = q_pop(a, lane);
@@ -1271,6 +1435,8 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       down_task<RD, 0>(a, ringmem, b, ti, lane, 0.f, 0.f, 0, s0, s1);
     } else if (mode == F_RESID) {
       s0 = resid_strip(a, b, ti, lane);
+    } else if (mode == F_COARSE) {
+      s0 = coarse_task(a, ringmem, b, lane);
     } else {
       const int x = ti * kStrip4 + 4 * lane;
       if (x < W) {
@@ -1314,10 +1480,11 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     if (lane == 0) tk = atomicAdd(&st->cnt1, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (a.debug) t_arr += now() - tq2;
-    if (tk != (unsigned)per - 1) continue;
+    const int ntask = (mode == F_COARSE) ? 1 : per;               // F_COARSE is a single task per image
+    if (tk != (unsigned)ntask - 1) continue;
     // ---- last strip of this image and phase: reduce, advance the state, publish the next phase ------
     __threadfence();
-    reduce_parts(part, per, lane, s0, s1);
+    reduce_parts(part, ntask, lane, s0, s1);
     if (lane != 0) continue;
     st->cnt1 = 0;
     int next = F_DONE;
@@ -1331,16 +1498,35 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       const int it = __ldcg(&st->iters) + 1;
       if (__ldcg(&st->epend)) st->epend = 0;                       // this DOWN applied both pending updates
       else { st->epend = 1; st->alpha_prev = __ldcg(&st->alpha); }  // this DOWN deferred its own update
-      st->iters = it; st->rr_rec = s0; st->rz = s1; st->first = 0;
-      st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
-      next = (s0 <= __ldcg(&st->rr_target) || it >= a.maxiter || !(s1 > 0.0)) ? F_FOLD : F_UP;
+      st->iters = it; st->rr_rec = s0;
+      if (s0 <= __ldcg(&st->rr_target) || it >= a.maxiter || !(s1 > 0.0)) {
+        next = F_FOLD;
+      } else if (a.cg.by) {                                        // r.z is completed by the coarse solve
+        st->rz_line = s1; st->fresh = 0;
+        next = F_COARSE;
+      } else {
+        st->rz = s1; st->first = 0;
+        st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
+        next = F_UP;
+      }
     } else if (mode == F_PRECOND) {
       // First round: start CG (p = z).  USAUG_CM_CONTINUE (experimental, rejected: more iterations): keep p.
       const double rz_old = __ldcg(&st->rz);
       const bool cont = __ldcg(&st->outer) > 0 && rz_old > 0.0 && a.restart;
-      st->rz = s1; st->first = cont ? 0 : 1; st->beta = cont ? s1 / rz_old : 0.0;
       st->epend = 0;                                               // F_FOLD consumed any pending update, e = 0 now
-      next = (s1 > 0.0) ? F_UP : F_FINAL;
+      if (a.cg.by) {
+        st->rz_line = s1; st->fresh = 1;
+        next = (s1 > 0.0) ? F_COARSE : F_FINAL;
+      } else {
+        st->rz = s1; st->first = cont ? 0 : 1; st->beta = cont ? s1 / rz_old : 0.0;
+        next = (s1 > 0.0) ? F_UP : F_FINAL;
+      }
+    } else if (mode == F_COARSE) {
+      // z = T^-1 r + P Ac^-1 P^T r  =>  r.z = sum ip h^2 (line part, from DOWN) + rc.zc (this task)
+      const double rz_new = __ldcg(&st->rz_line) + s0, rz_old = __ldcg(&st->rz);
+      if (__ldcg(&st->fresh)) { st->rz = rz_new; st->first = 1; st->beta = 0.0; next = F_UP; }
+      else if (rz_new > 0.0 && rz_old > 0.0) { st->beta = rz_new / rz_old; st->rz = rz_new; st->first = 0; next = F_UP; }
+      else next = F_FOLD;
     } else if (mode == F_RESID) {
       next = after_true_residual(st, s0, a.rtol2, a.inner_red2, a.maxiter) ? F_FINAL : F_PRECOND;
     } else if (mode == F_FOLD) {
@@ -1356,15 +1542,16 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       __threadfence();
       if (atomicAdd(a.done, 1u) == (unsigned)B - 1u) q_push_n(a, kPoison, 0u, nworkers);   // release every worker
     } else {
-      q_push_n(a, (unsigned)(b * per), 1u, (unsigned)per);
+      q_push_n(a, (unsigned)(b * per), 1u, (next == F_COARSE) ? 1u : (unsigned)per);
     }
   }
   if ((a.debug & 1) && lane == 0 && warp == 0 && (blockIdx.x % 74) == 0)
-    printf("[pcg queue dbg] block %d: wait %.1f us | UP %u x %.1f us | DOWN %u x %.1f us | PRECOND %u x %.1f | RESID %u x %.1f | arrive %.1f us total\n",
+    printf("[pcg queue dbg] block %d: wait %.1f us | UP %u x %.1f us | DOWN %u x %.1f us | PRECOND %u x %.1f | RESID %u x %.1f | COARSE %u x %.1f | arrive %.1f us total\n",
            blockIdx.x, t_wait * 1e-3, n_mode[F_UP], n_mode[F_UP] ? t_mode[F_UP] * 1e-3 / n_mode[F_UP] : 0.0, n_mode[F_DOWN],
            n_mode[F_DOWN] ? t_mode[F_DOWN] * 1e-3 / n_mode[F_DOWN] : 0.0, n_mode[F_PRECOND],
            n_mode[F_PRECOND] ? t_mode[F_PRECOND] * 1e-3 / n_mode[F_PRECOND] : 0.0, n_mode[F_RESID],
-           n_mode[F_RESID] ? t_mode[F_RESID] * 1e-3 / n_mode[F_RESID] : 0.0, t_arr * 1e-3);
+           n_mode[F_RESID] ? t_mode[F_RESID] * 1e-3 / n_mode[F_RESID] : 0.0, n_mode[F_COARSE],
+           n_mode[F_COARSE] ? t_mode[F_COARSE] * 1e-3 / n_mode[F_COARSE] : 0.0, t_arr * 1e-3);
 }
 
 struct CmLayout {
@@ -1377,6 +1564,9 @@ struct CmLayout {
   unsigned* done;
   unsigned long long *qslots, *qhead, *qtail;
   unsigned qcap;
+  CoarseGeom cg;
+  float *rc, *zc, *Lr, *Ur;
+  double* Ab;
   int nblk, nstrip1, nrb, nstrip2, pmax;
   size_t bytes;
 };
@@ -1408,6 +1598,12 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.qcap = (unsigned)(2 * ((W + kStrip4 - 1) / kStrip4) * B + 8192);
   L.qslots = cv.take<unsigned long long>(L.qcap);
   L.qhead = cv.take<unsigned long long>(1); L.qtail = cv.take<unsigned long long>(1);
+  // coarse-grid correction (fused fp32 kernel only)
+  L.cg = ((flags & (USAUG_CM_FP64_VECTORS | USAUG_CM_NO_COARSE)) || W % 4 != 0) ? CoarseGeom{} : coarse_geom(H, W);
+  const size_t nc = (size_t)L.cg.nc;
+  L.rc = cv.take<float>((size_t)B * nc); L.zc = cv.take<float>((size_t)B * nc);
+  L.Lr = cv.take<float>((size_t)B * nc * L.cg.kd1); L.Ur = cv.take<float>((size_t)B * nc * L.cg.kd1);
+  L.Ab = cv.take<double>((size_t)B * nc * (L.cg.kd + 1));
   L.bytes = cv.off;
   return L;
 }
@@ -1474,7 +1670,8 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.x64 = L.x64;
   a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z; a.p2 = (T*)L.p2;
   a.st = L.st; a.part = L.part; a.done = L.done;
-  a.qslots = L.qslots; a.qhead = L.qhead; a.qtail = L.qtail; a.qcap = L.qcap; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
+  a.qslots = L.qslots; a.qhead = L.qhead; a.qtail = L.qtail; a.qcap = L.qcap;
+  a.cg = L.cg; a.rc = L.rc; a.zc = L.zc; a.Lr = L.Lr; a.Ur = L.Ur; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
   a.nstrip1 = L.nstrip1; a.nrb = L.nrb; a.nstrip2 = L.nstrip2; a.pmax = L.pmax;
   a.vec4 = (std::is_same<T, float>::value && W % 4 == 0) ? 1 : 0;
   a.nstrip4 = (W + kStrip4 - 1) / kStrip4;
@@ -1561,6 +1758,13 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
                                                         (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.ip, L.c,
                                                         L.ipc, L.x64, L.bbpart);
   USAUG_CHECK_LAUNCH("cm_factor_kernel");
+  if (L.cg.by && !(flags & USAUG_CM_LEGACY_KERNEL)) {
+    coarse_assemble_kernel<<<dim3((L.cg.nc + 7) / 8, B), 256, 0, stream>>>(H, W, L.cg, L.wS, L.wE, L.wSE, L.wSW, L.Ab);
+    USAUG_CHECK_LAUNCH("coarse_assemble_kernel");
+    const size_t fsm = (size_t)(L.cg.kd + 1) * (L.cg.kd + 1) * sizeof(double);
+    coarse_factor_kernel<<<B, 32, fsm, stream>>>(L.cg, L.Ab, L.Lr, L.Ur);
+    USAUG_CHECK_LAUNCH("coarse_factor_kernel");
+  }
   cm_init_state_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, L.nblk, L.bbpart, L.st, L.done);
   USAUG_CHECK_LAUNCH("cm_init_state_kernel");
   if (flags & USAUG_CM_FP64_VECTORS)
