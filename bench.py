@@ -316,7 +316,7 @@ def run_ours(a):
                        "pcg_iters_mean": float(iters_all.mean().item()), "pcg_iters_max": float(iters_all.max().item()),
                        "pcg_wave": WAVE, "l2_policy": f"inputs larger than L2 ({nloc * H * W * 5 / 2**20:.0f} MiB per GPU)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": a.steps * (3 + 3 + 7 * waves),
+            "gpu_launches": a.steps * (3 + 3 + 11 * waves),   # K1: 3, K3: 3, confidence map: 10 setup kernels + the persistent PCG kernel per wave
         }
         print(json.dumps(line), flush=True)
     if world > 1:
