@@ -1,0 +1,21 @@
+"""Development aid: confidence-map parity sweep over many small shapes (fused kernel vs oracle)."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np, torch
+from oracle import confmap as ocm, synth as osynth
+from ultrasoundaugmentation_b200 import ops
+dev = torch.device("cuda", 0)
+bad = 0; n = 0
+for H in list(range(3, 20)) + [24, 31, 33, 40, 47, 48]:
+    for W in [4, 8, 12, 28, 32, 36, 60, 64, 68, 96, 100, 124, 128, 132, 140]:
+        for kind in (0, 1):
+            rng = np.random.default_rng(H * 1000 + W)
+            img = rng.random((2, H, W), dtype=np.float32) if kind == 0 else np.stack([osynth.make_bmode(H, W, 5 + b)[0] for b in range(2)])
+            ref = ocm.confidence_map_batch(img)
+            cm, it, rr = ops.confidence_map(torch.from_numpy(img).to(dev), rtol=1e-9, maxiter=100000, return_info=True)
+            err = np.abs(cm.cpu().numpy() - ref).max(); n += 1
+            if not (err <= 5e4 * 1e-9 + 1e-6 + 2e-5) or not (rr.cpu().numpy() <= 1e-9).all():
+                bad += 1
+                print("FAIL", H, W, kind, "err", err, "iters", it.tolist(), "relres", rr.tolist(), flush=True)
+print("cases", n, "bad", bad)

@@ -20,7 +20,7 @@ namespace usaug {
 // aggregate width: 32 pixel columns, or 64 for images wider than 960 (keeps the band <= 31)
 constexpr int kCoarseMaxN = 4096;     // coarse unknowns per image (the solve keeps the vector in shared memory)
 constexpr int kCoarseMaxBand = 31;    // nbx + 1: the register-window solver holds one element per lane
-constexpr int kCoarseTileRows = 16;   // factor rows staged per cp.async tile
+constexpr int kCoarseTileRows = 32;   // factor rows staged per cp.async tile = one 32-step block of the sweeps
 
 struct CoarseGeom {
   int by;        // aggregate height in rows (power of two), 0 = coarse correction disabled

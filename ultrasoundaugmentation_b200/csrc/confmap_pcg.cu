@@ -1246,7 +1246,7 @@ __device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned 
   const int n = g.nc, kd1 = g.kd1;
   float* ysb = reinterpret_cast<float*>(ringmem);                // 32 zeros | vector [n] | zeros up to kCoarseMaxN + 64
   float* ys = ysb + 32;
-  float* tiles = ysb + kCoarseMaxN + 96;                         // 2 x [kCoarseTileRows][32]
+  float* tiles = ysb + kCoarseMaxN + 96;                         // 2 x [32][32]
   const float* rc = a.rc + (size_t)b * n;
   float* zc = a.zc + (size_t)b * n;
   const float* U = a.Ur + (size_t)b * n * kd1;
@@ -1256,71 +1256,74 @@ __device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned 
   auto issue_tile = [&](const float* F, int t, float* buf) {
     if (t >= 0 && t < ntile) {
       const int r0 = t * kCoarseTileRows, rows = min(kCoarseTileRows, n - r0);
-      const int chunks = rows * kd1 / 4;
-      for (int c = lane; c < chunks; c += 32) cp_async16(buf + 4 * c, F + (size_t)r0 * kd1 + 4 * c, true);
+      const int chunks = rows * kd1 / 4;                         // rows past n are zero-filled (src-size 0)
+      for (int c = lane; c < kCoarseTileRows * 32 / 4; c += 32)
+        cp_async16(buf + 4 * c, F + (size_t)r0 * kd1 + 4 * (c < chunks ? c : 0), c < chunks);
     }
     cp_async_commit();
   };
   ysb[lane] = 0.f;
   for (int i = lane; i < n + 64; i += 32) ys[i] = (i < n) ? __ldcg(rc + i) : 0.f;
   __syncwarp();
+  // Both sweeps advance in blocks of 32 rows (= one factor tile).  Inside a block lane l admits exactly one
+  // element (prefetched into `nx` before the block) and retires exactly one (kept in `out`, stored after the
+  // block), so the inner step has no shared-memory store and its dependent chain is shuffle -> FMA -> select.
   // ---- forward: L y = rc, column-oriented (row i of Ur = scaled column i of L) -----------------------
   issue_tile(U, 0, tiles);
-  float w = ys[lane];                                            // window [0, 32)
+  float w = ys[lane];                                            // window [0, 32): lane l holds element l
   for (int t = 0; t < ntile; ++t) {
-    issue_tile(U, t + 1, tiles + ((t + 1) & 1) * kCoarseTileRows * kd1);
+    issue_tile(U, t + 1, tiles + ((t + 1) & 1) * kCoarseTileRows * 32);
+    const int i0 = t * 32;
+    const float nx = ys[i0 + 32 + lane];                         // element this lane admits during the block
+    float out = 0.f;
     cp_async_wait<1>();
     __syncwarp();
-    const float* T = tiles + (t & 1) * kCoarseTileRows * kd1;
-    const int i0 = t * kCoarseTileRows, i1 = min(i0 + kCoarseTileRows, n);
-#pragma unroll 4
-    for (int i = i0; i < i1; ++i) {
-      // branch-free step: uniform-address loads, a select, and a same-value store by all lanes
-      const float* row = T + (i - i0) * 32;
-      const int hl = i & 31;
+    const float* T = tiles + (t & 1) * kCoarseTileRows * 32;
+#pragma unroll 8
+    for (int hl = 0; hl < 32; ++hl) {                            // row i = i0 + hl; its element sits on lane hl
+      const float* row = T + hl * 32;
       const int d = (lane - hl) & 31;                            // this lane holds element i + d
-      const float f = (d == 0) ? 0.f : row[d];                   // rows are zero padded beyond the band
-      const float nxt = ys[i + 32];                              // element entering the window
+      const float f = row[d];                                    // zero padded beyond the band
       const float r0 = row[0];
       const float head = __shfl_sync(full, w, hl);               // element i, fully updated
-      w = fmaf(-f, head, w);
-      w = (d == 0) ? nxt : w;                                    // retire element i, admit element i + 32
-      ys[i] = head * r0;
+      const float wn = fmaf(-f, head, w);
+      w = (d == 0) ? nx : wn;                                    // retire element i, admit element i + 32
+      out = (d == 0) ? head * r0 : out;                          // y_i
     }
+    if (i0 + lane < n) ys[i0 + lane] = out;
     __syncwarp();
   }
   cp_async_wait<0>();
   __syncwarp();
-  // ---- backward: L^T x = y, row-oriented (row i of Lr = scaled row i of L) -----------------------------
-  // after the forward sweep ys[i] = y_i / 1 ... (already divided by L[i,i]); the backward recurrence is
-  //   x_i = (y_i - sum_{k>i} L[k,i] x_k) / L[i,i]  with y_i here meaning the forward result times L[i,i]^-1 ... see below
+  // ---- backward: L^T x = y, row-oriented (row i of Lr) ----------------------------------------------------
   issue_tile(L, ntile - 1, tiles);
-  // window (n-32, n-1]: lane l holds element j == l (mod 32)
   {
-    const int j = (n - 1) - (((n - 1) - lane) & 31);
-    w = (j >= 0) ? ys[j] : 0.f;
+    const int top = ntile * 32 - 1;                              // window (top-32, top]: lane l holds element j == l (mod 32)
+    const int j = top - ((top - lane) & 31);
+    w = ys[j];                                                   // ys is zero padded past n
   }
   for (int k = 0; k < ntile; ++k) {
     const int t = ntile - 1 - k;
-    issue_tile(L, t - 1, tiles + ((k + 1) & 1) * kCoarseTileRows * kd1);
+    issue_tile(L, t - 1, tiles + ((k + 1) & 1) * kCoarseTileRows * 32);
+    const int i0 = t * 32;
+    const float nx = ysb[i0 + lane];                             // = ys[i0 - 32 + lane]: element admitted during the block
+    float out = 0.f;
     cp_async_wait<1>();
     __syncwarp();
-    const float* T = tiles + (k & 1) * kCoarseTileRows * kd1;
-    const int i0 = t * kCoarseTileRows, i1 = min(i0 + kCoarseTileRows, n);
-#pragma unroll 4
-    for (int i = i1 - 1; i >= i0; --i) {
-      const float* row = T + (i - i0) * 32;
-      const int hl = i & 31;
+    const float* T = tiles + (k & 1) * kCoarseTileRows * 32;
+#pragma unroll 8
+    for (int hl = 31; hl >= 0; --hl) {                           // row i = i0 + hl
+      const float* row = T + hl * 32;
       const int d = (hl - lane) & 31;                            // this lane holds element i - d
-      const float f = (d == 0) ? 0.f : row[d];
-      const float nxt = ysb[i];                                  // = ys[i - 32] (zero below 0): element entering the window
+      const float f = row[d];
       const float r0 = row[0];
       const float head = __shfl_sync(full, w, hl);               // element i with all later rows eliminated
-      const float xi = head * r0;                                // x_i = head / L[i,i]
-      w = fmaf(-f, xi, w);
-      w = (d == 0) ? nxt : w;                                    // retire element i, admit element i - 32
-      ys[i] = xi;
+      const float xi = head * r0;                                // x_i = head / L[i,i]   (0 for padding rows: r0 = 0)
+      const float wn = fmaf(-f, xi, w);
+      w = (d == 0) ? nx : wn;                                    // retire element i, admit element i - 32
+      out = (d == 0) ? xi : out;
     }
+    if (i0 + lane < n) ys[i0 + lane] = out;
     __syncwarp();
   }
   cp_async_wait<0>();
