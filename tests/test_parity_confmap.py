@@ -91,3 +91,20 @@ def test_cm_monotone_for_constant_columns(cuda_device):
     img = np.tile(np.linspace(0.2, 0.9, H, dtype=np.float32)[None, :, None], (1, 1, W))
     cm, _, _ = gpu_cm(cuda_device, img, rtol=1e-9)
     assert (np.diff(cm[0], axis=0) <= 1e-6).all()
+
+
+@pytest.mark.parametrize("H,W,what", [(1500, 64, "tall: 4-row aggregates, 375 x 2 coarse grid"),
+                                      (3000, 256, "very tall: 8-row aggregates"),
+                                      (72, 1000, "wide: 64-column aggregates"),
+                                      (40, 2016, "too wide for the banded solver: line preconditioner only"),
+                                      (9, 64, "fewer than 8 unknown rows: coarse grid disabled")])
+def test_cm_coarse_grid_geometries(cuda_device, H, W, what):
+    """Every coarse-grid geometry of the fused kernel against the generic (line-only, grid-synchronous) kernel."""
+    from ultrasoundaugmentation_b200 import synth
+    img, _ = synth.make_batch(2, H, W, seed=H + W, device=cuda_device)
+    img = img.cpu().numpy()
+    a, ita, rra = gpu_cm(cuda_device, img, rtol=1e-9, maxiter=100000)
+    b, itb, rrb = gpu_cm(cuda_device, img, rtol=1e-9, maxiter=100000, legacy_kernel=True)
+    assert (rra <= 1e-9).all() and (rrb <= 1e-9).all(), what
+    assert np.abs(a - b).max() <= 2 * (2e5 * 1e-9) + 1e-6, what
+    assert np.all(a[:, 0] == 1.0) and np.all(a[:, -1] == 0.0)
