@@ -50,7 +50,6 @@ enum {
   USAUG_CM_ZERO_GUESS = 2,   /* start from x0 = 0 instead of the linear depth ramp */
   USAUG_CM_DEBUG_TIMING = 4, /* development: the kernel prints per-slot wall times of a few steps */
   USAUG_CM_LEGACY_KERNEL = 8, /* A/B testing: use the two-slot kernel even where the fused fp32 kernel applies */
-  USAUG_CM_CONTINUE = 16,     /* experimental: residual replacement every 2 decades, keep the search direction */
   USAUG_CM_NO_COARSE = 32     /* A/B testing: line preconditioner only (no aggregation coarse-grid correction) */
 };
 

@@ -47,9 +47,6 @@ def main():
             t0 = time.time()
             cm, it, rr = ops.confidence_map(img, rtol=rtol, fp64_vectors=fp64, return_info=True)
             torch.cuda.synchronize(); t = time.time() - t0
-            if B == 64:
-                _, it2, rr2 = ops.confidence_map(img, rtol=rtol, return_info=True, continue_cg=True)
-                print(f"   (continue variant: iters mean {it2.float().mean().item():.0f} max {it2.max().item()} relres {rr2.max().item():.2e})")
             itm = it.float().mean().item()
             eff = itm * 64 * (H - 2) * W * B / t / 1e9
             print(f"CM B={B} {H}x{W} rtol={rtol} fp64={fp64}: {t*1e3:.1f} ms  iters mean {itm:.0f} max {it.max().item()} "

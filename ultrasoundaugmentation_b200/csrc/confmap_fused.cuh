@@ -1,0 +1,777 @@
+// Fused fp32 confidence-map PCG kernel (production path).  Included by confmap_pcg.cu.
+#pragma once
+#include "confmap_generic.cuh"
+
+namespace usaug {
+
+// =============================================================================================
+// Fused fp32 kernel (W % 4 == 0): the production path.
+//   One grid-sync interval = one PHASE per image (images may be in different phases):
+//     F_UP    z = L^-T D^-1 h on the fly (never stored), p = z + beta p, q = A p, partial p.q
+//             -- the up sweep of iteration k fused with the stencil of iteration k+1
+//     F_DOWN  e += alpha p; r -= alpha q; h = L^-1 r (stored over q); partial r.r and r.z = sum ip h^2
+//   19 plane touches per unknown and iteration (UP: read h, ip, c, p, 4 weights, write p, q;
+//   DOWN: read p, e, r, q, c, ip, write e, r, h) instead of 22, and no z plane.
+//   Task = (image, 128-column strip), lane = 4 adjacent columns, rows staged through a private
+//   cp.async ring in shared memory (see stencil_task_v4); the column recurrences are 4-way
+//   independent per lane.  Strip halo columns: lane 0 / lane 31 carry one extra scalar recurrence;
+//   their six scalars per row are fetched by ONE cp.async.4 instruction (lanes 0-5 left, 16-21 right).
+// =============================================================================================
+enum FMode : int { F_RESID = 0, F_PRECOND = 1, F_UP = 2, F_DOWN = 3, F_FOLD = 4, F_FINAL = 5, F_DONE = 6, F_COARSE = 7 };
+
+struct RingU {   // one staged row of a 128-column strip for F_UP (2560 bytes)
+  float4 h[32], p[32], a[32];
+  uint4 ipc[32];
+  // 16-byte chunks that contain the strip's halo columns (cp.async.cg = L2, never a stale L1 line):
+  // [0..3] columns x0-4..x0-1 of h, ipc, p, a (.w is the left neighbour column);
+  // [16..19] columns x0+128..x0+131 of the same planes (.x is the right neighbour column)
+  float4 halo[32];
+};
+struct RingD {   // one staged row for F_DOWN / F_PRECOND (3072 bytes)
+  float4 p[32], pp[32], e[32], r[32], q[32];
+  uint4 ipc[32];
+};
+constexpr int kRingRowsPerCta = 80;                                   // 80 x 2560 B = 200 KB per CTA
+constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
+
+__device__ __forceinline__ float hsel(const float4& v, int lane) { return lane == 31 ? v.x : v.w; }
+
+struct RingUP {   // one staged row of a 128-column strip for F_UP, weight planes read from memory (4096 bytes)
+  float4 h[32], p[32], s[32], e[32], se[32], sw[32];
+  uint4 ipc[32];
+  // 16-byte chunks that contain the strip's halo columns (cp.async.cg = L2, never a stale L1 line):
+  // [0..4] columns x0-4..x0-1 of h, ipc, p, wE, wSE (.w is the left neighbour column);
+  // [16..19] columns x0+128..x0+131 of h, ipc, p, wSW (.x is the right neighbour column)
+  float4 halo[32];
+};
+
+// Prolongation P zc inside F_UP: the coarse value of this lane's aggregate column (and of the strip's halo
+// column on lanes 0 / 31), fetched one aggregate row ahead of use while the sweep marches upward.
+struct CoarseZ {
+  const float* zc;      // this image's coarse correction, nullptr = disabled
+  int sh, nbx, jown, jhalo, icur;
+  float cur, curh, nxt, nxth;
+  bool own, halo;
+  __device__ __forceinline__ void init(const PcgArgs<float>& a, int b, int x, int x0, int lane, bool valid, int W) {
+    zc = a.cg.by ? a.zc + (size_t)b * a.cg.nc : nullptr;
+    sh = a.cg.by_shift; nbx = a.cg.nbx; icur = -1;
+    own = valid; jown = valid ? (x >> a.cg.bx_shift) : 0;
+    const int hx = (lane == 0) ? x0 - 1 : x0 + kStrip4;
+    halo = (lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < W);
+    jhalo = halo ? (hx >> a.cg.bx_shift) : 0;
+    cur = curh = nxt = nxth = 0.f;
+  }
+  // returns the additive terms for row y (0 outside the unknown rows)
+  __device__ __forceinline__ void at_row(int y, int H, float& add, float& addh) {
+    add = 0.f; addh = 0.f;
+    if (zc == nullptr || y < 1 || y > H - 2) return;
+    const int I = (y - 1) >> sh;
+    if (I != icur) {
+      if (icur < 0) {
+        cur = own ? __ldcg(zc + I * nbx + jown) : 0.f;
+        curh = halo ? __ldcg(zc + I * nbx + jhalo) : 0.f;
+      } else {
+        cur = nxt; curh = nxth;
+      }
+      icur = I;
+      if (I > 0) {
+        nxt = own ? __ldcg(zc + (I - 1) * nbx + jown) : 0.f;
+        nxth = halo ? __ldcg(zc + (I - 1) * nbx + jhalo) : 0.f;
+      }
+    }
+    add = cur; addh = curh;
+  }
+};
+
+// Edge weights of one image row for the 4 columns of a lane (plus the three that belong to its
+// neighbours' columns), recomputed from the `a` plane.
+struct WRow {
+  float s[4], e[4], se[4], sw[4];
+  float eL;    // wE [row, x-1]
+  float seL;   // wSE[row, x-1]
+  float swR;   // wSW[row, x+4]
+};
+
+template <int R>
+__device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+                                          float beta, bool first, int pcur) {
+  RingU* ring = reinterpret_cast<RingU*>(ringmem);
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W;
+  const int x0 = strip * kStrip4, x = x0 + 4 * lane;
+  const bool valid = x < W;
+  const bool hasL = valid && x > 0, hasR = valid && (x + 4 < W);
+  const int xs = valid ? x : 0;
+  const uint32_t* __restrict__ IPC = a.ipc + base;
+  const float* __restrict__ Ap = a.aplane + base;
+  const float4 wk = a.wk[b];
+  // reads: h (z plane), p_old (pin); writes: p_new (pout), q.  Nothing is updated in place, because the
+  // halo columns of this strip belong to a neighbouring strip whose warp runs asynchronously.
+  const float* __restrict__ Hb = a.z + base;
+  const float* __restrict__ Pin = (pcur ? a.p2 : a.p) + base;
+  float* __restrict__ P = (pcur ? a.p : a.p2) + base;
+  float* __restrict__ Q = a.q + base;
+  // halo fetch role of this lane: k = which plane, left (lanes 0-3) or right (lanes 16-19) chunk
+  const int k = lane & 15;
+  const bool isL = lane < 16;
+  const int hx = isL ? x0 - 4 : x0 + kStrip4;
+  const bool hcol = isL ? (x0 > 0) : (x0 + kStrip4 < W);
+  const bool hrole = hcol && k <= 3;
+  const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin : Ap;
+  const int hxs = hrole ? hx : 0;
+
+  auto issue = [&](int y) {                       // stage row y (rows are visited bottom -> top, H-1 .. 0)
+    RingU* r = ring + ((H - 1 - y) % R);
+    const bool in = y >= 0;
+    const bool interior = y >= 1 && y <= H - 2;
+    const size_t o = (size_t)(in ? y : 0) * W;
+    cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
+    cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
+    cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
+    cp_async16(&r->a[lane], Ap + o + xs, in && valid);
+    cp_async16(&r->halo[lane], hsrc + o + hxs, in && hrole && (k == 3 || interior) && !(k == 2 && first));
+    cp_async_commit();
+  };
+  const unsigned full = 0xffffffffu;
+  float zn[4] = {0.f, 0.f, 0.f, 0.f}, zhn = 0.f;            // z of the row below (own columns, halo column)
+  float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pu[6];
+  float ab[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, au[6];     // a of the row below / of this row, columns x-1..x+4
+  WRow wc, wu;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wc.s[j] = wc.e[j] = wc.se[j] = wc.sw[j] = 0.f;
+  wc.eL = wc.seL = wc.swR = 0.f;
+  const int hoff = (lane == 31) ? 16 : 0;
+  CoarseZ cz;
+  cz.init(a, b, x, x0, lane, valid, W);
+
+#pragma unroll
+  for (int u = 0; u < R; ++u) issue(H - 1 - u);
+  double acc = 0.0;
+#pragma unroll 2
+  for (int y = H - 1; y >= 0; --y) {
+    cp_async_wait<R - 1>();
+    __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
+    {
+      const RingU* r = ring + ((H - 1 - y) % R);
+      const float4 h = r->h[lane], p = r->p[lane], av = r->a[lane];
+      const uint4 f = r->ipc[lane];
+      // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
+      const float hh = hsel(r->halo[hoff + 0], lane);
+      const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
+      const float hp = hsel(r->halo[hoff + 2], lane);
+      const float ha = hsel(r->halo[hoff + 3], lane);
+      float z[4];     // line part of z (the recurrence runs on it alone); the coarse part is added on top
+      z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
+      z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
+      const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
+      float zadd, zaddh;
+      cz.at_row(y, H, zadd, zaddh);
+      pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
+      pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
+      const float ph = fmaf(beta, hp, zh + zaddh);
+      const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
+      pu[0] = (lane == 0) ? ph : l;
+      pu[5] = (lane == 31) ? ph : rt;
+      zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
+      if (valid && y >= 1 && y <= H - 2)
+        *reinterpret_cast<float4*>(P + (size_t)y * W + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
+      au[1] = av.x; au[2] = av.y; au[3] = av.z; au[4] = av.w;
+      const float al = __shfl_up_sync(full, av.w, 1), ar = __shfl_down_sync(full, av.x, 1);
+      au[0] = (lane == 0) ? ha : al;
+      au[5] = (lane == 31) ? ha : ar;
+    }
+    __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
+    // weights of row y (edges inside the row and down to row y+1), masked where the edge does not exist
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      wu.s[j] = valid ? edge_w_fast(au[j + 1], ab[j + 1], wk.x, wk.y) : 0.f;
+      wu.e[j] = valid ? edge_w_fast(au[j + 1], au[j + 2], wk.x, wk.z) : 0.f;
+      wu.se[j] = valid ? edge_w_fast(au[j + 1], ab[j + 2], wk.x, wk.w) : 0.f;
+      wu.sw[j] = valid ? edge_w_fast(au[j + 1], ab[j], wk.x, wk.w) : 0.f;
+    }
+    wu.eL = hasL ? edge_w_fast(au[0], au[1], wk.x, wk.z) : 0.f;
+    wu.seL = hasL ? edge_w_fast(au[0], ab[1], wk.x, wk.w) : 0.f;
+    wu.swR = hasR ? edge_w_fast(au[5], ab[4], wk.x, wk.w) : 0.f;
+    if (!hasR) { wu.e[3] = 0.f; wu.se[3] = 0.f; }
+    if (!hasL) wu.sw[0] = 0.f;
+
+    const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
+    if (yc <= H - 2) {
+      const float E5[5] = {wc.eL, wc.e[0], wc.e[1], wc.e[2], wc.e[3]};
+      const float SEu[4] = {wu.seL, wu.se[0], wu.se[1], wu.se[2]};
+      const float SWu[4] = {wu.sw[1], wu.sw[2], wu.sw[3], wu.swR};
+      float q[4], dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pcj = pc[j + 1];
+        float t = wc.s[j] * (pcj - pl[j + 1]);
+        t = fmaf(wu.s[j], pcj - pu[j + 1], t);
+        t = fmaf(E5[j + 1], pcj - pc[j + 2], t);
+        t = fmaf(E5[j], pcj - pc[j], t);
+        t = fmaf(wc.se[j], pcj - pl[j + 2], t);
+        t = fmaf(wc.sw[j], pcj - pl[j], t);
+        t = fmaf(SEu[j], pcj - pu[j], t);
+        t = fmaf(SWu[j], pcj - pu[j + 2], t);
+        q[j] = t;
+        dot = fmaf(pcj, t, dot);
+      }
+      if (valid) {
+        *reinterpret_cast<float4*>(Q + (size_t)yc * W + x) = make_float4(q[0], q[1], q[2], q[3]);
+        acc += (double)dot;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[j]; ab[j] = au[j]; }
+    wc = wu;
+    issue(y - R);
+  }
+  cp_async_wait<0>();
+  return warp_sum(acc);
+}
+
+// Variant of F_UP that READS the four weight planes (9 plane touches instead of 6, but ~25 % fewer
+// instructions per row): used when there are too few tasks to be bandwidth-bound, where the single-warp
+// instruction latency of a strip, not HBM, sets the pace.
+template <int R>
+__device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+                                          float beta, bool first, int pcur) {
+  RingUP* ring = reinterpret_cast<RingUP*>(ringmem);
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W;
+  const int x0 = strip * kStrip4, x = x0 + 4 * lane;
+  const bool valid = x < W;
+  const int xs = valid ? x : 0;
+  const float* __restrict__ S = a.wS + base; const float* __restrict__ E = a.wE + base;
+  const float* __restrict__ SE = a.wSE + base; const float* __restrict__ SW = a.wSW + base;
+  const uint32_t* __restrict__ IPC = a.ipc + base;
+  // reads: h (z plane), p_old (pin); writes: p_new (pout), q.  Nothing is updated in place, because the
+  // halo columns of this strip belong to a neighbouring strip whose warp runs asynchronously.
+  const float* __restrict__ Hb = a.z + base;
+  const float* __restrict__ Pin = (pcur ? a.p2 : a.p) + base;
+  float* __restrict__ P = (pcur ? a.p : a.p2) + base;
+  float* __restrict__ Q = a.q + base;
+  // halo fetch role of this lane: k = which plane, left (lanes 0-4) or right (lanes 16-19) chunk
+  const int k = lane & 15;
+  const bool isL = lane < 16;
+  const int hx = isL ? x0 - 4 : x0 + kStrip4;
+  const bool hcol = isL ? (x0 > 0) : (x0 + kStrip4 < W);
+  const bool hrole = hcol && (k <= 3 || (k == 4 && isL));
+  const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin
+                      : (k == 3) ? (isL ? E : SW) : SE;
+  const int hxs = hrole ? hx : 0;
+
+  auto issue = [&](int y) {                       // stage row y (rows are visited bottom -> top)
+    RingUP* r = ring + ((H - 2 - y) % R);
+    const bool in = y >= 0;
+    const bool interior = y >= 1;
+    const size_t o = (size_t)(in ? y : 0) * W;
+    cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
+    cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
+    cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
+    cp_async16(&r->s[lane], S + o + xs, in && valid);
+    cp_async16(&r->e[lane], E + o + xs, interior && valid);
+    cp_async16(&r->se[lane], SE + o + xs, in && valid);
+    cp_async16(&r->sw[lane], SW + o + xs, in && valid);
+    cp_async16(&r->halo[lane], hsrc + o + hxs, in && hrole && (k >= 3 || interior) && !(k == 2 && first));
+    cp_async_commit();
+  };
+  const unsigned full = 0xffffffffu;
+  struct WRowP { float4 s, e, se, sw; float hw1, hw2; };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float zn[4] = {0.f, 0.f, 0.f, 0.f}, zhn = 0.f;            // z of the row below (own columns, halo column)
+  float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pu[6];
+  WRowP wc, wu;
+  wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
+  const int hoff = (lane == 31) ? 16 : 0;
+  CoarseZ cz;
+  cz.init(a, b, x, x0, lane, valid, W);
+
+#pragma unroll
+  for (int u = 0; u < R; ++u) issue(H - 2 - u);
+  double acc = 0.0;
+#pragma unroll 2
+  for (int y = H - 2; y >= 0; --y) {
+    cp_async_wait<R - 1>();
+    __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
+    {
+      const RingUP* r = ring + ((H - 2 - y) % R);
+      const float4 h = r->h[lane], p = r->p[lane];
+      const uint4 f = r->ipc[lane];
+      wu.s = r->s[lane]; wu.e = r->e[lane]; wu.se = r->se[lane]; wu.sw = r->sw[lane];
+      // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
+      const float hh = hsel(r->halo[hoff + 0], lane);
+      const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
+      const float hp = hsel(r->halo[hoff + 2], lane);
+      wu.hw1 = hsel(r->halo[hoff + 3], lane); wu.hw2 = hsel(r->halo[hoff + 4], lane);
+      float z[4];     // line part of z (the recurrence runs on it alone); the coarse part is added on top
+      z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
+      z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
+      const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
+      float zadd, zaddh;
+      cz.at_row(y, H, zadd, zaddh);
+      pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
+      pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
+      const float ph = fmaf(beta, hp, zh + zaddh);
+      const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
+      pu[0] = (lane == 0) ? ph : l;
+      pu[5] = (lane == 31) ? ph : rt;
+      zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
+      if (valid && y >= 1) *reinterpret_cast<float4*>(P + (size_t)y * W + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
+    }
+    __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
+    const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
+    if (yc <= H - 2) {
+      const float eL_s = __shfl_up_sync(full, wc.e.w, 1);
+      const float seL_s = __shfl_up_sync(full, wu.se.w, 1);
+      const float swR_s = __shfl_down_sync(full, wu.sw.x, 1);
+      const float eL = (lane == 0) ? wc.hw1 : eL_s;           // wE[c, x-1]
+      const float seL = (lane == 0) ? wu.hw2 : seL_s;         // wSE[u, x-1]
+      const float swR = (lane == 31) ? wu.hw1 : swR_s;        // wSW[u, x+4]
+      const float Sc[4] = {wc.s.x, wc.s.y, wc.s.z, wc.s.w};
+      const float Su[4] = {wu.s.x, wu.s.y, wu.s.z, wu.s.w};
+      const float E5[5] = {eL, wc.e.x, wc.e.y, wc.e.z, wc.e.w};
+      const float SEc[4] = {wc.se.x, wc.se.y, wc.se.z, wc.se.w};
+      const float SWc[4] = {wc.sw.x, wc.sw.y, wc.sw.z, wc.sw.w};
+      const float SEu[4] = {seL, wu.se.x, wu.se.y, wu.se.z};
+      const float SWu[4] = {wu.sw.y, wu.sw.z, wu.sw.w, swR};
+      float q[4], dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pcj = pc[j + 1];
+        float t = Sc[j] * (pcj - pl[j + 1]);
+        t = fmaf(Su[j], pcj - pu[j + 1], t);
+        t = fmaf(E5[j + 1], pcj - pc[j + 2], t);
+        t = fmaf(E5[j], pcj - pc[j], t);
+        t = fmaf(SEc[j], pcj - pl[j + 2], t);
+        t = fmaf(SWc[j], pcj - pl[j], t);
+        t = fmaf(SEu[j], pcj - pu[j], t);
+        t = fmaf(SWu[j], pcj - pu[j + 2], t);
+        q[j] = t;
+        dot = fmaf(pcj, t, dot);
+      }
+      if (valid) {
+        *reinterpret_cast<float4*>(Q + (size_t)yc * W + x) = make_float4(q[0], q[1], q[2], q[3]);
+        acc += (double)dot;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[j]; }
+    wc = wu;
+    issue(y - R);
+  }
+  cp_async_wait<0>();
+  return warp_sum(acc);
+}
+
+// F_DOWN / F_PRECOND.  KIND: 0 = PRECOND (fresh residual: h = L^-1 r, e = 0, nothing else updated),
+//   1 = DOWN that defers the e-update (r -= alpha q; h):              reads r, q, (ip,c)      writes r, h
+//   2 = DOWN that applies two e-updates (e += alpha_prev p_prev + alpha p; r -= alpha q; h):
+//                                                                     reads p, p_prev, e, r, q, (ip,c)  writes e, r, h
+// Alternating 1 / 2 halves the traffic of the e-update (the previous search direction is still intact
+// in the other p plane), 13 instead of 14 plane touches per iteration on average.
+template <int RD, int KIND>
+__device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+                                          float alpha, float alpha_prev, int pcur, double& rr_out, double& rz_out) {
+  RingD* ring = reinterpret_cast<RingD*>(ringmem);
+  const int H = a.H, W = a.W;
+  const size_t base = (size_t)b * H * W;
+  const int x = strip * kStrip4 + 4 * lane;
+  const bool valid = x < W;
+  const int xs = valid ? x : 0;
+  const uint32_t* __restrict__ IPC = a.ipc + base;
+  const float* __restrict__ P = (pcur ? a.p2 : a.p) + base;        // p of this iteration (written by the last F_UP)
+  const float* __restrict__ PP = (pcur ? a.p : a.p2) + base;       // p of the previous iteration
+  float* __restrict__ Ev = a.e + base; float* __restrict__ Rv = a.r + base;
+  const float* __restrict__ Q = a.q + base;
+  float* __restrict__ Hb = a.z + base;          // h = L^-1 r goes to the z plane (read by the next F_UP)
+  auto issue = [&](int y) {
+    RingD* r = ring + ((y - 1) % RD);
+    const bool in = (y <= H - 2) && valid;
+    const size_t o = (size_t)(y <= H - 2 ? y : 0) * W + xs;
+    if (KIND == 2) {
+      cp_async16(&r->p[lane], P + o, in);
+      cp_async16(&r->pp[lane], PP + o, in);
+      cp_async16(&r->e[lane], Ev + o, in);
+    }
+    if (KIND != 0) cp_async16(&r->q[lane], Q + o, in);
+    cp_async16(&r->r[lane], Rv + o, in);
+    cp_async16(&r->ipc[lane], IPC + o, in);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int u = 0; u < RD; ++u) issue(1 + u);
+  float hp[4] = {0.f, 0.f, 0.f, 0.f}, cp[4] = {0.f, 0.f, 0.f, 0.f};
+  float racc = 0.f;
+  double rr = 0.0, rz = 0.0;
+#pragma unroll 2
+  for (int y = 1; y <= H - 2; ++y) {
+    cp_async_wait<RD - 1>();
+    const RingD* r = ring + ((y - 1) % RD);
+    const float4 rv = r->r[lane];
+    const uint4 f = r->ipc[lane];
+    const float4 cv = make_float4(bf16_hi(f.x), bf16_hi(f.y), bf16_hi(f.z), bf16_hi(f.w));
+    const float4 iv = make_float4(bf16_lo(f.x), bf16_lo(f.y), bf16_lo(f.z), bf16_lo(f.w));
+    float rn[4] = {rv.x, rv.y, rv.z, rv.w};
+    if (KIND != 0) {
+      const float4 qv = r->q[lane];
+      rn[0] = fmaf(-alpha, qv.x, rv.x); rn[1] = fmaf(-alpha, qv.y, rv.y);
+      rn[2] = fmaf(-alpha, qv.z, rv.z); rn[3] = fmaf(-alpha, qv.w, rv.w);
+      if (valid) *reinterpret_cast<float4*>(Rv + (size_t)y * W + x) = make_float4(rn[0], rn[1], rn[2], rn[3]);
+      if (KIND == 2) {
+        const float4 pv = r->p[lane], pq = r->pp[lane], ev = r->e[lane];
+        const float4 en = make_float4(fmaf(alpha, pv.x, fmaf(alpha_prev, pq.x, ev.x)), fmaf(alpha, pv.y, fmaf(alpha_prev, pq.y, ev.y)),
+                                      fmaf(alpha, pv.z, fmaf(alpha_prev, pq.z, ev.z)), fmaf(alpha, pv.w, fmaf(alpha_prev, pq.w, ev.w)));
+        if (valid) *reinterpret_cast<float4*>(Ev + (size_t)y * W + x) = en;
+      }
+    } else if (valid) {
+      *reinterpret_cast<float4*>(Ev + (size_t)y * W + x) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = fmaf(cp[j], hp[j], rn[j]);
+    if (valid) *reinterpret_cast<float4*>(Hb + (size_t)y * W + x) = make_float4(h[0], h[1], h[2], h[3]);
+    const float srr = fmaf(rn[0], rn[0], fmaf(rn[1], rn[1], fmaf(rn[2], rn[2], rn[3] * rn[3])));
+    const float srz = fmaf(iv.x * h[0], h[0], fmaf(iv.y * h[1], h[1], fmaf(iv.z * h[2], h[2], iv.w * h[3] * h[3])));
+    rr += (double)srr; rz += (double)srz;
+    if (a.cg.by) {                               // restriction rc = P^T r: sum of the new residual over each aggregate
+      racc += (rn[0] + rn[1]) + (rn[2] + rn[3]);
+      if ((y & (a.cg.by - 1)) == 0 || y == H - 2) {          // (y-1) is the last row of its aggregate row
+        float v = racc;                                      // 8 (or 16) lanes share one aggregate column
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (a.cg.bx_shift == 6) v += __shfl_xor_sync(0xffffffffu, v, 8);
+        if ((lane & ((1 << (a.cg.bx_shift - 2)) - 1)) == 0 && valid)
+          a.rc[(size_t)b * a.cg.nc + (size_t)((y - 1) >> a.cg.by_shift) * a.cg.nbx + (x >> a.cg.bx_shift)] = v;
+        racc = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hp[j] = h[j];
+    cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
+    issue(y + RD);
+  }
+  cp_async_wait<0>();
+  rr_out = warp_sum(rr); rz_out = warp_sum(rz);
+}
+
+// F_COARSE: one warp solves Ac zc = rc for one image and returns rc . zc.
+// Two triangular sweeps in saxpy form with a ROTATING REGISTER WINDOW: lane l holds the vector element
+// j == l (mod 32) of the 32-wide window that starts at the current row, so a step is
+//   broadcast the head element (one shuffle)  ->  every lane: w -= F[i][d] * head  (one FMA)
+// and the dependent chain per row is shuffle + FMA (~30 cycles) instead of a shared-memory round trip.
+// Needs band width kd <= 31.  The factor rows are pre-scaled (F[i][d] = L[.]/L[i,i], F[i][0] = 1/L[i,i])
+// and staged in shared memory by cp.async tiles; the vector lives in shared memory only as input/output.
+__device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane) {
+  const CoarseGeom g = a.cg;
+  const int n = g.nc, kd1 = g.kd1;
+  float* ysb = reinterpret_cast<float*>(ringmem);                // 32 zeros | vector [n] | zeros up to kCoarseMaxN + 64
+  float* ys = ysb + 32;
+  float* tiles = ysb + kCoarseMaxN + 96;                         // 2 x [32][32]
+  const float* rc = a.rc + (size_t)b * n;
+  float* zc = a.zc + (size_t)b * n;
+  const float* U = a.Ur + (size_t)b * n * kd1;
+  const float* L = a.Lr + (size_t)b * n * kd1;
+  const unsigned full = 0xffffffffu;
+  const int ntile = (n + kCoarseTileRows - 1) / kCoarseTileRows;
+  auto issue_tile = [&](const float* F, int t, float* buf) {
+    if (t >= 0 && t < ntile) {
+      const int r0 = t * kCoarseTileRows, rows = min(kCoarseTileRows, n - r0);
+      const int chunks = rows * kd1 / 4;                         // rows past n are zero-filled (src-size 0)
+      for (int c = lane; c < kCoarseTileRows * 32 / 4; c += 32)
+        cp_async16(buf + 4 * c, F + (size_t)r0 * kd1 + 4 * (c < chunks ? c : 0), c < chunks);
+    }
+    cp_async_commit();
+  };
+  ysb[lane] = 0.f;
+  for (int i = lane; i < n + 64; i += 32) ys[i] = (i < n) ? __ldcg(rc + i) : 0.f;
+  __syncwarp();
+  // Both sweeps advance in blocks of 32 rows (= one factor tile).  Inside a block lane l admits exactly one
+  // element (prefetched into `nx` before the block) and retires exactly one (kept in `out`, stored after the
+  // block), so the inner step has no shared-memory store and its dependent chain is shuffle -> FMA -> select.
+  // ---- forward: L y = rc, column-oriented (row i of Ur = scaled column i of L) -----------------------
+  issue_tile(U, 0, tiles);
+  float w = ys[lane];                                            // window [0, 32): lane l holds element l
+  for (int t = 0; t < ntile; ++t) {
+    issue_tile(U, t + 1, tiles + ((t + 1) & 1) * kCoarseTileRows * 32);
+    const int i0 = t * 32;
+    const float nx = ys[i0 + 32 + lane];                         // element this lane admits during the block
+    float out = 0.f;
+    cp_async_wait<1>();
+    __syncwarp();
+    const float* T = tiles + (t & 1) * kCoarseTileRows * 32;
+#pragma unroll 8
+    for (int hl = 0; hl < 32; ++hl) {                            // row i = i0 + hl; its element sits on lane hl
+      const float* row = T + hl * 32;
+      const int d = (lane - hl) & 31;                            // this lane holds element i + d
+      const float f = row[d];                                    // zero padded beyond the band
+      const float r0 = row[0];
+      const float head = __shfl_sync(full, w, hl);               // element i, fully updated
+      const float wn = fmaf(-f, head, w);
+      w = (d == 0) ? nx : wn;                                    // retire element i, admit element i + 32
+      out = (d == 0) ? head * r0 : out;                          // y_i
+    }
+    if (i0 + lane < n) ys[i0 + lane] = out;
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  // ---- backward: L^T x = y, row-oriented (row i of Lr) ----------------------------------------------------
+  issue_tile(L, ntile - 1, tiles);
+  {
+    const int top = ntile * 32 - 1;                              // window (top-32, top]: lane l holds element j == l (mod 32)
+    const int j = top - ((top - lane) & 31);
+    w = ys[j];                                                   // ys is zero padded past n
+  }
+  for (int k = 0; k < ntile; ++k) {
+    const int t = ntile - 1 - k;
+    issue_tile(L, t - 1, tiles + ((k + 1) & 1) * kCoarseTileRows * 32);
+    const int i0 = t * 32;
+    const float nx = ysb[i0 + lane];                             // = ys[i0 - 32 + lane]: element admitted during the block
+    float out = 0.f;
+    cp_async_wait<1>();
+    __syncwarp();
+    const float* T = tiles + (k & 1) * kCoarseTileRows * 32;
+#pragma unroll 8
+    for (int hl = 31; hl >= 0; --hl) {                           // row i = i0 + hl
+      const float* row = T + hl * 32;
+      const int d = (hl - lane) & 31;                            // this lane holds element i - d
+      const float f = row[d];
+      const float r0 = row[0];
+      const float head = __shfl_sync(full, w, hl);               // element i with all later rows eliminated
+      const float xi = head * r0;                                // x_i = head / L[i,i]   (0 for padding rows: r0 = 0)
+      const float wn = fmaf(-f, xi, w);
+      w = (d == 0) ? nx : wn;                                    // retire element i, admit element i - 32
+      out = (d == 0) ? xi : out;
+    }
+    if (i0 + lane < n) ys[i0 + lane] = out;
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  double acc = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const float v = ys[i];
+    zc[i] = v;
+    acc += (double)v * (double)__ldcg(rc + i);
+  }
+  __syncwarp();
+  return warp_sum(acc);
+}
+
+// ---- ready queue (multi-producer / multi-consumer ticket ring in global memory) -------------------
+// Only the strips of ONE image have to meet between phases, so the fused kernel has no grid-wide
+// barrier: the last-arriving strip of an image publishes the image's next phase as nstrip4 new
+// tasks, and any idle warp pops the next task.  Work-conserving: no SM waits for a slower SM.
+constexpr unsigned kPoison = 0xffffffffu;
+
+// pushes n entries: payload0, payload0+stride, ...  (one lane; one reservation, one release fence)
+__device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, unsigned payload0, unsigned stride, unsigned n) {
+  const unsigned long long k0 = atomicAdd(a.qtail, (unsigned long long)n);
+  __threadfence();                                          // release: state written before the stamps
+  for (unsigned i = 0; i < n; ++i) {
+    const unsigned long long k = k0 + i;
+    volatile unsigned long long* slot = a.qslots + (k % a.qcap);
+    *slot = ((k + 1ull) << 32) | (unsigned long long)(payload0 + i * stride);
+  }
+}
+
+__device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {        // whole warp
+  // lane 0 takes the ticket; then ALL lanes poll the slot together (a warp with 31 lanes parked at a
+  // convergence barrier while one lane spins was measured to slow the other warps of the SM ~4x)
+  unsigned long long k = 0;
+  if (lane == 0) k = atomicAdd(a.qhead, 1ull);
+  k = __shfl_sync(0xffffffffu, k, 0);
+  volatile unsigned long long* slot = a.qslots + (k % a.qcap);
+  const unsigned stamp = (unsigned)(k + 1ull);
+  unsigned long long v;
+  unsigned ns = 32;
+  while ((unsigned)((v = *slot) >> 32) != stamp) { __nanosleep(ns); if (ns < 512) ns *= 2; }
+  __threadfence();                                          // acquire
+  return (unsigned)(v & 0xffffffffull);
+}
+
+// slots 0..T-1 hold the first phase (RESID) of every image, image index fastest
+__global__ void cm_init_queue_kernel(unsigned long long* __restrict__ slots, unsigned cap, int B, int nstrip4,
+                                     unsigned long long* __restrict__ head, unsigned long long* __restrict__ tail) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned T = (unsigned)(B * nstrip4);
+  if (i == 0) { *head = 0ull; *tail = (unsigned long long)T; }
+  if (i >= cap) return;
+  unsigned long long v = 0ull;
+  if (i < T) {
+    const unsigned b = i % (unsigned)B, ti = i / (unsigned)B;
+    v = ((unsigned long long)(i + 1u) << 32) | (unsigned long long)(b * (unsigned)nstrip4 + ti);
+  }
+  slots[i] = v;
+}
+
+// fp64 residual r = b - A x64 over one 128-column strip (rare: once per refinement round)
+__device__ __forceinline__ double resid_strip(const PcgArgs<float>& a, int b, int strip, int lane) {
+  const int x0 = strip * kStrip4, xe = min(x0 + kStrip4, a.W);
+  double s = 0.0;
+  for (int xb = x0; xb < xe; xb += kStripCols)
+    for (int rbk = 0; rbk < a.nrb; ++rbk)
+      s += stencil_task<float, true>(a, b, xb, min(kStripCols, xe - xb), rbk, lane, 0.f, true);
+  return s;
+}
+
+// AW = active warps per CTA (8 or 4): fewer active warps own deeper rings.
+// RECOMP = F_UP recomputes the edge weights from the `a` plane (bandwidth-bound regime) or reads them.
+template <int AW, bool RECOMP>
+__global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> a) {
+  constexpr size_t kWarpRing = kFusedSmem / AW;                   // ring bytes per active warp
+  constexpr int R = (int)(kWarpRing / (RECOMP ? sizeof(RingU) : sizeof(RingUP)));   // F_UP ring depth in rows
+  constexpr int RD = (int)(kWarpRing / sizeof(RingD));                              // F_DOWN ring depth
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= AW || warp >= a.wpb) return;                        // no block-wide barrier anywhere below
+  unsigned char* ringmem = smem_raw + (size_t)warp * kWarpRing;
+  const int B = a.B, H = a.H, W = a.W;
+  const int per = a.nstrip4;
+  const unsigned nworkers = gridDim.x * (unsigned)a.wpb;
+
+  auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  unsigned long long t_wait = 0, t_mode[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_arr = 0;
+  unsigned n_mode[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (;;) {
+    const unsigned long long tq0 = a.debug ? now() : 0ull;
+    const unsigned payload = q_pop(a, lane);
+    const unsigned long long tq1 = a.debug ? now() : 0ull;
+    t_wait += tq1 - tq0;
+    if (payload == kPoison) break;
+    const int b = (int)(payload / (unsigned)per), ti = (int)(payload % (unsigned)per);
+    ImgState* st = a.st + b;
+    const int mode = (int)(__ldcg(&st->fword) & 0xffffffffull);
+    double s0 = 0.0, s1 = 0.0;
+    if (mode == F_UP) {
+      if constexpr (RECOMP)
+        s0 = up_task<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+      else
+        s0 = up_task_planes<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+    } else if (mode == F_DOWN) {
+      if (__ldcg(&st->epend))
+        down_task<RD, 2>(a, ringmem, b, ti, lane, (float)__ldcg(&st->alpha), (float)__ldcg(&st->alpha_prev), __ldcg(&st->pcur), s0, s1);
+      else
+        down_task<RD, 1>(a, ringmem, b, ti, lane, (float)__ldcg(&st->alpha), 0.f, __ldcg(&st->pcur), s0, s1);
+    } else if (mode == F_PRECOND) {
+      down_task<RD, 0>(a, ringmem, b, ti, lane, 0.f, 0.f, 0, s0, s1);
+    } else if (mode == F_RESID) {
+      s0 = resid_strip(a, b, ti, lane);
+    } else if (mode == F_COARSE) {
+      s0 = coarse_task(a, ringmem, b, lane);
+    } else {
+      const int x = ti * kStrip4 + 4 * lane;
+      if (x < W) {
+        const size_t base = (size_t)b * H * W + x;
+        if (mode == F_FOLD) {
+          // x64 += e (+ the e-update of the last iteration if it is still pending)
+          const float ap = __ldcg(&st->epend) ? (float)__ldcg(&st->alpha_prev) : 0.f;
+          const float* Pl = (__ldcg(&st->pcur) ? a.p2 : a.p);
+#pragma unroll 4
+          for (int y = 1; y <= H - 2; ++y) {
+            const size_t o = base + (size_t)y * W;
+            float4 e = __ldcg(reinterpret_cast<const float4*>(a.e + o));
+            if (ap != 0.f) {
+              const float4 pv = __ldcg(reinterpret_cast<const float4*>(Pl + o));
+              e.x = fmaf(ap, pv.x, e.x); e.y = fmaf(ap, pv.y, e.y); e.z = fmaf(ap, pv.z, e.z); e.w = fmaf(ap, pv.w, e.w);
+            }
+            double2* xp = reinterpret_cast<double2*>(a.x64 + o);
+            double2 v0 = __ldcg(xp), v1 = __ldcg(xp + 1);
+            v0.x += (double)e.x; v0.y += (double)e.y; v1.x += (double)e.z; v1.y += (double)e.w;
+            xp[0] = v0; xp[1] = v1;
+          }
+        } else {   // F_FINAL
+#pragma unroll 4
+          for (int y = 0; y < H; ++y) {
+            const size_t o = base + (size_t)y * W;
+            const double2* xp = reinterpret_cast<const double2*>(a.x64 + o);
+            const double2 v0 = __ldcg(xp), v1 = __ldcg(xp + 1);
+            *reinterpret_cast<float4*>(a.cm + o) = make_float4((float)v0.x, (float)v0.y, (float)v1.x, (float)v1.y);
+          }
+        }
+      }
+    }
+    const unsigned long long tq2 = a.debug ? now() : 0ull;
+    if (a.debug) { t_mode[mode] += tq2 - tq1; n_mode[mode]++; }
+    // ---- arrival: every lane publishes its own stores, then lane 0 takes a ticket -------------------
+    double* part = a.part + (size_t)b * a.pmax * 2;
+    if (lane == 0) { part[2 * ti] = s0; part[2 * ti + 1] = s1; }
+    __threadfence();
+    __syncwarp();
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(&st->cnt1, 1u);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (a.debug) t_arr += now() - tq2;
+    const int ntask = (mode == F_COARSE) ? 1 : per;               // F_COARSE is a single task per image
+    if (tk != (unsigned)ntask - 1) continue;
+    // ---- last strip of this image and phase: reduce, advance the state, publish the next phase ------
+    __threadfence();
+    reduce_parts(part, ntask, lane, s0, s1);
+    if (lane != 0) continue;
+    st->cnt1 = 0;
+    int next = F_DONE;
+    if (mode == F_UP) {
+      if (s0 > 0.0) st->alpha = __ldcg(&st->rz) / s0;
+      else { st->alpha = 0.0; st->rr_target = 1e300; }          // breakdown: leave the inner solve
+      st->pcur = __ldcg(&st->pcur) ^ 1;                           // F_UP wrote the other p plane
+      next = F_DOWN;
+    } else if (mode == F_DOWN) {
+      const double rz_old = __ldcg(&st->rz);
+      const int it = __ldcg(&st->iters) + 1;
+      if (__ldcg(&st->epend)) st->epend = 0;                       // this DOWN applied both pending updates
+      else { st->epend = 1; st->alpha_prev = __ldcg(&st->alpha); }  // this DOWN deferred its own update
+      st->iters = it; st->rr_rec = s0;
+      if (s0 <= __ldcg(&st->rr_target) || it >= a.maxiter || !(s1 > 0.0)) {
+        next = F_FOLD;
+      } else if (a.cg.by) {                                        // r.z is completed by the coarse solve
+        st->rz_line = s1; st->fresh = 0;
+        next = F_COARSE;
+      } else {
+        st->rz = s1; st->first = 0;
+        st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
+        next = F_UP;
+      }
+    } else if (mode == F_PRECOND) {
+      // Every refinement round restarts CG (p = z).  Keeping p across rounds ("residual replacement") was
+      // measured to need 2300-3700 instead of 1600 iterations here and was dropped.
+      st->epend = 0;                                               // F_FOLD consumed any pending update, e = 0 now
+      if (a.cg.by) {
+        st->rz_line = s1; st->fresh = 1;
+        next = (s1 > 0.0) ? F_COARSE : F_FINAL;
+      } else {
+        st->rz = s1; st->first = 1; st->beta = 0.0;
+        next = (s1 > 0.0) ? F_UP : F_FINAL;
+      }
+    } else if (mode == F_COARSE) {
+      // z = T^-1 r + P Ac^-1 P^T r  =>  r.z = sum ip h^2 (line part, from DOWN) + rc.zc (this task)
+      const double rz_new = __ldcg(&st->rz_line) + s0, rz_old = __ldcg(&st->rz);
+      if (__ldcg(&st->fresh)) { st->rz = rz_new; st->first = 1; st->beta = 0.0; next = F_UP; }
+      else if (rz_new > 0.0 && rz_old > 0.0) { st->beta = rz_new / rz_old; st->rz = rz_new; st->first = 0; next = F_UP; }
+      else next = F_FOLD;
+    } else if (mode == F_RESID) {
+      next = after_true_residual(st, s0, a.rtol2, a.inner_red2, a.maxiter) ? F_FINAL : F_PRECOND;
+    } else if (mode == F_FOLD) {
+      next = F_RESID; st->outer = __ldcg(&st->outer) + 1;
+    } else {   // F_FINAL
+      const double bb = __ldcg(&st->bb);
+      if (a.iters_out) a.iters_out[b] = __ldcg(&st->iters);
+      if (a.relres_out) a.relres_out[b] = (bb > 0.0) ? sqrt(__ldcg(&st->rr_true) / bb) : 0.0;
+      next = F_DONE;
+    }
+    st->fword = (unsigned long long)next;
+    if (next == F_DONE) {
+      __threadfence();
+      if (atomicAdd(a.done, 1u) == (unsigned)B - 1u) q_push_n(a, kPoison, 0u, nworkers);   // release every worker
+    } else {
+      q_push_n(a, (unsigned)(b * per), 1u, (next == F_COARSE) ? 1u : (unsigned)per);
+    }
+  }
+  if ((a.debug & 1) && lane == 0 && warp == 0 && (blockIdx.x % 74) == 0)
+    printf("[pcg queue dbg] block %d: wait %.1f us | UP %u x %.1f us | DOWN %u x %.1f us | PRECOND %u x %.1f | RESID %u x %.1f | COARSE %u x %.1f | arrive %.1f us total\n",
+           blockIdx.x, t_wait * 1e-3, n_mode[F_UP], n_mode[F_UP] ? t_mode[F_UP] * 1e-3 / n_mode[F_UP] : 0.0, n_mode[F_DOWN],
+           n_mode[F_DOWN] ? t_mode[F_DOWN] * 1e-3 / n_mode[F_DOWN] : 0.0, n_mode[F_PRECOND],
+           n_mode[F_PRECOND] ? t_mode[F_PRECOND] * 1e-3 / n_mode[F_PRECOND] : 0.0, n_mode[F_RESID],
+           n_mode[F_RESID] ? t_mode[F_RESID] * 1e-3 / n_mode[F_RESID] : 0.0, n_mode[F_COARSE],
+           n_mode[F_COARSE] ? t_mode[F_COARSE] * 1e-3 / n_mode[F_COARSE] : 0.0, t_arr * 1e-3);
+}
+
+}  // namespace usaug

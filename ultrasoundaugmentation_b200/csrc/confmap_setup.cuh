@@ -1,0 +1,203 @@
+// Setup kernels of the confidence map: normalisation, attenuation, edge
+// weights, column-line factors, initial state.  Included by confmap_pcg.cu.
+#pragma once
+#include "confmap_types.cuh"
+
+namespace usaug {
+
+// ---------------------------------------------------------------------------------------------
+// setup kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void cm_depth_kernel(float* __restrict__ depth, int H, float alpha) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y < H) depth[y] = (float)(1.0 - exp(-(double)alpha * (double)y / (double)max(H - 1, 1)));
+}
+
+__device__ __forceinline__ void block_minmax(float& mn, float& mx) {
+  __shared__ float s_mn[8], s_mx[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mn = warp_min(mn); mx = warp_max(mx);
+  __syncthreads();
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  mn = s_mn[0]; mx = s_mx[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+}
+
+__global__ void __launch_bounds__(256) cm_minmax_kernel(const float* __restrict__ img, int N,
+                                                        float* __restrict__ mm) {
+  const int b = blockIdx.y, c = blockIdx.x;
+  const float* I = img + (size_t)b * N;
+  const int lo = (int)((long long)N * c / kChunks), hi = (int)((long long)N * (c + 1) / kChunks);
+  float mn = 3.0e38f, mx = -3.0e38f;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) { const float v = I[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  block_minmax(mn, mx);
+  if (threadIdx.x == 0) { mm[((size_t)b * kChunks + c) * 2] = mn; mm[((size_t)b * kChunks + c) * 2 + 1] = mx; }
+}
+
+__device__ __forceinline__ void read_mm(const float* __restrict__ mm, int b, float& mn, float& den) {
+  float lo = 3.0e38f, hi = -3.0e38f;
+#pragma unroll 8
+  for (int c = 0; c < kChunks; ++c) {
+    lo = fminf(lo, mm[((size_t)b * kChunks + c) * 2]);
+    hi = fmaxf(hi, mm[((size_t)b * kChunks + c) * 2 + 1]);
+  }
+  mn = lo;
+  den = __fadd_rn(__fsub_rn(hi, lo), kEps);
+}
+
+// attenuated, normalised intensity a = ((I - mn) / den) * depth[y]   (A.3 steps 1-2)
+__device__ __forceinline__ float atten(const float* __restrict__ I, const float* __restrict__ depth,
+                                       int y, int x, int W, float mn, float den) {
+  return __fmul_rn(__fdiv_rn(__fsub_rn(I[(size_t)y * W + x], mn), den), depth[y]);
+}
+
+__global__ void __launch_bounds__(256) cm_delta_kernel(const float* __restrict__ img, int H, int W,
+                                                       const float* __restrict__ depth,
+                                                       const float* __restrict__ mm1,
+                                                       float* __restrict__ mm2) {
+  const int b = blockIdx.y, c = blockIdx.x, N = H * W;
+  const float* I = img + (size_t)b * N;
+  float mn1, den1;
+  read_mm(mm1, b, mn1, den1);
+  const int lo = (int)((long long)N * c / kChunks), hi = (int)((long long)N * (c + 1) / kChunks);
+  float mn = 3.0e38f, mx = -3.0e38f;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    const int y = i / W, x = i - y * W;
+    const float a0 = atten(I, depth, y, x, W, mn1, den1);
+    if (x < W - 1) { const float d = fabsf(__fsub_rn(a0, atten(I, depth, y, x + 1, W, mn1, den1))); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+    if (y < H - 1) {
+      { const float d = fabsf(__fsub_rn(a0, atten(I, depth, y + 1, x, W, mn1, den1))); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+      if (x < W - 1) { const float d = fabsf(__fsub_rn(a0, atten(I, depth, y + 1, x + 1, W, mn1, den1))); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+      if (x > 0) { const float d = fabsf(__fsub_rn(a0, atten(I, depth, y + 1, x - 1, W, mn1, den1))); mn = fminf(mn, d); mx = fmaxf(mx, d); }
+    }
+  }
+  block_minmax(mn, mx);
+  if (threadIdx.x == 0) { mm2[((size_t)b * kChunks + c) * 2] = mn; mm2[((size_t)b * kChunks + c) * 2 + 1] = mx; }
+}
+
+// Edge weight w = exp(-beta * ((|a0 - a1| - mn) / den + pen)) + 1e-6  (A.3 steps 3-5), evaluated as
+//   ex2(k1 * |a0 - a1| + k0) + 1e-6,   k1 = -beta*log2(e)/den,   k0 = beta*log2(e)*(mn/den - pen)
+// with per-image constants (k1, k0 per edge type) formed in fp64.  ONE function for every kernel (weight
+// planes, line factors, fp64 residual, and the fused UP phase that recomputes the weights from the `a`
+// plane instead of reading four planes), so the matrix is bit-identical wherever it is applied.
+// Relative deviation from the oracle's exp(): <= ~5e-6 where w > 1e-6 matters (|arg| <= 20).
+__device__ __forceinline__ float edge_w_fast(float a0, float a1, float k1, float k0) {
+  float e;
+  const float arg = fmaf(fabsf(__fsub_rn(a0, a1)), k1, k0);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+  return __fadd_rn(e, kFloor);
+}
+
+// wk[b] = {k1, k0_vertical, k0_horizontal, k0_diagonal}
+__global__ void cm_wconst_kernel(int B, const float* __restrict__ mm2, float beta, float gamma,
+                                 float4* __restrict__ wk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float mn2, den2;
+  read_mm(mm2, b, mn2, den2);
+  const double L2E = 1.4426950408889634074, bd = (double)beta, dn = (double)den2, m = (double)mn2 / dn;
+  const double pen_h = (double)gamma, pen_d = (double)__fmul_rn(kSqrt2, gamma);
+  wk[b] = make_float4((float)(-bd * L2E / dn), (float)(bd * L2E * m), (float)(bd * L2E * (m - pen_h)),
+                      (float)(bd * L2E * (m - pen_d)));
+}
+
+__global__ void __launch_bounds__(256) cm_weights_kernel(
+    const float* __restrict__ img, int H, int W, const float* __restrict__ depth,
+    const float* __restrict__ mm1, const float4* __restrict__ wk, float* __restrict__ aplane,
+    float* __restrict__ wS, float* __restrict__ wE, float* __restrict__ wSE, float* __restrict__ wSW) {
+  const int b = blockIdx.y, N = H * W;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const float* I = img + (size_t)b * N;
+  float mn1, den1;
+  read_mm(mm1, b, mn1, den1);
+  const float4 k = wk[b];
+  const int y = i / W, x = i - y * W;
+  const float a0 = atten(I, depth, y, x, W, mn1, den1);
+  float s = 0.f, e = 0.f, se = 0.f, sw = 0.f;
+  if (x < W - 1) e = edge_w_fast(a0, atten(I, depth, y, x + 1, W, mn1, den1), k.x, k.z);
+  if (y < H - 1) {
+    s = edge_w_fast(a0, atten(I, depth, y + 1, x, W, mn1, den1), k.x, k.y);
+    if (x < W - 1) se = edge_w_fast(a0, atten(I, depth, y + 1, x + 1, W, mn1, den1), k.x, k.w);
+    if (x > 0) sw = edge_w_fast(a0, atten(I, depth, y + 1, x - 1, W, mn1, den1), k.x, k.w);
+  }
+  const size_t o = (size_t)b * N + i;
+  aplane[o] = a0;
+  wS[o] = s; wE[o] = e; wSE[o] = se; wSW[o] = sw;
+}
+
+// Column-line factorisation T = L D L^T (T = vertical couplings + full diagonal of L_UU):
+//   piv[y] = diag[y] - wS[y-1]^2 / piv[y-1],  ip = 1/piv,  c[y] = wS[y] * ip[y].
+// Jacobi: ip = 1/diag, c = 0.  Also writes the initial guess into x64 (seed rows 1 / 0) and the
+// per-block partial of ||b||^2.
+__global__ void __launch_bounds__(128) cm_factor_kernel(
+    int H, int W, const float* __restrict__ wS, const float* __restrict__ wE,
+    const float* __restrict__ wSE, const float* __restrict__ wSW, int precond, int zero_guess,
+    float* __restrict__ ip, float* __restrict__ c, uint32_t* __restrict__ ipc, double* __restrict__ x64,
+    double* __restrict__ bbpart) {
+  __shared__ double s_bb[4];
+  const int b = blockIdx.y;
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const size_t base = (size_t)b * H * W;
+  double bb = 0.0;
+  if (x < W) {
+    const float* S = wS + base; const float* E = wE + base;
+    const float* SE = wSE + base; const float* SW = wSW + base;
+    {
+      double bv = (double)S[x];
+      if (x > 0) bv += (double)SE[x - 1];
+      if (x < W - 1) bv += (double)SW[x + 1];
+      bb = bv * bv;
+    }
+    x64[base + x] = 1.0;
+    x64[base + (size_t)(H - 1) * W + x] = 0.0;
+    ip[base + x] = 0.f; c[base + x] = 0.f; ipc[base + x] = 0u;
+    ip[base + (size_t)(H - 1) * W + x] = 0.f; c[base + (size_t)(H - 1) * W + x] = 0.f;
+    ipc[base + (size_t)(H - 1) * W + x] = 0u;
+    double ip_prev = 0.0;   // row 0 is a seed: not part of T
+    float s_prev = S[x];
+    for (int y = 1; y <= H - 2; ++y) {
+      const size_t o = (size_t)y * W + x;
+      const float s = S[o];
+      double dg = (double)s + (double)s_prev + (double)E[o] + (double)SE[o] + (double)SW[o];
+      if (x > 0) dg += (double)E[o - 1] + (double)SE[o - W - 1];
+      if (x < W - 1) dg += (double)SW[o - W + 1];
+      double piv = dg;
+      if (precond == USAUG_PRECOND_LINE && y > 1) piv -= (double)s_prev * (double)s_prev * ip_prev;
+      const double ipv = 1.0 / piv;
+      const float ipf = (float)ipv;
+      const float cf = (precond == USAUG_PRECOND_LINE && y < H - 2) ? (float)((double)s * ipv) : 0.0f;
+      ip[base + o] = ipf;
+      c[base + o] = cf;
+      // fused kernel: both factors as bf16 in one word (low = ip, high = c).  M = L D L^T stays SPD for
+      // any positive ip and any c, and the iteration count is unchanged.
+      ipc[base + o] = bf16_bits(ipf) | (bf16_bits(cf) << 16);
+      x64[base + o] = zero_guess ? 0.0 : 1.0 - (double)y / (double)(H - 1);
+      // keep the recurrence consistent with the ROUNDED factors the sweeps will use
+      ip_prev = (double)(float)ipv;
+      s_prev = s;
+    }
+  }
+  bb = warp_sum(bb);
+  if ((threadIdx.x & 31) == 0) s_bb[threadIdx.x >> 5] = bb;
+  __syncthreads();
+  if (threadIdx.x == 0) bbpart[(size_t)b * gridDim.x + blockIdx.x] = s_bb[0] + s_bb[1] + s_bb[2] + s_bb[3];
+}
+
+__global__ void cm_init_state_kernel(int B, int nblk, const double* __restrict__ bbpart,
+                                     ImgState* __restrict__ st, unsigned* __restrict__ done) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *done = 0u;
+  if (b >= B) return;
+  double bb = 0.0;
+  for (int i = 0; i < nblk; ++i) bb += bbpart[(size_t)b * nblk + i];
+  ImgState s;
+  s.mode = M_RESID; s.iters = 0; s.first = 1; s.outer = 0;
+  s.rz = 0; s.alpha = 0; s.beta = 0; s.bb = bb; s.rr_true = 0; s.rr_prev = 1e300; s.rr_target = 0; s.rr_rec = 0;
+  s.cnt1 = 0; s.cnt2 = 0; s.fword = 0ull; s.pcur = 0; s.poor = 0; s.inner2 = 0.0; s.alpha_prev = 0.0; s.epend = 0; s.fresh = 0; s.rz_line = 0.0;
+  st[b] = s;
+}
+
+}  // namespace usaug

@@ -92,7 +92,7 @@ def fused_tgc_deform(image, label, d, tgc, taps):
 
 def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=20000,
                    precond="line", fp64_vectors=False, zero_guess=False, max_wave=None,
-                   return_info=False, timing: list | None = None, debug_timing=False, legacy_kernel=False, continue_cg=False, coarse=True):
+                   return_info=False, timing: list | None = None, debug_timing=False, legacy_kernel=False, coarse=True):
     """K2 (A.3).  image f32 [B,H,W] -> cm f32 [B,H,W] (+ iters int32 [B], true relres f64 [B]).
 
     The batch is solved in waves of at most ``max_wave`` images (workspace ~56 B/pixel/image
@@ -112,7 +112,6 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
     flags = (_ffi.CM_FP64_VECTORS if fp64_vectors else 0) | (_ffi.CM_ZERO_GUESS if zero_guess else 0)
     flags |= 4 if debug_timing else 0
     flags |= 8 if legacy_kernel else 0     # A/B testing: two-slot kernel instead of the fused fp32 kernel
-    flags |= 16 if continue_cg else 0      # experimental: residual replacement instead of restart
     flags |= 0 if coarse else 32           # A/B testing: without the coarse-grid correction
     with torch.cuda.device(dev):
         per_img = lib.usaug_confmap_workspace_bytes(1, H, W, pc, flags)
