@@ -557,51 +557,131 @@ __device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned 
   return warp_sum(acc);
 }
 
-// ---- ready queue (multi-producer / multi-consumer ticket ring in global memory) -------------------
+// ---- ready queue (two multi-producer / multi-consumer rings in global memory) ----------------------
 // Only the strips of ONE image have to meet between phases, so the fused kernel has no grid-wide
 // barrier: the last-arriving strip of an image publishes the image's next phase as nstrip4 new
 // tasks, and any idle warp pops the next task.  Work-conserving: no SM waits for a slower SM.
-constexpr unsigned kPoison = 0xffffffffu;
+//
+// Ring 1 is served before ring 0.  An image publishes into ring 1 while its predicted remaining
+// iteration count is above the mean over the running images (update_priority), so slowly converging
+// images advance at chain-latency speed while the memory system is kept busy by the rest, and all images
+// finish at about the same time instead of leaving a latency-bound tail of stragglers.
+// Slot k of a ring holds ((k + 1) << 32 | payload).  qavail[ring] counts entries completely written and not
+// yet claimed: a consumer decrements it and, only if it was positive, takes ticket k = head++ -- fetch-adds
+// throughout, so claims pipeline in L2 (a CAS on the head serialises the pops at one per round trip:
+// measured 1 us per task, 3.5x slower than this at 512 images).
+constexpr unsigned kNoTask = 0xffffffffu;
+constexpr unsigned kIdleSleepMaxNs = 2048;
+constexpr unsigned long long kWatchdogNs = 4000000000ull;   // an idle worker gives up after 4 s without any task
 
-// pushes n entries: payload0, payload0+stride, ...  (one lane; one reservation, one release fence)
-__device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, unsigned payload0, unsigned stride, unsigned n) {
-  const unsigned long long k0 = atomicAdd(a.qtail, (unsigned long long)n);
+// pushes n entries: payload0, payload0+stride, ...  (one lane)
+__device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsigned payload0, unsigned stride, unsigned n) {
+  const unsigned long long k0 = atomicAdd(a.qtail + ring, (unsigned long long)n);
   __threadfence();                                          // release: state written before the stamps
+  unsigned long long* slots = a.qslots + (size_t)ring * a.qcap;
   for (unsigned i = 0; i < n; ++i) {
     const unsigned long long k = k0 + i;
-    volatile unsigned long long* slot = a.qslots + (k % a.qcap);
+    volatile unsigned long long* slot = slots + (k % a.qcap);
     *slot = ((k + 1ull) << 32) | (unsigned long long)(payload0 + i * stride);
+  }
+  __threadfence();
+  atomicAdd(a.qavail + ring, (int)n);
+}
+
+// Whole warp.  Returns the payload of the next task, or kNoTask when every image is finished.
+// ALL lanes execute the polling loads (a warp with 31 lanes parked at a convergence barrier while one lane
+// spins was measured to slow the other warps of the SM ~4x); lane 0's values are broadcast and lane 0 claims.
+__device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {
+  unsigned ns = 32;
+  unsigned long long t_idle = 0;
+  for (;;) {
+    int av0, av1;
+    asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(av0), "=r"(av1) : "l"(a.qavail) : "memory");
+    int ring = (av1 > 0) ? 1 : (av0 > 0) ? 0 : -1;
+    ring = __shfl_sync(0xffffffffu, ring, 0);
+    if (ring >= 0) {
+      unsigned long long k = ~0ull;
+      if (lane == 0) {
+        if (atomicAdd(a.qavail + ring, -1) > 0) k = atomicAdd(a.qhead + ring, 1ull);
+        else atomicAdd(a.qavail + ring, 1);                  // lost the race for the last entries: give it back
+      }
+      k = __shfl_sync(0xffffffffu, k, 0);
+      if (k == ~0ull) continue;
+      // the entry is reserved for this warp; its producer may still be writing it (another producer's count came first)
+      volatile unsigned long long* slot = a.qslots + (size_t)ring * a.qcap + (k % a.qcap);
+      const unsigned stamp = (unsigned)(k + 1ull);
+      unsigned long long v;
+      unsigned spins = 0;
+      while ((unsigned)((v = *slot) >> 32) != stamp) {
+        __nanosleep(32);
+        if (++spins > (1u << 26)) { if (lane == 0) { atomicExch(a.done + 1, 1u); atomicMax(a.done, (unsigned)a.B); } return kNoTask; }
+      }
+      __threadfence();                                       // acquire
+      return (unsigned)(v & 0xffffffffull);
+    }
+    if (__ldcg(a.done) >= (unsigned)a.B) return kNoTask;
+    __nanosleep(ns);
+    if (ns < kIdleSleepMaxNs) { ns *= 2; continue; }
+    // watchdog: a scheduling bug must not hang the device.  Flag it, mark unfinished images, release everybody.
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t_idle == 0) t_idle = t;
+    else if (t - t_idle > kWatchdogNs) {
+      if (lane == 0 && atomicExch(a.done + 1, 1u) == 0u) {
+        for (int b = 0; b < a.B; ++b)
+          if ((int)(__ldcg(&a.st[b].fword) & 0xffffffffull) != F_DONE) {
+            if (a.iters_out) a.iters_out[b] = -1;
+            if (a.relres_out) a.relres_out[b] = __longlong_as_double(0x7ff8000000000000ll);
+          }
+        __threadfence();
+        atomicMax(a.done, (unsigned)a.B);
+      }
+      __syncwarp();
+      return kNoTask;
+    }
   }
 }
 
-__device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {        // whole warp
-  // lane 0 takes the ticket; then ALL lanes poll the slot together (a warp with 31 lanes parked at a
-  // convergence barrier while one lane spins was measured to slow the other warps of the SM ~4x)
-  unsigned long long k = 0;
-  if (lane == 0) k = atomicAdd(a.qhead, 1ull);
-  k = __shfl_sync(0xffffffffu, k, 0);
-  volatile unsigned long long* slot = a.qslots + (k % a.qcap);
-  const unsigned stamp = (unsigned)(k + 1ull);
-  unsigned long long v;
-  unsigned ns = 32;
-  while ((unsigned)((v = *slot) >> 32) != stamp) { __nanosleep(ns); if (ns < 512) ns *= 2; }
-  __threadfence();                                          // acquire
-  return (unsigned)(v & 0xffffffffull);
-}
-
-// slots 0..T-1 hold the first phase (RESID) of every image, image index fastest
+// ring 0 starts with the first phase (RESID) of every image, image index fastest; ring 1 starts empty
 __global__ void cm_init_queue_kernel(unsigned long long* __restrict__ slots, unsigned cap, int B, int nstrip4,
-                                     unsigned long long* __restrict__ head, unsigned long long* __restrict__ tail) {
+                                     unsigned long long* __restrict__ head, unsigned long long* __restrict__ tail,
+                                     int* __restrict__ avail, double* __restrict__ qsum, unsigned* __restrict__ qcnt) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned T = (unsigned)(B * nstrip4);
-  if (i == 0) { *head = 0ull; *tail = (unsigned long long)T; }
-  if (i >= cap) return;
+  if (i == 0) {
+    head[0] = 0ull; head[1] = 0ull; tail[0] = (unsigned long long)T; tail[1] = 0ull;
+    avail[0] = (int)T; avail[1] = 0; *qsum = 0.0; *qcnt = 0u;
+  }
+  if (i >= 2u * cap) return;
   unsigned long long v = 0ull;
   if (i < T) {
     const unsigned b = i % (unsigned)B, ti = i / (unsigned)B;
     v = ((unsigned long long)(i + 1u) << 32) | (unsigned long long)(b * (unsigned)nstrip4 + ti);
   }
   slots[i] = v;
+}
+
+// One lane, every 8th iteration of an image: predict the iterations it still needs from the fraction of the
+// log-residual distance to rtol covered so far, keep the running sum over images current, pick the ring.
+__device__ __forceinline__ void update_priority(const PcgArgs<float>& a, ImgState* st, int it, double rr) {
+  const double bb = __ldcg(&st->bb);
+  if (!(bb > 0.0) || !(rr > 0.0)) return;
+  const float covered = __log2f((float)(rr / bb)), whole = __log2f((float)a.rtol2);   // both negative
+  const float phi = fminf(fmaxf(covered / whole, 0.02f), 1.f);
+  const float rem = (float)it * (1.f - phi) / phi;
+  float old = 0.f;
+  if (__ldcg(&st->counted)) old = __ldcg(&st->rem);
+  else { st->counted = 1; atomicAdd(a.qcnt, 1u); }
+  st->rem = rem;
+  const double sum = atomicAdd(a.qsum, (double)rem - (double)old) + ((double)rem - (double)old);
+  const unsigned cnt = __ldcg(a.qcnt);
+  st->prio = ((double)rem * (double)(cnt ? cnt : 1u) > sum) ? 1 : 0;
+}
+__device__ __forceinline__ void leave_priority(const PcgArgs<float>& a, ImgState* st) {
+  if (!__ldcg(&st->counted)) return;
+  st->counted = 0;
+  atomicAdd(a.qsum, -(double)__ldcg(&st->rem));
+  atomicSub(a.qcnt, 1u);
 }
 
 // fp64 residual r = b - A x64 over one 128-column strip (rare: once per refinement round)
@@ -627,7 +707,6 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
   unsigned char* ringmem = smem_raw + (size_t)warp * kWarpRing;
   const int B = a.B, H = a.H, W = a.W;
   const int per = a.nstrip4;
-  const unsigned nworkers = gridDim.x * (unsigned)a.wpb;
 
   auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
   unsigned long long t_wait = 0, t_mode[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_arr = 0;
@@ -637,7 +716,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     const unsigned payload = q_pop(a, lane);
     const unsigned long long tq1 = a.debug ? now() : 0ull;
     t_wait += tq1 - tq0;
-    if (payload == kPoison) break;
+    if (payload == kNoTask) break;
     const int b = (int)(payload / (unsigned)per), ti = (int)(payload % (unsigned)per);
     ImgState* st = a.st + b;
     const int mode = (int)(__ldcg(&st->fword) & 0xffffffffull);
@@ -725,6 +804,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       } else if (a.cg.by) {                                        // r.z is completed by the coarse solve
         st->rz_line = s1; st->fresh = 0;
         next = F_COARSE;
+        if ((it & 7) == 0 && it >= 32) update_priority(a, st, it, s0);
       } else {
         st->rz = s1; st->first = 0;
         st->beta = (rz_old > 0.0) ? s1 / rz_old : 0.0;
@@ -755,14 +835,15 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       const double bb = __ldcg(&st->bb);
       if (a.iters_out) a.iters_out[b] = __ldcg(&st->iters);
       if (a.relres_out) a.relres_out[b] = (bb > 0.0) ? sqrt(__ldcg(&st->rr_true) / bb) : 0.0;
+      leave_priority(a, st);
       next = F_DONE;
     }
     st->fword = (unsigned long long)next;
     if (next == F_DONE) {
       __threadfence();
-      if (atomicAdd(a.done, 1u) == (unsigned)B - 1u) q_push_n(a, kPoison, 0u, nworkers);   // release every worker
+      atomicAdd(a.done, 1u);                                       // idle workers leave when done == B
     } else {
-      q_push_n(a, (unsigned)(b * per), 1u, (next == F_COARSE) ? 1u : (unsigned)per);
+      q_push_n(a, __ldcg(&st->prio), (unsigned)(b * per), 1u, (next == F_COARSE) ? 1u : (unsigned)per);
     }
   }
   if ((a.debug & 1) && lane == 0 && warp == 0 && (blockIdx.x % 74) == 0)

@@ -24,6 +24,9 @@ struct CmLayout {
   unsigned* done;
   unsigned long long *qslots, *qhead, *qtail;
   unsigned qcap;
+  int* qavail;
+  double* qsum;
+  unsigned* qcnt;
   CoarseGeom cg;
   float *rc, *zc, *Lr, *Ur;
   double* Ab;
@@ -53,11 +56,13 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.bbpart = cv.take<double>((size_t)B * L.nblk);
   L.part = cv.take<double>((size_t)B * L.pmax * 2);
   L.st = cv.take<ImgState>(B);
-  L.done = cv.take<unsigned>(1);
-  // ready queue: every image has at most nstrip4 ready tasks at a time; plus one poison per worker warp
-  L.qcap = (unsigned)(2 * ((W + kStrip4 - 1) / kStrip4) * B + 8192);
-  L.qslots = cv.take<unsigned long long>(L.qcap);
-  L.qhead = cv.take<unsigned long long>(1); L.qtail = cv.take<unsigned long long>(1);
+  L.done = cv.take<unsigned>(2);
+  // two ready rings; every image has at most nstrip4 ready tasks at a time, in one ring or the other
+  L.qcap = (unsigned)(2 * ((W + kStrip4 - 1) / kStrip4) * B + 1024);
+  L.qslots = cv.take<unsigned long long>(2 * (size_t)L.qcap);
+  L.qhead = cv.take<unsigned long long>(2); L.qtail = cv.take<unsigned long long>(2);   // separate 256-byte lines
+  L.qavail = cv.take<int>(2);
+  L.qsum = cv.take<double>(1); L.qcnt = cv.take<unsigned>(1);
   // coarse-grid correction (fused fp32 kernel only)
   L.cg = ((flags & (USAUG_CM_FP64_VECTORS | USAUG_CM_NO_COARSE)) || W % 4 != 0) ? CoarseGeom{} : coarse_geom(H, W);
   const size_t nc = (size_t)L.cg.nc;
@@ -88,7 +93,8 @@ static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t s
   // no more workers than tasks that can be ready at once: an idle worker only polls the queue
   a.wpb = (tasks + blocks - 1) / blocks;
   if (a.wpb > AW) a.wpb = AW;
-  cm_init_queue_kernel<<<(a.qcap + 255) / 256, 256, 0, stream>>>(a.qslots, a.qcap, a.B, a.nstrip4, a.qhead, a.qtail);
+  cm_init_queue_kernel<<<(2 * a.qcap + 255) / 256, 256, 0, stream>>>(a.qslots, a.qcap, a.B, a.nstrip4, a.qhead, a.qtail,
+                                                                        a.qavail, a.qsum, a.qcnt);
   USAUG_CHECK_LAUNCH("cm_init_queue_kernel");
   void* params[] = {(void*)&a};
   if (g_ev_start) USAUG_CUDA(cudaEventRecord(g_ev_start, stream));
@@ -124,7 +130,7 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.x64 = L.x64;
   a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z; a.p2 = (T*)L.p2;
   a.st = L.st; a.part = L.part; a.done = L.done;
-  a.qslots = L.qslots; a.qhead = L.qhead; a.qtail = L.qtail; a.qcap = L.qcap;
+  a.qslots = L.qslots; a.qhead = L.qhead; a.qtail = L.qtail; a.qcap = L.qcap; a.qavail = L.qavail; a.qsum = L.qsum; a.qcnt = L.qcnt;
   a.cg = L.cg; a.rc = L.rc; a.zc = L.zc; a.Lr = L.Lr; a.Ur = L.Ur; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
   a.nstrip1 = L.nstrip1; a.nrb = L.nrb; a.nstrip2 = L.nstrip2; a.pmax = L.pmax;
   a.vec4 = (std::is_same<T, float>::value && W % 4 == 0) ? 1 : 0;

@@ -34,6 +34,8 @@ struct ImgState {
   double alpha_prev;  // fused kernel: step length of the iteration whose e-update is still pending
   int epend, fresh;   // epend: 1 = e += alpha_prev * p_prev is deferred to the next DOWN / FOLD; fresh: COARSE follows a PRECOND
   double rz_line;     // line part of r.z of the current iteration (the COARSE task adds rc.zc)
+  int prio, counted;  // fused kernel: ready-queue class of this image's tasks (1 = served first); counted in qsum/qcnt
+  float rem;          // predicted remaining iterations (the contribution of this image to qsum)
 };
 
 constexpr int kStrip4 = 128;
@@ -74,13 +76,17 @@ struct PcgArgs {
   T *p2;                  // fused kernel: second search-direction plane (ping-pong); z holds h there
   ImgState* st;
   double* part;      // [B][pmax][2]
-  unsigned* done;
+  unsigned* done;    // [0] images finished, [1] set when the idle watchdog gave up
   float* cm;
   int* iters_out;
   double* relres_out;
   int nstrip1, nrb, nstrip2, pmax, max_steps;
-  unsigned long long *qslots, *qhead, *qtail;   // fused kernel: ready queue of (image, strip) tasks
+  // fused kernel: two ready rings of (image, strip) tasks, [0] = normal, [1] = served first
+  unsigned long long *qslots, *qhead, *qtail;   // qslots[2][qcap], qhead[2], qtail[2]
   unsigned qcap;
+  int* qavail;       // [2] entries written and not yet claimed
+  double* qsum;      // sum over the running images of their predicted remaining iterations
+  unsigned* qcnt;    // number of images in qsum
   int wpb;           // fused kernel: worker warps per block actually used (<= AW)
   CoarseGeom cg;     // coarse-grid correction geometry (cg.by == 0: disabled)
   float *rc, *zc;    // [B][nc] restricted residual / coarse correction
