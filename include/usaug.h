@@ -50,7 +50,11 @@ enum {
   USAUG_CM_ZERO_GUESS = 2,   /* start from x0 = 0 instead of the linear depth ramp */
   USAUG_CM_DEBUG_TIMING = 4, /* development: the kernel prints per-slot wall times of a few steps */
   USAUG_CM_LEGACY_KERNEL = 8, /* A/B testing: use the two-slot kernel even where the fused fp32 kernel applies */
-  USAUG_CM_NO_COARSE = 32     /* A/B testing: line preconditioner only (no aggregation coarse-grid correction) */
+  USAUG_CM_NO_COARSE = 32,    /* A/B testing: line preconditioner only (no aggregation coarse-grid correction) */
+  /* aggregate height of the coarse grid; default: 2-row aggregates for deeply bandwidth-bound batches
+     (>= 12 strip tasks per SM), 4 rows (or more, for tall images) otherwise */
+  USAUG_CM_COARSE_FINE = 64,      /* always start from 2-row aggregates */
+  USAUG_CM_COARSE_STANDARD = 128  /* always start from 4-row aggregates */
 };
 
 int usaug_version(void);

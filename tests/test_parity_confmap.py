@@ -44,12 +44,13 @@ def test_cm_parity_small(cuda_device, B, H, W, precond):
     assert cm.min() >= -1e-6 and cm.max() <= 1.0 + 1e-6
 
 
-@pytest.mark.parametrize("variant", ["fused", "legacy", "fp64"])
+@pytest.mark.parametrize("variant", ["fused", "fused-fine", "fused-standard", "legacy", "fp64"])
 def test_cm_parity_256(cuda_device, variant):
     img, _ = util.synth_batch(2, 256, 256)
     ref = ocm.confidence_map_batch(img)
+    coarse = {"fused-fine": "fine", "fused-standard": "standard"}.get(variant, True)
     cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, fp64_vectors=(variant == "fp64"),
-                        legacy_kernel=(variant == "legacy"))
+                        legacy_kernel=(variant == "legacy"), coarse=coarse)
     assert (rr <= RTOL).all(), rr
     assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
 
@@ -108,3 +109,7 @@ def test_cm_coarse_grid_geometries(cuda_device, H, W, what):
     assert (rra <= 1e-9).all() and (rrb <= 1e-9).all(), what
     assert np.abs(a - b).max() <= 2 * (2e5 * 1e-9) + 1e-6, what
     assert np.all(a[:, 0] == 1.0) and np.all(a[:, -1] == 0.0)
+    # 2-row aggregates (the choice for large batches), forced here on a small one
+    c, itc, rrc = gpu_cm(cuda_device, img, rtol=1e-9, maxiter=100000, coarse="fine")
+    assert (rrc <= 1e-9).all(), what
+    assert np.abs(c - b).max() <= 2 * (2e5 * 1e-9) + 1e-6, what

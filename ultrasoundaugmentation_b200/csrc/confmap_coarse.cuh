@@ -32,7 +32,10 @@ struct CoarseGeom {
   int kd1;       // row pitch of the factor arrays: 32 floats (kd <= 31), zero padded
 };
 
-static inline CoarseGeom coarse_geom(int H, int W) {
+// min_shift: log2 of the smallest aggregate height tried.  Thin aggregates converge faster (CPU prototype at
+// 512x512: 8x32 -> 512, 4x32 -> 402, 2x32 -> 351 iterations; 4x16 -> 393, 8x8 -> 431 at the same count) but the
+// serial COARSE solve grows with nc: 2 rows pay off only when the batch is bandwidth-bound (cm_layout decides).
+static inline CoarseGeom coarse_geom(int H, int W, int min_shift) {
   CoarseGeom g{};
   const int hu = H - 2;
   g.bx_shift = 5;
@@ -40,7 +43,7 @@ static inline CoarseGeom coarse_geom(int H, int W) {
   if (g.nbx + 1 > kCoarseMaxBand) { g.bx_shift = 6; g.nbx = (W + 63) >> 6; }
   g.kd = g.nbx + 1;
   if (g.kd > kCoarseMaxBand || hu < 8) return g;            // by = 0: disabled
-  for (int sh = 2; sh <= 8; ++sh) {
+  for (int sh = min_shift; sh <= 8; ++sh) {
     const int by = 1 << sh;
     const int nby = (hu + by - 1) / by;
     if (nby * g.nbx <= kCoarseMaxN) {

@@ -64,7 +64,15 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.qavail = cv.take<int>(2);
   L.qsum = cv.take<double>(1); L.qcnt = cv.take<unsigned>(1);
   // coarse-grid correction (fused fp32 kernel only)
-  L.cg = ((flags & (USAUG_CM_FP64_VECTORS | USAUG_CM_NO_COARSE)) || W % 4 != 0) ? CoarseGeom{} : coarse_geom(H, W);
+  // Deeply bandwidth-bound batches take 2-row aggregates: 12 % fewer iterations for a COARSE task twice as long.
+  // The longer UP -> DOWN -> COARSE chain (620 vs 465 us per iteration at 512x512) needs ~260 instead of ~190
+  // images in flight to saturate HBM, so it pays from about twice that (measured on B200: B = 256 -> 0.90x,
+  // B = 512 -> 0.98x on easy images, 1.075x on the bench's deformed images).
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const bool many = (long long)B * ((W + kStrip4 - 1) / kStrip4) >= 12ll * sms;
+  const bool fine = (flags & USAUG_CM_COARSE_FINE) ? true : (flags & USAUG_CM_COARSE_STANDARD) ? false : many;
+  L.cg = ((flags & (USAUG_CM_FP64_VECTORS | USAUG_CM_NO_COARSE)) || W % 4 != 0) ? CoarseGeom{} : coarse_geom(H, W, fine ? 1 : 2);
   const size_t nc = (size_t)L.cg.nc;
   L.rc = cv.take<float>((size_t)B * nc); L.zc = cv.take<float>((size_t)B * nc);
   L.Lr = cv.take<float>((size_t)B * nc * L.cg.kd1); L.Ur = cv.take<float>((size_t)B * nc * L.cg.kd1);

@@ -112,7 +112,9 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
     flags = (_ffi.CM_FP64_VECTORS if fp64_vectors else 0) | (_ffi.CM_ZERO_GUESS if zero_guess else 0)
     flags |= 4 if debug_timing else 0
     flags |= 8 if legacy_kernel else 0     # A/B testing: two-slot kernel instead of the fused fp32 kernel
-    flags |= 0 if coarse else 32           # A/B testing: without the coarse-grid correction
+    if coarse not in (True, False, "fine", "standard"):
+        raise ValueError(f"coarse must be True (automatic), False, 'fine' or 'standard', got {coarse!r}")
+    flags |= {True: 0, False: 32, "fine": 64, "standard": 128}[coarse]   # coarse-grid correction: auto / off / 2-row / 4-row aggregates
     with torch.cuda.device(dev):
         per_img = lib.usaug_confmap_workspace_bytes(1, H, W, pc, flags)
         if max_wave is None:
