@@ -71,6 +71,11 @@ size_t usaug_warp_workspace_bytes(int B, int H, int W);
 int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, float* out_img, uint8_t* out_lab,
                            int B, int H, int W, const float* d, const float* tgc, int K,
                            const float* taps, int R, void* ws, size_t ws_bytes, void* stream);
+/* 8-bit ingest: img holds 8-bit B-mode pixels, read as v / 255 (correctly rounded
+ * fp32); everything else as above.  2 B/px less HBM and 3 B/px less host-to-device traffic. */
+int usaug_fused_tgc_deform_u8(const uint8_t* img, const uint8_t* lab, float* out_img, uint8_t* out_lab,
+                              int B, int H, int W, const float* d, const float* tgc, int K,
+                              const float* taps, int R, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- K2: confidence map, matrix-free PCG on the 8-neighbour random-walk Laplacian (A.3) ----
  * cm[B,H,W] out (row 0 = 1, row H-1 = 0).  Stops per image when the TRUE residual satisfies
@@ -96,6 +101,10 @@ size_t usaug_snr_reverb_workspace_bytes(int B, int H, int W);
 int usaug_snr_reverb(const float* img, const float* cm, const uint8_t* lab, float* out, int B,
                      int H, int W, const float* a_snr, const float* rho, const int* nghost,
                      const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream);
+/* 8-bit egress: out = floor(255 * v + 0.5) of the fp32 result v (two individually rounded fp32 operations). */
+int usaug_snr_reverb_u8(const float* img, const float* cm, const uint8_t* lab, uint8_t* out, int B,
+                        int H, int W, const float* a_snr, const float* rho, const int* nghost,
+                        const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- bone bounding box of a label batch (A.1 step 2 / A.5 "bone-surface row") --------------
  * box[B,4] = {y_top, y_bottom, x_left, x_right}; y_top = -1 when the image has no bone.

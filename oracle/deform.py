@@ -128,8 +128,16 @@ def remap(image: np.ndarray, label: np.ndarray, y_src: np.ndarray, gain_y: np.nd
     return out, lab
 
 
+def ingest_u8(image_u8: np.ndarray) -> np.ndarray:
+    """8-bit B-mode ingest: v / 255, one correctly rounded fp32 division."""
+    return (np.asarray(image_u8, dtype=np.uint8).astype(f32) / f32(255.0)).astype(f32)
+
+
 def fused_tgc_deform(image, label, d, gains, taps):
-    """One image: A.1 + A.2.  Returns (image_out f32, label_out u8, info dict)."""
+    """One image: A.1 + A.2.  Returns (image_out f32, label_out u8, info dict).
+    A uint8 image is ingested with ``ingest_u8`` first."""
+    if np.asarray(image).dtype == np.uint8:
+        image = ingest_u8(image)
     image = np.asarray(image, dtype=f32)
     label = np.asarray(label)
     H, W = image.shape

@@ -74,6 +74,13 @@ def snr_reverb(image, cm, label, a_snr, rho, n_ghost, taps):
     return reverb(snr_apply(image, cm, a_snr), label, rho, n_ghost, taps)
 
 
+def quantize_u8(image: np.ndarray) -> np.ndarray:
+    """8-bit egress: floor(255 * v + 0.5), the product and the sum rounded to fp32 on their own."""
+    v = np.asarray(image, dtype=f32)
+    q = np.floor(((v * f32(255.0)).astype(f32) + f32(0.5)).astype(f32))
+    return q.astype(np.uint8)
+
+
 def snr_reverb_batch(images, cms, labels, a_snr, rho, n_ghost, taps):
     outs = []
     for b in range(images.shape[0]):

@@ -121,3 +121,16 @@ def test_synth_is_seeded_and_in_range():
     a, la = osynth.make_bmode(64, 64, 5); b, lb = osynth.make_bmode(64, 64, 5); c, _ = osynth.make_bmode(64, 64, 6)
     assert np.array_equal(a, b) and np.array_equal(la, lb) and not np.array_equal(a, c)
     assert a.min() >= 0 and a.max() == 1.0 and la.sum() > 0 and set(np.unique(la)) == {0, 1}
+
+
+def test_u8_ingest_and_egress_round_trip():
+    """8-bit pipeline KATs: v/255 is exact at the ends, egress inverts ingest for all 256 codes,
+    and the quantiser rounds half up."""
+    from oracle import snr_reverb as osr
+    codes = np.arange(256, dtype=np.uint8)
+    f = odeform.ingest_u8(codes)
+    assert f.dtype == np.float32 and f[0] == 0.0 and f[255] == 1.0
+    assert np.all(np.diff(f) > 0)
+    assert np.array_equal(f, (codes.astype(np.float64) / 255.0).astype(np.float32))   # correctly rounded
+    assert np.array_equal(osr.quantize_u8(f), codes)
+    assert np.array_equal(osr.quantize_u8(np.array([0.0, 0.5 / 255, 0.49 / 255, 1.0], np.float32)), [0, 1, 0, 255])

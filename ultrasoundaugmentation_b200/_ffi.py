@@ -28,6 +28,9 @@ SYMBOLS = {
     "usaug_fused_tgc_deform": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                        c_size_t, c_void_p]),
+    "usaug_fused_tgc_deform_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                          c_size_t, c_void_p]),
     "usaug_confmap_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "usaug_confmap_pcg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
                                   c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -37,6 +40,9 @@ SYMBOLS = {
     "usaug_snr_reverb": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                  c_void_p]),
+    "usaug_snr_reverb_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                    c_void_p]),
     "usaug_bone_box_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "usaug_bone_box": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

@@ -3,6 +3,8 @@
 //   out  = clip(I1 + sum_{k=1..n} rho^k * Mf[y-kD, x] * I1[y-kD, x], 0, 1)   D = first bone row
 // Mf = separable Gaussian feather of the bone mask.  The ghost term only exists inside the bone
 // bounding box (+R) shifted by k*D, so the 2-D tap loop runs for a small fraction of pixels.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace usaug {
@@ -20,9 +22,11 @@ __device__ __forceinline__ float snr_px(float I, float c, float k) {
 // shifted bone box (+R) meets the tile; there the feathered mask of the 16 x 128 source tile is built
 // SEPARABLY in shared memory (row pass over 16+2R label rows, then column pass: 2*(2R+1) MACs per
 // pixel instead of (2R+1)^2), in the oracle's order (rows first, increasing tap index).
+// TOut = float, or uint8_t: 8-bit egress q = floor(255 * v + 0.5) (two individually rounded fp32 operations).
+template <typename TOut>
 __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
     const float* __restrict__ img, const float* __restrict__ cm, const uint8_t* __restrict__ lab,
-    float* __restrict__ out, int H, int W, const float* __restrict__ a_snr,
+    TOut* __restrict__ out, int H, int W, const float* __restrict__ a_snr,
     const float* __restrict__ rho, const int* __restrict__ nghost, const int* __restrict__ box,
     const float* __restrict__ taps_g, int R) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -101,7 +105,13 @@ __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
 #pragma unroll
     for (int r = 0; r < kSrRows; ++r) {
       const int y = ya + r;
-      if (y < H) out[base + (size_t)y * W + x] = ghosts ? fminf(fmaxf(acc[r], 0.0f), 1.0f) : v[r];
+      if (y < H) {
+        const float o = ghosts ? fminf(fmaxf(acc[r], 0.0f), 1.0f) : v[r];
+        if constexpr (std::is_same<TOut, uint8_t>::value)
+          out[base + (size_t)y * W + x] = (uint8_t)__float2int_rd(__fadd_rn(__fmul_rn(o, 255.0f), 0.5f));
+        else
+          out[base + (size_t)y * W + x] = o;
+      }
     }
   }
 }
@@ -115,10 +125,11 @@ extern "C" size_t usaug_snr_reverb_workspace_bytes(int B, int H, int W) {
   return surface_scan_bytes(B, H, W) + align_up((size_t)B * 4 * sizeof(int));
 }
 
-extern "C" int usaug_snr_reverb(const float* img, const float* cm, const uint8_t* lab, float* out,
-                                int B, int H, int W, const float* a_snr, const float* rho,
-                                const int* nghost, const float* feather_taps, int R, void* ws,
-                                size_t ws_bytes, void* stream_) {
+template <typename TOut>
+static int snr_reverb_impl(const float* img, const float* cm, const uint8_t* lab, TOut* out,
+                           int B, int H, int W, const float* a_snr, const float* rho,
+                           const int* nghost, const float* feather_taps, int R, void* ws,
+                           size_t ws_bytes, void* stream_) {
   if (!img || !lab || !out || !a_snr || !rho || !nghost || !feather_taps || !ws) {
     set_error("usaug_snr_reverb: null pointer"); return USAUG_E_INVALID_ARG;
   }
@@ -126,7 +137,7 @@ extern "C" int usaug_snr_reverb(const float* img, const float* cm, const uint8_t
     set_error("usaug_snr_reverb: bad shape B=%d H=%d W=%d R=%d (need R<=32)", B, H, W, R);
     return USAUG_E_INVALID_ARG;
   }
-  if (img == out) { set_error("usaug_snr_reverb: out must not alias img"); return USAUG_E_INVALID_ARG; }
+  if ((const void*)img == (const void*)out) { set_error("usaug_snr_reverb: out must not alias img"); return USAUG_E_INVALID_ARG; }
   if (ws_bytes < usaug_snr_reverb_workspace_bytes(B, H, W)) {
     set_error("usaug_snr_reverb: workspace too small"); return USAUG_E_WORKSPACE_TOO_SMALL;
   }
@@ -139,9 +150,23 @@ extern "C" int usaug_snr_reverb(const float* img, const float* cm, const uint8_t
   dim3 grid((W + kSrCols - 1) / kSrCols, (H + kSrRows - 1) / kSrRows, B);
   const size_t smem = (size_t)(kSrRows + 2 * R) * kSrCols * sizeof(float) + (size_t)(kSrRows + 2 * R) * (kSrCols + 2 * R);
   if (smem > 48 * 1024)
-    USAUG_CUDA(cudaFuncSetAttribute(snr_reverb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  snr_reverb_kernel<<<grid, kSrCols, smem, stream>>>(img, cm, lab, out, H, W, a_snr, rho, nghost, box,
-                                                     feather_taps, R);
+    USAUG_CUDA(cudaFuncSetAttribute(snr_reverb_kernel<TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  snr_reverb_kernel<TOut><<<grid, kSrCols, smem, stream>>>(img, cm, lab, out, H, W, a_snr, rho, nghost, box,
+                                                           feather_taps, R);
   USAUG_CHECK_LAUNCH("snr_reverb_kernel");
   return USAUG_OK;
+}
+
+extern "C" int usaug_snr_reverb(const float* img, const float* cm, const uint8_t* lab, float* out,
+                                int B, int H, int W, const float* a_snr, const float* rho,
+                                const int* nghost, const float* feather_taps, int R, void* ws,
+                                size_t ws_bytes, void* stream) {
+  return snr_reverb_impl<float>(img, cm, lab, out, B, H, W, a_snr, rho, nghost, feather_taps, R, ws, ws_bytes, stream);
+}
+
+extern "C" int usaug_snr_reverb_u8(const float* img, const float* cm, const uint8_t* lab, uint8_t* out,
+                                   int B, int H, int W, const float* a_snr, const float* rho,
+                                   const int* nghost, const float* feather_taps, int R, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  return snr_reverb_impl<uint8_t>(img, cm, lab, out, B, H, W, a_snr, rho, nghost, feather_taps, R, ws, ws_bytes, stream);
 }

@@ -2,6 +2,8 @@
 // Implements SURVEY.md Appendix A.1 (steps 1-5) and A.2.  The coordinate path uses explicitly
 // rounded fp32 intrinsics (no FMA contraction) so nearest-neighbour label picks are bit-exact
 // against the oracle (oracle/deform.py).
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace usaug {
@@ -186,11 +188,23 @@ __global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ su
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarpRows = 16;
 
+// TIn = float (image in [0,1]) or uint8_t (8-bit B-mode ingest: v/255 in correctly rounded fp32, from a
+// 256-entry shared-memory table so the gather loop carries no divide).
+template <typename TIn>
 __global__ void __launch_bounds__(128) fused_warp_kernel(
-    const float* __restrict__ img, const uint8_t* __restrict__ lab, float* __restrict__ out_img,
+    const TIn* __restrict__ img, const uint8_t* __restrict__ lab, float* __restrict__ out_img,
     uint8_t* __restrict__ out_lab, int H, int W, const float* __restrict__ s_hat,
     const WarpInfo* __restrict__ info, const float* __restrict__ tgc, int K, float gscale) {
   __shared__ float s_gain[kWarpRows];
+  __shared__ float s_lut[std::is_same<TIn, uint8_t>::value ? 256 : 1];
+  if constexpr (std::is_same<TIn, uint8_t>::value) {
+    s_lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+    s_lut[threadIdx.x + 128] = __fdiv_rn((float)(threadIdx.x + 128), 255.0f);
+  }
+  auto px = [&](TIn v) -> float {
+    if constexpr (std::is_same<TIn, uint8_t>::value) return s_lut[v];
+    else return v;
+  };
   const int b = blockIdx.z;
   const int x = blockIdx.x * 128 + threadIdx.x;
   const int ya = blockIdx.y * kWarpRows;
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
   __syncthreads();
   if (x >= W) return;
   const size_t base = (size_t)b * H * W;
-  const float* __restrict__ I = img + base + x;          // column pointers; in-image offsets fit 32 bits
+  const TIn* __restrict__ I = img + base + x;            // column pointers; in-image offsets fit 32 bits
   const uint8_t* __restrict__ L = lab + base + x;
   float* __restrict__ OI = out_img + base + x;
   uint8_t* __restrict__ OL = out_lab + base + x;
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
     fr[r] = ys - (float)i0[r];
     yn[r] = __float2int_rd(__fadd_rn(ys, 0.5f));
   }
-  float v0[kWarpRows], v1[kWarpRows];
+  TIn v0[kWarpRows], v1[kWarpRows];
   uint8_t lv[kWarpRows];
   // Block-uniform fast path: 0 <= y_src <= y + |d|, so a tile whose last row + |d| + 2 stays inside
   // the image needs no bounds checks at all (every tile except the bottom few).
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
   if (interior) {
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r) {
-      const float* p0 = I + i0[r] * W;
+      const TIn* p0 = I + i0[r] * W;
       v0[r] = p0[0];
       v1[r] = p0[W];
       lv[r] = L[yn[r] * W];
@@ -251,7 +265,8 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
     uint8_t* pl = OL + ya * W;
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r) {
-      const float v = fmaf(fr[r], v1[r] - v0[r], v0[r]);
+      const float a0 = px(v0[r]), a1 = px(v1[r]);
+      const float v = fmaf(fr[r], a1 - a0, a0);
       po[r * W] = fminf(fmaxf(s_gain[r] * v, 0.0f), 1.0f);
       pl[r * W] = lv[r];
     }
@@ -260,15 +275,16 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
 #pragma unroll
   for (int r = 0; r < kWarpRows; ++r) {
     const bool in = ya + r < H;
-    v0[r] = (in && (unsigned)i0[r] < uH) ? I[i0[r] * W] : 0.0f;
-    v1[r] = (in && (unsigned)(i0[r] + 1) < uH) ? I[(i0[r] + 1) * W] : 0.0f;
+    v0[r] = (in && (unsigned)i0[r] < uH) ? I[i0[r] * W] : (TIn)0;
+    v1[r] = (in && (unsigned)(i0[r] + 1) < uH) ? I[(i0[r] + 1) * W] : (TIn)0;
     lv[r] = (in && (unsigned)yn[r] < uH) ? L[yn[r] * W] : (uint8_t)0;
   }
 #pragma unroll
   for (int r = 0; r < kWarpRows; ++r) {
     const int y = ya + r;
     if (y < H) {
-      const float v = fmaf(fr[r], v1[r] - v0[r], v0[r]);
+      const float a0 = px(v0[r]), a1 = px(v1[r]);
+      const float v = fmaf(fr[r], a1 - a0, a0);
       OI[y * W] = fminf(fmaxf(s_gain[r] * v, 0.0f), 1.0f);
       OL[y * W] = lv[r];
     }
@@ -314,10 +330,11 @@ extern "C" size_t usaug_warp_workspace_bytes(int B, int H, int W) {
          align_up((size_t)B * sizeof(WarpInfo));
 }
 
-extern "C" int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, float* out_img,
-                                      uint8_t* out_lab, int B, int H, int W, const float* d,
-                                      const float* tgc, int K, const float* taps, int R, void* ws,
-                                      size_t ws_bytes, void* stream_) {
+template <typename TIn>
+static int fused_tgc_deform_impl(const TIn* img, const uint8_t* lab, float* out_img,
+                                 uint8_t* out_lab, int B, int H, int W, const float* d,
+                                 const float* tgc, int K, const float* taps, int R, void* ws,
+                                 size_t ws_bytes, void* stream_) {
   if (!img || !lab || !out_img || !out_lab || !d || !tgc || !taps || !ws) {
     set_error("usaug_fused_tgc_deform: null pointer"); return USAUG_E_INVALID_ARG;
   }
@@ -325,7 +342,7 @@ extern "C" int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, floa
     set_error("usaug_fused_tgc_deform: bad shape B=%d H=%d W=%d K=%d R=%d (need 1<=W<=4096)", B, H, W, K, R);
     return USAUG_E_INVALID_ARG;
   }
-  if (img == out_img || lab == out_lab) {
+  if ((const void*)img == (const void*)out_img || lab == out_lab) {
     set_error("usaug_fused_tgc_deform: outputs must not alias inputs"); return USAUG_E_INVALID_ARG;
   }
   if (ws_bytes < usaug_warp_workspace_bytes(B, H, W)) {
@@ -344,10 +361,24 @@ extern "C" int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, floa
   USAUG_CHECK_LAUNCH("profile_kernel");
   const float gscale = (H > 1 && K > 1) ? (float)((double)(K - 1) / (double)(H - 1)) : 0.0f;
   dim3 grid((W + 127) / 128, (H + kWarpRows - 1) / kWarpRows, B);
-  fused_warp_kernel<<<grid, 128, 0, stream>>>(img, lab, out_img, out_lab, H, W, s_hat, info, tgc,
-                                              (H > 1) ? K : 1, gscale);
+  fused_warp_kernel<TIn><<<grid, 128, 0, stream>>>(img, lab, out_img, out_lab, H, W, s_hat, info, tgc,
+                                                   (H > 1) ? K : 1, gscale);
   USAUG_CHECK_LAUNCH("fused_warp_kernel");
   return USAUG_OK;
+}
+
+extern "C" int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, float* out_img,
+                                      uint8_t* out_lab, int B, int H, int W, const float* d,
+                                      const float* tgc, int K, const float* taps, int R, void* ws,
+                                      size_t ws_bytes, void* stream) {
+  return fused_tgc_deform_impl<float>(img, lab, out_img, out_lab, B, H, W, d, tgc, K, taps, R, ws, ws_bytes, stream);
+}
+
+extern "C" int usaug_fused_tgc_deform_u8(const uint8_t* img, const uint8_t* lab, float* out_img,
+                                         uint8_t* out_lab, int B, int H, int W, const float* d,
+                                         const float* tgc, int K, const float* taps, int R, void* ws,
+                                         size_t ws_bytes, void* stream) {
+  return fused_tgc_deform_impl<uint8_t>(img, lab, out_img, out_lab, B, H, W, d, tgc, K, taps, R, ws, ws_bytes, stream);
 }
 
 extern "C" size_t usaug_bone_box_workspace_bytes(int B, int H, int W) {

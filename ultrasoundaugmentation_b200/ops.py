@@ -53,8 +53,11 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def _check_pair(image, label):
-    image = _need_cuda(image, "image", torch.float32)
+def _check_pair(image, label, allow_u8_image=False):
+    if allow_u8_image and isinstance(image, torch.Tensor) and image.dtype == torch.uint8:
+        image = _need_cuda(image, "image", torch.uint8)
+    else:
+        image = _need_cuda(image, "image", torch.float32)
     label = _need_cuda(label, "label", torch.uint8)
     if image.dim() != 3 or image.shape != label.shape or image.device != label.device:
         raise ValueError(f"image/label must both be [B,H,W] on one device, got {tuple(image.shape)} / {tuple(label.shape)}")
@@ -62,9 +65,10 @@ def _check_pair(image, label):
 
 
 def fused_tgc_deform(image, label, d, tgc, taps):
-    """K1 (A.1 + A.2).  image f32 [B,H,W], label u8 [B,H,W], d [B], tgc [B,K], taps [2R+1]."""
+    """K1 (A.1 + A.2).  image f32 [B,H,W] in [0,1] -- or uint8 (8-bit B-mode ingest, read as v/255) --,
+    label u8 [B,H,W], d [B], tgc [B,K], taps [2R+1].  Returns (image f32, label u8)."""
     lib = _ffi.load()
-    image, label = _check_pair(image, label)
+    image, label = _check_pair(image, label, allow_u8_image=True)
     B, H, W = image.shape
     dev = image.device
     tgc_t = torch.as_tensor(tgc, dtype=torch.float32)
@@ -78,14 +82,14 @@ def fused_tgc_deform(image, label, d, tgc, taps):
         if taps_t.numel() % 2 != 1:
             raise ValueError("taps must have odd length 2R+1")
         R = (taps_t.numel() - 1) // 2
-        out_img = torch.empty_like(image)
+        out_img = torch.empty(image.shape, dtype=torch.float32, device=dev)
         out_lab = torch.empty_like(label)
         nbytes = lib.usaug_warp_workspace_bytes(B, H, W)
         ws = _ws(nbytes, dev)
-        rc = lib.usaug_fused_tgc_deform(image.data_ptr(), label.data_ptr(), out_img.data_ptr(),
-                                        out_lab.data_ptr(), B, H, W, d_t.data_ptr(), tgc_t.data_ptr(),
-                                        K, taps_t.data_ptr(), R, ws.data_ptr(), ws.numel(),
-                                        _stream_ptr(dev))
+        entry = lib.usaug_fused_tgc_deform_u8 if image.dtype == torch.uint8 else lib.usaug_fused_tgc_deform
+        rc = entry(image.data_ptr(), label.data_ptr(), out_img.data_ptr(), out_lab.data_ptr(), B, H, W,
+                   d_t.data_ptr(), tgc_t.data_ptr(), K, taps_t.data_ptr(), R, ws.data_ptr(), ws.numel(),
+                   _stream_ptr(dev))
         _ffi.check(rc, "usaug_fused_tgc_deform")
     return out_img, out_lab
 
@@ -144,8 +148,11 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
     return cm
 
 
-def snr_reverb(image, cm, label, a_snr, rho, n_ghost, feather_taps):
-    """K3 (A.4 + A.5).  cm may be None (reverb only); n_ghost = 0 disables the ghosts."""
+def snr_reverb(image, cm, label, a_snr, rho, n_ghost, feather_taps, out_dtype=torch.float32):
+    """K3 (A.4 + A.5).  cm may be None (reverb only); n_ghost = 0 disables the ghosts.
+    out_dtype=torch.uint8 quantises the result on the way out: floor(255 v + 0.5) (8-bit egress)."""
+    if out_dtype not in (torch.float32, torch.uint8):
+        raise TypeError(f"out_dtype must be torch.float32 or torch.uint8, got {out_dtype}")
     lib = _ffi.load()
     image, label = _check_pair(image, label)
     B, H, W = image.shape
@@ -162,9 +169,10 @@ def snr_reverb(image, cm, label, a_snr, rho, n_ghost, feather_taps):
         if taps_t.numel() % 2 != 1:
             raise ValueError("feather_taps must have odd length 2R+1")
         R = (taps_t.numel() - 1) // 2
-        out = torch.empty_like(image)
+        out = torch.empty(image.shape, dtype=out_dtype, device=dev)
         ws = _ws(lib.usaug_snr_reverb_workspace_bytes(B, H, W), dev)
-        rc = lib.usaug_snr_reverb(image.data_ptr(), 0 if cm is None else cm.data_ptr(), label.data_ptr(),
+        entry = lib.usaug_snr_reverb_u8 if out_dtype == torch.uint8 else lib.usaug_snr_reverb
+        rc = entry(image.data_ptr(), 0 if cm is None else cm.data_ptr(), label.data_ptr(),
                                   out.data_ptr(), B, H, W, a_t.data_ptr(), r_t.data_ptr(), n_t.data_ptr(),
                                   taps_t.data_ptr(), R, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
         _ffi.check(rc, "usaug_snr_reverb")

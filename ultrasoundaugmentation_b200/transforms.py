@@ -197,9 +197,16 @@ class PhysicsChain:
 
     Accepts any subset of the four transforms (at most one of each); the physical order is fixed
     (SURVEY.md Appendix A "Chain order").
+
+    8-bit pipelines: a uint8 image is ingested as v/255 inside the first kernel, and
+    ``output_dtype=torch.uint8`` quantises the result inside the last one (floor(255 v + 0.5)) -- 2 instead of
+    5 bytes per pixel over PCIe in each direction.  The arithmetic in between is fp32 either way.
     """
 
-    def __init__(self, transforms: Sequence[_Transform]):
+    def __init__(self, transforms: Sequence[_Transform], output_dtype=torch.float32):
+        if output_dtype not in (torch.float32, torch.uint8):
+            raise TypeError(f"output_dtype must be torch.float32 or torch.uint8, got {output_dtype}")
+        self.output_dtype = output_dtype
         self.deform = self.tgc = self.snr = self.reverb = None
         for t in transforms:
             if isinstance(t, ProbePressureDeformation):
@@ -220,9 +227,9 @@ class PhysicsChain:
             raise ValueError("empty chain")
 
     @classmethod
-    def full(cls, seed: int = 0, **snr_kwargs) -> "PhysicsChain":
+    def full(cls, seed: int = 0, output_dtype=torch.float32, **snr_kwargs) -> "PhysicsChain":
         return cls([ProbePressureDeformation(seed=seed), TimeGainCompensation(seed=seed),
-                    ConfidenceSNR(seed=seed, **snr_kwargs), Reverberation(seed=seed)])
+                    ConfidenceSNR(seed=seed, **snr_kwargs), Reverberation(seed=seed)], output_dtype=output_dtype)
 
     def get_params(self, batch_size, generator=None, sample_index=None, image_size=None) -> dict:
         out = {}
@@ -236,8 +243,8 @@ class PhysicsChain:
         if not img.is_cuda or not lab.is_cuda:
             raise ValueError("PhysicsChain needs CUDA tensors (no CPU fallback exists); "
                              "use augment_host() for host buffers")
-        if img.dtype != torch.float32:
-            raise TypeError(f"image must be float32, got {img.dtype}")
+        if img.dtype not in (torch.float32, torch.uint8):
+            raise TypeError(f"image must be float32 (or uint8 for 8-bit ingest), got {img.dtype}")
         if lab.dtype != torch.uint8:
             raise TypeError(f"label must be uint8, got {lab.dtype}")
         B, H, W = img.shape
@@ -248,7 +255,9 @@ class PhysicsChain:
 
     def _run(self, img, lab, params):
         B, H, W = img.shape
-        if self.deform is not None or self.tgc is not None:
+        u8_out = self.output_dtype == torch.uint8
+        # a uint8 image always passes the first kernel (identity warp if need be): that is where it is ingested
+        if self.deform is not None or self.tgc is not None or img.dtype == torch.uint8:
             d = params["d"] if self.deform is not None else torch.zeros(B)
             tgc = params["tgc"] if self.tgc is not None else torch.ones(B, 1)
             taps = self.deform.taps(W) if self.deform is not None else ops.gaussian_taps(0.0, 0)
@@ -256,13 +265,14 @@ class PhysicsChain:
         cm = None
         if self.snr is not None:
             cm = self.snr.confidence_map(img)
-        if self.snr is not None or self.reverb is not None:
+        # ... and a uint8 result always leaves through the last kernel (pass-through if need be)
+        if self.snr is not None or self.reverb is not None or u8_out:
             a = params["a_snr"] if self.snr is not None else torch.ones(B)
             if self.reverb is not None:
                 rho, n, taps = params["rho"], params["n_ghost"], self.reverb.taps()
             else:
                 rho, n, taps = torch.zeros(B), torch.zeros(B, dtype=torch.int32), ops.gaussian_taps(0.0, 0)
-            img = ops.snr_reverb(img, cm, lab, a, rho, n, taps)
+            img = ops.snr_reverb(img, cm, lab, a, rho, n, taps, out_dtype=self.output_dtype)
         return img, lab
 
     # ---- host path: pinned host buffers in, pinned host buffers out ---------------------------
@@ -285,7 +295,7 @@ class PhysicsChain:
             d_lab = lab.contiguous().to(device, non_blocking=True)
             o_img, o_lab = self._run(d_img, d_lab, params)
             if out is None:
-                h_img = torch.empty((B, H, W), dtype=torch.float32, pin_memory=True)
+                h_img = torch.empty((B, H, W), dtype=self.output_dtype, pin_memory=True)
                 h_lab = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
             else:
                 h_img, h_lab = out[0].reshape(B, H, W), out[1].reshape(B, H, W)
@@ -293,3 +303,61 @@ class PhysicsChain:
             h_lab.copy_(o_lab, non_blocking=True)
             torch.cuda.current_stream(device).synchronize()
         return h_img.reshape(shp), h_lab.reshape(shp)
+
+    def augment_host_stream(self, batches, device=None, depth: int = 2):
+        """Double-buffered host pipeline: generator over augmented batches.
+
+        ``batches`` yields ``(image, label)`` or ``(image, label, sample_index)`` host tensors (pinned
+        memory for true overlap).  The host-to-device copy of batch i+1 and the device-to-host copy of
+        batch i-1 run on their own streams while batch i computes, so PCIe traffic hides behind the
+        kernels.  Results come back in order as pinned host tensors from a ring of ``depth + 2`` buffer
+        pairs: a yielded pair stays valid while the consumer fetches ONE further batch -- copy it if it has
+        to live longer.  Input tensors must stay unmodified until their batch has been yielded.
+        Bitwise identical to ``augment_host`` batch by batch.
+        """
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(device):
+            s_in, s_run, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device), torch.cuda.Stream(device)
+            ring, pending = {}, []
+
+            def drain_one():
+                ev, h_img, h_lab, shp, keep = pending.pop(0)
+                ev.synchronize()
+                del keep
+                return h_img.reshape(shp), h_lab.reshape(shp)
+
+            for i, item in enumerate(batches):
+                image, label = item[0], item[1]
+                sample_index = item[2] if len(item) > 2 else None
+                if image.is_cuda or label.is_cuda:
+                    raise ValueError("augment_host_stream takes host tensors")
+                img, lab, shp = _to_bhw(image, label)
+                B, H, W = img.shape
+                params = self.get_params(B, None, sample_index, (H, W))
+                with torch.cuda.stream(s_in):
+                    d_img = img.contiguous().to(device, non_blocking=True)
+                    d_lab = lab.contiguous().to(device, non_blocking=True)
+                    ev_in = torch.cuda.Event(); ev_in.record(s_in)
+                with torch.cuda.stream(s_run):
+                    s_run.wait_event(ev_in)
+                    d_img.record_stream(s_run); d_lab.record_stream(s_run)
+                    o_img, o_lab = self._run(d_img, d_lab, params)
+                    ev_run = torch.cuda.Event(); ev_run.record(s_run)
+                key = (i % (depth + 2), B, H, W)
+                if key not in ring:
+                    ring[key] = (torch.empty((B, H, W), dtype=self.output_dtype, pin_memory=True),
+                                 torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True))
+                h_img, h_lab = ring[key]
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_run)
+                    o_img.record_stream(s_out); o_lab.record_stream(s_out)
+                    h_img.copy_(o_img, non_blocking=True)
+                    h_lab.copy_(o_lab, non_blocking=True)
+                    ev_out = torch.cuda.Event(); ev_out.record(s_out)
+                pending.append((ev_out, h_img, h_lab, shp, (d_img, d_lab, o_img, o_lab)))
+                if len(pending) > depth:
+                    yield drain_one()
+            while pending:
+                yield drain_one()
