@@ -106,6 +106,25 @@ int usaug_snr_reverb_u8(const float* img, const float* cm, const uint8_t* lab, u
                         int H, int W, const float* a_snr, const float* rho, const int* nghost,
                         const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream);
 
+/* General form of A.4: I1 = clip(I + (a-1) * C * S) with the signal map
+ * S = sig * sig_scale[b] instead of S = I (sig, sig_scale nullable together: NULL = the form above).
+ * out is float* or, with out_is_u8 != 0, uint8_t*. */
+int usaug_snr_reverb_signal(const float* img, const float* cm, const float* sig, const float* sig_scale,
+                            const uint8_t* lab, void* out, int out_is_u8, int B, int H, int W,
+                            const float* a_snr, const float* rho, const int* nghost,
+                            const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- monogenic-signal local energy ------------------------------------
+ * energy[B,H,W] = sqrt(even^2 + odd1^2 + odd2^2) of the image filtered with the sum of `scales`
+ * log-Gabor band-pass filters (wavelengths lambda_min * mult^s pixels, bandwidth sigma_f) and their
+ * Riesz transforms; scale[B] = 1 / max(energy) per image (0 if the image has no band-pass content),
+ * so energy * scale is the normalised map in [0,1] that usaug_snr_reverb_signal takes.
+ * Hand-written batched 2-D FFT: H and W must be powers of two in [8, 2048]; 1 <= scales <= 4. */
+size_t usaug_local_energy_workspace_bytes(int B, int H, int W);
+int usaug_local_energy(const float* img, float* energy, float* scale, int B, int H, int W,
+                       float lambda_min, float mult, int scales, float sigma_f, void* ws,
+                       size_t ws_bytes, void* stream);
+
 /* ---- bone bounding box of a label batch (A.1 step 2 / A.5 "bone-surface row") --------------
  * box[B,4] = {y_top, y_bottom, x_left, x_right}; y_top = -1 when the image has no bone.
  */

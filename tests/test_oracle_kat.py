@@ -134,3 +134,31 @@ def test_u8_ingest_and_egress_round_trip():
     assert np.array_equal(f, (codes.astype(np.float64) / 255.0).astype(np.float32))   # correctly rounded
     assert np.array_equal(osr.quantize_u8(f), codes)
     assert np.array_equal(osr.quantize_u8(np.array([0.0, 0.5 / 255, 0.49 / 255, 1.0], np.float32)), [0, 1, 0, 255])
+
+
+def test_local_energy_known_answers():
+    """Monogenic local energy, pins independent of any implementation:
+    constant image -> 0; plane wave -> constant energy G(f0) (quadrature); flips commute; scaling is linear."""
+    from oracle import local_energy as ole
+    H, W = 64, 128
+    assert np.all(ole.local_energy_raw(np.full((H, W), 0.37)) < 1e-12)
+    assert np.all(ole.local_energy(np.full((H, W), 0.37)) == 0.0)
+    for k0, axis in [(8, 1), (5, 0), (16, 1)]:
+        n = W if axis == 1 else H
+        t = np.cos(2 * np.pi * k0 * np.arange(n) / n + 0.3)
+        img = np.tile(t[None, :], (H, 1)) if axis == 1 else np.tile(t[:, None], (1, W))
+        G = ole.log_gabor_sum(H, W)[0]
+        want = G[0, k0] if axis == 1 else G[k0, 0]
+        E = ole.local_energy_raw(img)
+        assert np.allclose(E, want, rtol=0, atol=1e-12), (k0, axis)
+        assert np.allclose(ole.local_energy(img), 1.0, atol=1e-10)
+    img, _ = osynth.make_bmode(H, W, 3)
+    E = ole.local_energy_raw(img)
+    assert np.allclose(ole.local_energy_raw(img[:, ::-1]), E[:, ::-1], atol=1e-12)
+    assert np.allclose(ole.local_energy_raw(img[::-1]), E[::-1], atol=1e-12)
+    assert np.allclose(ole.local_energy_raw(2.5 * img), 2.5 * E, atol=1e-12)
+    Eh = ole.local_energy(img)
+    assert Eh.min() >= 0.0 and Eh.max() == 1.0
+    # A.4 general form reduces to the hot-path form for E = I
+    cm = np.random.default_rng(0).random((H, W)).astype(np.float32)
+    assert np.array_equal(ole.snr_apply_signal(img, cm, img, 1.3), osr.snr_apply(img, cm, 1.3))

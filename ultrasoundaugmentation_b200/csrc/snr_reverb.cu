@@ -1,5 +1,6 @@
 // K3: confidence-map SNR change fused with the reverberation artifact.
-//   I1   = clip(I + (a-1) * C * I, 0, 1)                                   (skipped when C == NULL)
+//   I1   = clip(I + (a-1) * C * S, 0, 1)                                   (skipped when C == NULL)
+//          S = I, or S = sig * sig_scale[b] when a signal plane is given (monogenic local energy, 8(f) row 1)
 //   out  = clip(I1 + sum_{k=1..n} rho^k * Mf[y-kD, x] * I1[y-kD, x], 0, 1)   D = first bone row
 // Mf = separable Gaussian feather of the bone mask.  The ghost term only exists inside the bone
 // bounding box (+R) shifted by k*D, so the 2-D tap loop runs for a small fraction of pixels.
@@ -13,9 +14,9 @@ constexpr int kSrRows = 16;
 constexpr int kSrCols = 128;
 constexpr int kMaxTaps = 65;   // R <= 32
 
-__device__ __forceinline__ float snr_px(float I, float c, float k) {
-  // (k*c)*I then + I, as the oracle (oracle/snr_reverb.py: snr_apply)
-  return fminf(fmaxf(I + (k * c) * I, 0.0f), 1.0f);
+__device__ __forceinline__ float snr_px(float I, float c, float k, float S) {
+  // (k*c)*S then + I, as the oracle (oracle/snr_reverb.py: snr_apply, oracle/local_energy.py: snr_apply_signal)
+  return fminf(fmaxf(I + (k * c) * S, 0.0f), 1.0f);
 }
 
 // Block = 128 scanlines x 16 output rows, thread = scanline.  The ghost term only exists where the
@@ -26,6 +27,7 @@ __device__ __forceinline__ float snr_px(float I, float c, float k) {
 template <typename TOut>
 __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
     const float* __restrict__ img, const float* __restrict__ cm, const uint8_t* __restrict__ lab,
+    const float* __restrict__ sig, const float* __restrict__ sig_scale,
     TOut* __restrict__ out, int H, int W, const float* __restrict__ a_snr,
     const float* __restrict__ rho, const int* __restrict__ nghost, const int* __restrict__ box,
     const float* __restrict__ taps_g, int R) {
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
   const size_t base = (size_t)b * H * W;
   const float* I = img + base;
   const float* C = cm ? cm + base : nullptr;
+  const float* S = (cm && sig) ? sig + base : nullptr;
+  const float ss = S ? sig_scale[b] : 0.0f;
   const uint8_t* L = lab + base;
   const float ks = C ? (a_snr[b] - 1.0f) : 0.0f;
   const int ytop = box[b * 4 + 0], ybot = box[b * 4 + 1], xl = box[b * 4 + 2], xr = box[b * 4 + 3];
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
     float t = 0.f;
     if (xin && y < H) {
       t = I[(size_t)y * W + x];
-      if (C) t = snr_px(t, C[(size_t)y * W + x], ks);
+      if (C) t = snr_px(t, C[(size_t)y * W + x], ks, S ? S[(size_t)y * W + x] * ss : t);
     }
     v[r] = t; acc[r] = t;
   }
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
         if (m > 0.0f) {
           const size_t so = (size_t)ys * W + x;
           float sv = I[so];
-          if (C) sv = snr_px(sv, C[so], ks);
+          if (C) sv = snr_px(sv, C[so], ks, S ? S[so] * ss : sv);
           acc[r] += coef * (m * sv);
         }
       }
@@ -126,12 +130,16 @@ extern "C" size_t usaug_snr_reverb_workspace_bytes(int B, int H, int W) {
 }
 
 template <typename TOut>
-static int snr_reverb_impl(const float* img, const float* cm, const uint8_t* lab, TOut* out,
+static int snr_reverb_impl(const float* img, const float* cm, const float* sig, const float* sig_scale,
+                           const uint8_t* lab, TOut* out,
                            int B, int H, int W, const float* a_snr, const float* rho,
                            const int* nghost, const float* feather_taps, int R, void* ws,
                            size_t ws_bytes, void* stream_) {
   if (!img || !lab || !out || !a_snr || !rho || !nghost || !feather_taps || !ws) {
     set_error("usaug_snr_reverb: null pointer"); return USAUG_E_INVALID_ARG;
+  }
+  if ((sig == nullptr) != (sig_scale == nullptr)) {
+    set_error("usaug_snr_reverb: sig and sig_scale must be given together"); return USAUG_E_INVALID_ARG;
   }
   if (B <= 0 || H <= 0 || W <= 0 || R < 0 || 2 * R + 1 > kMaxTaps) {
     set_error("usaug_snr_reverb: bad shape B=%d H=%d W=%d R=%d (need R<=32)", B, H, W, R);
@@ -151,8 +159,8 @@ static int snr_reverb_impl(const float* img, const float* cm, const uint8_t* lab
   const size_t smem = (size_t)(kSrRows + 2 * R) * kSrCols * sizeof(float) + (size_t)(kSrRows + 2 * R) * (kSrCols + 2 * R);
   if (smem > 48 * 1024)
     USAUG_CUDA(cudaFuncSetAttribute(snr_reverb_kernel<TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  snr_reverb_kernel<TOut><<<grid, kSrCols, smem, stream>>>(img, cm, lab, out, H, W, a_snr, rho, nghost, box,
-                                                           feather_taps, R);
+  snr_reverb_kernel<TOut><<<grid, kSrCols, smem, stream>>>(img, cm, lab, sig, sig_scale, out, H, W, a_snr, rho, nghost,
+                                                           box, feather_taps, R);
   USAUG_CHECK_LAUNCH("snr_reverb_kernel");
   return USAUG_OK;
 }
@@ -161,12 +169,25 @@ extern "C" int usaug_snr_reverb(const float* img, const float* cm, const uint8_t
                                 int B, int H, int W, const float* a_snr, const float* rho,
                                 const int* nghost, const float* feather_taps, int R, void* ws,
                                 size_t ws_bytes, void* stream) {
-  return snr_reverb_impl<float>(img, cm, lab, out, B, H, W, a_snr, rho, nghost, feather_taps, R, ws, ws_bytes, stream);
+  return snr_reverb_impl<float>(img, cm, nullptr, nullptr, lab, out, B, H, W, a_snr, rho, nghost, feather_taps, R, ws,
+                                ws_bytes, stream);
 }
 
 extern "C" int usaug_snr_reverb_u8(const float* img, const float* cm, const uint8_t* lab, uint8_t* out,
                                    int B, int H, int W, const float* a_snr, const float* rho,
                                    const int* nghost, const float* feather_taps, int R, void* ws,
                                    size_t ws_bytes, void* stream) {
-  return snr_reverb_impl<uint8_t>(img, cm, lab, out, B, H, W, a_snr, rho, nghost, feather_taps, R, ws, ws_bytes, stream);
+  return snr_reverb_impl<uint8_t>(img, cm, nullptr, nullptr, lab, out, B, H, W, a_snr, rho, nghost, feather_taps, R, ws,
+                                  ws_bytes, stream);
+}
+
+extern "C" int usaug_snr_reverb_signal(const float* img, const float* cm, const float* sig, const float* sig_scale,
+                                       const uint8_t* lab, void* out, int out_is_u8, int B, int H, int W,
+                                       const float* a_snr, const float* rho, const int* nghost,
+                                       const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream) {
+  if (out_is_u8)
+    return snr_reverb_impl<uint8_t>(img, cm, sig, sig_scale, lab, static_cast<uint8_t*>(out), B, H, W, a_snr, rho, nghost,
+                                    feather_taps, R, ws, ws_bytes, stream);
+  return snr_reverb_impl<float>(img, cm, sig, sig_scale, lab, static_cast<float*>(out), B, H, W, a_snr, rho, nghost,
+                                feather_taps, R, ws, ws_bytes, stream);
 }

@@ -148,9 +148,34 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
     return cm
 
 
-def snr_reverb(image, cm, label, a_snr, rho, n_ghost, feather_taps, out_dtype=torch.float32):
+def local_energy(image, lambda_min=8.0, mult=2.1, scales=3, sigma_f=0.55):
+    """Monogenic-signal local energy.  image f32 [B,H,W], H and W powers of two in
+    [8, 2048].  Returns (energy f32 [B,H,W], scale f32 [B]) with scale = 1 / max(energy) per image (0 for an
+    image without band-pass content): energy * scale[:, None, None] is the normalised map in [0,1]."""
+    lib = _ffi.load()
+    image = _need_cuda(image, "image", torch.float32)
+    if image.dim() != 3:
+        raise ValueError(f"image must be [B,H,W], got {tuple(image.shape)}")
+    B, H, W = image.shape
+    dev = image.device
+    for n, name in ((H, "H"), (W, "W")):
+        if n < 8 or n > 2048 or (n & (n - 1)):
+            raise ValueError(f"local energy needs power-of-two image sizes in [8, 2048], got {name}={n}")
+    with torch.cuda.device(dev):
+        energy = torch.empty_like(image)
+        scale = torch.empty((B,), dtype=torch.float32, device=dev)
+        ws = _ws(lib.usaug_local_energy_workspace_bytes(B, H, W), dev)
+        rc = lib.usaug_local_energy(image.data_ptr(), energy.data_ptr(), scale.data_ptr(), B, H, W, float(lambda_min),
+                                    float(mult), int(scales), float(sigma_f), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _ffi.check(rc, "usaug_local_energy")
+    return energy, scale
+
+
+def snr_reverb(image, cm, label, a_snr, rho, n_ghost, feather_taps, out_dtype=torch.float32, signal=None,
+               signal_scale=None):
     """K3 (A.4 + A.5).  cm may be None (reverb only); n_ghost = 0 disables the ghosts.
-    out_dtype=torch.uint8 quantises the result on the way out: floor(255 v + 0.5) (8-bit egress)."""
+    out_dtype=torch.uint8 quantises the result on the way out: floor(255 v + 0.5) (8-bit egress).
+    signal / signal_scale (from ``local_energy``): SNR term (a-1) * C * signal * scale instead of (a-1) * C * I."""
     if out_dtype not in (torch.float32, torch.uint8):
         raise TypeError(f"out_dtype must be torch.float32 or torch.uint8, got {out_dtype}")
     lib = _ffi.load()
@@ -171,10 +196,20 @@ def snr_reverb(image, cm, label, a_snr, rho, n_ghost, feather_taps, out_dtype=to
         R = (taps_t.numel() - 1) // 2
         out = torch.empty(image.shape, dtype=out_dtype, device=dev)
         ws = _ws(lib.usaug_snr_reverb_workspace_bytes(B, H, W), dev)
-        entry = lib.usaug_snr_reverb_u8 if out_dtype == torch.uint8 else lib.usaug_snr_reverb
-        rc = entry(image.data_ptr(), 0 if cm is None else cm.data_ptr(), label.data_ptr(),
-                                  out.data_ptr(), B, H, W, a_t.data_ptr(), r_t.data_ptr(), n_t.data_ptr(),
-                                  taps_t.data_ptr(), R, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        if signal is not None:
+            signal = _need_cuda(signal, "signal", torch.float32)
+            signal_scale = _need_cuda(signal_scale, "signal_scale", torch.float32)
+            if signal.shape != image.shape or tuple(signal_scale.shape) != (B,):
+                raise ValueError("signal must have the image's shape and signal_scale shape [B]")
+            rc = lib.usaug_snr_reverb_signal(image.data_ptr(), 0 if cm is None else cm.data_ptr(), signal.data_ptr(),
+                                             signal_scale.data_ptr(), label.data_ptr(), out.data_ptr(),
+                                             1 if out_dtype == torch.uint8 else 0, B, H, W, a_t.data_ptr(), r_t.data_ptr(),
+                                             n_t.data_ptr(), taps_t.data_ptr(), R, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        else:
+            entry = lib.usaug_snr_reverb_u8 if out_dtype == torch.uint8 else lib.usaug_snr_reverb
+            rc = entry(image.data_ptr(), 0 if cm is None else cm.data_ptr(), label.data_ptr(), out.data_ptr(), B, H, W,
+                       a_t.data_ptr(), r_t.data_ptr(), n_t.data_ptr(), taps_t.data_ptr(), R, ws.data_ptr(), ws.numel(),
+                       _stream_ptr(dev))
         _ffi.check(rc, "usaug_snr_reverb")
     return out
 

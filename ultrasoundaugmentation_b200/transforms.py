@@ -125,17 +125,29 @@ class TimeGainCompensation(_Transform):
 
 
 class ConfidenceSNR(_Transform):
-    """A.3 + A.4: confidence map of the (deformed) image, then I + (a-1) * C * I, clipped."""
+    """A.3 + A.4: confidence map of the (deformed) image, then I + (a-1) * C * S, clipped.
+
+    ``signal="intensity"`` (default, the hot path): S = I.  ``signal="local_energy"``:
+    S = the image's monogenic-signal local energy, normalised to [0,1] -- sum of ``scales`` log-Gabor band-pass
+    filters with wavelengths ``lambda_min * mult**s`` pixels and their Riesz transforms (needs power-of-two
+    image sizes: the FFT is hand-written)."""
 
     _stream = 3
 
     def __init__(self, a_range: Sequence[float] = (0.7, 1.4), alpha: float = 2.0, beta: float = 90.0,
                  gamma: float = 0.05, rtol: float = 1e-8, maxiter: int = 20000, precond: str = "line",
                  fp64_vectors: bool = False, max_wave: Optional[int] = None, p: float = 1.0,
-                 seed: int = 0):
+                 seed: int = 0, signal: str = "intensity", lambda_min: float = 8.0, mult: float = 2.1,
+                 scales: int = 3, sigma_f: float = 0.55):
         super().__init__(p, seed)
         if precond not in ("line", "jacobi"):
             raise ValueError("precond must be 'line' or 'jacobi'")
+        if signal not in ("intensity", "local_energy"):
+            raise ValueError("signal must be 'intensity' or 'local_energy'")
+        if not (1 <= int(scales) <= 4 and lambda_min >= 2.0 and mult > 0.0 and 0.0 < sigma_f < 1.0):
+            raise ValueError("local-energy filter: 1 <= scales <= 4, lambda_min >= 2, mult > 0, 0 < sigma_f < 1")
+        self.signal = signal
+        self.lambda_min, self.mult, self.scales, self.sigma_f = float(lambda_min), float(mult), int(scales), float(sigma_f)
         self.a_range = (float(a_range[0]), float(a_range[1]))
         self.alpha, self.beta, self.gamma = float(alpha), float(beta), float(gamma)
         self.rtol, self.maxiter, self.precond = float(rtol), int(maxiter), precond
@@ -156,6 +168,12 @@ class ConfidenceSNR(_Transform):
                                         max_wave=self.max_wave, return_info=True, timing=self.timing)
         self.last_info = (it, rr)
         return cm
+
+    def signal_map(self, image_bhw: torch.Tensor):
+        """(signal plane, per-image scale) for ops.snr_reverb, or (None, None) for signal = intensity."""
+        if self.signal == "intensity":
+            return None, None
+        return ops.local_energy(image_bhw, self.lambda_min, self.mult, self.scales, self.sigma_f)
 
     def __getstate__(self):
         s = dict(self.__dict__)
@@ -262,9 +280,10 @@ class PhysicsChain:
             tgc = params["tgc"] if self.tgc is not None else torch.ones(B, 1)
             taps = self.deform.taps(W) if self.deform is not None else ops.gaussian_taps(0.0, 0)
             img, lab = ops.fused_tgc_deform(img, lab, d, tgc, taps)
-        cm = None
+        cm = sig = sig_scale = None
         if self.snr is not None:
             cm = self.snr.confidence_map(img)
+            sig, sig_scale = self.snr.signal_map(img)
         # ... and a uint8 result always leaves through the last kernel (pass-through if need be)
         if self.snr is not None or self.reverb is not None or u8_out:
             a = params["a_snr"] if self.snr is not None else torch.ones(B)
@@ -272,7 +291,8 @@ class PhysicsChain:
                 rho, n, taps = params["rho"], params["n_ghost"], self.reverb.taps()
             else:
                 rho, n, taps = torch.zeros(B), torch.zeros(B, dtype=torch.int32), ops.gaussian_taps(0.0, 0)
-            img = ops.snr_reverb(img, cm, lab, a, rho, n, taps, out_dtype=self.output_dtype)
+            img = ops.snr_reverb(img, cm, lab, a, rho, n, taps, out_dtype=self.output_dtype, signal=sig,
+                                 signal_scale=sig_scale)
         return img, lab
 
     # ---- host path: pinned host buffers in, pinned host buffers out ---------------------------
