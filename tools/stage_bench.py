@@ -71,6 +71,21 @@ def k3(B, H, W):
                 achieved_GBps=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK, img_per_s=B / ms * 1e3)
 
 
+def le(B, H, W):
+    img, _ = synth.make_batch(B, H, W, device=dev)
+    energy = torch.empty_like(img); scale = torch.empty(B, device=dev)
+    ws = torch.empty(lib.usaug_local_energy_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    def fn():
+        rc = lib.usaug_local_energy(img.data_ptr(), energy.data_ptr(), scale.data_ptr(), B, H, W, 8.0, 2.1, 3, 0.55,
+                                    ws.data_ptr(), ws.numel(), st)
+        assert rc == 0
+    ms = timed(fn, 10, False)
+    gb = 56 * B * H * W / 1e9
+    return dict(stage="local energy (rows fwd + cols + rows inv + scale)", B=B, H=H, W=W, us=ms * 1e3, bytes_per_px=56,
+                achieved_GBps=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK, img_per_s=B / ms * 1e3)
+
+
 def cm(B, H, W, rtol=1e-8):
     img, _ = synth.make_batch(B, H, W, device=dev)
     ops.confidence_map(img, rtol=rtol)
@@ -100,12 +115,14 @@ def chain(B, H, W, rtol=1e-8):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["k1", "k3", "cm", "chain"]
+    which = sys.argv[1:] or ["k1", "k3", "le", "cm", "chain"]
     out = []
     if "k1" in which:
         out += [k1(256, 256, 256, True), k1(256, 256, 256, False), k1(1024, 512, 512, False)]
     if "k3" in which:
         out += [k3(1024, 512, 512)]
+    if "le" in which:
+        out += [le(512, 512, 512), le(64, 1024, 1024), le(256, 256, 256)]
     if "cm" in which:
         out += [cm(64, 512, 512)]
     if "chain" in which:

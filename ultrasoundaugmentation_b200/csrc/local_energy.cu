@@ -37,39 +37,76 @@ __device__ __forceinline__ void make_twiddles(float2* tw, int n) {
   }
 }
 
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
 // nseq sequences of n = 1 << lg points, sequence q at data + q * pitch.  Natural order in, bit-reversed order out.
+// Radix-2 decimation in frequency, two stages per shared-memory pass (a thread owns a quad of points), so an
+// n-point transform takes ceil(lg / 2) passes and barriers instead of lg.
 __device__ __forceinline__ void fft_dif(float2* data, int pitch, int nseq, int lg, const float2* tw) {
-  const int half_n = 1 << (lg - 1);
-  for (int s = lg - 1; s >= 0; --s) {
-    const int half = 1 << s;
+  int s = lg - 1;
+  for (; s >= 1; s -= 2) {                       // stages s (half = 2^s) and s-1 (half = 2^(s-1))
+    const int quarter = 1 << (s - 1);
+    const int nquad = 1 << (lg - 2);
+    for (int idx = threadIdx.x; idx < nseq * nquad; idx += blockDim.x) {
+      const int q = idx >> (lg - 2), j = idx & (nquad - 1);
+      const int pos = j & (quarter - 1);
+      float2* x = data + q * pitch + (((j >> (s - 1)) << (s + 1)) | pos);
+      const float2 a0 = x[0], a1 = x[quarter], a2 = x[2 * quarter], a3 = x[3 * quarter];
+      // stage s: (0,2) and (1,3)
+      const float2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), tw[pos << (lg - 1 - s)]);
+      const float2 b1 = cadd(a1, a3), b3 = cmul(csub(a1, a3), tw[(pos + quarter) << (lg - 1 - s)]);
+      // stage s-1: (0,1) and (2,3)
+      const float2 w = tw[pos << (lg - s)];
+      x[0] = cadd(b0, b1); x[quarter] = cmul(csub(b0, b1), w);
+      x[2 * quarter] = cadd(b2, b3); x[3 * quarter] = cmul(csub(b2, b3), w);
+    }
+    __syncthreads();
+  }
+  if (s == 0) {                                  // odd lg: one plain radix-2 stage with half = 1 (twiddle 1)
+    const int half_n = 1 << (lg - 1);
     for (int idx = threadIdx.x; idx < nseq * half_n; idx += blockDim.x) {
       const int q = idx >> (lg - 1), j = idx & (half_n - 1);
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> s) << (s + 1)) | pos;
-      float2* x = data + q * pitch;
-      const float2 a = x[i0], b = x[i0 + half];
-      x[i0] = make_float2(a.x + b.x, a.y + b.y);
-      x[i0 + half] = cmul(make_float2(a.x - b.x, a.y - b.y), tw[pos << (lg - 1 - s)]);
+      float2* x = data + q * pitch + 2 * j;
+      const float2 a = x[0], b = x[1];
+      x[0] = cadd(a, b); x[1] = csub(a, b);
     }
     __syncthreads();
   }
 }
 
 // inverse transform (conjugate twiddles, unscaled).  Bit-reversed order in, natural order out.
+// Radix-2 decimation in time, two stages per pass like fft_dif.
 __device__ __forceinline__ void ifft_dit(float2* data, int pitch, int nseq, int lg, const float2* tw) {
-  const int half_n = 1 << (lg - 1);
-  for (int s = 0; s < lg; ++s) {
-    const int half = 1 << s;
+  int s = 0;
+  if (lg & 1) {                                  // odd lg: stage 0 alone (half = 1, twiddle 1)
+    const int half_n = 1 << (lg - 1);
     for (int idx = threadIdx.x; idx < nseq * half_n; idx += blockDim.x) {
       const int q = idx >> (lg - 1), j = idx & (half_n - 1);
+      float2* x = data + q * pitch + 2 * j;
+      const float2 a = x[0], b = x[1];
+      x[0] = cadd(a, b); x[1] = csub(a, b);
+    }
+    __syncthreads();
+    s = 1;
+  }
+  for (; s + 1 < lg; s += 2) {                   // stages s (half = 2^s) and s+1 (half = 2^(s+1))
+    const int half = 1 << s;
+    const int nquad = 1 << (lg - 2);
+    for (int idx = threadIdx.x; idx < nseq * nquad; idx += blockDim.x) {
+      const int q = idx >> (lg - 2), j = idx & (nquad - 1);
       const int pos = j & (half - 1);
-      const int i0 = ((j >> s) << (s + 1)) | pos;
-      float2* x = data + q * pitch;
-      float2 w = tw[pos << (lg - 1 - s)];
-      w.y = -w.y;
-      const float2 a = x[i0], t = cmul(x[i0 + half], w);
-      x[i0] = make_float2(a.x + t.x, a.y + t.y);
-      x[i0 + half] = make_float2(a.x - t.x, a.y - t.y);
+      float2* x = data + q * pitch + (((j >> s) << (s + 2)) | pos);
+      const float2 w = cconj(tw[pos << (lg - 1 - s)]);
+      const float2 a0 = x[0], t1 = cmul(x[half], w), a2 = x[2 * half], t3 = cmul(x[3 * half], w);
+      // stage s: (0,1) and (2,3)
+      const float2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
+      // stage s+1: (0,2) and (1,3)
+      const float2 u2 = cmul(b2, cconj(tw[pos << (lg - 2 - s)]));
+      const float2 u3 = cmul(b3, cconj(tw[(pos + half) << (lg - 2 - s)]));
+      x[0] = cadd(b0, u2); x[2 * half] = csub(b0, u2);
+      x[half] = cadd(b1, u3); x[3 * half] = csub(b1, u3);
     }
     __syncthreads();
   }
@@ -214,7 +251,8 @@ static LeLayout le_layout(void* ws, int B, int H, int W) {
   L.rb_fwd = 4096 / W; if (L.rb_fwd < 1) L.rb_fwd = 1; if (L.rb_fwd > 16) L.rb_fwd = 16;
   L.rb_inv = 4096 / W; if (L.rb_inv < 1) L.rb_inv = 1; if (L.rb_inv > 16) L.rb_inv = 16;
   while (H % L.rb_inv) L.rb_inv >>= 1;
-  L.tc = 8192 / H; if (L.tc < 1) L.tc = 1; if (L.tc > 16) L.tc = 16; if (L.tc > W) L.tc = W;
+  // columns per block: 64 KB of sequences (two buffers) so that three blocks share an SM
+  L.tc = 4096 / H; if (L.tc < 1) L.tc = 1; if (L.tc > 16) L.tc = 16; if (L.tc > W) L.tc = W;
   L.nblk_inv = H / L.rb_inv;
   Carver cv(ws);
   L.spec = cv.take<float2>(N); L.odd = cv.take<float2>(N); L.even = cv.take<float2>(N);
