@@ -119,7 +119,8 @@ int usaug_snr_reverb_signal(const float* img, const float* cm, const float* sig,
  * log-Gabor band-pass filters (wavelengths lambda_min * mult^s pixels, bandwidth sigma_f) and their
  * Riesz transforms; scale[B] = 1 / max(energy) per image (0 if the image has no band-pass content),
  * so energy * scale is the normalised map in [0,1] that usaug_snr_reverb_signal takes.
- * Hand-written batched 2-D FFT: H and W must be powers of two in [8, 2048]; 1 <= scales <= 4. */
+ * Hand-written batched 2-D FFT, 4 <= H, W <= 2048: sizes that are not powers of two are mirror-extended
+ * (bottom / right) to the next power of two, and the energy is cropped back.  1 <= scales <= 4. */
 size_t usaug_local_energy_workspace_bytes(int B, int H, int W);
 int usaug_local_energy(const float* img, float* energy, float* scale, int B, int H, int W,
                        float lambda_min, float mult, int scales, float sigma_f, void* ws,

@@ -12,6 +12,8 @@ parity unpinned).  Method [LIT: Felsberg & Sommer 2001 monogenic signal; Kovesi 
     E      = sqrt(even^2 + odd1^2 + odd2^2);   E_hat = E / max E   (0 for a constant image)
 
 u, v are the FFT frequencies in cycles/pixel along x (columns) and y (rows), rho = sqrt(u^2 + v^2).
+Sizes that are not powers of two: the image is mirror-extended (numpy.pad mode="symmetric", at the bottom and
+right) to the next power of two in that direction, transformed there, and E is cropped back before normalising.
 Everything here is fp64 (numpy.fft); the CUDA path computes the same in fp32 (stated tolerance in the tests).
 Pins that do not depend on any implementation: a constant image has E = 0; a plane wave cos(2 pi k0 x / W)
 has E = G(k0 / W) everywhere (even and odd parts are in quadrature), so E_hat = 1.
@@ -44,9 +46,23 @@ def log_gabor_sum(H: int, W: int, lambda_min=DEFAULT_LAMBDA_MIN, mult=DEFAULT_MU
     return G, u, v, rho
 
 
+def next_pow2(n: int) -> int:
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
 def local_energy_raw(image, **kw) -> np.ndarray:
     """E (not normalised), fp64 [H,W]."""
     img = np.asarray(image, dtype=np.float64)
+    H0, W0 = img.shape
+    Hp, Wp = max(next_pow2(H0), 8), max(next_pow2(W0), 8)
+    if (Hp, Wp) != (H0, W0):
+        if Hp - H0 > H0 or Wp - W0 > W0:
+            raise ValueError("image too small to mirror-extend (needs at least 4 pixels per side)")
+        ext = np.pad(img, ((0, Hp - H0), (0, Wp - W0)), mode="symmetric")
+        return local_energy_raw(ext, **kw)[:H0, :W0]
     H, W = img.shape
     G, u, v, rho = log_gabor_sum(H, W, **kw)
     F = np.fft.fft2(img)

@@ -28,7 +28,9 @@ def gpu_energy(dev, img, **kw):
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 128, 256), (2, 512, 512), (1, 1024, 1024), (2, 8, 8), (1, 2048, 16),
-                                    (1, 16, 2048)])
+                                    (1, 16, 2048),
+                                    # not powers of two: mirror-extended to the next one
+                                    (2, 97, 131), (2, 100, 64), (1, 480, 640), (2, 5, 9), (1, 4, 4), (1, 1030, 33)])
 def test_local_energy_parity(cuda_device, B, H, W):
     img, _ = util.synth_batch(B, H, W)
     e, s = gpu_energy(cuda_device, img)
@@ -77,7 +79,7 @@ def test_local_energy_flip_and_batch_independence(cuda_device):
 
 def test_local_energy_rejects_bad_shapes(cuda_device):
     from ultrasoundaugmentation_b200 import ops
-    for shape in [(1, 100, 128), (1, 128, 96), (1, 4, 128), (1, 4096, 8)]:
+    for shape in [(1, 3, 128), (1, 128, 2), (1, 4096, 8), (1, 8, 2049)]:
         with pytest.raises(ValueError):
             ops.local_energy(torch.zeros(shape, device=cuda_device))
     with pytest.raises(ValueError):
@@ -103,9 +105,9 @@ def test_snr_with_local_energy_signal(cuda_device):
     assert util.rel_err(got.cpu().numpy(), ref) <= util.REL_TOL
 
 
-def test_full_chain_with_local_energy(cuda_device):
+@pytest.mark.parametrize("B,H,W", [(2, 128, 128), (1, 97, 132)])
+def test_full_chain_with_local_energy(cuda_device, B, H, W):
     import ultrasoundaugmentation_b200 as us
-    B, H, W = 2, 128, 128
     RTOL = 1e-8
     img, lab = util.synth_batch(B, H, W)
     chain = us.PhysicsChain.full(seed=5, rtol=RTOL, signal="local_energy")

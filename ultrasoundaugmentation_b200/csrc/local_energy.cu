@@ -9,6 +9,8 @@
 //   le_scale      per image: 1 / max E (0 for an image without band-pass content)
 //
 // Pairing a DIF forward with a DIT inverse transform means no bit-reversal permutation is ever executed.
+// Sizes that are not powers of two are mirror-extended (bottom / right, edge included) to the next power of two
+// (Hp x Wp) on the way into le_rows_fwd; rows and columns beyond H x W are never written back.
 // HBM traffic: 4 + 8 | 8 + 16 | 16 + 4 = 56 B/px; everything else stays in shared memory.
 #include "kernels.cuh"
 
@@ -116,8 +118,9 @@ __device__ __forceinline__ void ifft_dit(float2* data, int pitch, int nseq, int 
 __device__ __forceinline__ int signed_bin(int k, int n) { return (k < n / 2) ? k : k - n; }
 
 // ---- rows, forward: block = rb rows ---------------------------------------------------------------
+// img is [B][H0][W0]; spec is [B][H][W] with H, W the padded (power-of-two) sizes
 __global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restrict__ img, float2* __restrict__ spec,
-                                                          int W, int lgW, int rb, size_t nrows) {
+                                                          int H0, int W0, int H, int W, int lgW, int rb, size_t nrows) {
   extern __shared__ __align__(16) unsigned char le_smem[];
   float2* tw = reinterpret_cast<float2*>(le_smem);          // [W/2]
   float2* data = tw + W / 2;                                // [rb][W]
@@ -125,7 +128,13 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restric
   make_twiddles(tw, W);
   for (int i = threadIdx.x; i < rb * W; i += blockDim.x) {
     const size_t r = row0 + i / W;
-    data[i] = make_float2(r < nrows ? img[r * W + (i % W)] : 0.f, 0.f);
+    float v = 0.f;
+    if (r < nrows) {
+      const int b = (int)(r / H), yp = (int)(r % H), xp = i % W;
+      const int y = (yp < H0) ? yp : 2 * H0 - 1 - yp, x = (xp < W0) ? xp : 2 * W0 - 1 - xp;   // mirror extension
+      v = img[((size_t)b * H0 + y) * W0 + x];
+    }
+    data[i] = make_float2(v, 0.f);
   }
   __syncthreads();
   fft_dif(data, W, rb, lgW, tw);
@@ -137,8 +146,8 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restric
 
 // ---- columns: block = tc columns of one image ---------------------------------------------------------
 __global__ void __launch_bounds__(kLeThreads) le_cols(const float2* __restrict__ spec, float2* __restrict__ odd,
-                                                      float2* __restrict__ even, int H, int W, int lgH, int lgW, int tc,
-                                                      LeFilter flt) {
+                                                      float2* __restrict__ even, int H0, int H, int W, int lgH, int lgW,
+                                                      int tc, LeFilter flt) {
   extern __shared__ __align__(16) unsigned char le_smem[];
   const int pitch = H + 1;                                  // odd pitch: the tc columns of one row hit different banks
   float2* tw = reinterpret_cast<float2*>(le_smem);          // [H/2]
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(kLeThreads) le_cols(const float2* __restrict__
   }
   __syncthreads();
   ifft_dit(A, pitch, 2 * tc, lgH, tw);                      // A and Bv are contiguous: 2 tc sequences
-  for (int i = threadIdx.x; i < tc * H; i += blockDim.x) {
+  for (int i = threadIdx.x; i < tc * H0; i += blockDim.x) {   // rows of the mirror extension are not needed again
     const int c = i % tc, y = i / tc;
     const size_t o = base + (size_t)y * W + x0 + c;
     odd[o] = A[c * pitch + y];
@@ -191,13 +200,13 @@ __global__ void __launch_bounds__(kLeThreads) le_cols(const float2* __restrict__
 // ---- rows, inverse + energy: block = rb rows -----------------------------------------------------------
 __global__ void __launch_bounds__(kLeThreads) le_rows_inv(const float2* __restrict__ odd, const float2* __restrict__ even,
                                                           float* __restrict__ energy, float* __restrict__ part,
-                                                          int H, int W, int lgW, int rb, float norm) {
+                                                          int H0, int W0, int H, int W, int lgW, int rb, float norm) {
   extern __shared__ __align__(16) unsigned char le_smem[];
   __shared__ float s_max[kLeThreads / 32];
   float2* tw = reinterpret_cast<float2*>(le_smem);          // [W/2]
   float2* data = tw + W / 2;                                // [2 rb][W]: odd rows, then even rows
   const int b = blockIdx.y;
-  const int row0 = blockIdx.x * rb;                         // H % rb == 0
+  const int row0 = blockIdx.x * rb;                         // H % rb == 0; only blocks with row0 < H0 are launched
   const size_t base = ((size_t)b * H + row0) * W;
   make_twiddles(tw, W);
   for (int i = threadIdx.x; i < rb * W; i += blockDim.x) {
@@ -208,10 +217,12 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_inv(const float2* __restri
   ifft_dit(data, W, 2 * rb, lgW, tw);
   float m = 0.f;
   for (int i = threadIdx.x; i < rb * W; i += blockDim.x) {
+    const int y = row0 + i / W, x = i % W;
+    if (y >= H0 || x >= W0) continue;                       // mirror extension: not part of the result
     const float2 q = data[i];
     const float e = data[rb * W + i].x;
     const float en = sqrtf(fmaf(e, e, fmaf(q.x, q.x, q.y * q.y))) * norm;
-    energy[base + i] = en;
+    energy[((size_t)b * H0 + y) * W0 + x] = en;
     m = fmaxf(m, en);
   }
   m = warp_max(m);
@@ -244,7 +255,14 @@ struct LeLayout {
   size_t bytes;
 };
 
-static LeLayout le_layout(void* ws, int B, int H, int W) {
+static int next_pow2_min8(int n) {
+  int p = 8;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// H, W: padded sizes; H0: image rows
+static LeLayout le_layout(void* ws, int B, int H0, int H, int W) {
   LeLayout L;
   const size_t N = (size_t)B * H * W;
   // rows per block: 32 KB of sequences (forward) / 64 KB (inverse: two planes), at least 1, at most 16
@@ -253,7 +271,7 @@ static LeLayout le_layout(void* ws, int B, int H, int W) {
   while (H % L.rb_inv) L.rb_inv >>= 1;
   // columns per block: 64 KB of sequences (two buffers) so that three blocks share an SM
   L.tc = 4096 / H; if (L.tc < 1) L.tc = 1; if (L.tc > 16) L.tc = 16; if (L.tc > W) L.tc = W;
-  L.nblk_inv = H / L.rb_inv;
+  L.nblk_inv = (H0 + L.rb_inv - 1) / L.rb_inv;
   Carver cv(ws);
   L.spec = cv.take<float2>(N); L.odd = cv.take<float2>(N); L.even = cv.take<float2>(N);
   L.part = cv.take<float>((size_t)B * L.nblk_inv);
@@ -265,33 +283,32 @@ static LeLayout le_layout(void* ws, int B, int H, int W) {
 
 using namespace usaug;
 
-static bool le_shape_ok(int B, int H, int W) {
-  return B > 0 && ilog2_exact(H) >= 3 && ilog2_exact(W) >= 3 && H <= kLeMaxN && W <= kLeMaxN;
-}
+static bool le_shape_ok(int B, int H, int W) { return B > 0 && H >= 4 && W >= 4 && H <= kLeMaxN && W <= kLeMaxN; }
 
 extern "C" size_t usaug_local_energy_workspace_bytes(int B, int H, int W) {
   if (!le_shape_ok(B, H, W)) return 0;
-  return le_layout(nullptr, B, H, W).bytes;
+  return le_layout(nullptr, B, H, next_pow2_min8(H), next_pow2_min8(W)).bytes;
 }
 
-extern "C" int usaug_local_energy(const float* img, float* energy, float* scale, int B, int H, int W,
+extern "C" int usaug_local_energy(const float* img, float* energy, float* scale, int B, int H0, int W0,
                                   float lambda_min, float mult, int scales, float sigma_f, void* ws,
                                   size_t ws_bytes, void* stream_) {
   if (!img || !energy || !scale || !ws) { set_error("usaug_local_energy: null pointer"); return USAUG_E_INVALID_ARG; }
-  if (!le_shape_ok(B, H, W)) {
-    set_error("usaug_local_energy: H=%d W=%d must be powers of two in [8, %d] (B=%d)", H, W, kLeMaxN, B);
+  if (!le_shape_ok(B, H0, W0)) {
+    set_error("usaug_local_energy: H=%d W=%d must lie in [4, %d] (B=%d)", H0, W0, kLeMaxN, B);
     return USAUG_E_INVALID_ARG;
   }
+  const int H = next_pow2_min8(H0), W = next_pow2_min8(W0);   // mirror-extended transform size
   if (scales < 1 || scales > kLeMaxScales || !(lambda_min >= 2.f) || !(mult > 0.f) || !(sigma_f > 0.f) || !(sigma_f < 1.f)) {
     set_error("usaug_local_energy: bad filter (lambda_min=%g >= 2, mult=%g > 0, 1 <= scales=%d <= %d, 0 < sigma_f=%g < 1)",
               lambda_min, mult, scales, kLeMaxScales, sigma_f);
     return USAUG_E_INVALID_ARG;
   }
-  if (ws_bytes < usaug_local_energy_workspace_bytes(B, H, W)) {
+  if (ws_bytes < usaug_local_energy_workspace_bytes(B, H0, W0)) {
     set_error("usaug_local_energy: workspace too small"); return USAUG_E_WORKSPACE_TOO_SMALL;
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const LeLayout L = le_layout(ws, B, H, W);
+  const LeLayout L = le_layout(ws, B, H0, H, W);
   const int lgH = ilog2_exact(H), lgW = ilog2_exact(W);
   LeFilter flt{};
   flt.scales = scales;
@@ -307,12 +324,13 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
   if (sm_col > 48 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_col));
   if (sm_inv > 48 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv));
 
-  le_rows_fwd<<<(unsigned)((nrows + L.rb_fwd - 1) / L.rb_fwd), kLeThreads, sm_fwd, stream>>>(img, L.spec, W, lgW, L.rb_fwd, nrows);
+  le_rows_fwd<<<(unsigned)((nrows + L.rb_fwd - 1) / L.rb_fwd), kLeThreads, sm_fwd, stream>>>(img, L.spec, H0, W0, H, W, lgW,
+                                                                                            L.rb_fwd, nrows);
   USAUG_CHECK_LAUNCH("le_rows_fwd");
-  le_cols<<<dim3(W / L.tc, B), kLeThreads, sm_col, stream>>>(L.spec, L.odd, L.even, H, W, lgH, lgW, L.tc, flt);
+  le_cols<<<dim3(W / L.tc, B), kLeThreads, sm_col, stream>>>(L.spec, L.odd, L.even, H0, H, W, lgH, lgW, L.tc, flt);
   USAUG_CHECK_LAUNCH("le_cols");
-  le_rows_inv<<<dim3(L.nblk_inv, B), kLeThreads, sm_inv, stream>>>(L.odd, L.even, energy, L.part, H, W, lgW, L.rb_inv,
-                                                                  (float)(1.0 / ((double)H * (double)W)));
+  le_rows_inv<<<dim3(L.nblk_inv, B), kLeThreads, sm_inv, stream>>>(L.odd, L.even, energy, L.part, H0, W0, H, W, lgW,
+                                                                  L.rb_inv, (float)(1.0 / ((double)H * (double)W)));
   USAUG_CHECK_LAUNCH("le_rows_inv");
   le_scale<<<(B + 127) / 128, 128, 0, stream>>>(L.part, L.nblk_inv, scale, B);
   USAUG_CHECK_LAUNCH("le_scale");

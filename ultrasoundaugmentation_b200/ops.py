@@ -149,8 +149,8 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
 
 
 def local_energy(image, lambda_min=8.0, mult=2.1, scales=3, sigma_f=0.55):
-    """Monogenic-signal local energy.  image f32 [B,H,W], H and W powers of two in
-    [8, 2048].  Returns (energy f32 [B,H,W], scale f32 [B]) with scale = 1 / max(energy) per image (0 for an
+    """Monogenic-signal local energy.  image f32 [B,H,W], 4 <= H, W <= 2048 (sizes that
+    are not powers of two are mirror-extended to the next one for the transform).  Returns (energy f32 [B,H,W], scale f32 [B]) with scale = 1 / max(energy) per image (0 for an
     image without band-pass content): energy * scale[:, None, None] is the normalised map in [0,1]."""
     lib = _ffi.load()
     image = _need_cuda(image, "image", torch.float32)
@@ -159,8 +159,8 @@ def local_energy(image, lambda_min=8.0, mult=2.1, scales=3, sigma_f=0.55):
     B, H, W = image.shape
     dev = image.device
     for n, name in ((H, "H"), (W, "W")):
-        if n < 8 or n > 2048 or (n & (n - 1)):
-            raise ValueError(f"local energy needs power-of-two image sizes in [8, 2048], got {name}={n}")
+        if n < 4 or n > 2048:
+            raise ValueError(f"local energy needs image sizes in [4, 2048], got {name}={n}")
     with torch.cuda.device(dev):
         energy = torch.empty_like(image)
         scale = torch.empty((B,), dtype=torch.float32, device=dev)

@@ -129,8 +129,8 @@ class ConfidenceSNR(_Transform):
 
     ``signal="intensity"`` (default, the hot path): S = I.  ``signal="local_energy"``:
     S = the image's monogenic-signal local energy, normalised to [0,1] -- sum of ``scales`` log-Gabor band-pass
-    filters with wavelengths ``lambda_min * mult**s`` pixels and their Riesz transforms (needs power-of-two
-    image sizes: the FFT is hand-written)."""
+    filters with wavelengths ``lambda_min * mult**s`` pixels and their Riesz transforms (image sizes 4...2048;
+    the hand-written FFT runs on the next power of two, mirror-extended)."""
 
     _stream = 3
 
