@@ -134,6 +134,15 @@ __global__ void __launch_bounds__(32) coarse_factor_kernel(CoarseGeom g, const d
   extern __shared__ double win[];          // [(kd+1)][(kd+1)]: win[r % (kd+1)][d] = current A[j+r, j+r-d]
   const int lane = threadIdx.x, b = blockIdx.x;
   const int n = g.nc, kd = g.kd, m = kd + 1;
+  // (r1, r2) of the t-th trailing-update pair, r1-major (pairs with r1 <= rmax form a prefix), unranked once
+  unsigned short* pair_tab = reinterpret_cast<unsigned short*>(win + m * m);   // [kd (kd + 1) / 2]
+  for (int t = lane; t < kd * (kd + 1) / 2; t += 32) {
+    int r1 = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while ((r1 + 1) * (r1 + 2) / 2 <= t) ++r1;
+    while (r1 * (r1 + 1) / 2 > t) --r1;
+    const int r2 = t - r1 * (r1 + 1) / 2 + 1;
+    pair_tab[t] = (unsigned short)(((r1 + 1) << 8) | r2);
+  }
   const double* A = Ab + (size_t)b * n * m;
   float* L_ = Lr + (size_t)b * n * g.kd1;
   float* U_ = Ur + (size_t)b * n * g.kd1;
@@ -141,40 +150,40 @@ __global__ void __launch_bounds__(32) coarse_factor_kernel(CoarseGeom g, const d
   for (int r = 0; r < m && r < n; ++r)
     for (int d = lane; d < m; d += 32) win[r * m + d] = A[(size_t)r * m + d];
   __syncwarp();
+  int slot = 0;                                    // j % m, kept incrementally
   for (int j = 0; j < n; ++j) {
     // column j of L lives on the diagonal-offset line of the window: L[j+r, j] = win[(j+r) % m][r] / L[j,j]
-    const double ajj = win[(j % m) * m + 0];
+    const double ajj = win[slot * m + 0];
     const double ljj = sqrt(fmax(ajj, 1e-300));
     const double inv = 1.0 / ljj;
     const int rmax = min(kd, n - 1 - j);
     // scale the column
-    for (int r = 1 + lane; r <= rmax; r += 32) win[((j + r) % m) * m + r] *= inv;
+    for (int r = 1 + lane; r <= rmax; r += 32) { int rs = slot + r; if (rs >= m) rs -= m; win[rs * m + r] *= inv; }
     __syncwarp();
     // trailing update: A[j+r1, j+r2] -= L[j+r1, j] * L[j+r2, j]   for 1 <= r2 <= r1 <= rmax
     const int npair = rmax * (rmax + 1) / 2;
     for (int t = lane; t < npair; t += 32) {
-      // unrank t -> (r1, r2), r1 >= r2 >= 1
-      int r1 = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-      while ((r1 + 1) * (r1 + 2) / 2 <= t) ++r1;
-      while (r1 * (r1 + 1) / 2 > t) --r1;
-      const int r2 = t - r1 * (r1 + 1) / 2 + 1;
-      r1 += 1;
-      const double l1 = win[((j + r1) % m) * m + r1], l2 = win[((j + r2) % m) * m + r2];
-      win[((j + r1) % m) * m + (r1 - r2)] -= l1 * l2;
+      const int pr = pair_tab[t], r1 = pr >> 8, r2 = pr & 255;
+      int s1 = slot + r1; if (s1 >= m) s1 -= m;
+      int s2 = slot + r2; if (s2 >= m) s2 -= m;
+      const double l1 = win[s1 * m + r1], l2 = win[s2 * m + r2];
+      win[s1 * m + (r1 - r2)] -= l1 * l2;
     }
     __syncwarp();
     // write out column j (as row j of Ur) and scatter it into the rows of Lr
     if (lane == 0) { U_[(size_t)j * g.kd1] = (float)inv; L_[(size_t)j * g.kd1] = (float)inv; }
     for (int r = 1 + lane; r <= rmax; r += 32) {
-      const float v = (float)win[((j + r) % m) * m + r];
+      int rs = slot + r; if (rs >= m) rs -= m;
+      const float v = (float)win[rs * m + r];
       U_[(size_t)j * g.kd1 + r] = v * (float)inv;
       L_[(size_t)(j + r) * g.kd1 + r] = v;
     }
     __syncwarp();
     // slide the window: row j leaves, row j + m enters in its slot
     if (j + m < n)
-      for (int d = lane; d < m; d += 32) win[(j % m) * m + d] = A[(size_t)(j + m) * m + d];
+      for (int d = lane; d < m; d += 32) win[slot * m + d] = A[(size_t)(j + m) * m + d];
     __syncwarp();
+    if (++slot == m) slot = 0;
   }
 }
 

@@ -224,7 +224,7 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   if (L.cg.by && !(flags & USAUG_CM_LEGACY_KERNEL)) {
     coarse_assemble_kernel<<<dim3((L.cg.nc + 7) / 8, B), 256, 0, stream>>>(H, W, L.cg, L.wS, L.wE, L.wSE, L.wSW, L.Ab);
     USAUG_CHECK_LAUNCH("coarse_assemble_kernel");
-    const size_t fsm = (size_t)(L.cg.kd + 1) * (L.cg.kd + 1) * sizeof(double);
+    const size_t fsm = (size_t)(L.cg.kd + 1) * (L.cg.kd + 1) * sizeof(double) + (size_t)L.cg.kd * (L.cg.kd + 1);   // window + pair table
     coarse_factor_kernel<<<B, 32, fsm, stream>>>(L.cg, L.Ab, L.Lr, L.Ur);
     USAUG_CHECK_LAUNCH("coarse_factor_kernel");
   }
