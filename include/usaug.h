@@ -126,6 +126,18 @@ int usaug_local_energy(const float* img, float* energy, float* scale, int B, int
                        float lambda_min, float mult, int scales, float sigma_f, void* ws,
                        size_t ws_bytes, void* stream);
 
+/* ---- curvilinear (convex-probe) geometry: scan conversion ----------------
+ * direction 0: Cartesian img/lab [B,H,W] -> polar out [B,n_samples,n_rays], sampled at
+ *              (x, y) = (apex_x, apex_y) + r_i * (ray_sin[j], ray_cos[j]),  r_i = r_min + i * dr;
+ * direction 1: polar img/lab [B,n_samples,n_rays] -> Cartesian out [B,H,W], sampled at
+ *              i* = (r - r_min) * inv_dr,  j* = (theta + theta_max) * inv_dtheta  (0 outside the sector).
+ * Image 4-tap bilinear (zeros outside), label nearest.  ray_sin / ray_cos [n_rays] are device tables
+ * (needed for direction 0 only).  All coordinates are individually rounded fp32 operations. */
+int usaug_scan_convert(const float* img, const uint8_t* lab, float* out_img, uint8_t* out_lab, int B,
+                       int H, int W, int n_samples, int n_rays, int direction, float apex_x, float apex_y,
+                       float theta_max, float r_min, float dr, float inv_dr, float inv_dtheta,
+                       const float* ray_sin, const float* ray_cos, void* stream);
+
 /* ---- bone bounding box of a label batch (A.1 step 2 / A.5 "bone-surface row") --------------
  * box[B,4] = {y_top, y_bottom, x_left, x_right}; y_top = -1 when the image has no bone.
  */

@@ -162,3 +162,40 @@ def test_local_energy_known_answers():
     # A.4 general form reduces to the hot-path form for E = I
     cm = np.random.default_rng(0).random((H, W)).astype(np.float32)
     assert np.array_equal(ole.snr_apply_signal(img, cm, img, 1.3), osr.snr_apply(img, cm, 1.3))
+
+
+def test_scan_conversion_known_answers():
+    """Convex-probe scan conversion: the spec'd arctangent is accurate, the two coordinate
+    maps invert each other, an affine image survives Cartesian -> polar exactly (bilinear is exact on affine
+    functions) and the round trip reproduces a smooth image inside the sector."""
+    from oracle import scanconv as osc
+    z = np.linspace(0, 1, 20001, dtype=np.float32)
+    assert np.abs(osc.spec_atan(z).astype(np.float64) - np.arctan(z.astype(np.float64))).max() <= 2e-7
+    dx = np.array([-3.0, -1.0, 0.0, 0.5, 2.0, 7.0], np.float32); dy = np.array([1.0, 1.0, 2.0, 4.0, 2.0, 1.0], np.float32)
+    assert np.abs(osc.spec_atan2_pos(dx, dy) - np.arctan2(dx.astype(np.float64), dy)).max() <= 3e-7
+    H, W = 96, 128
+    g = osc.default_geometry(H, W, theta_max=0.35)      # narrow enough that the fan stays inside the image sideways
+    y, x = osc.polar_coords_of_grid(g)
+    i_s, j_s, below = osc.grid_coords_of_cart(g, H, W)
+    # the two maps invert each other: the (i*, j*) fields, interpolated at the Cartesian position of node (i, j), give (i, j)
+    node_ok = (y >= 1) & (y <= H - 2) & (x >= 1) & (x <= W - 2)
+    ii, jj = np.meshgrid(np.arange(g.n_samples), np.arange(g.n_rays), indexing="ij")
+    assert node_ok.mean() > 0.3
+    assert np.abs(osc._bilinear(i_s, y, x)[node_ok] - ii[node_ok]).max() < 2e-2
+    assert np.abs(osc._bilinear(j_s, y, x)[node_ok] - jj[node_ok]).max() < 2e-2
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    affine = (0.1 + 0.002 * xx + 0.004 * yy).astype(np.float32)
+    lab = ((yy - 50) ** 2 + (xx - 64) ** 2 < 15 ** 2).astype(np.uint8)
+    pi, pl = osc.cart_to_polar(affine, lab, g)
+    inside = (y >= 0) & (y <= H - 1) & (x >= 0) & (x <= W - 1)
+    want = 0.1 + 0.002 * x.astype(np.float64) + 0.004 * y.astype(np.float64)
+    assert np.abs(pi[inside] - want[inside]).max() <= 2e-6
+    assert pl.dtype == np.uint8 and 0 < pl.sum() < pl.size
+    smooth = (0.5 + 0.4 * np.sin(xx / 17.0) * np.cos(yy / 23.0)).astype(np.float32)
+    ps, _ = osc.cart_to_polar(smooth, lab, g)
+    back, back_l = osc.polar_to_cart(ps, pl, g, H, W)
+    core = (i_s > 5) & (i_s < g.n_samples - 2) & (j_s > 1) & (j_s < g.n_rays - 2) & below
+    assert core.mean() > 0.3
+    assert np.abs(back[core] - smooth[core]).max() <= 5e-3
+    assert (back_l[core] != lab[core]).mean() <= 0.02          # only pixels on the disc's boundary may flip
+    assert np.all(back[~below] == 0)

@@ -5,10 +5,11 @@ Host code is Python (transform callables + parameter sampling); all compute runs
 hand-written sm_100a CUDA kernels behind the C ABI of include/usaug.h (libusaug.so).
 There is no CPU fallback and no other backend.
 """
-from . import ops, params, sharding, synth  # noqa: F401
+from . import geometry, ops, params, sharding, synth  # noqa: F401
+from .geometry import ConvexGeometry
 from .transforms import (ConfidenceSNR, PhysicsChain, ProbePressureDeformation, Reverberation,
                          TimeGainCompensation)
 
 __all__ = ["ProbePressureDeformation", "TimeGainCompensation", "ConfidenceSNR", "Reverberation",
-           "PhysicsChain", "ops", "params", "sharding", "synth"]
+           "PhysicsChain", "ConvexGeometry", "geometry", "ops", "params", "sharding", "synth"]
 __version__ = "1.1.0"

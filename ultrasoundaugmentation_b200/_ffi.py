@@ -49,6 +49,9 @@ SYMBOLS = {
     "usaug_local_energy_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "usaug_local_energy": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int,
                                    c_float, c_void_p, c_size_t, c_void_p]),
+    "usaug_scan_convert": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
+                                   c_void_p]),
     "usaug_bone_box_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "usaug_bone_box": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

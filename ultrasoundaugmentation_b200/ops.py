@@ -214,6 +214,43 @@ def snr_reverb(image, cm, label, a_snr, rho, n_ghost, feather_taps, out_dtype=to
     return out
 
 
+def _scan_convert(image, label, geom, direction, H, W):
+    lib = _ffi.load()
+    image, label = _check_pair(image, label)
+    B = image.shape[0]
+    dev = image.device
+    ns, nr = int(geom.n_samples), int(geom.n_rays)
+    want = (B, H, W) if direction == 0 else (B, ns, nr)
+    if tuple(image.shape) != want:
+        raise ValueError(f"expected input of shape {want}, got {tuple(image.shape)}")
+    out_shape = (B, ns, nr) if direction == 0 else (B, H, W)
+    ax, ay, thm, rmin, dr, inv_dr, inv_dth = (float(v) for v in geom.scalars())
+    with torch.cuda.device(dev):
+        out_img = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        out_lab = torch.empty(out_shape, dtype=torch.uint8, device=dev)
+        sin_t = cos_t = None
+        if direction == 0:
+            s, c = geom.tables()
+            sin_t = torch.from_numpy(s).to(dev, non_blocking=True)
+            cos_t = torch.from_numpy(c).to(dev, non_blocking=True)
+        rc = lib.usaug_scan_convert(image.data_ptr(), label.data_ptr(), out_img.data_ptr(), out_lab.data_ptr(), B, H, W,
+                                    ns, nr, direction, ax, ay, thm, rmin, dr, inv_dr, inv_dth,
+                                    0 if sin_t is None else sin_t.data_ptr(), 0 if cos_t is None else cos_t.data_ptr(),
+                                    _stream_ptr(dev))
+        _ffi.check(rc, "usaug_scan_convert")
+    return out_img, out_lab
+
+
+def cart_to_polar(image, label, geom):
+    """Cartesian [B,H,W] -> polar [B,n_samples,n_rays] of a ``geometry.ConvexGeometry`` (image bilinear, label nearest)."""
+    return _scan_convert(image, label, geom, 0, int(image.shape[1]), int(image.shape[2]))
+
+
+def polar_to_cart(image_p, label_p, geom, H, W):
+    """polar [B,n_samples,n_rays] -> Cartesian [B,H,W]; pixels outside the sector are 0."""
+    return _scan_convert(image_p, label_p, geom, 1, int(H), int(W))
+
+
 def bone_box(label):
     """[B,4] int32 {y_top, y_bottom, x_left, x_right}; y_top = -1 for an image without bone."""
     lib = _ffi.load()

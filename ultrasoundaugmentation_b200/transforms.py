@@ -221,10 +221,15 @@ class PhysicsChain:
     5 bytes per pixel over PCIe in each direction.  The arithmetic in between is fp32 either way.
     """
 
-    def __init__(self, transforms: Sequence[_Transform], output_dtype=torch.float32):
+    def __init__(self, transforms: Sequence[_Transform], output_dtype=torch.float32, geometry=None):
         if output_dtype not in (torch.float32, torch.uint8):
             raise TypeError(f"output_dtype must be torch.float32 or torch.uint8, got {output_dtype}")
+        if geometry is not None and output_dtype != torch.float32:
+            raise ValueError("a probe geometry needs float32 images in and out")
         self.output_dtype = output_dtype
+        # geometry.ConvexGeometry: the chain runs on the polar grid of rays x samples (SURVEY.md 8(f) row 4);
+        # None = linear probe, scanlines are the image columns
+        self.geometry = geometry
         self.deform = self.tgc = self.snr = self.reverb = None
         for t in transforms:
             if isinstance(t, ProbePressureDeformation):
@@ -245,15 +250,20 @@ class PhysicsChain:
             raise ValueError("empty chain")
 
     @classmethod
-    def full(cls, seed: int = 0, output_dtype=torch.float32, **snr_kwargs) -> "PhysicsChain":
+    def full(cls, seed: int = 0, output_dtype=torch.float32, geometry=None, **snr_kwargs) -> "PhysicsChain":
         return cls([ProbePressureDeformation(seed=seed), TimeGainCompensation(seed=seed),
-                    ConfidenceSNR(seed=seed, **snr_kwargs), Reverberation(seed=seed)], output_dtype=output_dtype)
+                    ConfidenceSNR(seed=seed, **snr_kwargs), Reverberation(seed=seed)], output_dtype=output_dtype,
+                   geometry=geometry)
 
     def get_params(self, batch_size, generator=None, sample_index=None, image_size=None) -> dict:
         out = {}
         for t in self.transforms:
             out.update(t.get_params(batch_size, generator, sample_index, image_size))
         return out
+
+    def _scanline_grid(self, H, W):
+        """(samples per scanline, scanlines) the transforms act on: the image itself, or the polar grid of a convex probe."""
+        return (H, W) if self.geometry is None else (int(self.geometry.n_samples), int(self.geometry.n_rays))
 
     # ---- device path --------------------------------------------------------------------------
     def __call__(self, image, label, params: Optional[dict] = None, sample_index=None):
@@ -267,11 +277,21 @@ class PhysicsChain:
             raise TypeError(f"label must be uint8, got {lab.dtype}")
         B, H, W = img.shape
         if params is None:
-            params = self.get_params(B, None, sample_index, (H, W))
+            params = self.get_params(B, None, sample_index, self._scanline_grid(H, W))
         out_img, out_lab = self._run(img.contiguous(), lab.contiguous(), params)
         return out_img.reshape(shp), out_lab.reshape(shp)
 
     def _run(self, img, lab, params):
+        if self.geometry is not None:
+            if img.dtype != torch.float32:
+                raise TypeError("a probe geometry needs a float32 image")
+            Hc, Wc = int(img.shape[1]), int(img.shape[2])
+            pi, pl = ops.cart_to_polar(img, lab, self.geometry)
+            pi, pl = self._run_scanlines(pi, pl, params)
+            return ops.polar_to_cart(pi, pl, self.geometry, Hc, Wc)
+        return self._run_scanlines(img, lab, params)
+
+    def _run_scanlines(self, img, lab, params):
         B, H, W = img.shape
         u8_out = self.output_dtype == torch.uint8
         # a uint8 image always passes the first kernel (identity warp if need be): that is where it is ingested
@@ -309,7 +329,7 @@ class PhysicsChain:
         img, lab, shp = _to_bhw(image, label)
         B, H, W = img.shape
         if params is None:
-            params = self.get_params(B, None, sample_index, (H, W))
+            params = self.get_params(B, None, sample_index, self._scanline_grid(H, W))
         with torch.cuda.device(device):
             d_img = img.contiguous().to(device, non_blocking=True)
             d_lab = lab.contiguous().to(device, non_blocking=True)
@@ -355,7 +375,7 @@ class PhysicsChain:
                     raise ValueError("augment_host_stream takes host tensors")
                 img, lab, shp = _to_bhw(image, label)
                 B, H, W = img.shape
-                params = self.get_params(B, None, sample_index, (H, W))
+                params = self.get_params(B, None, sample_index, self._scanline_grid(H, W))
                 with torch.cuda.stream(s_in):
                     d_img = img.contiguous().to(device, non_blocking=True)
                     d_lab = lab.contiguous().to(device, non_blocking=True)
