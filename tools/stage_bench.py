@@ -86,6 +86,28 @@ def le(B, H, W):
                 achieved_GBps=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK, img_per_s=B / ms * 1e3)
 
 
+def sc(B, H, W):
+    img, lab = synth.make_batch(B, H, W, device=dev)
+    g = us.ConvexGeometry.default(H, W, theta_max=0.4)
+    ax, ay, thm, rmin, dr, inv_dr, inv_dth = (float(v) for v in g.scalars())
+    s_, c_ = g.tables()
+    sin_t, cos_t = torch.from_numpy(s_).to(dev), torch.from_numpy(c_).to(dev)
+    pi, pl = torch.empty_like(img), torch.empty_like(lab)
+    ci, cl = torch.empty_like(img), torch.empty_like(lab)
+    st = torch.cuda.current_stream().cuda_stream
+    out = []
+    for direction, (a, b, c, d_) in ((0, (img, lab, pi, pl)), (1, (pi, pl, ci, cl))):
+        def fn():
+            rc = lib.usaug_scan_convert(a.data_ptr(), b.data_ptr(), c.data_ptr(), d_.data_ptr(), B, H, W, H, W, direction,
+                                        ax, ay, thm, rmin, dr, inv_dr, inv_dth, sin_t.data_ptr(), cos_t.data_ptr(), st)
+            assert rc == 0
+        ms = timed(fn, 20, False)
+        gb = 10 * B * H * W / 1e9
+        out.append(dict(stage="scan conversion " + ("Cartesian -> polar" if direction == 0 else "polar -> Cartesian"), B=B, H=H, W=W,
+                        us=ms * 1e3, bytes_per_px=10, achieved_GBps=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK, img_per_s=B / ms * 1e3))
+    return out
+
+
 def cm(B, H, W, rtol=1e-8):
     img, _ = synth.make_batch(B, H, W, device=dev)
     ops.confidence_map(img, rtol=rtol)
@@ -115,7 +137,7 @@ def chain(B, H, W, rtol=1e-8):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["k1", "k3", "le", "cm", "chain"]
+    which = sys.argv[1:] or ["k1", "k3", "le", "sc", "cm", "chain"]
     out = []
     if "k1" in which:
         out += [k1(256, 256, 256, True), k1(256, 256, 256, False), k1(1024, 512, 512, False)]
@@ -123,6 +145,8 @@ if __name__ == "__main__":
         out += [k3(1024, 512, 512)]
     if "le" in which:
         out += [le(512, 512, 512), le(64, 1024, 1024), le(256, 256, 256)]
+    if "sc" in which:
+        out += sc(1024, 512, 512)
     if "cm" in which:
         out += [cm(64, 512, 512)]
     if "chain" in which:
