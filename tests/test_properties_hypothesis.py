@@ -75,3 +75,61 @@ def test_confmap_fuzz(cuda_device, H, W, seed, B):
     # white-noise images amplify the residual more than speckle (measured K = err/relres up to 1.4e5 vs <= 2.9e4),
     # so the fuzz bound uses 2e5 * rtol instead of tol_cm's 5e4 * rtol
     assert np.abs(cm.cpu().numpy() - ref).max() <= 2e5 * 1e-9 + 2e-5
+
+
+@settings(**SETTINGS)
+@given(H=st.integers(4, 90), W=st.integers(4, 150), seed=st.integers(0, 10_000), scales=st.integers(1, 4),
+       lam=st.floats(3.0, 20.0), mult=st.floats(1.3, 3.0), sf=st.floats(0.35, 0.8))
+def test_local_energy_fuzz(cuda_device, H, W, seed, scales, lam, mult, sf):
+    """Any size in [4, ...] (mirror-extended to the next power of two) and any admissible filter against the oracle."""
+    from oracle import local_energy as ole
+    from ultrasoundaugmentation_b200 import ops
+    rng = np.random.default_rng(seed)
+    img = rng.random((2, H, W), dtype=np.float32)
+    if seed % 3 == 0:
+        img[1] = osynth.make_bmode(H, W, seed)[0]
+    kw = dict(lambda_min=lam, mult=mult, scales=scales, sigma_f=sf)
+    e, s = ops.local_energy(util.cuda(img, cuda_device), **kw)
+    got = (e * s[:, None, None]).cpu().numpy()
+    assert np.abs(got - ole.local_energy_batch(img, **kw)).max() <= 2e-5
+    assert got.min() >= 0.0 and got.max() <= 1.0 + 1e-6
+
+
+@settings(**SETTINGS)
+@given(H=st.integers(8, 80), W=st.integers(8, 120), ns=st.integers(2, 90), nr=st.integers(2, 130),
+       th=st.floats(0.05, 1.4), above=st.floats(0.0, 1.0), seed=st.integers(0, 10_000))
+def test_scan_conversion_fuzz(cuda_device, H, W, ns, nr, th, above, seed):
+    """Any fan geometry, both directions: labels bit-exact, image 1e-5 relative."""
+    from oracle import scanconv as osc
+    import ultrasoundaugmentation_b200 as us
+    from ultrasoundaugmentation_b200 import ops
+    rng = np.random.default_rng(seed)
+    img = rng.random((1, H, W), dtype=np.float32)
+    lab = (rng.integers(0, 3, (1, H, W)) * 100).astype(np.uint8)
+    g = osc.default_geometry(H, W, n_samples=ns, n_rays=nr, theta_max=th, apex_above=above + 0.01)
+    gp = us.ConvexGeometry(g.apex_x, g.apex_y, g.theta_max, g.r_min, g.r_max, g.n_samples, g.n_rays)
+    pi, pl = ops.cart_to_polar(util.cuda(img, cuda_device), util.cuda(lab, cuda_device), gp)
+    ri, rl = osc.cart_to_polar(img[0], lab[0], g)
+    assert np.array_equal(pl[0].cpu().numpy(), rl)
+    assert util.rel_err(pi[0].cpu().numpy(), ri) <= util.REL_TOL
+    ci, cl = ops.polar_to_cart(util.cuda(ri[None], cuda_device), util.cuda(rl[None], cuda_device), gp, H, W)
+    bi, bl = osc.polar_to_cart(ri, rl, g, H, W)
+    assert np.array_equal(cl[0].cpu().numpy(), bl)
+    assert util.rel_err(ci[0].cpu().numpy(), bi) <= util.REL_TOL
+
+
+@settings(**SETTINGS)
+@given(H=st.integers(3, 60), W=st.integers(1, 140), seed=st.integers(0, 10_000), d=st.floats(-20, 20))
+def test_u8_ingest_fuzz(cuda_device, H, W, seed, d):
+    from ultrasoundaugmentation_b200 import ops
+    rng = np.random.default_rng(seed)
+    img8 = rng.integers(0, 256, (1, H, W)).astype(np.uint8)
+    lab = (rng.random((1, H, W)) < 0.2).astype(np.uint8)
+    tgc = rng.uniform(0.5, 1.5, (1, 3)).astype(np.float32)
+    taps = odeform.gaussian_taps(1.0)
+    dd = np.array([d], np.float32)
+    ref_i, ref_l = odeform.fused_tgc_deform_batch(img8, lab, dd, tgc, taps)
+    gi, gl = ops.fused_tgc_deform(util.cuda(img8, cuda_device), util.cuda(lab, cuda_device), torch.from_numpy(dd),
+                                  torch.from_numpy(tgc), torch.from_numpy(taps))
+    assert np.array_equal(gl.cpu().numpy(), ref_l)
+    assert util.rel_err(gi.cpu().numpy(), ref_i) <= util.REL_TOL
