@@ -48,6 +48,32 @@ struct Carver {
 int device_sm_count();
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// A short chain of small kernels (scan -> profile -> warp) pays a launch gap at every boundary.  A kernel
+// launched with launch_pdl may start while its predecessor on the stream drains: every block of the
+// predecessor calls pdl_trigger() when it starts, the dependent kernel runs whatever does not need the
+// predecessor's results and then pdl_wait()s -- which returns once the predecessor grid has completed and
+// its memory is visible.  Kernels launched normally treat both calls as no-ops.
+// RULE (measured on B200, CUDA 12.9 / driver 580): only use this for a kernel that is followed, inside the same
+// C-ABI call, by a NORMALLY launched kernel.  A small host-to-device copy of pageable memory enqueued after a
+// PDL-launched kernel was observed to land before that kernel had finished (torch hands the parameter
+// buffers of one call to the next, so late blocks read the next call's parameters): the last kernel of every
+// call is therefore launched normally, which restores plain stream order for whatever the caller does next.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -194,7 +194,7 @@ static int snr_reverb_impl(const float* img, const float* cm, const float* sig, 
   Carver cv(ws);
   int* surf = cv.take<int>((size_t)B * scan_tiles(H) * W * 2);
   int* box = cv.take<int>((size_t)B * 4);
-  int rc = usaug_bone_box(lab, B, H, W, box, surf, surface_scan_bytes(B, H, W), stream_);
+  int rc = launch_bone_box(lab, B, H, W, box, surf, stream, true);
   if (rc) return rc;
   dim3 grid((W + kSrCols - 1) / kSrCols, (H + kSrRows - 1) / kSrRows, B);
   const size_t smem = (size_t)(kSrRows + 2 * R) * kSrCols * sizeof(float) + (size_t)(kSrRows + 2 * R) * (kSrCols + 2 * R);

@@ -9,7 +9,8 @@
 namespace usaug {
 
 // ---------------------------------------------------------------------------------------------
-// Surface scan: every label byte is read exactly once, fully parallel (no early-exit chains).
+// Surface scan: every label byte is read exactly once, fully parallel (no early-exit chains); rows whose
+// bytes are all zero are skipped with one test per load.
 // Block = 256 threads = 8 warps; a block covers 32*VEC columns x kScanRows rows; lane owns VEC
 // adjacent columns, warps interleave rows.  Per-column first/last bone row inside the tile is
 // merged through shared memory and written as one partial per (tile, column): no memset, no atomics.
@@ -19,8 +20,10 @@ constexpr int kScanRows = 64;
 template <int VEC>
 __global__ void __launch_bounds__(256) surface_scan_kernel(const uint8_t* __restrict__ lab, int H,
                                                            int W, int* __restrict__ surf) {
-  __shared__ int s_first[8][32 * VEC];
-  __shared__ int s_last[8][32 * VEC];
+  pdl_trigger();                                       // the consumer of surf may start launching (it pdl_wait()s)
+  constexpr int PITCH = VEC + (VEC > 1 ? 1 : 0);      // odd lane pitch: the VEC stores of a lane hit distinct banks
+  __shared__ int s_first[8][32 * PITCH];
+  __shared__ int s_last[8][32 * PITCH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.z;
   const int x0 = (blockIdx.x * 32 + lane) * VEC;
@@ -30,26 +33,39 @@ __global__ void __launch_bounds__(256) surface_scan_kernel(const uint8_t* __rest
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { first[v] = kNone; last[v] = -1; }
   if (x0 < W) {
-    uint32_t vals[kScanRows / 8];
+    constexpr int NW = (VEC + 3) / 4;                 // 32-bit words per load: 1 (VEC = 1, 4), 2 (VEC = 8) or 4 (VEC = 16: one 128-bit load)
+    uint32_t vals[kScanRows / 8][NW];
 #pragma unroll
     for (int i = 0; i < kScanRows / 8; ++i) {
       const int y = y0 + warp + 8 * i;
-      uint32_t w = 0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) vals[i][k] = 0;
       if (y < H) {
-        if (VEC == 4) {
-          w = *reinterpret_cast<const uint32_t*>(L + (size_t)y * W + x0);
+        if (VEC == 16) {
+          const uint4 q = *reinterpret_cast<const uint4*>(L + (size_t)y * W + x0);
+          vals[i][0] = q.x; vals[i][NW > 1 ? 1 : 0] = q.y; vals[i][NW > 2 ? 2 : 0] = q.z; vals[i][NW > 3 ? 3 : 0] = q.w;
+        } else if (VEC == 8) {
+          const uint2 q = *reinterpret_cast<const uint2*>(L + (size_t)y * W + x0);
+          vals[i][0] = q.x; vals[i][NW > 1 ? 1 : 0] = q.y;
+        } else if (VEC == 4) {
+          vals[i][0] = *reinterpret_cast<const uint32_t*>(L + (size_t)y * W + x0);
         } else {
-          w = L[(size_t)y * W + x0];
+          vals[i][0] = L[(size_t)y * W + x0];
         }
       }
-      vals[i] = w;
     }
+    // the scan is ALU-bound if every byte is examined (5 instructions per byte); almost all words are zero
+    // (bone covers a few per cent of the pixels), so a row is examined only if it holds a set byte at all
 #pragma unroll
     for (int i = 0; i < kScanRows / 8; ++i) {
+      uint32_t any = 0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) any |= vals[i][k];
+      if (any == 0) continue;
       const int y = y0 + warp + 8 * i;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        if ((vals[i] >> (8 * v)) & 0xffu) {
+        if ((vals[i][v / 4] >> (8 * (v & 3))) & 0xffu) {
           first[v] = min(first[v], y);
           last[v] = max(last[v], y);
         }
@@ -58,16 +74,16 @@ __global__ void __launch_bounds__(256) surface_scan_kernel(const uint8_t* __rest
   }
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    s_first[warp][lane * VEC + v] = first[v];
-    s_last[warp][lane * VEC + v] = last[v];
+    s_first[warp][lane * PITCH + v] = first[v];
+    s_last[warp][lane * PITCH + v] = last[v];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
     int f = kNone, l = -1;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      f = min(f, s_first[w][c]);
-      l = max(l, s_last[w][c]);
+      f = min(f, s_first[w][c + (PITCH - VEC) * (c / VEC)]);
+      l = max(l, s_last[w][c + (PITCH - VEC) * (c / VEC)]);
     }
     const int x = blockIdx.x * 32 * VEC + c;
     if (x < W) {   // one partial per (image, row tile, column): no memset, no atomics
@@ -95,7 +111,15 @@ size_t surface_scan_bytes(int B, int H, int W) { return align_up((size_t)B * sca
 
 int launch_surface_scan(const uint8_t* lab, int B, int H, int W, int* surf, cudaStream_t stream) {
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(lab) & 3u) == 0);
-  if (vec) {
+  const bool vec16 = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(lab) & 15u) == 0) && W >= 512;
+  const bool vec8 = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(lab) & 7u) == 0) && W >= 256;
+  if (vec16) {        // 128-bit loads: a warp row covers 512 columns
+    dim3 grid((W + 511) / 512, (H + kScanRows - 1) / kScanRows, B);
+    surface_scan_kernel<16><<<grid, 256, 0, stream>>>(lab, H, W, surf);
+  } else if (vec8) {  // 64-bit loads: a warp row covers 256 columns
+    dim3 grid((W + 255) / 256, (H + kScanRows - 1) / kScanRows, B);
+    surface_scan_kernel<8><<<grid, 256, 0, stream>>>(lab, H, W, surf);
+  } else if (vec) {
     dim3 grid((W + 127) / 128, (H + kScanRows - 1) / kScanRows, B);
     surface_scan_kernel<4><<<grid, 256, 0, stream>>>(lab, H, W, surf);
   } else {
@@ -127,6 +151,7 @@ __global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ su
   __shared__ float s_red_f[8];
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();                                          // surf comes from the scan kernel before us
 
   int ytop = kNone;
   for (int x = threadIdx.x; x < W; x += blockDim.x) {
@@ -186,7 +211,7 @@ __global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ su
 // Per output pixel: 2 image taps + 1 label tap gathered along the scanline, TGC gain, clip.
 // 10 algorithmic bytes per pixel (4+1 in, 4+1 out).
 // ---------------------------------------------------------------------------------------------
-constexpr int kWarpRows = 16;
+constexpr int kWarpRows = 8;
 
 // TIn = float (image in [0,1]) or uint8_t (8-bit B-mode ingest: v/255 in correctly rounded fp32, from a
 // 256-entry shared-memory table so the gather loop carries no divide).
@@ -234,19 +259,38 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
   const float den = __fsub_rn(s_hat[(size_t)b * W + x], de);
   const unsigned uH = (unsigned)H;
 
-  // Phase 1: source coordinates of all 16 rows (the IEEE divide has a slow-path call that would
-  // otherwise fence the loads of one row from the next).  Phase 2: all gathers back-to-back.
+  // Phase 1: source coordinates of all 16 rows.  Phase 2: all gathers back-to-back.
+  // t = y / den must be the correctly rounded quotient (label picks are bit-exact).  For 1 <= den < 2^16 and
+  // integer y < min(den, 8192) it is computed as  q = RN(y r), e = RN(y - q den), t = RN(q + e r)  with
+  // r = RN(1 / den) once per column -- proven equal to the IEEE division for EVERY such pair by the exhaustive run
+  // of tools/div_check.cu (3.09e11 quotients, 0 mismatches; Markstein's theorem).  No slow-path call, no branch.
   int i0[kWarpRows], yn[kWarpRows];
   float fr[kWarpRows];
+  const bool fastdiv = (den >= 1.0f) && (den < 65536.0f) && (H <= 8192);
+  if (fastdiv) {
+    const float rden = __frcp_rn(den);
 #pragma unroll
-  for (int r = 0; r < kWarpRows; ++r) {
-    const float yf = (float)(ya + r);
-    float t = 1.0f;
-    if (yf < den) t = __fdiv_rn(yf, den);                 // rows at / below the bone surface skip the divide
-    const float ys = __fadd_rn(yf, __fmul_rn(de, t));
-    i0[r] = __float2int_rd(ys);
-    fr[r] = ys - (float)i0[r];
-    yn[r] = __float2int_rd(__fadd_rn(ys, 0.5f));
+    for (int r = 0; r < kWarpRows; ++r) {
+      const float yf = (float)(ya + r);
+      const float q = __fmul_rn(yf, rden);
+      const float e = __fmaf_rn(-q, den, yf);
+      const float t = (yf < den) ? __fmaf_rn(e, rden, q) : 1.0f;       // rows at / below the bone surface: t = 1
+      const float ys = __fadd_rn(yf, __fmul_rn(de, t));
+      i0[r] = __float2int_rd(ys);
+      fr[r] = ys - (float)i0[r];
+      yn[r] = __float2int_rd(__fadd_rn(ys, 0.5f));
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < kWarpRows; ++r) {
+      const float yf = (float)(ya + r);
+      float t = 1.0f;
+      if (yf < den) t = __fdiv_rn(yf, den);
+      const float ys = __fadd_rn(yf, __fmul_rn(de, t));
+      i0[r] = __float2int_rd(ys);
+      fr[r] = ys - (float)i0[r];
+      yn[r] = __float2int_rd(__fadd_rn(ys, 0.5f));
+    }
   }
   TIn v0[kWarpRows], v1[kWarpRows];
   uint8_t lv[kWarpRows];
@@ -298,6 +342,7 @@ __global__ void __launch_bounds__(256) bone_box_kernel(const int* __restrict__ s
                                                        int* __restrict__ box) {
   __shared__ int s_red[4][8];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();                                          // surf comes from the scan kernel before us
   int yt = kNone, yb = -1, xl = kNone, xr = -1;
   for (int x = threadIdx.x; x < W; x += blockDim.x) {
     int f, l;
@@ -357,12 +402,12 @@ static int fused_tgc_deform_impl(const TIn* img, const uint8_t* lab, float* out_
 
   int rc = launch_surface_scan(lab, B, H, W, surf, stream);
   if (rc) return rc;
-  profile_kernel<<<B, 256, (size_t)W * 8, stream>>>(surf, scan_tiles(H), H, W, d, taps, R, s_hat, info);
-  USAUG_CHECK_LAUNCH("profile_kernel");
+  USAUG_CUDA(launch_pdl(profile_kernel, dim3(B), dim3(256), (size_t)W * 8, stream, surf, scan_tiles(H), H, W, d, taps, R,
+                        s_hat, info));
   const float gscale = (H > 1 && K > 1) ? (float)((double)(K - 1) / (double)(H - 1)) : 0.0f;
   dim3 grid((W + 127) / 128, (H + kWarpRows - 1) / kWarpRows, B);
   fused_warp_kernel<TIn><<<grid, 128, 0, stream>>>(img, lab, out_img, out_lab, H, W, s_hat, info, tgc,
-                                                   (H > 1) ? K : 1, gscale);
+                                                   (H > 1) ? K : 1, gscale);     // last kernel of the call: normal launch
   USAUG_CHECK_LAUNCH("fused_warp_kernel");
   return USAUG_OK;
 }
@@ -386,6 +431,22 @@ extern "C" size_t usaug_bone_box_workspace_bytes(int B, int H, int W) {
   return surface_scan_bytes(B, H, W);
 }
 
+namespace usaug {
+// scan + box reduction; `followed_by_kernel`: the caller enqueues another (normally launched) kernel right after,
+// so the box kernel may use a programmatic dependent launch (see common.cuh for the rule)
+int launch_bone_box(const uint8_t* lab, int B, int H, int W, int* box, int* surf, cudaStream_t stream, bool followed_by_kernel) {
+  int rc = launch_surface_scan(lab, B, H, W, surf, stream);
+  if (rc) return rc;
+  if (followed_by_kernel) {
+    USAUG_CUDA(launch_pdl(bone_box_kernel, dim3(B), dim3(256), 0, stream, surf, scan_tiles(H), H, W, box));
+  } else {
+    bone_box_kernel<<<B, 256, 0, stream>>>(surf, scan_tiles(H), H, W, box);
+    USAUG_CHECK_LAUNCH("bone_box_kernel");
+  }
+  return USAUG_OK;
+}
+}  // namespace usaug
+
 extern "C" int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box, void* ws,
                               size_t ws_bytes, void* stream_) {
   if (!lab || !box || !ws) { set_error("usaug_bone_box: null pointer"); return USAUG_E_INVALID_ARG; }
@@ -393,11 +454,5 @@ extern "C" int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box,
   if (ws_bytes < usaug_bone_box_workspace_bytes(B, H, W)) {
     set_error("usaug_bone_box: workspace too small"); return USAUG_E_WORKSPACE_TOO_SMALL;
   }
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int* surf = static_cast<int*>(ws);
-  int rc = launch_surface_scan(lab, B, H, W, surf, stream);
-  if (rc) return rc;
-  bone_box_kernel<<<B, 256, 0, stream>>>(surf, scan_tiles(H), H, W, box);
-  USAUG_CHECK_LAUNCH("bone_box_kernel");
-  return USAUG_OK;
+  return launch_bone_box(lab, B, H, W, box, static_cast<int*>(ws), static_cast<cudaStream_t>(stream_), false);
 }
