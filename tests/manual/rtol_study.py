@@ -1,7 +1,7 @@
 """Development aid: max|C_gpu - C_oracle| as a function of the PCG rtol (feeds DESIGN.md's tolerance)."""
 import sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np, torch
 from oracle import confmap as ocm, synth as osynth
 from ultrasoundaugmentation_b200 import ops

@@ -1,7 +1,7 @@
 """Small shapes through every kernel, for compute-sanitizer (memcheck / racecheck) runs."""
 import sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np, torch
 import ultrasoundaugmentation_b200 as us
 from oracle import synth as osynth
