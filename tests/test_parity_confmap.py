@@ -113,3 +113,22 @@ def test_cm_coarse_grid_geometries(cuda_device, H, W, what):
     c, itc, rrc = gpu_cm(cuda_device, img, rtol=1e-9, maxiter=100000, coarse="fine")
     assert (rrc <= 1e-9).all(), what
     assert np.abs(c - b).max() <= 2 * (2e5 * 1e-9) + 1e-6, what
+
+
+@pytest.mark.parametrize("B,H,W,what", [(1800, 40, 128, ">= 12 tasks per SM: weight-recomputing kernel, 2-row aggregates"),
+                                         (900, 48, 128, ">= 6 tasks per SM: weight-recomputing kernel, 4-row aggregates"),
+                                         (1000, 36, 132, "two strips per image, the second one 4 columns wide")])
+def test_cm_large_batch_kernel_variants(cuda_device, B, H, W, what):
+    """The kernel variants that only large batches select (launch_fused / cm_layout), on many tiny images so that
+    the oracle stays affordable: every image converges, a sample of them is checked against the direct solve."""
+    img = np.stack([util.synth_batch(1, H, W, seed0=3000 + (b % 97))[0][0] for b in range(97)])
+    img = np.concatenate([img] * (B // 97 + 1))[:B]
+    rng = np.random.default_rng(1)
+    img = np.clip(img + 0.02 * rng.standard_normal(img.shape).astype(np.float32), 0, 1).astype(np.float32)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL)
+    assert (rr <= RTOL).all(), what
+    assert (it > 0).all() and np.all(cm[:, 0] == 1.0) and np.all(cm[:, -1] == 0.0)
+    for b in range(0, B, max(B // 12, 1)):
+        assert np.abs(cm[b] - ocm.confidence_map(img[b])).max() <= util.tol_cm(RTOL), (what, b)
+    cm2, it2, _ = gpu_cm(cuda_device, img, rtol=RTOL)
+    assert np.array_equal(cm, cm2) and np.array_equal(it, it2)           # repeatable under dynamic scheduling

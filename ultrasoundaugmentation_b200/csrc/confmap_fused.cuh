@@ -465,7 +465,7 @@ __device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned 
   const int n = g.nc, kd1 = g.kd1;
   float* ysb = reinterpret_cast<float*>(ringmem);                // 32 zeros | vector [n] | zeros up to kCoarseMaxN + 64
   float* ys = ysb + 32;
-  float* tiles = ysb + kCoarseMaxN + 96;                         // 2 x [32][32]
+  float* tiles = ysb + ((n + 31) & ~31) + 96;                    // 2 x [32][32], right behind the padded vector
   const float* rc = a.rc + (size_t)b * n;
   float* zc = a.zc + (size_t)b * n;
   const float* U = a.Ur + (size_t)b * n * kd1;
@@ -698,7 +698,7 @@ __device__ __forceinline__ double resid_strip(const PcgArgs<float>& a, int b, in
 // RECOMP = F_UP recomputes the edge weights from the `a` plane (bandwidth-bound regime) or reads them.
 template <int AW, bool RECOMP>
 __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> a) {
-  constexpr size_t kWarpRing = kFusedSmem / AW;                   // ring bytes per active warp
+  constexpr size_t kWarpRing = (kFusedSmem / AW) & ~(size_t)127;  // ring bytes per active warp
   constexpr int R = (int)(kWarpRing / (RECOMP ? sizeof(RingU) : sizeof(RingUP)));   // F_UP ring depth in rows
   constexpr int RD = (int)(kWarpRing / sizeof(RingD));                              // F_DOWN ring depth
   extern __shared__ __align__(16) unsigned char smem_raw[];
