@@ -43,75 +43,184 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
-// nseq sequences of n = 1 << lg points, sequence q at data + q * pitch.  Natural order in, bit-reversed order out.
-// Radix-2 decimation in frequency, two stages per shared-memory pass (a thread owns a quad of points), so an
-// n-point transform takes ceil(lg / 2) passes and barriers instead of lg.
-__device__ __forceinline__ void fft_dif(float2* data, int pitch, int nseq, int lg, const float2* tw) {
-  int s = lg - 1;
-  for (; s >= 1; s -= 2) {                       // stages s (half = 2^s) and s-1 (half = 2^(s-1))
-    const int quarter = 1 << (s - 1);
-    const int nquad = 1 << (lg - 2);
-    for (int idx = threadIdx.x; idx < nseq * nquad; idx += blockDim.x) {
-      const int q = idx >> (lg - 2), j = idx & (nquad - 1);
-      const int pos = j & (quarter - 1);
-      float2* x = data + q * pitch + (((j >> (s - 1)) << (s + 1)) | pos);
-      const float2 a0 = x[0], a1 = x[quarter], a2 = x[2 * quarter], a3 = x[3 * quarter];
-      // stage s: (0,2) and (1,3)
-      const float2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), tw[pos << (lg - 1 - s)]);
-      const float2 b1 = cadd(a1, a3), b3 = cmul(csub(a1, a3), tw[(pos + quarter) << (lg - 1 - s)]);
-      // stage s-1: (0,1) and (2,3)
-      const float2 w = tw[pos << (lg - s)];
-      x[0] = cadd(b0, b1); x[quarter] = cmul(csub(b0, b1), w);
-      x[2 * quarter] = cadd(b2, b3); x[3 * quarter] = cmul(csub(b2, b3), w);
+// ---- in-place radix-2 FFT of nseq sequences of n = 1 << lg points (sequence q at data + q * pitch) ----------
+// Stage s pairs elements half = 2^s apart; its twiddle for position pos (< half) is tw[pos << (lg - 1 - s)].
+//   * stages with half >= 128 run through shared memory, two stages per pass (a thread owns a quad): the four
+//     accesses of a quad are >= 64 elements apart and consecutive threads touch consecutive elements -> no bank
+//     conflicts;
+//   * all stages with half <= 64 run INSIDE A WARP: a warp loads a 128-point block with contiguous accesses into four
+//     registers per lane (elements lane, lane + 32, lane + 64, lane + 96), does half = 64 and 32 in-thread and
+//     half = 16 .. 1 with shuffles, and writes the block back.  An n = 512 transform is 2 conflict-free
+//     shared-memory round trips instead of 5 passes whose small strides replayed ~57 % of the wavefronts (ncu).
+// fft_dif: decimation in frequency, natural order in, bit-reversed order out.  ifft_dit: inverse transform
+// (conjugate twiddles, unscaled), decimation in time, bit-reversed order in, natural order out.
+
+__device__ __forceinline__ void smem_radix2_stage(float2* data, int pitch, int nseq, int lg, int s, const float2* tw,
+                                                  bool inverse) {
+  const int half = 1 << s, half_n = 1 << (lg - 1);
+  for (int idx = threadIdx.x; idx < nseq * half_n; idx += blockDim.x) {
+    const int q = idx >> (lg - 1), j = idx & (half_n - 1);
+    const int pos = j & (half - 1);
+    float2* x = data + q * pitch + (((j >> s) << (s + 1)) | pos);
+    float2 w = tw[pos << (lg - 1 - s)];
+    if (inverse) {
+      w.y = -w.y;
+      const float2 a = x[0], t = cmul(x[half], w);
+      x[0] = cadd(a, t); x[half] = csub(a, t);
+    } else {
+      const float2 a = x[0], c = x[half];
+      x[0] = cadd(a, c); x[half] = cmul(csub(a, c), w);
     }
-    __syncthreads();
   }
-  if (s == 0) {                                  // odd lg: one plain radix-2 stage with half = 1 (twiddle 1)
-    const int half_n = 1 << (lg - 1);
-    for (int idx = threadIdx.x; idx < nseq * half_n; idx += blockDim.x) {
-      const int q = idx >> (lg - 1), j = idx & (half_n - 1);
-      float2* x = data + q * pitch + 2 * j;
-      const float2 a = x[0], b = x[1];
-      x[0] = cadd(a, b); x[1] = csub(a, b);
-    }
-    __syncthreads();
-  }
+  __syncthreads();
 }
 
-// inverse transform (conjugate twiddles, unscaled).  Bit-reversed order in, natural order out.
-// Radix-2 decimation in time, two stages per pass like fft_dif.
+// stages s (half = 2^s) and s-1 of the forward transform in one pass
+__device__ __forceinline__ void smem_radix4_dif(float2* data, int pitch, int nseq, int lg, int s, const float2* tw) {
+  const int quarter = 1 << (s - 1), nquad = 1 << (lg - 2);
+  for (int idx = threadIdx.x; idx < nseq * nquad; idx += blockDim.x) {
+    const int q = idx >> (lg - 2), j = idx & (nquad - 1);
+    const int pos = j & (quarter - 1);
+    float2* x = data + q * pitch + (((j >> (s - 1)) << (s + 1)) | pos);
+    const float2 a0 = x[0], a1 = x[quarter], a2 = x[2 * quarter], a3 = x[3 * quarter];
+    const float2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), tw[pos << (lg - 1 - s)]);
+    const float2 b1 = cadd(a1, a3), b3 = cmul(csub(a1, a3), tw[(pos + quarter) << (lg - 1 - s)]);
+    const float2 w = tw[pos << (lg - s)];
+    x[0] = cadd(b0, b1); x[quarter] = cmul(csub(b0, b1), w);
+    x[2 * quarter] = cadd(b2, b3); x[3 * quarter] = cmul(csub(b2, b3), w);
+  }
+  __syncthreads();
+}
+
+// stages s (half = 2^s) and s+1 of the inverse transform in one pass
+__device__ __forceinline__ void smem_radix4_dit(float2* data, int pitch, int nseq, int lg, int s, const float2* tw) {
+  const int half = 1 << s, nquad = 1 << (lg - 2);
+  for (int idx = threadIdx.x; idx < nseq * nquad; idx += blockDim.x) {
+    const int q = idx >> (lg - 2), j = idx & (nquad - 1);
+    const int pos = j & (half - 1);
+    float2* x = data + q * pitch + (((j >> s) << (s + 2)) | pos);
+    const float2 w = cconj(tw[pos << (lg - 1 - s)]);
+    const float2 a0 = x[0], t1 = cmul(x[half], w), a2 = x[2 * half], t3 = cmul(x[3 * half], w);
+    const float2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
+    const float2 u2 = cmul(b2, cconj(tw[pos << (lg - 2 - s)]));
+    const float2 u3 = cmul(b3, cconj(tw[(pos + half) << (lg - 2 - s)]));
+    x[0] = cadd(b0, u2); x[2 * half] = csub(b0, u2);
+    x[half] = cadd(b1, u3); x[3 * half] = csub(b1, u3);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
+// All stages with half <= 16 * RPL of the blocks of 32 * RPL points, in registers (RPL = 1, 2 or 4 values per lane).
+template <int RPL, bool INVERSE>
+__device__ __forceinline__ void warp_stages(float2* data, int pitch, int nseq, int lg, const float2* tw) {
+  constexpr int BS = 32 * RPL;                    // block size; the transform has n >= BS points
+  constexpr int LB = (RPL == 4) ? 7 : (RPL == 2) ? 6 : 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nblk = nseq << (lg - LB);             // blocks in all sequences
+  // The twiddles of the register stages depend on the lane only: fetched once per call.  (Read per block, the
+  // strided table reads of the shuffle stages were 16-way bank conflicts.)
+  float2 wsh[5], w5 = make_float2(1.f, 0.f), w6a = w5, w6b = w5;
+#pragma unroll
+  for (int s = 0; s <= 4; ++s) wsh[s] = tw[(lane & ((1 << s) - 1)) << (lg - 1 - s)];
+  if (RPL >= 2) w5 = tw[lane << (lg - 6)];
+  if (RPL == 4) { w6a = tw[lane << (lg - 7)]; w6b = tw[(lane + 32) << (lg - 7)]; }
+  if (INVERSE) {
+#pragma unroll
+    for (int s = 0; s <= 4; ++s) wsh[s].y = -wsh[s].y;
+    w5.y = -w5.y; w6a.y = -w6a.y; w6b.y = -w6b.y;
+  }
+  for (int blk = warp; blk < nblk; blk += nwarp) {
+    const int q = blk >> (lg - LB);
+    float2* x = data + q * pitch + ((blk & ((1 << (lg - LB)) - 1)) << LB);
+    float2 v[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) v[k] = x[k * 32 + lane];
+    if (!INVERSE) {
+      // half = 64: (0,2) (1,3); half = 32: (0,1) (2,3); element index inside the block = k * 32 + lane
+      if (RPL == 4) {
+        const float2 a0 = v[0], a1 = v[1];
+        v[0] = cadd(a0, v[2]); v[2] = cmul(csub(a0, v[2]), w6a);
+        v[1] = cadd(a1, v[3]); v[3] = cmul(csub(a1, v[3]), w6b);
+      }
+      if (RPL >= 2) {
+#pragma unroll
+        for (int k = 0; k < RPL; k += 2) {
+          const float2 a = v[k];
+          v[k] = cadd(a, v[k + 1]); v[k + 1] = cmul(csub(a, v[k + 1]), w5);
+        }
+      }
+#pragma unroll
+      for (int s = 4; s >= 0; --s) {              // half = 16 .. 1 across lanes
+        const int h = 1 << s;
+        const bool up = lane & h;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          const float2 o = shfl_xor2(v[k], h);
+          v[k] = up ? cmul(csub(o, v[k]), wsh[s]) : cadd(v[k], o);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s <= 4; ++s) {              // half = 1 .. 16 across lanes
+        const int h = 1 << s;
+        const bool up = lane & h;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          const float2 t = up ? cmul(v[k], wsh[s]) : v[k];  // the upper element is twiddled before the exchange
+          const float2 o = shfl_xor2(t, h);
+          v[k] = up ? csub(o, t) : cadd(t, o);
+        }
+      }
+      if (RPL >= 2) {
+#pragma unroll
+        for (int k = 0; k < RPL; k += 2) {
+          const float2 t = cmul(v[k + 1], w5), a = v[k];
+          v[k] = cadd(a, t); v[k + 1] = csub(a, t);
+        }
+      }
+      if (RPL == 4) {
+        const float2 t2 = cmul(v[2], w6a), t3 = cmul(v[3], w6b);
+        const float2 a0 = v[0], a1 = v[1];
+        v[0] = cadd(a0, t2); v[2] = csub(a0, t2);
+        v[1] = cadd(a1, t3); v[3] = csub(a1, t3);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) x[k * 32 + lane] = v[k];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void fft_dif(float2* data, int pitch, int nseq, int lg, const float2* tw) {
+  if (lg < 5) {                                   // n = 8, 16: plain shared-memory stages
+    for (int s = lg - 1; s >= 0; --s) smem_radix2_stage(data, pitch, nseq, lg, s, tw, false);
+    return;
+  }
+  const int lb = lg < 7 ? lg : 7;                 // stages below lb run in registers
+  int s = lg - 1;
+  if ((lg - lb) & 1) { smem_radix2_stage(data, pitch, nseq, lg, s, tw, false); --s; }
+  for (; s >= lb; s -= 2) smem_radix4_dif(data, pitch, nseq, lg, s, tw);
+  if (lb == 7) warp_stages<4, false>(data, pitch, nseq, lg, tw);
+  else if (lb == 6) warp_stages<2, false>(data, pitch, nseq, lg, tw);
+  else warp_stages<1, false>(data, pitch, nseq, lg, tw);
+}
+
 __device__ __forceinline__ void ifft_dit(float2* data, int pitch, int nseq, int lg, const float2* tw) {
-  int s = 0;
-  if (lg & 1) {                                  // odd lg: stage 0 alone (half = 1, twiddle 1)
-    const int half_n = 1 << (lg - 1);
-    for (int idx = threadIdx.x; idx < nseq * half_n; idx += blockDim.x) {
-      const int q = idx >> (lg - 1), j = idx & (half_n - 1);
-      float2* x = data + q * pitch + 2 * j;
-      const float2 a = x[0], b = x[1];
-      x[0] = cadd(a, b); x[1] = csub(a, b);
-    }
-    __syncthreads();
-    s = 1;
+  if (lg < 5) {
+    for (int s = 0; s < lg; ++s) smem_radix2_stage(data, pitch, nseq, lg, s, tw, true);
+    return;
   }
-  for (; s + 1 < lg; s += 2) {                   // stages s (half = 2^s) and s+1 (half = 2^(s+1))
-    const int half = 1 << s;
-    const int nquad = 1 << (lg - 2);
-    for (int idx = threadIdx.x; idx < nseq * nquad; idx += blockDim.x) {
-      const int q = idx >> (lg - 2), j = idx & (nquad - 1);
-      const int pos = j & (half - 1);
-      float2* x = data + q * pitch + (((j >> s) << (s + 2)) | pos);
-      const float2 w = cconj(tw[pos << (lg - 1 - s)]);
-      const float2 a0 = x[0], t1 = cmul(x[half], w), a2 = x[2 * half], t3 = cmul(x[3 * half], w);
-      // stage s: (0,1) and (2,3)
-      const float2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
-      // stage s+1: (0,2) and (1,3)
-      const float2 u2 = cmul(b2, cconj(tw[pos << (lg - 2 - s)]));
-      const float2 u3 = cmul(b3, cconj(tw[(pos + half) << (lg - 2 - s)]));
-      x[0] = cadd(b0, u2); x[2 * half] = csub(b0, u2);
-      x[half] = cadd(b1, u3); x[3 * half] = csub(b1, u3);
-    }
-    __syncthreads();
-  }
+  const int lb = lg < 7 ? lg : 7;
+  if (lb == 7) warp_stages<4, true>(data, pitch, nseq, lg, tw);
+  else if (lb == 6) warp_stages<2, true>(data, pitch, nseq, lg, tw);
+  else warp_stages<1, true>(data, pitch, nseq, lg, tw);
+  int s = lb;
+  for (; s + 1 < lg; s += 2) smem_radix4_dit(data, pitch, nseq, lg, s, tw);
+  if (s < lg) smem_radix2_stage(data, pitch, nseq, lg, s, tw, true);
 }
 
 // signed DFT frequency index of bin k (numpy.fft.fftfreq * n): the Nyquist bin is -n/2
