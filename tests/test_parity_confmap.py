@@ -132,3 +132,17 @@ def test_cm_large_batch_kernel_variants(cuda_device, B, H, W, what):
         assert np.abs(cm[b] - ocm.confidence_map(img[b])).max() <= util.tol_cm(RTOL), (what, b)
     cm2, it2, _ = gpu_cm(cuda_device, img, rtol=RTOL)
     assert np.array_equal(cm, cm2) and np.array_equal(it, it2)           # repeatable under dynamic scheduling
+
+
+def test_cm_watchdog_ignores_starved_workers(cuda_device, monkeypatch):
+    """The scheduler's watchdog must watch global progress, not a worker's own luck: with one slowly converging image
+    left among many trivial ones, most workers find no task for far longer than the (here: 20 ms) watchdog period while
+    the solve is healthy.  Every image must still come back converged."""
+    monkeypatch.setenv("USAUG_CM_WATCHDOG_MS", "20")
+    H = W = 512
+    img = np.full((64, H, W), 0.3, np.float32)                 # constant images: done after the first residual
+    img[17] = util.synth_batch(1, H, W)[0][0]                  # one real image: ~500 iterations, ~0.25 s
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL)
+    assert (it >= 0).all() and np.isfinite(rr).all(), "watchdog fired on a healthy solve"
+    assert (rr <= RTOL).all() and it[17] > 100
+    assert np.abs(cm[17] - ocm.confidence_map(img[17])).max() <= util.tol_cm(RTOL)

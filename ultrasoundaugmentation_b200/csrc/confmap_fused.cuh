@@ -572,7 +572,7 @@ __device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned 
 // measured 1 us per task, 3.5x slower than this at 512 images).
 constexpr unsigned kNoTask = 0xffffffffu;
 constexpr unsigned kIdleSleepMaxNs = 2048;
-constexpr unsigned long long kWatchdogNs = 4000000000ull;   // an idle worker gives up after 4 s without any task
+constexpr unsigned long long kWatchdogNs = 4000000000ull;   // default: idle workers give up when NOBODY has claimed a task for 4 s
 
 // pushes n entries: payload0, payload0+stride, ...  (one lane)
 __device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsigned payload0, unsigned stride, unsigned n) {
@@ -593,7 +593,7 @@ __device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsi
 // spins was measured to slow the other warps of the SM ~4x); lane 0's values are broadcast and lane 0 claims.
 __device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {
   unsigned ns = 32;
-  unsigned long long t_idle = 0;
+  unsigned long long t_idle = 0, last_claimed = 0;
   for (;;) {
     int av0, av1;
     asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(av0), "=r"(av1) : "l"(a.qavail) : "memory");
@@ -622,11 +622,14 @@ __device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {
     if (__ldcg(a.done) >= (unsigned)a.B) return kNoTask;
     __nanosleep(ns);
     if (ns < kIdleSleepMaxNs) { ns *= 2; continue; }
-    // watchdog: a scheduling bug must not hang the device.  Flag it, mark unfinished images, release everybody.
+    // watchdog: a scheduling bug must not hang the device.  It watches GLOBAL progress (tasks claimed by anybody),
+    // not this worker's own luck: with one slowly converging image left, a worker can lose the race for its few
+    // tasks for a long time while the solve is perfectly healthy.
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (t_idle == 0) t_idle = t;
-    else if (t - t_idle > kWatchdogNs) {
+    const unsigned long long claimed = *(volatile unsigned long long*)(a.qhead) + *(volatile unsigned long long*)(a.qhead + 1);
+    if (t_idle == 0 || claimed != last_claimed) { t_idle = t; last_claimed = claimed; }
+    else if (t - t_idle > a.watchdog_ns) {
       if (lane == 0 && atomicExch(a.done + 1, 1u) == 0u) {
         for (int b = 0; b < a.B; ++b)
           if ((int)(__ldcg(&a.st[b].fword) & 0xffffffffull) != F_DONE) {

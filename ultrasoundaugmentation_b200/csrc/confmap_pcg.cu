@@ -146,6 +146,8 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   // every inner iteration is one step; each refinement round adds <= 3 steps and needs >= 1 iteration
   a.max_steps = 4 * maxiter + 16;
   a.debug = g_debug;
+  a.watchdog_ns = kWatchdogNs;
+  if (const char* w = getenv("USAUG_CM_WATCHDOG_MS")) a.watchdog_ns = (unsigned long long)atoll(w) * 1000000ull;   // test hook
 
   if constexpr (std::is_same<T, float>::value) {
     if (a.vec4 && !g_legacy) return launch_fused(a, L, B, stream);

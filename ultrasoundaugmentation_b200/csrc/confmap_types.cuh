@@ -88,6 +88,7 @@ struct PcgArgs {
   double* qsum;      // sum over the running images of their predicted remaining iterations
   unsigned* qcnt;    // number of images in qsum
   int wpb;           // fused kernel: worker warps per block actually used (<= AW)
+  unsigned long long watchdog_ns;   // fused kernel: idle workers give up when no task was claimed by anybody for this long
   CoarseGeom cg;     // coarse-grid correction geometry (cg.by == 0: disabled)
   float *rc, *zc;    // [B][nc] restricted residual / coarse correction
   const float *Lr, *Ur;   // [B][nc][kd1] banded Cholesky factor of Ac, row- and column-oriented
