@@ -788,9 +788,17 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     // ---- last strip of this image and phase: reduce, advance the state, publish the next phase ------
     __threadfence();
     reduce_parts(part, ntask, lane, s0, s1);
-    if (lane != 0) continue;
-    st->cnt1 = 0;
     int next = F_DONE;
+    // the F_COARSE decision, also used after the inline coarse solve below
+    auto after_coarse = [&](double rc_zc) {
+      // z = T^-1 r + P Ac^-1 P^T r  =>  r.z = sum ip h^2 (line part, from DOWN) + rc.zc (the coarse solve)
+      const double rz_new = __ldcg(&st->rz_line) + rc_zc, rz_old = __ldcg(&st->rz);
+      if (__ldcg(&st->fresh)) { st->rz = rz_new; st->first = 1; st->beta = 0.0; return (int)F_UP; }
+      if (rz_new > 0.0 && rz_old > 0.0) { st->beta = rz_new / rz_old; st->rz = rz_new; st->first = 0; return (int)F_UP; }
+      return (int)F_FOLD;
+    };
+    if (lane == 0) {
+    st->cnt1 = 0;
     if (mode == F_UP) {
       if (s0 > 0.0) st->alpha = __ldcg(&st->rz) / s0;
       else { st->alpha = 0.0; st->rr_target = 1e300; }          // breakdown: leave the inner solve
@@ -825,11 +833,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
         next = (s1 > 0.0) ? F_UP : F_FINAL;
       }
     } else if (mode == F_COARSE) {
-      // z = T^-1 r + P Ac^-1 P^T r  =>  r.z = sum ip h^2 (line part, from DOWN) + rc.zc (this task)
-      const double rz_new = __ldcg(&st->rz_line) + s0, rz_old = __ldcg(&st->rz);
-      if (__ldcg(&st->fresh)) { st->rz = rz_new; st->first = 1; st->beta = 0.0; next = F_UP; }
-      else if (rz_new > 0.0 && rz_old > 0.0) { st->beta = rz_new / rz_old; st->rz = rz_new; st->first = 0; next = F_UP; }
-      else next = F_FOLD;
+      next = after_coarse(s0);
     } else if (mode == F_RESID) {
       next = after_true_residual(st, s0, a.rtol2, a.inner_red2, a.maxiter) ? F_FINAL : F_PRECOND;
     } else if (mode == F_FOLD) {
@@ -841,6 +845,22 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       leave_priority(a, st);
       next = F_DONE;
     }
+    }
+    next = __shfl_sync(0xffffffffu, next, 0);
+    if (!RECOMP && next == F_COARSE) {
+      // Latency-bound launches (few tasks, the !RECOMP kernel): the coarse solve is a single-warp task, so the warp
+      // that completed the phase runs it right here instead of handing it to another worker through the queue -- one
+      // hand-off less on the UP -> DOWN -> COARSE chain (+2 % at B <= 64).  Bandwidth-bound launches keep it in
+      // the queue: there it is the two service classes that decide who runs next (inline: -11 % at B = 512).
+      const unsigned long long tc0 = a.debug ? now() : 0ull;
+      const double rc_zc = coarse_task(a, ringmem, b, lane);
+      __threadfence();                                          // every lane publishes its part of zc
+      __syncwarp();
+      if (a.debug) { t_mode[F_COARSE] += now() - tc0; n_mode[F_COARSE]++; }
+      if (lane == 0) next = after_coarse(rc_zc);
+      next = __shfl_sync(0xffffffffu, next, 0);
+    }
+    if (lane != 0) continue;
     st->fword = (unsigned long long)next;
     if (next == F_DONE) {
       __threadfence();
