@@ -15,7 +15,8 @@ for H in list(range(3, 20)) + [24, 31, 33, 40, 47, 48]:
             ref = ocm.confidence_map_batch(img)
             cm, it, rr = ops.confidence_map(torch.from_numpy(img).to(dev), rtol=1e-9, maxiter=100000, return_info=True)
             err = np.abs(cm.cpu().numpy() - ref).max(); n += 1
-            if not (err <= 5e4 * 1e-9 + 1e-6 + 2e-5) or not (rr.cpu().numpy() <= 1e-9).all():
+            # noise images can have an error/residual constant above 5e4 (48 x 68: K = 1.35e5): same bound as the hypothesis fuzz
+            if not (err <= 2e5 * 1e-9 + 2e-5) or not (rr.cpu().numpy() <= 1e-9).all():
                 bad += 1
                 print("FAIL", H, W, kind, "err", err, "iters", it.tolist(), "relres", rr.tolist(), flush=True)
 print("cases", n, "bad", bad)
