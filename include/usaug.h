@@ -54,7 +54,15 @@ enum {
   /* aggregate height of the coarse grid; default: 2-row aggregates for deeply bandwidth-bound batches
      (>= 12 strip tasks per SM), 4 rows (or more, for tall images) otherwise */
   USAUG_CM_COARSE_FINE = 64,      /* always start from 2-row aggregates */
-  USAUG_CM_COARSE_STANDARD = 128  /* always start from 4-row aggregates */
+  USAUG_CM_COARSE_STANDARD = 128, /* always start from 4-row aggregates */
+  /* Twisted column-line factorisation (two half sweeps per strip; halves the dependent chain of one image):
+     default on unless the launch is deeply bandwidth-bound (>= 12 strip tasks per SM) */
+  USAUG_CM_TWIST_ON = 256,
+  USAUG_CM_TWIST_OFF = 512,
+  /* F_UP phase of the fused kernel: recompute the edge weights from the attenuation plane (default for >= 6 strip
+     tasks per SM) or read the weight planes.  Pinning the variant makes results independent of the batch size. */
+  USAUG_CM_FORCE_RECOMPUTE = 1024,
+  USAUG_CM_FORCE_PLANES = 2048
 };
 
 int usaug_version(void);

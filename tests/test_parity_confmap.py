@@ -55,6 +55,34 @@ def test_cm_parity_256(cuda_device, variant):
     assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
 
 
+@pytest.mark.parametrize("twist", [False, True])
+@pytest.mark.parametrize("up_variant", ["planes", "recompute"])
+@pytest.mark.parametrize("coarse", ["fine", "standard", False])
+@pytest.mark.parametrize("H,W", [(40, 128), (67, 132), (96, 260), (131, 64)])
+def test_cm_solver_variants_small(cuda_device, H, W, coarse, up_variant, twist):
+    """Every pinned variant of the fused kernel (twisted / plain line factorisation x weights recomputed / read x coarse
+    grid) against the oracle, on shapes with one, two and three strips, odd heights and a 4-column last strip."""
+    img, _ = util.synth_batch(2, H, W, seed0=77 + H)
+    ref = ocm.confidence_map_batch(img)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, coarse=coarse, up_variant=up_variant, twist=twist, maxiter=60000)
+    assert (rr <= RTOL).all(), rr
+    assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
+    assert np.all(cm[:, 0] == 1.0) and np.all(cm[:, -1] == 0.0)
+
+
+@pytest.mark.parametrize("twist", [False, True])
+@pytest.mark.parametrize("up_variant", ["planes", "recompute"])
+def test_cm_solver_variants_256(cuda_device, up_variant, twist):
+    img, _ = util.synth_batch(2, 256, 256)
+    ref = ocm.confidence_map_batch(img)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, up_variant=up_variant, twist=twist)
+    assert (rr <= RTOL).all(), rr
+    assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
+    # the twisted factorisation is the same preconditioner: the iteration count must not move
+    _, it0, _ = gpu_cm(cuda_device, img, rtol=RTOL, up_variant=up_variant, twist=False)
+    assert np.abs(it.astype(int) - it0.astype(int)).max() <= 0.05 * it0.max() + 8
+
+
 def test_cm_batch_independence_and_determinism(cuda_device):
     """An image's map does not depend on its batch mates; repeated runs are bitwise identical."""
     img, _ = util.synth_batch(5, 96, 64)

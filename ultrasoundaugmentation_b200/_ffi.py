@@ -19,6 +19,10 @@ PRECOND_JACOBI = 0
 PRECOND_LINE = 1
 CM_FP64_VECTORS = 1
 CM_ZERO_GUESS = 2
+CM_TWIST_ON = 256
+CM_TWIST_OFF = 512
+CM_FORCE_RECOMPUTE = 1024
+CM_FORCE_PLANES = 2048
 
 # every symbol include/usaug.h declares: name -> (restype, argtypes)
 SYMBOLS = {

@@ -1,64 +1,64 @@
 // Coarse-grid correction of the confidence-map PCG (included by confmap_pcg.cu).
 //
 // Two-level ADDITIVE preconditioner   M^-1 = T^-1 + P Ac^-1 P^T
-//   T   column-line tridiagonal part of A (the sweeps in confmap_pcg.cu)
-//   P   piecewise-constant prolongation from aggregates of `by` rows x 32 columns of unknowns
+//   T   column-line tridiagonal part of A (the sweeps in confmap_fused.cuh)
+//   P   piecewise-constant prolongation from aggregates of `by` rows x `bx` columns of unknowns
 //   Ac  = P^T A P, the Laplacian of the aggregate graph (+ the couplings to the seed rows on the diagonal):
-//         a 9-point operator on an nby x nbx grid, symmetric positive definite, band width nbx + 1.
+//         a 9-point operator on an nby x nbx grid, symmetric positive definite.
 // The line preconditioner moves information one column per CG iteration; the coarse space carries the
-// slow, blob-like error modes of these heterogeneous systems across the image at once.  Measured on the
-// CPU prototype at 512x512 (beta = 90): 1460 -> ~390 iterations with 4 x 32 aggregates.
+// slow, blob-like error modes of these heterogeneous systems across the image at once.
 //
-// Setup (once per image):   coarse_assemble_kernel -> coarse_factor_kernel (banded Cholesky, fp64 -> fp32)
-// Per iteration:            DOWN restricts the new residual (rc = P^T r), the single-warp COARSE task solves
-//                           Ac zc = rc with two triangular sweeps in shared memory, UP adds P zc to z.
-// M^-1 stays symmetric positive definite for ANY stored factor L: the operator applied is exactly (L L^T)^-1.
+// Ac is BLOCK TRIDIAGONAL with nbx x nbx blocks (one block row = one row of aggregates):
+//     D_I (tridiagonal) on the diagonal,  E_I (tridiagonal) = coupling of aggregate row I to row I-1.
+// Setup (once per image, fp64): block LDL^T
+//     Delta_0 = D_0,   Delta_I = D_I - E_I W_{I-1} E_I^T,   W_I = Delta_I^-1   (dense, symmetrised, stored in fp32)
+// Per iteration (one warp per image, confmap_fused.cuh: coarse_task):
+//     forward    v_I = rc_I - E_I (W_{I-1} v_{I-1})
+//     backward   zc_I = W_I (v_I - E_{I+1}^T zc_{I+1})              and   rc . zc = sum_I v_I . (W_I v_I)
+// i.e. per aggregate ROW one dense nbx x nbx matrix-vector product spread over the 32 lanes plus a three-point
+// stencil -- a dependent chain of ~130 cycles per row of aggregates, instead of one shuffle + FMA step (~57 cycles)
+// per aggregate in a scalar banded triangular solve (round 1: 129 us for 4080 aggregates; now ~35 us for 8160).
+// The operator applied is exactly (I+S)^-T W (I+S)^-1 with S_I = E_I W_{I-1}: symmetric for ANY stored E and
+// symmetric W, positive definite as long as the rounded W_I are (their condition numbers are O(100)).
+// Nothing is kept in shared memory across steps, so the number of aggregates is not limited by it.
 #pragma once
 
 namespace usaug {
 
-// aggregate width: 32 pixel columns, or 64 for images wider than 960 (keeps the band <= 31)
-constexpr int kCoarseMaxN = 4096;     // coarse unknowns per image (the solve keeps the vector in shared memory)
-constexpr int kCoarseMaxBand = 31;    // nbx + 1: the register-window solver holds one element per lane
-constexpr int kCoarseTileRows = 32;   // factor rows staged per cp.async tile = one 32-step block of the sweeps
-
 struct CoarseGeom {
   int by;        // aggregate height in rows (power of two), 0 = coarse correction disabled
   int by_shift;  // log2(by)
-  int bx_shift;  // log2(aggregate width): 5 or 6
+  int bx_shift;  // log2(aggregate width): 4 ... 7 (nbx <= 32)
   int nbx, nby;  // coarse grid
-  int nc;        // nbx * nby
-  int kd;        // band width nbx + 1
-  int kd1;       // row pitch of the factor arrays: 32 floats (kd <= 31), zero padded
+  int nb;        // block size: nbx padded to 8, 16 or 32 = row pitch of rc / zc and of the W blocks
+  int nc;        // nby * nb: padded coarse vector length per image
+  int rec;       // floats per block-row record: nb*nb (W_I) + 4*nb (E_I: centre, left, right, spare)
 };
 
 // min_shift: log2 of the smallest aggregate height tried.  Thin aggregates converge faster (CPU prototype at
-// 512x512: 8x32 -> 512, 4x32 -> 402, 2x32 -> 351 iterations; 4x16 -> 393, 8x8 -> 431 at the same count) but the
-// serial COARSE solve grows with nc: 2 rows pay off only when the batch is bandwidth-bound (cm_layout decides).
-static inline CoarseGeom coarse_geom(int H, int W, int min_shift) {
+// 512x512: 8x32 -> 512, 4x32 -> 435, 2x32 -> 404 iterations; 8x8 -> 462 at the same count as 2x32).
+static inline CoarseGeom coarse_geom(int H, int W, int min_shift, int min_bx_shift = 5) {
   CoarseGeom g{};
   const int hu = H - 2;
-  g.bx_shift = 5;
-  g.nbx = (W + 31) >> 5;
-  if (g.nbx + 1 > kCoarseMaxBand) { g.bx_shift = 6; g.nbx = (W + 63) >> 6; }
-  g.kd = g.nbx + 1;
-  if (g.kd > kCoarseMaxBand || hu < 8) return g;            // by = 0: disabled
-  for (int sh = min_shift; sh <= 8; ++sh) {
-    const int by = 1 << sh;
-    const int nby = (hu + by - 1) / by;
-    if (nby * g.nbx <= kCoarseMaxN) {
-      g.by = by; g.by_shift = sh; g.nby = nby; g.nc = nby * g.nbx;
-      g.kd1 = 32;                          // rows padded with zeros to one entry per lane
-      return g;
-    }
-  }
+  g.bx_shift = min_bx_shift;
+  while (((W + (1 << g.bx_shift) - 1) >> g.bx_shift) > 32) ++g.bx_shift;
+  g.nbx = (W + (1 << g.bx_shift) - 1) >> g.bx_shift;
+  if (g.bx_shift > 7 || hu < 8) return g;                   // by = 0: disabled (W > 4096 or a very short image)
+  g.nb = g.nbx <= 8 ? 8 : g.nbx <= 16 ? 16 : 32;
+  int sh = min_shift;
+  while (((hu + (1 << sh) - 1) >> sh) > 1024) ++sh;         // at most 1024 aggregate rows
+  g.by = 1 << sh; g.by_shift = sh;
+  g.nby = (hu + g.by - 1) >> sh;
+  g.nc = g.nby * g.nb;
+  g.rec = g.nb * g.nb + 4 * g.nb;
   return g;
 }
 
 #ifdef __CUDACC__
 
 // ---------------------------------------------------------------------------------------------
-// Ac in lower band form: Ab[i][d] = Ac[i, i-d], d = 0..kd, i = I*nbx + J.  One warp per aggregate,
+// Ac in block form: Ab[b][I][k][nb] (fp64), k = 0 diagonal, 1 coupling to (I, J-1), 2 / 3 / 4 coupling to
+// (I-1, J) / (I-1, J-1) / (I-1, J+1); zero for the padding columns J >= nbx.  One warp per aggregate,
 // lane = pixel column inside the aggregate; butterfly sums => deterministic.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, CoarseGeom g,
@@ -69,7 +69,12 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, Coar
   const int agg = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.y;
   if (agg >= g.nc) return;
-  const int I = agg / g.nbx, J = agg - I * g.nbx;
+  const int I = agg / g.nb, J = agg - I * g.nb;
+  double* out = Ab + ((size_t)b * g.nby + I) * 5 * g.nb + J;
+  if (J >= g.nbx) {
+    if (lane < 5) out[lane * g.nb] = 0.0;
+    return;
+  }
   const size_t base = (size_t)b * H * W;
   const float* S = wS + base; const float* E = wE + base; const float* SE = wSE + base; const float* SW = wSW + base;
   double sum[9];   // sum[(dI+1)*3 + (dJ+1)]: weight to the neighbouring aggregate; [4] collects the seed couplings
@@ -106,84 +111,90 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, Coar
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k) sum[k] = warp_sum(sum[k]);
-  double diag = 0.0;
+  if (lane == 0) {
+    double diag = 0.0;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) diag += sum[k];
-  double* row = Ab + ((size_t)b * g.nc + agg) * (g.kd + 1);
-  for (int d = lane; d <= g.kd; d += 32) {
-    double v = 0.0;
-    if (d == 0) v = diag;
-    // lower neighbours (index i - d): several can share one offset when nbx <= 2, so accumulate
-    if (J > 0 && d == 1) v -= sum[1 * 3 + 0];                                 // (I, J-1)
-    if (I > 0) {
-      if (J < g.nbx - 1 && d == g.nbx - 1) v -= sum[0 * 3 + 2];               // (I-1, J+1)
-      if (d == g.nbx) v -= sum[0 * 3 + 1];                                    // (I-1, J)
-      if (J > 0 && d == g.nbx + 1) v -= sum[0 * 3 + 0];                       // (I-1, J-1)
-    }
-    row[d] = v;
+    for (int k = 0; k < 9; ++k) diag += sum[k];
+    out[0] = diag;
+    out[1 * g.nb] = (J > 0) ? -sum[1 * 3 + 0] : 0.0;                          // (I, J-1)
+    out[2 * g.nb] = (I > 0) ? -sum[0 * 3 + 1] : 0.0;                          // (I-1, J)
+    out[3 * g.nb] = (I > 0 && J > 0) ? -sum[0 * 3 + 0] : 0.0;                 // (I-1, J-1)
+    out[4 * g.nb] = (I > 0 && J < g.nbx - 1) ? -sum[0 * 3 + 2] : 0.0;         // (I-1, J+1)
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Banded Cholesky Ac = L L^T, right-looking, one warp per image, fp64 in a sliding shared-memory window.
-//   Lr[i][0] = 1/L[i,i],  Lr[i][d] = L[i, i-d]              (row i of L:    backward sweep in saxpy form)
-//   Ur[i][0] = 1/L[i,i],  Ur[i][d] = L[i+d, i] / L[i,i]     (column i of L, pre-scaled: forward sweep)
+// Block LDL^T of Ac, one 128-thread block per image, fp64 in shared memory:
+//   Delta_I = D_I - E_I W_{I-1} E_I^T,  W_I = Delta_I^-1 by in-place Gauss-Jordan (SPD, no pivoting).
+// Record I of Wt[b] = { W_I [NB][NB] (symmetrised, fp32, zero in the padding), eC[NB], eL[NB], eR[NB], 0[NB] }.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) coarse_factor_kernel(CoarseGeom g, const double* __restrict__ Ab,
-                                                           float* __restrict__ Lr, float* __restrict__ Ur) {
-  extern __shared__ double win[];          // [(kd+1)][(kd+1)]: win[r % (kd+1)][d] = current A[j+r, j+r-d]
-  const int lane = threadIdx.x, b = blockIdx.x;
-  const int n = g.nc, kd = g.kd, m = kd + 1;
-  // (r1, r2) of the t-th trailing-update pair, r1-major (pairs with r1 <= rmax form a prefix), unranked once
-  unsigned short* pair_tab = reinterpret_cast<unsigned short*>(win + m * m);   // [kd (kd + 1) / 2]
-  for (int t = lane; t < kd * (kd + 1) / 2; t += 32) {
-    int r1 = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-    while ((r1 + 1) * (r1 + 2) / 2 <= t) ++r1;
-    while (r1 * (r1 + 1) / 2 > t) --r1;
-    const int r2 = t - r1 * (r1 + 1) / 2 + 1;
-    pair_tab[t] = (unsigned short)(((r1 + 1) << 8) | r2);
-  }
-  const double* A = Ab + (size_t)b * n * m;
-  float* L_ = Lr + (size_t)b * n * g.kd1;
-  float* U_ = Ur + (size_t)b * n * g.kd1;
-  for (int i = lane; i < n * g.kd1; i += 32) { L_[i] = 0.f; U_[i] = 0.f; }
-  for (int r = 0; r < m && r < n; ++r)
-    for (int d = lane; d < m; d += 32) win[r * m + d] = A[(size_t)r * m + d];
-  __syncwarp();
-  int slot = 0;                                    // j % m, kept incrementally
-  for (int j = 0; j < n; ++j) {
-    // column j of L lives on the diagonal-offset line of the window: L[j+r, j] = win[(j+r) % m][r] / L[j,j]
-    const double ajj = win[slot * m + 0];
-    const double ljj = sqrt(fmax(ajj, 1e-300));
-    const double inv = 1.0 / ljj;
-    const int rmax = min(kd, n - 1 - j);
-    // scale the column
-    for (int r = 1 + lane; r <= rmax; r += 32) { int rs = slot + r; if (rs >= m) rs -= m; win[rs * m + r] *= inv; }
-    __syncwarp();
-    // trailing update: A[j+r1, j+r2] -= L[j+r1, j] * L[j+r2, j]   for 1 <= r2 <= r1 <= rmax
-    const int npair = rmax * (rmax + 1) / 2;
-    for (int t = lane; t < npair; t += 32) {
-      const int pr = pair_tab[t], r1 = pr >> 8, r2 = pr & 255;
-      int s1 = slot + r1; if (s1 >= m) s1 -= m;
-      int s2 = slot + r2; if (s2 >= m) s2 -= m;
-      const double l1 = win[s1 * m + r1], l2 = win[s2 * m + r2];
-      win[s1 * m + (r1 - r2)] -= l1 * l2;
+template <int NB>
+__global__ void __launch_bounds__(128) coarse_factor_kernel(CoarseGeom g, const double* __restrict__ Ab,
+                                                            float* __restrict__ Wt) {
+  constexpr int P = NB + 1;                      // odd pitch: column accesses are conflict-free
+  __shared__ double Wp[NB * P], M[NB * P], X[NB * P];
+  __shared__ double ab[5 * NB], prow[NB], pcol[NB];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const int nbx = g.nbx;
+  const double* A = Ab + (size_t)b * g.nby * 5 * NB;
+  float* out = Wt + (size_t)b * g.nby * g.rec;
+  for (int I = 0; I < g.nby; ++I) {
+    for (int i = tid; i < 5 * NB; i += 128) ab[i] = A[(size_t)I * 5 * NB + i];
+    __syncthreads();
+    const double *dC = ab, *dL = ab + NB, *eC = ab + 2 * NB, *eL = ab + 3 * NB, *eR = ab + 4 * NB;
+    if (I > 0) {                                 // X = E_I W_{I-1}
+      for (int i = tid; i < NB * NB; i += 128) {
+        const int j = i / NB, k = i - j * NB;
+        double v = eC[j] * Wp[j * P + k];
+        if (j > 0) v += eL[j] * Wp[(j - 1) * P + k];
+        if (j < NB - 1) v += eR[j] * Wp[(j + 1) * P + k];
+        X[j * P + k] = v;
+      }
     }
-    __syncwarp();
-    // write out column j (as row j of Ur) and scatter it into the rows of Lr
-    if (lane == 0) { U_[(size_t)j * g.kd1] = (float)inv; L_[(size_t)j * g.kd1] = (float)inv; }
-    for (int r = 1 + lane; r <= rmax; r += 32) {
-      int rs = slot + r; if (rs >= m) rs -= m;
-      const float v = (float)win[rs * m + r];
-      U_[(size_t)j * g.kd1 + r] = v * (float)inv;
-      L_[(size_t)(j + r) * g.kd1 + r] = v;
+    __syncthreads();
+    for (int i = tid; i < NB * NB; i += 128) {   // M = D_I - X E_I^T  (identity in the padding)
+      const int j = i / NB, k = i - j * NB;
+      double v = 0.0;
+      if (j >= nbx || k >= nbx) v = (j == k) ? 1.0 : 0.0;
+      else {
+        if (j == k) v = dC[j];
+        else if (k == j - 1) v = dL[j];
+        else if (k == j + 1) v = dL[k];
+        if (I > 0) {
+          double t = X[j * P + k] * eC[k];
+          if (k > 0) t += X[j * P + k - 1] * eL[k];
+          if (k < NB - 1) t += X[j * P + k + 1] * eR[k];
+          v -= t;
+        }
+      }
+      M[j * P + k] = v;
     }
-    __syncwarp();
-    // slide the window: row j leaves, row j + m enters in its slot
-    if (j + m < n)
-      for (int d = lane; d < m; d += 32) win[slot * m + d] = A[(size_t)(j + m) * m + d];
-    __syncwarp();
-    if (++slot == m) slot = 0;
+    __syncthreads();
+    for (int p = 0; p < nbx; ++p) {              // in-place Gauss-Jordan inversion
+      if (tid < NB) { prow[tid] = M[p * P + tid]; pcol[tid] = M[tid * P + p]; }
+      __syncthreads();
+      const double piv = 1.0 / fmax(prow[p], 1e-300);
+      for (int i = tid; i < NB * NB; i += 128) {
+        const int j = i / NB, k = i - j * NB;
+        if (j >= nbx || k >= nbx) continue;
+        double v;
+        if (j == p) v = (k == p) ? piv : prow[k] * piv;
+        else if (k == p) v = -pcol[j] * piv;
+        else v = M[j * P + k] - pcol[j] * prow[k] * piv;
+        M[j * P + k] = v;
+      }
+      __syncthreads();
+    }
+    float* rec = out + (size_t)I * g.rec;
+    for (int i = tid; i < NB * NB; i += 128) {
+      const int j = i / NB, k = i - j * NB;
+      const bool in = j < nbx && k < nbx;
+      const double w = in ? 0.5 * (M[j * P + k] + M[k * P + j]) : 0.0;
+      rec[i] = (float)w;
+      Wp[j * P + k] = (double)(float)w;          // the next Schur complement is formed with the ROUNDED inverse
+    }
+    for (int i = tid; i < 4 * NB; i += 128) rec[NB * NB + i] = (i < 3 * NB) ? (float)ab[2 * NB + i] : 0.f;
+    __syncthreads();
   }
 }
 

@@ -49,21 +49,25 @@ struct RingUP {   // one staged row of a 128-column strip for F_UP, weight plane
 // column on lanes 0 / 31), fetched one aggregate row ahead of use while the sweep marches upward.
 struct CoarseZ {
   const float* zc;      // this image's coarse correction, nullptr = disabled
-  int sh, nbx, jown, jhalo, icur;
+  int sh, nbx, jown, jhalo, icur, nby, dir, H;
   float cur, curh, nxt, nxth;
-  bool own, halo;
-  __device__ __forceinline__ void init(const PcgArgs<float>& a, int b, int x, int x0, int lane, bool valid, int W) {
+  bool own, halo, flip;
+  // flip: the sweep runs on the vertically mirrored view (row yv of the view = image row H-1-yv), so the
+  // aggregate rows come in INCREASING order
+  __device__ __forceinline__ void init(const PcgArgs<float>& a, int b, int x, int x0, int lane, bool valid, int W, bool flip_) {
     zc = a.cg.by ? a.zc + (size_t)b * a.cg.nc : nullptr;
-    sh = a.cg.by_shift; nbx = a.cg.nbx; icur = -1;
+    sh = a.cg.by_shift; nbx = a.cg.nb; icur = -1;   // nbx: row pitch of zc
+    nby = a.cg.nby; flip = flip_; dir = flip_ ? 1 : -1; H = a.H;
     own = valid; jown = valid ? (x >> a.cg.bx_shift) : 0;
     const int hx = (lane == 0) ? x0 - 1 : x0 + kStrip4;
     halo = (lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < W);
     jhalo = halo ? (hx >> a.cg.bx_shift) : 0;
     cur = curh = nxt = nxth = 0.f;
   }
-  // returns the additive terms for row y (0 outside the unknown rows)
-  __device__ __forceinline__ void at_row(int y, int H, float& add, float& addh) {
+  // returns the additive terms for row yv of the view (0 outside the unknown rows)
+  __device__ __forceinline__ void at_row(int yv, float& add, float& addh) {
     add = 0.f; addh = 0.f;
+    const int y = flip ? H - 1 - yv : yv;
     if (zc == nullptr || y < 1 || y > H - 2) return;
     const int I = (y - 1) >> sh;
     if (I != icur) {
@@ -74,12 +78,36 @@ struct CoarseZ {
         cur = nxt; curh = nxth;
       }
       icur = I;
-      if (I > 0) {
-        nxt = own ? __ldcg(zc + (I - 1) * nbx + jown) : 0.f;
-        nxth = halo ? __ldcg(zc + (I - 1) * nbx + jhalo) : 0.f;
+      const int In = I + dir;
+      if (In >= 0 && In < nby) {
+        nxt = own ? __ldcg(zc + In * nbx + jown) : 0.f;
+        nxth = halo ? __ldcg(zc + In * nbx + jhalo) : 0.f;
       }
     }
     add = cur; addh = curh;
+  }
+};
+
+// Row range and addressing of one F_UP / F_DOWN task.  Untwisted (a.tw_m == 0): one task per strip sweeps all
+// unknown rows.  Twisted line factorisation (a.tw_m = m > 0): T = N D N^T is eliminated from BOTH ends towards
+// row m, so DOWN runs two independent half sweeps (rows 1..m downwards, rows H-2..m+1 upwards) and UP runs
+// two independent half sweeps from row m outwards: twice the tasks, half the dependent chain, the same T^-1.
+// The lower half works on the vertically mirrored view yv = H-1-y, in which it looks exactly like the upper
+// half: the factor plane stores, per row, the coupling TOWARDS row m, and the edge weights are either
+// recomputed from the `a` plane (symmetric in the two pixels) or read from mirrored weight planes.
+struct HalfView {
+  bool flip;            // lower half: mirrored view
+  int yown;             // own rows of the task in the view: 1 .. yown
+  int ys;               // F_UP starts here (yown + 1 = the first row of the other half, or the seed row H-1)
+  ptrdiff_t rs;         // row stride in the view (+-W)
+  size_t base;          // element offset of view row 0
+  __device__ __forceinline__ HalfView(const PcgArgs<float>& a, int b, int half) {
+    const int H = a.H, W = a.W, m = a.tw_m;
+    flip = (half != 0);
+    yown = m ? (flip ? H - 2 - m : m) : H - 2;
+    ys = m ? yown + 1 : H - 1;
+    rs = flip ? -(ptrdiff_t)W : (ptrdiff_t)W;
+    base = (size_t)b * H * W + (flip ? (size_t)(H - 1) * W : 0);
   }
 };
 
@@ -92,12 +120,31 @@ struct WRow {
   float swR;   // wSW[row, x+4]
 };
 
+// Twisted factorisation, upper half: its F_UP sweep starts one row beyond row m (the first row of the lower half,
+// which the stencil of row m needs), and that row's recurrence runs the other way: z[m+1] = c[m+1] z[m] + ip[m+1] h[m+1].
+// z[m] = ip[m] h[m] has no recurrence term, so it is formed directly here and seeds the sweep.
+__device__ __forceinline__ void twist_seed(const PcgArgs<float>& a, const HalfView& hv, const float* Hb, const uint32_t* IPC,
+                                           int x, int x0, int lane, bool valid, float (&zn)[4], float& zhn) {
+  if (a.tw_m == 0 || hv.flip) return;
+  const size_t o = (size_t)a.tw_m * a.W;
+  if (valid) {
+    const float4 h = __ldcg(reinterpret_cast<const float4*>(Hb + o + x));
+    const uint4 f = __ldcg(reinterpret_cast<const uint4*>(IPC + o + x));
+    zn[0] = bf16_lo(f.x) * h.x; zn[1] = bf16_lo(f.y) * h.y; zn[2] = bf16_lo(f.z) * h.z; zn[3] = bf16_lo(f.w) * h.w;
+  }
+  const int hx = (lane == 0) ? x0 - 1 : x0 + kStrip4;
+  if ((lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < a.W)) zhn = bf16_lo(__ldcg(IPC + o + hx)) * __ldcg(Hb + o + hx);
+}
+
 template <int R>
-__device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+__device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int half, int lane,
                                           float beta, bool first, int pcur) {
   RingU* ring = reinterpret_cast<RingU*>(ringmem);
   const int H = a.H, W = a.W;
-  const size_t base = (size_t)b * H * W;
+  const HalfView hv(a, b, half);
+  const size_t base = hv.base;
+  const ptrdiff_t rs = hv.rs;
+  const int ys = hv.ys, yown = hv.yown;
   const int x0 = strip * kStrip4, x = x0 + 4 * lane;
   const bool valid = x < W;
   const bool hasL = valid && x > 0, hasR = valid && (x + 4 < W);
@@ -120,11 +167,11 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin : Ap;
   const int hxs = hrole ? hx : 0;
 
-  auto issue = [&](int y) {                       // stage row y (rows are visited bottom -> top, H-1 .. 0)
-    RingU* r = ring + ((H - 1 - y) % R);
+  auto issue = [&](int y) {                       // stage view row y (rows are visited ys .. 0)
+    RingU* r = ring + ((ys - y) % R);
     const bool in = y >= 0;
     const bool interior = y >= 1 && y <= H - 2;
-    const size_t o = (size_t)(in ? y : 0) * W;
+    const ptrdiff_t o = (ptrdiff_t)(in ? y : 0) * rs;
     cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
     cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
@@ -142,17 +189,18 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   wc.eL = wc.seL = wc.swR = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
   CoarseZ cz;
-  cz.init(a, b, x, x0, lane, valid, W);
+  cz.init(a, b, x, x0, lane, valid, W, hv.flip);
 
 #pragma unroll
-  for (int u = 0; u < R; ++u) issue(H - 1 - u);
+  for (int u = 0; u < R; ++u) issue(ys - u);
+  twist_seed(a, hv, Hb, IPC, x, x0, lane, valid, zn, zhn);
   double acc = 0.0;
 #pragma unroll 2
-  for (int y = H - 1; y >= 0; --y) {
+  for (int y = ys; y >= 0; --y) {
     cp_async_wait<R - 1>();
     __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
     {
-      const RingU* r = ring + ((H - 1 - y) % R);
+      const RingU* r = ring + ((ys - y) % R);
       const float4 h = r->h[lane], p = r->p[lane], av = r->a[lane];
       const uint4 f = r->ipc[lane];
       // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
@@ -165,7 +213,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
       z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
       const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
       float zadd, zaddh;
-      cz.at_row(y, H, zadd, zaddh);
+      cz.at_row(y, zadd, zaddh);
       pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
       pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
       const float ph = fmaf(beta, hp, zh + zaddh);
@@ -173,8 +221,8 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
       pu[0] = (lane == 0) ? ph : l;
       pu[5] = (lane == 31) ? ph : rt;
       zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
-      if (valid && y >= 1 && y <= H - 2)
-        *reinterpret_cast<float4*>(P + (size_t)y * W + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
+      if (valid && y >= 1 && y <= yown)
+        *reinterpret_cast<float4*>(P + (ptrdiff_t)y * rs + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
       au[1] = av.x; au[2] = av.y; au[3] = av.z; au[4] = av.w;
       const float al = __shfl_up_sync(full, av.w, 1), ar = __shfl_down_sync(full, av.x, 1);
       au[0] = (lane == 0) ? ha : al;
@@ -196,7 +244,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
     if (!hasL) wu.sw[0] = 0.f;
 
     const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
-    if (yc <= H - 2) {
+    if (yc <= yown) {
       const float E5[5] = {wc.eL, wc.e[0], wc.e[1], wc.e[2], wc.e[3]};
       const float SEu[4] = {wu.seL, wu.se[0], wu.se[1], wu.se[2]};
       const float SWu[4] = {wu.sw[1], wu.sw[2], wu.sw[3], wu.swR};
@@ -216,7 +264,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
         dot = fmaf(pcj, t, dot);
       }
       if (valid) {
-        *reinterpret_cast<float4*>(Q + (size_t)yc * W + x) = make_float4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<float4*>(Q + (ptrdiff_t)yc * rs + x) = make_float4(q[0], q[1], q[2], q[3]);
         acc += (double)dot;
       }
     }
@@ -233,16 +281,20 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
 // instructions per row): used when there are too few tasks to be bandwidth-bound, where the single-warp
 // instruction latency of a strip, not HBM, sets the pace.
 template <int R>
-__device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+__device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int half, int lane,
                                           float beta, bool first, int pcur) {
   RingUP* ring = reinterpret_cast<RingUP*>(ringmem);
   const int H = a.H, W = a.W;
-  const size_t base = (size_t)b * H * W;
+  const HalfView hv(a, b, half);
+  const size_t base = hv.base;
+  const ptrdiff_t rs = hv.rs;
+  const int ys = hv.ys, yown = hv.yown;
   const int x0 = strip * kStrip4, x = x0 + 4 * lane;
   const bool valid = x < W;
   const int xs = valid ? x : 0;
-  const float* __restrict__ S = a.wS + base; const float* __restrict__ E = a.wE + base;
-  const float* __restrict__ SE = a.wSE + base; const float* __restrict__ SW = a.wSW + base;
+  // the mirrored view reads the mirrored weight planes (edges towards the row ABOVE in the image)
+  const float* __restrict__ S = (hv.flip ? a.wS2 : a.wS) + base; const float* __restrict__ E = a.wE + base;
+  const float* __restrict__ SE = (hv.flip ? a.wSE2 : a.wSE) + base; const float* __restrict__ SW = (hv.flip ? a.wSW2 : a.wSW) + base;
   const uint32_t* __restrict__ IPC = a.ipc + base;
   // reads: h (z plane), p_old (pin); writes: p_new (pout), q.  Nothing is updated in place, because the
   // halo columns of this strip belong to a neighbouring strip whose warp runs asynchronously.
@@ -260,11 +312,12 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
                       : (k == 3) ? (isL ? E : SW) : SE;
   const int hxs = hrole ? hx : 0;
 
-  auto issue = [&](int y) {                       // stage row y (rows are visited bottom -> top)
-    RingUP* r = ring + ((H - 2 - y) % R);
+  const int y1 = ys < H - 2 ? ys : H - 2;         // first row of the sweep (the seed row H-1 carries nothing here)
+  auto issue = [&](int y) {                       // stage view row y (rows are visited y1 .. 0)
+    RingUP* r = ring + ((y1 - y) % R);
     const bool in = y >= 0;
     const bool interior = y >= 1;
-    const size_t o = (size_t)(in ? y : 0) * W;
+    const ptrdiff_t o = (ptrdiff_t)(in ? y : 0) * rs;
     cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
     cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
@@ -284,17 +337,18 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
   CoarseZ cz;
-  cz.init(a, b, x, x0, lane, valid, W);
+  cz.init(a, b, x, x0, lane, valid, W, hv.flip);
 
 #pragma unroll
-  for (int u = 0; u < R; ++u) issue(H - 2 - u);
+  for (int u = 0; u < R; ++u) issue(y1 - u);
+  twist_seed(a, hv, Hb, IPC, x, x0, lane, valid, zn, zhn);
   double acc = 0.0;
 #pragma unroll 2
-  for (int y = H - 2; y >= 0; --y) {
+  for (int y = y1; y >= 0; --y) {
     cp_async_wait<R - 1>();
     __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
     {
-      const RingUP* r = ring + ((H - 2 - y) % R);
+      const RingUP* r = ring + ((y1 - y) % R);
       const float4 h = r->h[lane], p = r->p[lane];
       const uint4 f = r->ipc[lane];
       wu.s = r->s[lane]; wu.e = r->e[lane]; wu.se = r->se[lane]; wu.sw = r->sw[lane];
@@ -308,7 +362,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
       z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
       const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
       float zadd, zaddh;
-      cz.at_row(y, H, zadd, zaddh);
+      cz.at_row(y, zadd, zaddh);
       pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
       pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
       const float ph = fmaf(beta, hp, zh + zaddh);
@@ -316,11 +370,11 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
       pu[0] = (lane == 0) ? ph : l;
       pu[5] = (lane == 31) ? ph : rt;
       zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
-      if (valid && y >= 1) *reinterpret_cast<float4*>(P + (size_t)y * W + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
+      if (valid && y >= 1 && y <= yown) *reinterpret_cast<float4*>(P + (ptrdiff_t)y * rs + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
     }
     __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
     const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
-    if (yc <= H - 2) {
+    if (yc <= yown) {
       const float eL_s = __shfl_up_sync(full, wc.e.w, 1);
       const float seL_s = __shfl_up_sync(full, wu.se.w, 1);
       const float swR_s = __shfl_down_sync(full, wu.sw.x, 1);
@@ -350,7 +404,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
         dot = fmaf(pcj, t, dot);
       }
       if (valid) {
-        *reinterpret_cast<float4*>(Q + (size_t)yc * W + x) = make_float4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<float4*>(Q + (ptrdiff_t)yc * rs + x) = make_float4(q[0], q[1], q[2], q[3]);
         acc += (double)dot;
       }
     }
@@ -370,11 +424,17 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
 // Alternating 1 / 2 halves the traffic of the e-update (the previous search direction is still intact
 // in the other p plane), 13 instead of 14 plane touches per iteration on average.
 template <int RD, int KIND>
-__device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int lane,
+__device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int half, int lane,
                                           float alpha, float alpha_prev, int pcur, double& rr_out, double& rz_out) {
   RingD* ring = reinterpret_cast<RingD*>(ringmem);
   const int H = a.H, W = a.W;
-  const size_t base = (size_t)b * H * W;
+  const HalfView hv(a, b, half);
+  const size_t base = hv.base;
+  const ptrdiff_t rs = hv.rs;
+  // rows 1 .. ylast of the view.  Twisted: the upper half also takes row m, but only its part of h[m] (the last
+  // arriver of the phase adds the lower half's term and the row's share of r.z, see twist_fix)
+  const int ylast = hv.yown;
+  const int ymid = (a.tw_m && !hv.flip) ? a.tw_m : -1;
   const int x = strip * kStrip4 + 4 * lane;
   const bool valid = x < W;
   const int xs = valid ? x : 0;
@@ -386,8 +446,8 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   float* __restrict__ Hb = a.z + base;          // h = L^-1 r goes to the z plane (read by the next F_UP)
   auto issue = [&](int y) {
     RingD* r = ring + ((y - 1) % RD);
-    const bool in = (y <= H - 2) && valid;
-    const size_t o = (size_t)(y <= H - 2 ? y : 0) * W + xs;
+    const bool in = (y <= ylast) && valid;
+    const ptrdiff_t o = (ptrdiff_t)(y <= ylast ? y : 0) * rs + xs;
     if (KIND == 2) {
       cp_async16(&r->p[lane], P + o, in);
       cp_async16(&r->pp[lane], PP + o, in);
@@ -404,7 +464,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   float racc = 0.f;
   double rr = 0.0, rz = 0.0;
 #pragma unroll 2
-  for (int y = 1; y <= H - 2; ++y) {
+  for (int y = 1; y <= ylast; ++y) {
     cp_async_wait<RD - 1>();
     const RingD* r = ring + ((y - 1) % RD);
     const float4 rv = r->r[lane];
@@ -416,31 +476,36 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
       const float4 qv = r->q[lane];
       rn[0] = fmaf(-alpha, qv.x, rv.x); rn[1] = fmaf(-alpha, qv.y, rv.y);
       rn[2] = fmaf(-alpha, qv.z, rv.z); rn[3] = fmaf(-alpha, qv.w, rv.w);
-      if (valid) *reinterpret_cast<float4*>(Rv + (size_t)y * W + x) = make_float4(rn[0], rn[1], rn[2], rn[3]);
+      if (valid) *reinterpret_cast<float4*>(Rv + (ptrdiff_t)y * rs + x) = make_float4(rn[0], rn[1], rn[2], rn[3]);
       if (KIND == 2) {
         const float4 pv = r->p[lane], pq = r->pp[lane], ev = r->e[lane];
         const float4 en = make_float4(fmaf(alpha, pv.x, fmaf(alpha_prev, pq.x, ev.x)), fmaf(alpha, pv.y, fmaf(alpha_prev, pq.y, ev.y)),
                                       fmaf(alpha, pv.z, fmaf(alpha_prev, pq.z, ev.z)), fmaf(alpha, pv.w, fmaf(alpha_prev, pq.w, ev.w)));
-        if (valid) *reinterpret_cast<float4*>(Ev + (size_t)y * W + x) = en;
+        if (valid) *reinterpret_cast<float4*>(Ev + (ptrdiff_t)y * rs + x) = en;
       }
     } else if (valid) {
-      *reinterpret_cast<float4*>(Ev + (size_t)y * W + x) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(Ev + (ptrdiff_t)y * rs + x) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = fmaf(cp[j], hp[j], rn[j]);
-    if (valid) *reinterpret_cast<float4*>(Hb + (size_t)y * W + x) = make_float4(h[0], h[1], h[2], h[3]);
+    if (valid) *reinterpret_cast<float4*>(Hb + (ptrdiff_t)y * rs + x) = make_float4(h[0], h[1], h[2], h[3]);
     const float srr = fmaf(rn[0], rn[0], fmaf(rn[1], rn[1], fmaf(rn[2], rn[2], rn[3] * rn[3])));
     const float srz = fmaf(iv.x * h[0], h[0], fmaf(iv.y * h[1], h[1], fmaf(iv.z * h[2], h[2], iv.w * h[3] * h[3])));
-    rr += (double)srr; rz += (double)srz;
+    rr += (double)srr;
+    if (y != ymid) rz += (double)srz;
     if (a.cg.by) {                               // restriction rc = P^T r: sum of the new residual over each aggregate
       racc += (rn[0] + rn[1]) + (rn[2] + rn[3]);
-      if ((y & (a.cg.by - 1)) == 0 || y == H - 2) {          // (y-1) is the last row of its aggregate row
-        float v = racc;                                      // 8 (or 16) lanes share one aggregate column
-        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if (a.cg.bx_shift == 6) v += __shfl_xor_sync(0xffffffffu, v, 8);
+      const int ya = hv.flip ? H - 1 - y : y;    // image row
+      // the last row of an aggregate row in the order of travel
+      if (hv.flip ? (((ya - 1) & (a.cg.by - 1)) == 0) : ((ya & (a.cg.by - 1)) == 0 || ya == H - 2)) {
+        float v = racc;                                      // 4 ... 32 lanes share one aggregate column
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (a.cg.bx_shift >= 5) v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (a.cg.bx_shift >= 6) v += __shfl_xor_sync(0xffffffffu, v, 8);
+        if (a.cg.bx_shift == 7) v += __shfl_xor_sync(0xffffffffu, v, 16);
         if ((lane & ((1 << (a.cg.bx_shift - 2)) - 1)) == 0 && valid)
-          a.rc[(size_t)b * a.cg.nc + (size_t)((y - 1) >> a.cg.by_shift) * a.cg.nbx + (x >> a.cg.bx_shift)] = v;
+          a.rc[(size_t)b * a.cg.nc + (size_t)((ya - 1) >> a.cg.by_shift) * a.cg.nb + (x >> a.cg.bx_shift)] = v;
         racc = 0.f;
       }
     }
@@ -453,108 +518,145 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   rr_out = warp_sum(rr); rz_out = warp_sum(rz);
 }
 
-// F_COARSE: one warp solves Ac zc = rc for one image and returns rc . zc.
-// Two triangular sweeps in saxpy form with a ROTATING REGISTER WINDOW: lane l holds the vector element
-// j == l (mod 32) of the 32-wide window that starts at the current row, so a step is
-//   broadcast the head element (one shuffle)  ->  every lane: w -= F[i][d] * head  (one FMA)
-// and the dependent chain per row is shuffle + FMA (~30 cycles) instead of a shared-memory round trip.
-// Needs band width kd <= 31.  The factor rows are pre-scaled (F[i][d] = L[.]/L[i,i], F[i][0] = 1/L[i,i])
-// and staged in shared memory by cp.async tiles; the vector lives in shared memory only as input/output.
-__device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane) {
+// F_COARSE: one warp solves Ac zc = rc for one image and returns rc . zc (block LDL^T, see confmap_coarse.cuh).
+//   forward    v_I = rc_I - E_I w_{I-1},  w_I = W_I v_I          (v_I parked in the zc array)
+//   backward   zc_I = W_I (v_I - E_{I+1}^T zc_{I+1})
+// Lane l owns element row = l % NB of the current block row (32 / NB lanes share a row and split the columns of
+// W_I between them); the vector is broadcast through a double-buffered shared-memory line, W_I is read from a
+// cp.async ring of block-row records with 128-bit, conflict-free loads (row pitch NB + 4).  One __syncwarp per step.
+template <int NB>
+struct CoarseSlot {
+  float W[NB * (NB + 4)];
+  float E[4 * NB];     // couplings of this block row to the one above: centre, left (J-1), right (J+1), spare
+  float vec[NB];       // forward: rc_I; backward: v_I
+};
+
+template <int NB, int RING_BYTES>
+__device__ __forceinline__ double coarse_task_nb(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane) {
+  using Slot = CoarseSlot<NB>;
+  constexpr int Dfit = (RING_BYTES - 2 * NB * (int)sizeof(float)) / (int)sizeof(Slot);
+  constexpr int D = Dfit > 16 ? 16 : Dfit;                       // ring depth in block rows
+  static_assert(D >= 3, "coarse ring too shallow");
+  constexpr int LPR = 32 / NB;                                   // lanes per row
+  constexpr int CP = NB / LPR;                                   // columns of W per lane
+  constexpr int WCH = NB * NB / 4;                               // 16-byte chunks of W_I
+  constexpr int KW = (WCH + 31) / 32;                            // ... per lane
   const CoarseGeom g = a.cg;
-  const int n = g.nc, kd1 = g.kd1;
-  float* ysb = reinterpret_cast<float*>(ringmem);                // 32 zeros | vector [n] | zeros up to kCoarseMaxN + 64
-  float* ys = ysb + 32;
-  float* tiles = ysb + ((n + 31) & ~31) + 96;                    // 2 x [32][32], right behind the padded vector
-  const float* rc = a.rc + (size_t)b * n;
-  float* zc = a.zc + (size_t)b * n;
-  const float* U = a.Ur + (size_t)b * n * kd1;
-  const float* L = a.Lr + (size_t)b * n * kd1;
+  const int nby = g.nby;
+  Slot* ring = reinterpret_cast<Slot*>(ringmem);
+  float* vs = reinterpret_cast<float*>(ringmem + (size_t)D * sizeof(Slot));      // [2][NB]
+  const float* rec = a.Wt + (size_t)b * nby * g.rec;
+  const float* rc = a.rc + (size_t)b * g.nc;
+  float* zc = a.zc + (size_t)b * g.nc;
+  const int row = lane & (NB - 1), c0 = (lane / NB) * CP;
+  const bool owner = lane < NB;
   const unsigned full = 0xffffffffu;
-  const int ntile = (n + kCoarseTileRows - 1) / kCoarseTileRows;
-  auto issue_tile = [&](const float* F, int t, float* buf) {
-    if (t >= 0 && t < ntile) {
-      const int r0 = t * kCoarseTileRows, rows = min(kCoarseTileRows, n - r0);
-      const int chunks = rows * kd1 / 4;                         // rows past n are zero-filled (src-size 0)
-      for (int c = lane; c < kCoarseTileRows * 32 / 4; c += 32)
-        cp_async16(buf + 4 * c, F + (size_t)r0 * kd1 + 4 * (c < chunks ? c : 0), c < chunks);
+  // copy roles of this lane, fixed for the whole task: KW chunks of W_I, and one chunk of E_I or of the vector
+  const bool w_on = (WCH >= 32) || lane < WCH;
+  const int wr = lane / (NB / 4), wq = lane - wr * (NB / 4);
+  const int w_s = wr * (NB + 4) + 4 * wq;                        // float offset inside Slot::W; + k * (128 / NB) rows
+  const bool e_on = lane < NB;                                   // E_I: NB chunks
+  const bool v_on = (NB == 32) ? lane < 8 : (lane >= NB && lane < NB + NB / 4);
+  const int v_q = (NB == 32) ? lane : lane - NB;
+
+  auto issue = [&](int k, int I, const float* vec) {             // stage block row I into slot k % D
+    if (I >= 0 && I < nby) {
+      Slot* s = ring + (k % D);
+      const float* src = rec + (size_t)I * g.rec;
+#pragma unroll
+      for (int j = 0; j < KW; ++j)
+        if (w_on) cp_async16(&s->W[w_s + j * (128 / NB) * (NB + 4)], src + 4 * lane + 128 * j, true);
+      if constexpr (NB == 32) {
+        cp_async16(&s->E[4 * lane], src + NB * NB + 4 * lane, true);
+        if (v_on) cp_async16(&s->vec[4 * v_q], vec + (size_t)I * NB + 4 * v_q, true);
+      } else {
+        const float* asrc = e_on ? src + NB * NB + 4 * lane : vec + (size_t)I * NB + 4 * v_q;
+        float* adst = e_on ? &s->E[4 * lane] : &s->vec[4 * v_q];
+        if (e_on || v_on) cp_async16(adst, asrc, true);
+      }
     }
     cp_async_commit();
   };
-  ysb[lane] = 0.f;
-  for (int i = lane; i < n + 64; i += 32) ys[i] = (i < n) ? __ldcg(rc + i) : 0.f;
-  __syncwarp();
-  // Both sweeps advance in blocks of 32 rows (= one factor tile).  Inside a block lane l admits exactly one
-  // element (prefetched into `nx` before the block) and retires exactly one (kept in `out`, stored after the
-  // block), so the inner step has no shared-memory store and its dependent chain is shuffle -> FMA -> select.
-  // ---- forward: L y = rc, column-oriented (row i of Ur = scaled column i of L) -----------------------
-  issue_tile(U, 0, tiles);
-  float w = ys[lane];                                            // window [0, 32): lane l holds element l
-  for (int t = 0; t < ntile; ++t) {
-    issue_tile(U, t + 1, tiles + ((t + 1) & 1) * kCoarseTileRows * 32);
-    const int i0 = t * 32;
-    const float nx = ys[i0 + 32 + lane];                         // element this lane admits during the block
-    float out = 0.f;
-    cp_async_wait<1>();
-    __syncwarp();
-    const float* T = tiles + (t & 1) * kCoarseTileRows * 32;
-#pragma unroll 8
-    for (int hl = 0; hl < 32; ++hl) {                            // row i = i0 + hl; its element sits on lane hl
-      const float* row = T + hl * 32;
-      const int d = (lane - hl) & 31;                            // this lane holds element i + d
-      const float f = row[d];                                    // zero padded beyond the band
-      const float r0 = row[0];
-      const float head = __shfl_sync(full, w, hl);               // element i, fully updated
-      const float wn = fmaf(-f, head, w);
-      w = (d == 0) ? nx : wn;                                    // retire element i, admit element i + 32
-      out = (d == 0) ? head * r0 : out;                          // y_i
+  auto matvec = [&](const Slot* s, const float* v) {             // (W_I v)[row], complete in every lane
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (CP >= 4) {
+#pragma unroll
+      for (int q = 0; q < CP / 4; ++q) {
+        const float4 wv = *reinterpret_cast<const float4*>(&s->W[row * (NB + 4) + c0 + 4 * q]);
+        const float4 vv = *reinterpret_cast<const float4*>(&v[c0 + 4 * q]);
+        acc[0] = fmaf(wv.x, vv.x, acc[0]); acc[1] = fmaf(wv.y, vv.y, acc[1]);
+        acc[2] = fmaf(wv.z, vv.z, acc[2]); acc[3] = fmaf(wv.w, vv.w, acc[3]);
+      }
+    } else {
+      const float2 wv = *reinterpret_cast<const float2*>(&s->W[row * (NB + 4) + c0]);
+      const float2 vv = *reinterpret_cast<const float2*>(&v[c0]);
+      acc[0] = wv.x * vv.x; acc[1] = wv.y * vv.y;
     }
-    if (i0 + lane < n) ys[i0 + lane] = out;
+    float r = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int o = NB; o < 32; o <<= 1) r += __shfl_xor_sync(full, r, o);
+    return r;
+  };
+
+  // ---- forward ----------------------------------------------------------------------------------
+  for (int u = 0; u < D - 1; ++u) issue(u, u, rc);
+  cp_async_wait<D - 2>();
+  __syncwarp();
+  float w = 0.f;                                                 // (W_{I-1} v_{I-1})[row]
+  float pvw = 0.f;                                               // v . w of the previous step (added one step late:
+  double dot = 0.0;                                              //  the fp64 add then hides behind the shuffles)
+  for (int I = 0; I < nby; ++I) {
+    const Slot* s = ring + (I % D);
+    const float wls = __shfl_up_sync(full, w, 1), wrs = __shfl_down_sync(full, w, 1);
+    const float e0 = s->E[row], e1 = s->E[NB + row], e2 = s->E[2 * NB + row], r0 = s->vec[row];
+    dot += (double)pvw;
+    const float wl = (row == 0) ? 0.f : wls, wr = (row == NB - 1) ? 0.f : wrs;
+    const float v = r0 - fmaf(e0, w, fmaf(e1, wl, e2 * wr));
+    float* vb = vs + (I & 1) * NB;
+    if (owner) vb[row] = v;
+    cp_async_wait<D - 3>();                                      // this lane's pieces of block row I + 1 have landed
+    __syncwarp();                                                // publishes vb and block row I + 1; everybody is done with row I - 1
+    w = matvec(s, vb);
+    if (owner) zc[(size_t)I * NB + row] = v;
+    issue(I + D - 1, I + D - 1, rc);                             // refills the slot of block row I - 1
+    pvw = owner ? v * w : 0.f;
+  }
+  dot += (double)pvw;
+  cp_async_wait<0>();
+  __threadfence();                                               // v (in zc) is re-read through cp.async below
+  __syncwarp();
+  // ---- backward ---------------------------------------------------------------------------------
+  for (int u = 0; u < D - 1; ++u) issue(u, nby - 1 - u, zc);
+  cp_async_wait<D - 2>();
+  __syncwarp();
+  float z = 0.f, eC = 0.f, eL = 0.f, eR = 0.f;                   // zc_{I+1}[row] and E_{I+1}[row]
+  for (int k = 0; k < nby; ++k) {
+    const int I = nby - 1 - k;
+    const Slot* s = ring + (k % D);
+    // (E_{I+1}^T z)[j] = eC[j] z[j] + eL[j+1] z[j+1] + eR[j-1] z[j-1]
+    const float tb = eL * z, tc = eR * z;
+    const float tbs = __shfl_down_sync(full, tb, 1), tcs = __shfl_up_sync(full, tc, 1);
+    const float v0 = s->vec[row];
+    const float u = v0 - (fmaf(eC, z, (row == NB - 1) ? 0.f : tbs) + ((row == 0) ? 0.f : tcs));
+    float* vb = vs + (k & 1) * NB;
+    if (owner) vb[row] = u;
+    eC = s->E[row]; eL = s->E[NB + row]; eR = s->E[2 * NB + row];
+    cp_async_wait<D - 3>();
     __syncwarp();
+    z = matvec(s, vb);
+    if (owner) zc[(size_t)I * NB + row] = z;
+    issue(k + D - 1, I - (D - 1), zc);
   }
   cp_async_wait<0>();
   __syncwarp();
-  // ---- backward: L^T x = y, row-oriented (row i of Lr) ----------------------------------------------------
-  issue_tile(L, ntile - 1, tiles);
-  {
-    const int top = ntile * 32 - 1;                              // window (top-32, top]: lane l holds element j == l (mod 32)
-    const int j = top - ((top - lane) & 31);
-    w = ys[j];                                                   // ys is zero padded past n
-  }
-  for (int k = 0; k < ntile; ++k) {
-    const int t = ntile - 1 - k;
-    issue_tile(L, t - 1, tiles + ((k + 1) & 1) * kCoarseTileRows * 32);
-    const int i0 = t * 32;
-    const float nx = ysb[i0 + lane];                             // = ys[i0 - 32 + lane]: element admitted during the block
-    float out = 0.f;
-    cp_async_wait<1>();
-    __syncwarp();
-    const float* T = tiles + (k & 1) * kCoarseTileRows * 32;
-#pragma unroll 8
-    for (int hl = 31; hl >= 0; --hl) {                           // row i = i0 + hl
-      const float* row = T + hl * 32;
-      const int d = (hl - lane) & 31;                            // this lane holds element i - d
-      const float f = row[d];
-      const float r0 = row[0];
-      const float head = __shfl_sync(full, w, hl);               // element i with all later rows eliminated
-      const float xi = head * r0;                                // x_i = head / L[i,i]   (0 for padding rows: r0 = 0)
-      const float wn = fmaf(-f, xi, w);
-      w = (d == 0) ? nx : wn;                                    // retire element i, admit element i - 32
-      out = (d == 0) ? xi : out;
-    }
-    if (i0 + lane < n) ys[i0 + lane] = out;
-    __syncwarp();
-  }
-  cp_async_wait<0>();
-  __syncwarp();
-  double acc = 0.0;
-  for (int i = lane; i < n; i += 32) {
-    const float v = ys[i];
-    zc[i] = v;
-    acc += (double)v * (double)__ldcg(rc + i);
-  }
-  __syncwarp();
-  return warp_sum(acc);
+  return warp_sum(dot);
+}
+
+template <int RING_BYTES>
+__device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane) {
+  if (a.cg.nb == 16) return coarse_task_nb<16, RING_BYTES>(a, ringmem, b, lane);
+  if (a.cg.nb == 32) return coarse_task_nb<32, RING_BYTES>(a, ringmem, b, lane);
+  return coarse_task_nb<8, RING_BYTES>(a, ringmem, b, lane);
 }
 
 // ---- ready queue (two multi-producer / multi-consumer rings in global memory) ----------------------
@@ -687,14 +789,38 @@ __device__ __forceinline__ void leave_priority(const PcgArgs<float>& a, ImgState
   atomicSub(a.qcnt, 1u);
 }
 
-// fp64 residual r = b - A x64 over one 128-column strip (rare: once per refinement round)
-__device__ __forceinline__ double resid_strip(const PcgArgs<float>& a, int b, int strip, int lane) {
+// fp64 residual r = b - A x64 over one 128-column strip (rare: once per refinement round); with the twisted
+// factorisation the two half tasks of a strip split the row blocks
+__device__ __forceinline__ double resid_strip(const PcgArgs<float>& a, int b, int strip, int half, int lane) {
   const int x0 = strip * kStrip4, xe = min(x0 + kStrip4, a.W);
+  const int r0 = (a.tw_m && half) ? a.nrb / 2 : 0, r1 = (a.tw_m && !half) ? a.nrb / 2 : a.nrb;
   double s = 0.0;
   for (int xb = x0; xb < xe; xb += kStripCols)
-    for (int rbk = 0; rbk < a.nrb; ++rbk)
+    for (int rbk = r0; rbk < r1; ++rbk)
       s += stencil_task<float, true>(a, b, xb, min(kStripCols, xe - xb), rbk, lane, 0.f, true);
   return s;
+}
+
+// Twisted factorisation: after F_DOWN / F_PRECOND the h plane holds, in row m, only the upper half's part
+// r[m] + c[m-1] h[m-1].  The last arriver of the phase (one warp) adds the lower half's term c[m+1] h[m+1], stores the
+// complete row and returns the row's share of r.z = sum ip h^2.
+__device__ __forceinline__ double twist_fix(const PcgArgs<float>& a, int b, int lane) {
+  const int W = a.W, m = a.tw_m;
+  const size_t o = (size_t)b * a.H * W + (size_t)m * W;
+  float* Hm = a.z + o;
+  const float* Hn = a.z + o + W;
+  const uint32_t* Fm = a.ipc + o;
+  const uint32_t* Fn = a.ipc + o + W;
+  double acc = 0.0;
+  for (int x = 4 * lane; x < W; x += 128) {
+    const float4 ht = __ldcg(reinterpret_cast<const float4*>(Hm + x)), hb = __ldcg(reinterpret_cast<const float4*>(Hn + x));
+    const uint4 fm = __ldcg(reinterpret_cast<const uint4*>(Fm + x)), fn = __ldcg(reinterpret_cast<const uint4*>(Fn + x));
+    const float4 h = make_float4(fmaf(bf16_hi(fn.x), hb.x, ht.x), fmaf(bf16_hi(fn.y), hb.y, ht.y),
+                                 fmaf(bf16_hi(fn.z), hb.z, ht.z), fmaf(bf16_hi(fn.w), hb.w, ht.w));
+    *reinterpret_cast<float4*>(Hm + x) = h;
+    acc += (double)fmaf(bf16_lo(fm.x) * h.x, h.x, fmaf(bf16_lo(fm.y) * h.y, h.y, fmaf(bf16_lo(fm.z) * h.z, h.z, bf16_lo(fm.w) * h.w * h.w)));
+  }
+  return warp_sum(acc);
 }
 
 // AW = active warps per CTA (8 or 4): fewer active warps own deeper rings.
@@ -708,8 +834,8 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp >= AW || warp >= a.wpb) return;                        // no block-wide barrier anywhere below
   unsigned char* ringmem = smem_raw + (size_t)warp * kWarpRing;
-  const int B = a.B, H = a.H, W = a.W;
-  const int per = a.nstrip4;
+  const int H = a.H, W = a.W;
+  const int per = a.per;                                          // tasks per image and phase: strips x halves
 
   auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
   unsigned long long t_wait = 0, t_mode[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_arr = 0;
@@ -721,27 +847,30 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     t_wait += tq1 - tq0;
     if (payload == kNoTask) break;
     const int b = (int)(payload / (unsigned)per), ti = (int)(payload % (unsigned)per);
+    const int strip = ti % a.nstrip4, half = ti / a.nstrip4;      // half = 1: lower half of a twisted factorisation
     ImgState* st = a.st + b;
     const int mode = (int)(__ldcg(&st->fword) & 0xffffffffull);
     double s0 = 0.0, s1 = 0.0;
     if (mode == F_UP) {
       if constexpr (RECOMP)
-        s0 = up_task<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+        s0 = up_task<R>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
       else
-        s0 = up_task_planes<R>(a, ringmem, b, ti, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+        s0 = up_task_planes<R>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
     } else if (mode == F_DOWN) {
       if (__ldcg(&st->epend))
-        down_task<RD, 2>(a, ringmem, b, ti, lane, (float)__ldcg(&st->alpha), (float)__ldcg(&st->alpha_prev), __ldcg(&st->pcur), s0, s1);
+        down_task<RD, 2>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->alpha), (float)__ldcg(&st->alpha_prev), __ldcg(&st->pcur), s0, s1);
       else
-        down_task<RD, 1>(a, ringmem, b, ti, lane, (float)__ldcg(&st->alpha), 0.f, __ldcg(&st->pcur), s0, s1);
+        down_task<RD, 1>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->alpha), 0.f, __ldcg(&st->pcur), s0, s1);
     } else if (mode == F_PRECOND) {
-      down_task<RD, 0>(a, ringmem, b, ti, lane, 0.f, 0.f, 0, s0, s1);
+      down_task<RD, 0>(a, ringmem, b, strip, half, lane, 0.f, 0.f, 0, s0, s1);
     } else if (mode == F_RESID) {
-      s0 = resid_strip(a, b, ti, lane);
+      s0 = resid_strip(a, b, strip, half, lane);
     } else if (mode == F_COARSE) {
-      s0 = coarse_task(a, ringmem, b, lane);
+      s0 = coarse_task<(int)kWarpRing>(a, ringmem, b, lane);
     } else {
-      const int x = ti * kStrip4 + 4 * lane;
+      const int x = strip * kStrip4 + 4 * lane;
+      // rows of this task: all of them, or one side of row m
+      const int ylo = (a.tw_m && half) ? a.tw_m + 1 : 0, yhi = (a.tw_m && !half) ? a.tw_m : H - 1;
       if (x < W) {
         const size_t base = (size_t)b * H * W + x;
         if (mode == F_FOLD) {
@@ -749,7 +878,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
           const float ap = __ldcg(&st->epend) ? (float)__ldcg(&st->alpha_prev) : 0.f;
           const float* Pl = (__ldcg(&st->pcur) ? a.p2 : a.p);
 #pragma unroll 4
-          for (int y = 1; y <= H - 2; ++y) {
+          for (int y = max(ylo, 1); y <= min(yhi, H - 2); ++y) {
             const size_t o = base + (size_t)y * W;
             float4 e = __ldcg(reinterpret_cast<const float4*>(a.e + o));
             if (ap != 0.f) {
@@ -763,7 +892,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
           }
         } else {   // F_FINAL
 #pragma unroll 4
-          for (int y = 0; y < H; ++y) {
+          for (int y = ylo; y <= yhi; ++y) {
             const size_t o = base + (size_t)y * W;
             const double2* xp = reinterpret_cast<const double2*>(a.x64 + o);
             const double2 v0 = __ldcg(xp), v1 = __ldcg(xp + 1);
@@ -788,6 +917,11 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     // ---- last strip of this image and phase: reduce, advance the state, publish the next phase ------
     __threadfence();
     reduce_parts(part, ntask, lane, s0, s1);
+    if (a.tw_m && (mode == F_DOWN || mode == F_PRECOND)) {
+      s1 += twist_fix(a, b, lane);
+      __threadfence();                                            // every lane publishes its part of row m
+      __syncwarp();
+    }
     int next = F_DONE;
     // the F_COARSE decision, also used after the inline coarse solve below
     auto after_coarse = [&](double rc_zc) {
@@ -853,7 +987,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       // hand-off less on the UP -> DOWN -> COARSE chain (+2 % at B <= 64).  Bandwidth-bound launches keep it in
       // the queue: there it is the two service classes that decide who runs next (inline: -11 % at B = 512).
       const unsigned long long tc0 = a.debug ? now() : 0ull;
-      const double rc_zc = coarse_task(a, ringmem, b, lane);
+      const double rc_zc = coarse_task<(int)kWarpRing>(a, ringmem, b, lane);
       __threadfence();                                          // every lane publishes its part of zc
       __syncwarp();
       if (a.debug) { t_mode[F_COARSE] += now() - tc0; n_mode[F_COARSE]++; }

@@ -16,6 +16,9 @@ namespace usaug {
 
 struct CmLayout {
   float *depth, *mm1, *mm2, *wS, *wE, *wSE, *wSW, *ip, *c, *aplane;
+  float *wS2, *wSE2, *wSW2;   // mirrored weight planes (twisted factorisation + weight-reading F_UP only)
+  bool fused, recomp;         // fused fp32 kernel; its F_UP recomputes the edge weights
+  int tw_m, per;              // twisted line factorisation: meeting row (0 = off); tasks per image and phase
   uint32_t* ipc;
   float4* wk;
   double *x64, *bbpart, *part;
@@ -28,7 +31,7 @@ struct CmLayout {
   double* qsum;
   unsigned* qcnt;
   CoarseGeom cg;
-  float *rc, *zc, *Lr, *Ur;
+  float *rc, *zc, *Wt;
   double* Ab;
   int nblk, nstrip1, nrb, nstrip2, pmax;
   size_t bytes;
@@ -38,11 +41,37 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   CmLayout L;
   const size_t N = (size_t)B * H * W;
   const size_t tsz = (flags & USAUG_CM_FP64_VECTORS) ? 8 : 4;
+  // ---- solver variant: a function of the launch's size only (flags can pin every choice) ------------------
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int nstrip4 = (W + kStrip4 - 1) / kStrip4;
+  const long long tasks = (long long)B * nstrip4;               // 128-column strips in flight
+  L.fused = !(flags & (USAUG_CM_FP64_VECTORS | USAUG_CM_LEGACY_KERNEL)) && W % 4 == 0;
+  // few tasks: the single-warp instruction latency of a strip sets the pace, so F_UP reads the weight planes
+  // (fewer instructions per row); many tasks: HBM sets the pace, so it recomputes them (fewer bytes)
+  L.recomp = (flags & USAUG_CM_FORCE_RECOMPUTE) ? true : (flags & USAUG_CM_FORCE_PLANES) ? false : tasks >= 6ll * sms;
+  const bool many = tasks >= 12ll * sms;
+  const bool fine = (flags & USAUG_CM_COARSE_FINE) ? true : (flags & USAUG_CM_COARSE_STANDARD) ? false : many;
+  int min_shift = fine ? 1 : 2, min_bx_shift = 5;
+  if (const char* e = getenv("USAUG_CM_COARSE_SHIFT")) min_shift = atoi(e);          // development knobs
+  if (const char* e = getenv("USAUG_CM_COARSE_BXSHIFT")) min_bx_shift = atoi(e);
+  L.cg = (!L.fused || (flags & USAUG_CM_NO_COARSE)) ? CoarseGeom{} : coarse_geom(H, W, min_shift, min_bx_shift);
+  // Twisted line factorisation (two half sweeps per strip): halves the dependent UP -> DOWN chain of an image, which
+  // is what bounds launches that cannot fill the GPU; deeply bandwidth-bound launches gain nothing from it.
+  L.tw_m = 0;
+  const bool twist = (flags & USAUG_CM_TWIST_ON) ? true : (flags & USAUG_CM_TWIST_OFF) ? false : !many;
+  if (L.fused && twist && H - 2 >= 32) {
+    const int by = L.cg.by ? L.cg.by : 1;
+    const int m = ((H - 1) / 2) & ~(by - 1);                    // on an aggregate-row boundary: rows 1..m | m+1..H-2
+    if (m >= 2 && m <= H - 4) L.tw_m = m;
+  }
+  L.per = nstrip4 * (L.tw_m ? 2 : 1);
   L.nblk = (W + 127) / 128;
   L.nstrip1 = (W + kStripCols - 1) / kStripCols;
   L.nrb = (H - 2 + kRowBlock - 1) / kRowBlock;
   L.nstrip2 = (W + 31) / 32;
   L.pmax = L.nstrip1 * L.nrb > L.nstrip2 ? L.nstrip1 * L.nrb : L.nstrip2;
+  if (L.pmax < 2 * L.nblk) L.pmax = 2 * L.nblk;                 // fused kernel: one partial per (strip, half) task
   Carver cv(ws);
   L.depth = cv.take<float>(H);
   L.mm1 = cv.take<float>((size_t)B * kChunks * 2);
@@ -50,6 +79,9 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.wS = cv.take<float>(N); L.wE = cv.take<float>(N); L.wSE = cv.take<float>(N); L.wSW = cv.take<float>(N);
   L.ip = cv.take<float>(N); L.c = cv.take<float>(N); L.ipc = cv.take<uint32_t>(N);
   L.aplane = cv.take<float>(N); L.wk = cv.take<float4>(B);
+  const size_t nmir = (L.tw_m && !L.recomp) ? N : 0;
+  L.wS2 = cv.take<float>(nmir); L.wSE2 = cv.take<float>(nmir); L.wSW2 = cv.take<float>(nmir);
+  if (!nmir) L.wS2 = L.wSE2 = L.wSW2 = nullptr;
   L.x64 = cv.take<double>(N);
   L.e = cv.take<char>(N * tsz); L.r = cv.take<char>(N * tsz); L.p = cv.take<char>(N * tsz);
   L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz); L.p2 = cv.take<char>(N * tsz);
@@ -57,26 +89,17 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.part = cv.take<double>((size_t)B * L.pmax * 2);
   L.st = cv.take<ImgState>(B);
   L.done = cv.take<unsigned>(2);
-  // two ready rings; every image has at most nstrip4 ready tasks at a time, in one ring or the other
-  L.qcap = (unsigned)(2 * ((W + kStrip4 - 1) / kStrip4) * B + 1024);
+  // two ready rings; every image has at most `per` ready tasks at a time, in one ring or the other
+  L.qcap = (unsigned)(2 * L.per * B + 1024);
   L.qslots = cv.take<unsigned long long>(2 * (size_t)L.qcap);
   L.qhead = cv.take<unsigned long long>(2); L.qtail = cv.take<unsigned long long>(2);   // separate 256-byte lines
   L.qavail = cv.take<int>(2);
   L.qsum = cv.take<double>(1); L.qcnt = cv.take<unsigned>(1);
   // coarse-grid correction (fused fp32 kernel only)
-  // Deeply bandwidth-bound batches take 2-row aggregates: 12 % fewer iterations for a COARSE task twice as long.
-  // The longer UP -> DOWN -> COARSE chain (620 vs 465 us per iteration at 512x512) needs ~260 instead of ~190
-  // images in flight to saturate HBM, so it pays from about twice that (measured on B200: B = 256 -> 0.90x,
-  // B = 512 -> 0.98x on easy images, 1.075x on the bench's deformed images).
-  int sms = device_sm_count();
-  if (sms <= 0) sms = 148;
-  const bool many = (long long)B * ((W + kStrip4 - 1) / kStrip4) >= 12ll * sms;
-  const bool fine = (flags & USAUG_CM_COARSE_FINE) ? true : (flags & USAUG_CM_COARSE_STANDARD) ? false : many;
-  L.cg = ((flags & (USAUG_CM_FP64_VECTORS | USAUG_CM_NO_COARSE)) || W % 4 != 0) ? CoarseGeom{} : coarse_geom(H, W, fine ? 1 : 2);
   const size_t nc = (size_t)L.cg.nc;
   L.rc = cv.take<float>((size_t)B * nc); L.zc = cv.take<float>((size_t)B * nc);
-  L.Lr = cv.take<float>((size_t)B * nc * L.cg.kd1); L.Ur = cv.take<float>((size_t)B * nc * L.cg.kd1);
-  L.Ab = cv.take<double>((size_t)B * nc * (L.cg.kd + 1));
+  L.Wt = cv.take<float>((size_t)B * L.cg.nby * L.cg.rec);
+  L.Ab = cv.take<double>((size_t)B * nc * 5);
   L.bytes = cv.off;
   return L;
 }
@@ -94,14 +117,14 @@ static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t s
   USAUG_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<AW, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
   USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel<AW, RECOMP>, 256, kFusedSmem));
   if (per_sm < 1) { set_error("pcg_fused_kernel cannot be resident"); return USAUG_E_CUDA; }
-  const int tasks = a.nstrip4 * a.B;
+  const int tasks = a.per * a.B;
   int blocks = tasks;
   if (blocks > blocks_cap_sms) blocks = blocks_cap_sms;
   if (blocks < 1) blocks = 1;
   // no more workers than tasks that can be ready at once: an idle worker only polls the queue
   a.wpb = (tasks + blocks - 1) / blocks;
   if (a.wpb > AW) a.wpb = AW;
-  cm_init_queue_kernel<<<(2 * a.qcap + 255) / 256, 256, 0, stream>>>(a.qslots, a.qcap, a.B, a.nstrip4, a.qhead, a.qtail,
+  cm_init_queue_kernel<<<(2 * a.qcap + 255) / 256, 256, 0, stream>>>(a.qslots, a.qcap, a.B, a.per, a.qhead, a.qtail,
                                                                         a.qavail, a.qsum, a.qcnt);
   USAUG_CHECK_LAUNCH("cm_init_queue_kernel");
   void* params[] = {(void*)&a};
@@ -114,15 +137,14 @@ static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t s
 }
 
 static int launch_fused(PcgArgs<float>& a, const CmLayout& L, int B, cudaStream_t stream) {
-  (void)L;
+  (void)B;
   int dev = 0, sms = 0;
   USAUG_CUDA(cudaGetDevice(&dev));
   USAUG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // every inner iteration is two phases; a refinement round adds four
   a.max_steps = 6 * a.maxiter + 64;   // worst case: a refinement round (5 phases) after every iteration
-  const int tasks = a.nstrip4 * B;
-  // few tasks: 4 active warps per CTA with rings twice as deep keep enough bytes in flight
-  if (tasks >= 6 * sms) return launch_fused_aw<8, true>(a, sms, stream);
+  // few tasks (weight-reading F_UP): 4 active warps per CTA with rings twice as deep keep enough bytes in flight
+  if (L.recomp) return launch_fused_aw<8, true>(a, sms, stream);
   return launch_fused_aw<4, false>(a, sms, stream);
 }
 
@@ -139,10 +161,11 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.e = (T*)L.e; a.r = (T*)L.r; a.p = (T*)L.p; a.q = (T*)L.q; a.z = (T*)L.z; a.p2 = (T*)L.p2;
   a.st = L.st; a.part = L.part; a.done = L.done;
   a.qslots = L.qslots; a.qhead = L.qhead; a.qtail = L.qtail; a.qcap = L.qcap; a.qavail = L.qavail; a.qsum = L.qsum; a.qcnt = L.qcnt;
-  a.cg = L.cg; a.rc = L.rc; a.zc = L.zc; a.Lr = L.Lr; a.Ur = L.Ur; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
+  a.cg = L.cg; a.rc = L.rc; a.zc = L.zc; a.Wt = L.Wt; a.cm = cm; a.iters_out = iters; a.relres_out = relres;
   a.nstrip1 = L.nstrip1; a.nrb = L.nrb; a.nstrip2 = L.nstrip2; a.pmax = L.pmax;
   a.vec4 = (std::is_same<T, float>::value && W % 4 == 0) ? 1 : 0;
   a.nstrip4 = (W + kStrip4 - 1) / kStrip4;
+  a.tw_m = L.tw_m; a.per = L.per; a.wS2 = L.wS2; a.wSE2 = L.wSE2; a.wSW2 = L.wSW2;
   // every inner iteration is one step; each refinement round adds <= 3 steps and needs >= 1 iteration
   a.max_steps = 4 * maxiter + 16;
   a.debug = g_debug;
@@ -150,7 +173,7 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   if (const char* w = getenv("USAUG_CM_WATCHDOG_MS")) a.watchdog_ns = (unsigned long long)atoll(w) * 1000000ull;   // test hook
 
   if constexpr (std::is_same<T, float>::value) {
-    if (a.vec4 && !g_legacy) return launch_fused(a, L, B, stream);
+    if (L.fused) return launch_fused(a, L, B, stream);
   }
   // generic grid-synchronous kernel (fp64 vectors, W % 4 != 0, or USAUG_CM_LEGACY_KERNEL)
   int dev = 0, sms = 0, per_sm = 0;
@@ -217,18 +240,22 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   cm_wconst_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, L.mm2, beta, gamma, L.wk);
   USAUG_CHECK_LAUNCH("cm_wconst_kernel");
   cm_weights_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(img, H, W, L.depth, L.mm1, L.wk, L.aplane,
-                                                                 L.wS, L.wE, L.wSE, L.wSW);
+                                                                 L.wS, L.wE, L.wSE, L.wSW, L.wS2, L.wSE2, L.wSW2);
   USAUG_CHECK_LAUNCH("cm_weights_kernel");
   cm_factor_kernel<<<dim3(L.nblk, B), 128, 0, stream>>>(H, W, L.wS, L.wE, L.wSE, L.wSW, precond,
-                                                        (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.ip, L.c,
+                                                        (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.tw_m, L.ip, L.c,
                                                         L.ipc, L.x64, L.bbpart);
   USAUG_CHECK_LAUNCH("cm_factor_kernel");
-  if (L.cg.by && !(flags & USAUG_CM_LEGACY_KERNEL)) {
+  if (L.cg.by) {
     coarse_assemble_kernel<<<dim3((L.cg.nc + 7) / 8, B), 256, 0, stream>>>(H, W, L.cg, L.wS, L.wE, L.wSE, L.wSW, L.Ab);
     USAUG_CHECK_LAUNCH("coarse_assemble_kernel");
-    const size_t fsm = (size_t)(L.cg.kd + 1) * (L.cg.kd + 1) * sizeof(double) + (size_t)L.cg.kd * (L.cg.kd + 1);   // window + pair table
-    coarse_factor_kernel<<<B, 32, fsm, stream>>>(L.cg, L.Ab, L.Lr, L.Ur);
+    if (L.cg.nb == 8) coarse_factor_kernel<8><<<B, 128, 0, stream>>>(L.cg, L.Ab, L.Wt);
+    else if (L.cg.nb == 16) coarse_factor_kernel<16><<<B, 128, 0, stream>>>(L.cg, L.Ab, L.Wt);
+    else coarse_factor_kernel<32><<<B, 128, 0, stream>>>(L.cg, L.Ab, L.Wt);
     USAUG_CHECK_LAUNCH("coarse_factor_kernel");
+    // the padding columns of the coarse vectors are never written by the sweeps
+    USAUG_CUDA(cudaMemsetAsync(L.rc, 0, (size_t)B * L.cg.nc * sizeof(float), stream));
+    USAUG_CUDA(cudaMemsetAsync(L.zc, 0, (size_t)B * L.cg.nc * sizeof(float), stream));
   }
   cm_init_state_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, L.nblk, L.bbpart, L.st, L.done);
   USAUG_CHECK_LAUNCH("cm_init_state_kernel");

@@ -106,7 +106,8 @@ __global__ void cm_wconst_kernel(int B, const float* __restrict__ mm2, float bet
 __global__ void __launch_bounds__(256) cm_weights_kernel(
     const float* __restrict__ img, int H, int W, const float* __restrict__ depth,
     const float* __restrict__ mm1, const float4* __restrict__ wk, float* __restrict__ aplane,
-    float* __restrict__ wS, float* __restrict__ wE, float* __restrict__ wSE, float* __restrict__ wSW) {
+    float* __restrict__ wS, float* __restrict__ wE, float* __restrict__ wSE, float* __restrict__ wSW,
+    float* __restrict__ wS2, float* __restrict__ wSE2, float* __restrict__ wSW2) {
   const int b = blockIdx.y, N = H * W;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= N) return;
@@ -126,6 +127,17 @@ __global__ void __launch_bounds__(256) cm_weights_kernel(
   const size_t o = (size_t)b * N + i;
   aplane[o] = a0;
   wS[o] = s; wE[o] = e; wSE[o] = se; wSW[o] = sw;
+  if (wS2) {
+    // mirrored planes for the vertically flipped view of the lower half: the same edges, stored at their LOWER pixel
+    // (S2[y,x] = S[y-1,x], SE2[y,x] = SW[y-1,x+1], SW2[y,x] = SE[y-1,x-1]); |a0 - a1| is symmetric, so the bits agree
+    float s2 = 0.f, se2 = 0.f, sw2 = 0.f;
+    if (y > 0) {
+      s2 = edge_w_fast(atten(I, depth, y - 1, x, W, mn1, den1), a0, k.x, k.y);
+      if (x < W - 1) se2 = edge_w_fast(atten(I, depth, y - 1, x + 1, W, mn1, den1), a0, k.x, k.w);
+      if (x > 0) sw2 = edge_w_fast(atten(I, depth, y - 1, x - 1, W, mn1, den1), a0, k.x, k.w);
+    }
+    wS2[o] = s2; wSE2[o] = se2; wSW2[o] = sw2;
+  }
 }
 
 // Column-line factorisation T = L D L^T (T = vertical couplings + full diagonal of L_UU):
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(256) cm_weights_kernel(
 // per-block partial of ||b||^2.
 __global__ void __launch_bounds__(128) cm_factor_kernel(
     int H, int W, const float* __restrict__ wS, const float* __restrict__ wE,
-    const float* __restrict__ wSE, const float* __restrict__ wSW, int precond, int zero_guess,
+    const float* __restrict__ wSE, const float* __restrict__ wSW, int precond, int zero_guess, int tw_m,
     float* __restrict__ ip, float* __restrict__ c, uint32_t* __restrict__ ipc, double* __restrict__ x64,
     double* __restrict__ bbpart) {
   __shared__ double s_bb[4];
@@ -157,6 +169,7 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
     ip[base + (size_t)(H - 1) * W + x] = 0.f; c[base + (size_t)(H - 1) * W + x] = 0.f;
     ipc[base + (size_t)(H - 1) * W + x] = 0u;
     double ip_prev = 0.0;   // row 0 is a seed: not part of T
+    double ip_up = 0.0;     // twisted factorisation: 1 / piv[m-1] of the downward front
     float s_prev = S[x];
     for (int y = 1; y <= H - 2; ++y) {
       const size_t o = (size_t)y * W + x;
@@ -173,11 +186,34 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
       c[base + o] = cf;
       // fused kernel: both factors as bf16 in one word (low = ip, high = c).  M = L D L^T stays SPD for
       // any positive ip and any c, and the iteration count is unchanged.
-      ipc[base + o] = bf16_bits(ipf) | (bf16_bits(cf) << 16);
+      if (tw_m == 0 || y < tw_m) ipc[base + o] = bf16_bits(ipf) | (bf16_bits(cf) << 16);
+      if (y == tw_m - 1) ip_up = (double)(float)ipv;
       x64[base + o] = zero_guess ? 0.0 : 1.0 - (double)y / (double)(H - 1);
       // keep the recurrence consistent with the ROUNDED factors the sweeps will use
       ip_prev = (double)(float)ipv;
       s_prev = s;
+    }
+    if (tw_m) {
+      // Twisted factorisation T = N D N^T for the fused kernel: rows below m are eliminated from the bottom,
+      //   piv[y] = diag[y] - wS[y]^2 / piv[y+1],   c[y] = wS[y-1] / piv[y]  (the coupling TOWARDS row m),
+      // and both fronts meet in row m:  piv[m] = diag[m] - wS[m-1]^2 / piv[m-1] - wS[m]^2 / piv[m+1],  c[m] = 0.
+      double ip_next = 0.0;
+      for (int y = H - 2; y >= tw_m; --y) {
+        const size_t o = (size_t)y * W + x;
+        const float s = S[o], sa = S[o - W];                     // edges to row y+1 / to row y-1
+        double dg = (double)s + (double)sa + (double)E[o] + (double)SE[o] + (double)SW[o];
+        if (x > 0) dg += (double)E[o - 1] + (double)SE[o - W - 1];
+        if (x < W - 1) dg += (double)SW[o - W + 1];
+        double piv = dg;
+        if (precond == USAUG_PRECOND_LINE) {
+          if (y < H - 2) piv -= (double)s * (double)s * ip_next;
+          if (y == tw_m && y > 1) piv -= (double)sa * (double)sa * ip_up;
+        }
+        const double ipv = 1.0 / piv;
+        const float cf = (precond == USAUG_PRECOND_LINE && y > tw_m) ? (float)((double)sa * ipv) : 0.0f;
+        ipc[base + o] = bf16_bits((float)ipv) | (bf16_bits(cf) << 16);
+        ip_next = (double)(float)ipv;
+      }
     }
   }
   bb = warp_sum(bb);

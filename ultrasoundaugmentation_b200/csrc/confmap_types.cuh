@@ -91,8 +91,12 @@ struct PcgArgs {
   unsigned long long watchdog_ns;   // fused kernel: idle workers give up when no task was claimed by anybody for this long
   CoarseGeom cg;     // coarse-grid correction geometry (cg.by == 0: disabled)
   float *rc, *zc;    // [B][nc] restricted residual / coarse correction
-  const float *Lr, *Ur;   // [B][nc][kd1] banded Cholesky factor of Ac, row- and column-oriented
+  const float* Wt;   // [B][nby][rec] block LDL^T of Ac: per aggregate row the dense inverse W_I and the couplings E_I
   int vec4, nstrip4; // vectorised stencil (fp32 vectors, W % 4 == 0): 128-column strips
+  // fused kernel, twisted line factorisation: tw_m = 0 (off) or the row m where the two elimination fronts meet;
+  // per = tasks per image and phase = nstrip4 * (tw_m ? 2 : 1)
+  int tw_m, per;
+  const float *wS2, *wSE2, *wSW2;   // mirrored weight planes (edges towards the row above), read by the lower half
   int debug;         // USAUG_CM_DEBUG_TIMING: block 0 prints per-slot wall times of a few steps
 };
 

@@ -96,13 +96,20 @@ def fused_tgc_deform(image, label, d, tgc, taps):
 
 def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=20000,
                    precond="line", fp64_vectors=False, zero_guess=False, max_wave=None,
-                   return_info=False, timing: list | None = None, debug_timing=False, legacy_kernel=False, coarse=True):
+                   return_info=False, timing: list | None = None, debug_timing=False, legacy_kernel=False, coarse=True,
+                   twist=None, up_variant=None):
     """K2 (A.3).  image f32 [B,H,W] -> cm f32 [B,H,W] (+ iters int32 [B], true relres f64 [B]).
 
     The batch is solved in waves of at most ``max_wave`` images (workspace ~56 B/pixel/image
     with fp32 vectors); default keeps the workspace under ~16 GiB.  ``timing`` (measurement
     only): a list that receives one (start_event, stop_event, lo, n) tuple per wave, recorded on
     the launching stream right around the persistent PCG kernel.
+
+    Solver variants (all solve the same system to the same ``rtol``; they differ in rounding only).  By default the
+    library picks them from the size of a launch -- pin them for results that do not depend on the batch size:
+    ``coarse``: True (automatic), False, "fine" (2-row aggregates) or "standard" (4-row);
+    ``twist``: None (automatic), True / False -- twisted column-line factorisation, two half sweeps per strip;
+    ``up_variant``: None (automatic), "recompute" or "planes" -- edge weights recomputed or read in the UP phase.
     """
     lib = _ffi.load()
     image = _need_cuda(image, "image", torch.float32)
@@ -119,6 +126,12 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
     if coarse not in (True, False, "fine", "standard"):
         raise ValueError(f"coarse must be True (automatic), False, 'fine' or 'standard', got {coarse!r}")
     flags |= {True: 0, False: 32, "fine": 64, "standard": 128}[coarse]   # coarse-grid correction: auto / off / 2-row / 4-row aggregates
+    if twist not in (None, True, False):
+        raise ValueError(f"twist must be None (automatic), True or False, got {twist!r}")
+    flags |= {None: 0, True: _ffi.CM_TWIST_ON, False: _ffi.CM_TWIST_OFF}[twist]
+    if up_variant not in (None, "recompute", "planes"):
+        raise ValueError(f"up_variant must be None (automatic), 'recompute' or 'planes', got {up_variant!r}")
+    flags |= {None: 0, "recompute": _ffi.CM_FORCE_RECOMPUTE, "planes": _ffi.CM_FORCE_PLANES}[up_variant]
     with torch.cuda.device(dev):
         per_img = lib.usaug_confmap_workspace_bytes(1, H, W, pc, flags)
         if max_wave is None:
