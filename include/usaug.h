@@ -62,7 +62,8 @@ enum {
   /* F_UP phase of the fused kernel: recompute the edge weights from the attenuation plane (default for >= 6 strip
      tasks per SM) or read the weight planes.  Pinning the variant makes results independent of the batch size. */
   USAUG_CM_FORCE_RECOMPUTE = 1024,
-  USAUG_CM_FORCE_PLANES = 2048
+  USAUG_CM_FORCE_PLANES = 2048,
+  USAUG_CM_NO_LEVEL = 4096 /* A/B testing: without the level preconditioner (line solve on 1 x 4 aggregates) */
 };
 
 int usaug_version(void);

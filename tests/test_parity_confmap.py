@@ -58,7 +58,7 @@ def test_cm_parity_256(cuda_device, variant):
 @pytest.mark.parametrize("twist", [False, True])
 @pytest.mark.parametrize("up_variant", ["planes", "recompute"])
 @pytest.mark.parametrize("coarse", ["fine", "standard", False])
-@pytest.mark.parametrize("H,W", [(40, 128), (67, 132), (96, 260), (131, 64)])
+@pytest.mark.parametrize("H,W", [(40, 128), (67, 132), (96, 260), (131, 64), (50, 1100)])
 def test_cm_solver_variants_small(cuda_device, H, W, coarse, up_variant, twist):
     """Every pinned variant of the fused kernel (twisted / plain line factorisation x weights recomputed / read x coarse
     grid) against the oracle, on shapes with one, two and three strips, odd heights and a 4-column last strip."""
@@ -72,15 +72,19 @@ def test_cm_solver_variants_small(cuda_device, H, W, coarse, up_variant, twist):
 
 @pytest.mark.parametrize("twist", [False, True])
 @pytest.mark.parametrize("up_variant", ["planes", "recompute"])
-def test_cm_solver_variants_256(cuda_device, up_variant, twist):
+@pytest.mark.parametrize("level", [True, False])
+def test_cm_solver_variants_256(cuda_device, level, up_variant, twist):
     img, _ = util.synth_batch(2, 256, 256)
     ref = ocm.confidence_map_batch(img)
-    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, up_variant=up_variant, twist=twist)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, up_variant=up_variant, twist=twist, level=level)
     assert (rr <= RTOL).all(), rr
     assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
     # the twisted factorisation is the same preconditioner: the iteration count must not move
-    _, it0, _ = gpu_cm(cuda_device, img, rtol=RTOL, up_variant=up_variant, twist=False)
+    _, it0, _ = gpu_cm(cuda_device, img, rtol=RTOL, up_variant=up_variant, twist=False, level=level)
     assert np.abs(it.astype(int) - it0.astype(int)).max() <= 0.05 * it0.max() + 8
+    if level:       # the level preconditioner (line solve on 1 x 4 aggregates) must pay for itself
+        _, it1, _ = gpu_cm(cuda_device, img, rtol=RTOL, up_variant=up_variant, twist=twist, level=False)
+        assert it.max() <= 0.9 * it1.max()
 
 
 def test_cm_batch_independence_and_determinism(cuda_device):
@@ -103,7 +107,7 @@ def test_cm_fused_and_legacy_kernels_agree(cuda_device):
     assert (rra <= 1e-9).all() and (rrb <= 1e-9).all()
     assert np.abs(a - b).max() <= 2 * util.tol_cm(1e-9)
     assert (ita <= itb + 5).all()          # the coarse-grid correction of the fused kernel never costs iterations
-    c, itc, rrc = gpu_cm(cuda_device, img, rtol=1e-9, coarse=False)
+    c, itc, rrc = gpu_cm(cuda_device, img, rtol=1e-9, coarse=False, level=False)
     assert (rrc <= 1e-9).all() and np.abs(a - c).max() <= 2 * util.tol_cm(1e-9)
     assert np.abs(itc.astype(int) - itb.astype(int)).max() <= 0.1 * itb.max() + 5   # same preconditioner as the two-slot kernel
 

@@ -23,6 +23,7 @@ CM_TWIST_ON = 256
 CM_TWIST_OFF = 512
 CM_FORCE_RECOMPUTE = 1024
 CM_FORCE_PLANES = 2048
+CM_NO_LEVEL = 4096
 
 # every symbol include/usaug.h declares: name -> (restype, argtypes)
 SYMBOLS = {

@@ -27,9 +27,10 @@ struct RingU {   // one staged row of a 128-column strip for F_UP (2560 bytes)
   // [16..19] columns x0+128..x0+131 of the same planes (.x is the right neighbour column)
   float4 halo[32];
 };
-struct RingD {   // one staged row for F_DOWN / F_PRECOND (3072 bytes)
+struct RingD {   // one staged row for F_DOWN / F_PRECOND (3200 bytes)
   float4 p[32], pp[32], e[32], r[32], q[32];
   uint4 ipc[32];
+  uint32_t ipc4[32];   // level preconditioner: line factor of each lane's four-column aggregate
 };
 constexpr int kRingRowsPerCta = 80;                                   // 80 x 2560 B = 200 KB per CTA
 constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
@@ -43,49 +44,6 @@ struct RingUP {   // one staged row of a 128-column strip for F_UP, weight plane
   // [0..4] columns x0-4..x0-1 of h, ipc, p, wE, wSE (.w is the left neighbour column);
   // [16..19] columns x0+128..x0+131 of h, ipc, p, wSW (.x is the right neighbour column)
   float4 halo[32];
-};
-
-// Prolongation P zc inside F_UP: the coarse value of this lane's aggregate column (and of the strip's halo
-// column on lanes 0 / 31), fetched one aggregate row ahead of use while the sweep marches upward.
-struct CoarseZ {
-  const float* zc;      // this image's coarse correction, nullptr = disabled
-  int sh, nbx, jown, jhalo, icur, nby, dir, H;
-  float cur, curh, nxt, nxth;
-  bool own, halo, flip;
-  // flip: the sweep runs on the vertically mirrored view (row yv of the view = image row H-1-yv), so the
-  // aggregate rows come in INCREASING order
-  __device__ __forceinline__ void init(const PcgArgs<float>& a, int b, int x, int x0, int lane, bool valid, int W, bool flip_) {
-    zc = a.cg.by ? a.zc + (size_t)b * a.cg.nc : nullptr;
-    sh = a.cg.by_shift; nbx = a.cg.nb; icur = -1;   // nbx: row pitch of zc
-    nby = a.cg.nby; flip = flip_; dir = flip_ ? 1 : -1; H = a.H;
-    own = valid; jown = valid ? (x >> a.cg.bx_shift) : 0;
-    const int hx = (lane == 0) ? x0 - 1 : x0 + kStrip4;
-    halo = (lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < W);
-    jhalo = halo ? (hx >> a.cg.bx_shift) : 0;
-    cur = curh = nxt = nxth = 0.f;
-  }
-  // returns the additive terms for row yv of the view (0 outside the unknown rows)
-  __device__ __forceinline__ void at_row(int yv, float& add, float& addh) {
-    add = 0.f; addh = 0.f;
-    const int y = flip ? H - 1 - yv : yv;
-    if (zc == nullptr || y < 1 || y > H - 2) return;
-    const int I = (y - 1) >> sh;
-    if (I != icur) {
-      if (icur < 0) {
-        cur = own ? __ldcg(zc + I * nbx + jown) : 0.f;
-        curh = halo ? __ldcg(zc + I * nbx + jhalo) : 0.f;
-      } else {
-        cur = nxt; curh = nxth;
-      }
-      icur = I;
-      const int In = I + dir;
-      if (In >= 0 && In < nby) {
-        nxt = own ? __ldcg(zc + In * nbx + jown) : 0.f;
-        nxth = halo ? __ldcg(zc + In * nbx + jhalo) : 0.f;
-      }
-    }
-    add = cur; addh = curh;
-  }
 };
 
 // Row range and addressing of one F_UP / F_DOWN task.  Untwisted (a.tw_m == 0): one task per strip sweeps all
@@ -111,6 +69,67 @@ struct HalfView {
   }
 };
 
+// What the otherwise idle lanes of an F_UP row's halo-copy instruction fetch (16-byte chunks into Ring*::halo):
+//   halo[5..7]    three chunks of this image's coarse correction zc around the strip's aggregate columns
+//   halo[8..15]   h4: the level preconditioner's forward-eliminated residual of the strip's 32 four-column aggregates
+//   halo[20..27]  ipc4: their line factors
+//   halo[28..31]  the chunks that hold the aggregates left / right of the strip: h4 left, ipc4 left, h4 right, ipc4 right
+// Everything is zero-filled where it does not exist (seed rows, image border, feature disabled), so the consumer adds
+// the terms unconditionally.  (Round 1 fetched zc with plain loads one aggregate row ahead; ncu showed the sweep
+// waiting on exactly those loads at the next warp barrier: 19 % of the F_UP stall samples of a latency-bound launch.)
+struct UpAux {
+  const float* base;     // this lane's source: view row 0 of a level plane / row 0 of zc, chunk offset included
+  ptrdiff_t stride;      // elements per view row (0 for the coarse lanes, whose row comes from the aggregate index)
+  bool on, isz, flip;
+  int sh, nb, H;
+  int zown, zhal;        // float index inside halo[5..7] of the lane's own / halo aggregate column
+  int hoff4;             // 28 (lane 0: left neighbour aggregate) or 30 (lane 31: right one)
+  float z4n, z4hn;       // level recurrence: z4 of the previous row (own aggregate, halo aggregate)
+  __device__ __forceinline__ void init(const PcgArgs<float>& a, const HalfView& hv, int b, int x, int x0, int lane, int W) {
+    flip = hv.flip; H = a.H; sh = a.cg.by_shift; nb = a.cg.nb;
+    on = false; isz = false; base = a.z; stride = 0;
+    z4n = z4hn = 0.f;
+    hoff4 = (lane == 31) ? 30 : 28;
+    const int cb = ((x0 >> a.cg.bx_shift) >> 2) - 1;                 // first of the three zc chunks
+    const int hx = (lane == 0) ? x0 - 1 : x0 + kStrip4;
+    zown = min(max((x >> a.cg.bx_shift) - 4 * cb, 0), 11);
+    zhal = min(max((hx >> a.cg.bx_shift) - 4 * cb, 0), 11);
+    if (lane >= 5 && lane <= 7) {
+      const int c = cb + lane - 5;
+      if (a.cg.by && c >= 0 && 4 * c < nb) { on = isz = true; base = a.zc + (size_t)b * a.cg.nc + 4 * c; }
+    }
+    if (a.h4 != nullptr) {
+      const int W4 = a.w4p, X0 = x0 >> 2;
+      const size_t base4 = (size_t)b * H * W4 + (flip ? (size_t)(H - 1) * W4 : 0);
+      const ptrdiff_t rs4 = flip ? -(ptrdiff_t)W4 : (ptrdiff_t)W4;
+      const float* F4 = reinterpret_cast<const float*>(a.ipc4);
+      int e = -1; const float* pl = nullptr;
+      if (lane >= 8 && lane < 16) { e = X0 + 4 * (lane - 8); pl = a.h4; }
+      else if (lane >= 20 && lane < 28) { e = X0 + 4 * (lane - 20); pl = F4; }
+      else if (lane >= 28 && lane < 30 && x0 > 0) { e = X0 - 4; pl = (lane == 28) ? a.h4 : F4; }
+      else if (lane >= 30 && x0 + kStrip4 < W) { e = X0 + 32; pl = (lane == 30) ? a.h4 : F4; }
+      if (pl != nullptr && e >= 0 && e < W4) { on = true; base = pl + base4 + e; stride = rs4; }
+    }
+  }
+  // source of this lane's chunk for view row yv (only meaningful for an interior row)
+  __device__ __forceinline__ const float* src(int yv) const {
+    const int y = flip ? H - 1 - yv : yv;
+    return base + (isz ? (ptrdiff_t)(((y - 1) >> sh) * nb) : (ptrdiff_t)yv * stride);
+  }
+  // additive terms of view row y for the lane's own columns and for its halo column: P zc + level correction
+  __device__ __forceinline__ void at_row(const float4* halo, int lane, float& add, float& addh) {
+    const float* f = reinterpret_cast<const float*>(halo);
+    const float h4 = f[32 + lane];
+    const uint32_t f4 = __float_as_uint(f[80 + lane]);
+    const float h4h = f[4 * hoff4 + (lane == 31 ? 0 : 3)];
+    const uint32_t f4h = __float_as_uint(f[4 * hoff4 + 4 + (lane == 31 ? 0 : 3)]);
+    z4n = fmaf(bf16_hi(f4), z4n, bf16_lo(f4) * h4);
+    z4hn = fmaf(bf16_hi(f4h), z4hn, bf16_lo(f4h) * h4h);
+    add = f[20 + zown] + z4n;
+    addh = f[20 + zhal] + z4hn;
+  }
+};
+
 // Edge weights of one image row for the 4 columns of a lane (plus the three that belong to its
 // neighbours' columns), recomputed from the `a` plane.
 struct WRow {
@@ -124,9 +143,15 @@ struct WRow {
 // which the stencil of row m needs), and that row's recurrence runs the other way: z[m+1] = c[m+1] z[m] + ip[m+1] h[m+1].
 // z[m] = ip[m] h[m] has no recurrence term, so it is formed directly here and seeds the sweep.
 __device__ __forceinline__ void twist_seed(const PcgArgs<float>& a, const HalfView& hv, const float* Hb, const uint32_t* IPC,
-                                           int x, int x0, int lane, bool valid, float (&zn)[4], float& zhn) {
+                                           int b, int x, int x0, int lane, bool valid, float (&zn)[4], float& zhn, UpAux& ax) {
   if (a.tw_m == 0 || hv.flip) return;
   const size_t o = (size_t)a.tw_m * a.W;
+  if (a.h4 != nullptr) {                                          // the level preconditioner's recurrences, same seed
+    const size_t o4 = ((size_t)b * a.H + a.tw_m) * a.w4p;
+    const int X = x >> 2, Xh = ((lane == 0) ? x0 - 1 : x0 + kStrip4) >> 2;
+    if (valid) ax.z4n = bf16_lo(__ldcg(a.ipc4 + o4 + X)) * __ldcg(a.h4 + o4 + X);
+    if ((lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < a.W)) ax.z4hn = bf16_lo(__ldcg(a.ipc4 + o4 + Xh)) * __ldcg(a.h4 + o4 + Xh);
+  }
   if (valid) {
     const float4 h = __ldcg(reinterpret_cast<const float4*>(Hb + o + x));
     const uint4 f = __ldcg(reinterpret_cast<const uint4*>(IPC + o + x));
@@ -166,9 +191,15 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   const bool hrole = hcol && k <= 3;
   const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin : Ap;
   const int hxs = hrole ? hx : 0;
+  UpAux ax;
+  ax.init(a, hv, b, x, x0, lane, W);
+  const bool h_in_only = hrole && k == 3;         // the a plane is also needed from the seed rows
+  const bool h_interior = (hrole && k != 3 && !(k == 2 && first)) || ax.on;
 
+  int slot_i = 0;                                 // ring slot of the next row to stage
   auto issue = [&](int y) {                       // stage view row y (rows are visited ys .. 0)
-    RingU* r = ring + ((ys - y) % R);
+    RingU* r = ring + slot_i;
+    slot_i = (slot_i + 1 == R) ? 0 : slot_i + 1;
     const bool in = y >= 0;
     const bool interior = y >= 1 && y <= H - 2;
     const ptrdiff_t o = (ptrdiff_t)(in ? y : 0) * rs;
@@ -176,7 +207,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
     cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
     cp_async16(&r->a[lane], Ap + o + xs, in && valid);
-    cp_async16(&r->halo[lane], hsrc + o + hxs, in && hrole && (k == 3 || interior) && !(k == 2 && first));
+    cp_async16(&r->halo[lane], ax.on ? ax.src(interior ? y : 1) : hsrc + o + hxs, (in && h_in_only) || (interior && h_interior));
     cp_async_commit();
   };
   const unsigned full = 0xffffffffu;
@@ -188,19 +219,19 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   for (int j = 0; j < 4; ++j) wc.s[j] = wc.e[j] = wc.se[j] = wc.sw[j] = 0.f;
   wc.eL = wc.seL = wc.swR = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
-  CoarseZ cz;
-  cz.init(a, b, x, x0, lane, valid, W, hv.flip);
 
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(ys - u);
-  twist_seed(a, hv, Hb, IPC, x, x0, lane, valid, zn, zhn);
+  twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
   double acc = 0.0;
+  int slot_c = 0;                                 // ring slot of the row being consumed
 #pragma unroll 2
   for (int y = ys; y >= 0; --y) {
     cp_async_wait<R - 1>();
     __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
     {
-      const RingU* r = ring + ((ys - y) % R);
+      const RingU* r = ring + slot_c;
+      slot_c = (slot_c + 1 == R) ? 0 : slot_c + 1;
       const float4 h = r->h[lane], p = r->p[lane], av = r->a[lane];
       const uint4 f = r->ipc[lane];
       // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
@@ -213,7 +244,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
       z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
       const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
       float zadd, zaddh;
-      cz.at_row(y, zadd, zaddh);
+      ax.at_row(r->halo, lane, zadd, zaddh);
       pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
       pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
       const float ph = fmaf(beta, hp, zh + zaddh);
@@ -311,10 +342,16 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin
                       : (k == 3) ? (isL ? E : SW) : SE;
   const int hxs = hrole ? hx : 0;
+  UpAux ax;
+  ax.init(a, hv, b, x, x0, lane, W);
+  const bool h_in_only = hrole && k >= 3;         // weights are also needed from the seed row 0
+  const bool h_interior = (hrole && k < 3 && !(k == 2 && first)) || ax.on;
 
   const int y1 = ys < H - 2 ? ys : H - 2;         // first row of the sweep (the seed row H-1 carries nothing here)
+  int slot_i = 0;                                 // ring slot of the next row to stage
   auto issue = [&](int y) {                       // stage view row y (rows are visited y1 .. 0)
-    RingUP* r = ring + ((y1 - y) % R);
+    RingUP* r = ring + slot_i;
+    slot_i = (slot_i + 1 == R) ? 0 : slot_i + 1;
     const bool in = y >= 0;
     const bool interior = y >= 1;
     const ptrdiff_t o = (ptrdiff_t)(in ? y : 0) * rs;
@@ -325,7 +362,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
     cp_async16(&r->e[lane], E + o + xs, interior && valid);
     cp_async16(&r->se[lane], SE + o + xs, in && valid);
     cp_async16(&r->sw[lane], SW + o + xs, in && valid);
-    cp_async16(&r->halo[lane], hsrc + o + hxs, in && hrole && (k >= 3 || interior) && !(k == 2 && first));
+    cp_async16(&r->halo[lane], ax.on ? ax.src(interior ? y : 1) : hsrc + o + hxs, (in && h_in_only) || (interior && h_interior));
     cp_async_commit();
   };
   const unsigned full = 0xffffffffu;
@@ -336,19 +373,19 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   WRowP wc, wu;
   wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
-  CoarseZ cz;
-  cz.init(a, b, x, x0, lane, valid, W, hv.flip);
 
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(y1 - u);
-  twist_seed(a, hv, Hb, IPC, x, x0, lane, valid, zn, zhn);
+  twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
   double acc = 0.0;
+  int slot_c = 0;                                 // ring slot of the row being consumed
 #pragma unroll 2
   for (int y = y1; y >= 0; --y) {
     cp_async_wait<R - 1>();
     __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
     {
-      const RingUP* r = ring + ((y1 - y) % R);
+      const RingUP* r = ring + slot_c;
+      slot_c = (slot_c + 1 == R) ? 0 : slot_c + 1;
       const float4 h = r->h[lane], p = r->p[lane];
       const uint4 f = r->ipc[lane];
       wu.s = r->s[lane]; wu.e = r->e[lane]; wu.se = r->se[lane]; wu.sw = r->sw[lane];
@@ -362,7 +399,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
       z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
       const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
       float zadd, zaddh;
-      cz.at_row(y, zadd, zaddh);
+      ax.at_row(r->halo, lane, zadd, zaddh);
       pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
       pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
       const float ph = fmaf(beta, hp, zh + zaddh);
@@ -444,10 +481,23 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   float* __restrict__ Ev = a.e + base; float* __restrict__ Rv = a.r + base;
   const float* __restrict__ Q = a.q + base;
   float* __restrict__ Hb = a.z + base;          // h = L^-1 r goes to the z plane (read by the next F_UP)
+  // level preconditioner (four-column aggregates = one lane): h4 = L4^-1 (P4^T r), its own plane of pitch w4p
+  const bool lv = a.h4 != nullptr;
+  const int W4 = a.w4p;
+  const size_t base4 = (size_t)b * H * W4 + (hv.flip ? (size_t)(H - 1) * W4 : 0);
+  const ptrdiff_t rs4 = hv.flip ? -(ptrdiff_t)W4 : (ptrdiff_t)W4;
+  // every lane stages its own level factor: 4-byte cp.async goes through L1, which is safe for a plane that is
+  // constant during the solve (and needs no cross-lane hand-off, unlike a 16-byte chunk copied by a quarter of the lanes)
+  const uint32_t* __restrict__ F4 = lv ? a.ipc4 + base4 + (valid ? (x >> 2) : 0) : a.ipc;
+  float* __restrict__ H4 = lv ? a.h4 + base4 + (x >> 2) : a.z;
+  float h4p = 0.f, c4p = 0.f;
+  int slot_i = 0, slot_c = 0;
   auto issue = [&](int y) {
-    RingD* r = ring + ((y - 1) % RD);
+    RingD* r = ring + slot_i;
+    slot_i = (slot_i + 1 == RD) ? 0 : slot_i + 1;
     const bool in = (y <= ylast) && valid;
     const ptrdiff_t o = (ptrdiff_t)(y <= ylast ? y : 0) * rs + xs;
+    if (lv) cp_async4(&r->ipc4[lane], F4 + (ptrdiff_t)(y <= ylast ? y : 0) * rs4, in);
     if (KIND == 2) {
       cp_async16(&r->p[lane], P + o, in);
       cp_async16(&r->pp[lane], PP + o, in);
@@ -466,7 +516,8 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
 #pragma unroll 2
   for (int y = 1; y <= ylast; ++y) {
     cp_async_wait<RD - 1>();
-    const RingD* r = ring + ((y - 1) % RD);
+    const RingD* r = ring + slot_c;
+    slot_c = (slot_c + 1 == RD) ? 0 : slot_c + 1;
     const float4 rv = r->r[lane];
     const uint4 f = r->ipc[lane];
     const float4 cv = make_float4(bf16_hi(f.x), bf16_hi(f.y), bf16_hi(f.z), bf16_hi(f.w));
@@ -491,11 +542,19 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
     for (int j = 0; j < 4; ++j) h[j] = fmaf(cp[j], hp[j], rn[j]);
     if (valid) *reinterpret_cast<float4*>(Hb + (ptrdiff_t)y * rs + x) = make_float4(h[0], h[1], h[2], h[3]);
     const float srr = fmaf(rn[0], rn[0], fmaf(rn[1], rn[1], fmaf(rn[2], rn[2], rn[3] * rn[3])));
-    const float srz = fmaf(iv.x * h[0], h[0], fmaf(iv.y * h[1], h[1], fmaf(iv.z * h[2], h[2], iv.w * h[3] * h[3])));
+    float srz = fmaf(iv.x * h[0], h[0], fmaf(iv.y * h[1], h[1], fmaf(iv.z * h[2], h[2], iv.w * h[3] * h[3])));
+    const float r4 = (rn[0] + rn[1]) + (rn[2] + rn[3]);             // P4^T r: the lane's four columns
+    if (lv) {
+      const uint32_t f4 = r->ipc4[lane];
+      const float h4 = fmaf(c4p, h4p, r4);
+      if (valid) H4[(ptrdiff_t)y * rs4] = h4;
+      srz = fmaf(bf16_lo(f4) * h4, h4, srz);
+      h4p = h4; c4p = bf16_hi(f4);
+    }
     rr += (double)srr;
     if (y != ymid) rz += (double)srz;
     if (a.cg.by) {                               // restriction rc = P^T r: sum of the new residual over each aggregate
-      racc += (rn[0] + rn[1]) + (rn[2] + rn[3]);
+      racc += r4;
       const int ya = hv.flip ? H - 1 - y : y;    // image row
       // the last row of an aggregate row in the order of travel
       if (hv.flip ? (((ya - 1) & (a.cg.by - 1)) == 0) : ((ya & (a.cg.by - 1)) == 0 || ya == H - 2)) {
@@ -819,6 +878,14 @@ __device__ __forceinline__ double twist_fix(const PcgArgs<float>& a, int b, int 
                                  fmaf(bf16_hi(fn.z), hb.z, ht.z), fmaf(bf16_hi(fn.w), hb.w, ht.w));
     *reinterpret_cast<float4*>(Hm + x) = h;
     acc += (double)fmaf(bf16_lo(fm.x) * h.x, h.x, fmaf(bf16_lo(fm.y) * h.y, h.y, fmaf(bf16_lo(fm.z) * h.z, h.z, bf16_lo(fm.w) * h.w * h.w)));
+  }
+  if (a.h4 != nullptr) {                                            // the same for the level preconditioner's plane
+    const size_t o4 = ((size_t)b * a.H + m) * a.w4p;
+    for (int X = lane; X < (W >> 2); X += 32) {
+      const float h = fmaf(bf16_hi(__ldcg(a.ipc4 + o4 + a.w4p + X)), __ldcg(a.h4 + o4 + a.w4p + X), __ldcg(a.h4 + o4 + X));
+      a.h4[o4 + X] = h;
+      acc += (double)(bf16_lo(__ldcg(a.ipc4 + o4 + X)) * h * h);
+    }
   }
   return warp_sum(acc);
 }

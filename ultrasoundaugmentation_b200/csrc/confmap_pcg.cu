@@ -17,6 +17,7 @@ namespace usaug {
 struct CmLayout {
   float *depth, *mm1, *mm2, *wS, *wE, *wSE, *wSW, *ip, *c, *aplane;
   float *wS2, *wSE2, *wSW2;   // mirrored weight planes (twisted factorisation + weight-reading F_UP only)
+  float* h4; uint32_t* ipc4; int w4p;   // level preconditioner planes (fused kernel, line preconditioner)
   bool fused, recomp;         // fused fp32 kernel; its F_UP recomputes the edge weights
   int tw_m, per;              // twisted line factorisation: meeting row (0 = off); tasks per image and phase
   uint32_t* ipc;
@@ -53,8 +54,7 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   const bool many = tasks >= 12ll * sms;
   const bool fine = (flags & USAUG_CM_COARSE_FINE) ? true : (flags & USAUG_CM_COARSE_STANDARD) ? false : many;
   int min_shift = fine ? 1 : 2, min_bx_shift = 5;
-  if (const char* e = getenv("USAUG_CM_COARSE_SHIFT")) min_shift = atoi(e);          // development knobs
-  if (const char* e = getenv("USAUG_CM_COARSE_BXSHIFT")) min_bx_shift = atoi(e);
+  if (const char* e = getenv("USAUG_CM_COARSE_SHIFT")) min_shift = atoi(e);          // development knob
   L.cg = (!L.fused || (flags & USAUG_CM_NO_COARSE)) ? CoarseGeom{} : coarse_geom(H, W, min_shift, min_bx_shift);
   // Twisted line factorisation (two half sweeps per strip): halves the dependent UP -> DOWN chain of an image, which
   // is what bounds launches that cannot fill the GPU; deeply bandwidth-bound launches gain nothing from it.
@@ -82,6 +82,10 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   const size_t nmir = (L.tw_m && !L.recomp) ? N : 0;
   L.wS2 = cv.take<float>(nmir); L.wSE2 = cv.take<float>(nmir); L.wSW2 = cv.take<float>(nmir);
   if (!nmir) L.wS2 = L.wSE2 = L.wSW2 = nullptr;
+  L.w4p = ((W >> 2) + 3) & ~3;
+  const size_t n4 = (L.fused && !(flags & USAUG_CM_NO_LEVEL)) ? (size_t)B * H * L.w4p : 0;
+  L.h4 = cv.take<float>(n4); L.ipc4 = cv.take<uint32_t>(n4);
+  if (!n4) { L.h4 = nullptr; L.ipc4 = nullptr; }
   L.x64 = cv.take<double>(N);
   L.e = cv.take<char>(N * tsz); L.r = cv.take<char>(N * tsz); L.p = cv.take<char>(N * tsz);
   L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz); L.p2 = cv.take<char>(N * tsz);
@@ -166,6 +170,7 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.vec4 = (std::is_same<T, float>::value && W % 4 == 0) ? 1 : 0;
   a.nstrip4 = (W + kStrip4 - 1) / kStrip4;
   a.tw_m = L.tw_m; a.per = L.per; a.wS2 = L.wS2; a.wSE2 = L.wSE2; a.wSW2 = L.wSW2;
+  a.h4 = L.h4; a.ipc4 = L.ipc4; a.w4p = L.w4p;
   // every inner iteration is one step; each refinement round adds <= 3 steps and needs >= 1 iteration
   a.max_steps = 4 * maxiter + 16;
   a.debug = g_debug;
@@ -246,6 +251,14 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
                                                         (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.tw_m, L.ip, L.c,
                                                         L.ipc, L.x64, L.bbpart);
   USAUG_CHECK_LAUNCH("cm_factor_kernel");
+  if (L.h4 && precond != USAUG_PRECOND_LINE) { L.h4 = nullptr; L.ipc4 = nullptr; }   // the level solve belongs to the line preconditioner
+  if (L.h4) {
+    // padding columns and seed rows of the level planes must read as zero
+    USAUG_CUDA(cudaMemsetAsync(L.h4, 0, (size_t)B * H * L.w4p * sizeof(float), stream));
+    USAUG_CUDA(cudaMemsetAsync(L.ipc4, 0, (size_t)B * H * L.w4p * sizeof(uint32_t), stream));
+    cm_factor4_kernel<<<dim3(((W >> 2) + 127) / 128, B), 128, 0, stream>>>(H, W, L.w4p, L.wS, L.wE, L.wSE, L.wSW, L.tw_m, L.ipc4);
+    USAUG_CHECK_LAUNCH("cm_factor4_kernel");
+  }
   if (L.cg.by) {
     coarse_assemble_kernel<<<dim3((L.cg.nc + 7) / 8, B), 256, 0, stream>>>(H, W, L.cg, L.wS, L.wE, L.wSE, L.wSW, L.Ab);
     USAUG_CHECK_LAUNCH("coarse_assemble_kernel");

@@ -222,6 +222,65 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
   if (threadIdx.x == 0) bbpart[(size_t)b * gridDim.x + blockIdx.x] = s_bb[0] + s_bb[1] + s_bb[2] + s_bb[3];
 }
 
+// Level preconditioner of the fused kernel: column-line factorisation of A4 = P4^T A P4 for the aggregates of
+// 1 row x 4 columns (P4 piecewise constant).  Per aggregate column X (pixel columns 4X .. 4X+3):
+//   diag4[y] = sum of the four pixel diagonals - 2 x the three horizontal edges inside the aggregate
+//   s4[y]    = all edges between aggregate (y, X) and (y+1, X): four vertical + three SE + three SW
+// factorised like the pixel columns (plain or twisted), stored as bf16 ip | bf16 c << 16 in ipc4[B][H][w4p].
+__global__ void __launch_bounds__(128) cm_factor4_kernel(
+    int H, int W, int w4p, const float* __restrict__ wS, const float* __restrict__ wE,
+    const float* __restrict__ wSE, const float* __restrict__ wSW, int tw_m, uint32_t* __restrict__ ipc4) {
+  const int b = blockIdx.y;
+  const int X = blockIdx.x * 128 + threadIdx.x;
+  if (X >= (W >> 2)) return;
+  const size_t base = (size_t)b * H * W;
+  const float* S = wS + base; const float* E = wE + base; const float* SE = wSE + base; const float* SW = wSW + base;
+  uint32_t* out = ipc4 + (size_t)b * H * w4p + X;
+  const int x0 = 4 * X;
+  auto diag4 = [&](int y) {
+    double dg = 0.0;
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + j;
+      const size_t o = (size_t)y * W + x;
+      dg += (double)S[o] + (double)S[o - W] + (double)E[o] + (double)SE[o] + (double)SW[o];
+      if (x > 0) dg += (double)E[o - 1] + (double)SE[o - W - 1];
+      if (x < W - 1) dg += (double)SW[o - W + 1];
+    }
+    const size_t o = (size_t)y * W + x0;
+    return dg - 2.0 * ((double)E[o] + (double)E[o + 1] + (double)E[o + 2]);
+  };
+  auto s4 = [&](int y) {                         // coupling between rows y and y+1
+    const size_t o = (size_t)y * W + x0;
+    return (double)S[o] + (double)S[o + 1] + (double)S[o + 2] + (double)S[o + 3] + (double)SE[o] + (double)SE[o + 1] +
+           (double)SE[o + 2] + (double)SW[o + 1] + (double)SW[o + 2] + (double)SW[o + 3];
+  };
+  const int ytop = tw_m ? tw_m - 1 : H - 2;      // rows eliminated from the top
+  double ip_prev = 0.0, s_prev = 0.0, ip_up = 0.0, s_up = 0.0;
+  for (int y = 1; y <= ytop; ++y) {
+    double piv = diag4(y);
+    if (y > 1) piv -= s_prev * s_prev * ip_prev;
+    const double ipv = 1.0 / piv;
+    const double s = (y < H - 2) ? s4(y) : 0.0;
+    const float cf = (y < H - 2) ? (float)(s * ipv) : 0.f;
+    out[(size_t)y * w4p] = bf16_bits((float)ipv) | (bf16_bits(cf) << 16);
+    ip_prev = (double)(float)ipv; s_prev = s;
+    ip_up = ip_prev; s_up = s;
+  }
+  if (tw_m) {
+    double ip_next = 0.0, s_next = 0.0;          // s_next = s4(y): coupling of row y to row y+1
+    for (int y = H - 2; y >= tw_m; --y) {
+      const double sa = s4(y - 1);               // coupling to row y-1
+      double piv = diag4(y);
+      if (y < H - 2) piv -= s_next * s_next * ip_next;
+      if (y == tw_m && y > 1) piv -= s_up * s_up * ip_up;
+      const double ipv = 1.0 / piv;
+      const float cf = (y > tw_m) ? (float)(sa * ipv) : 0.f;
+      out[(size_t)y * w4p] = bf16_bits((float)ipv) | (bf16_bits(cf) << 16);
+      ip_next = (double)(float)ipv; s_next = sa;
+    }
+  }
+}
+
 __global__ void cm_init_state_kernel(int B, int nblk, const double* __restrict__ bbpart,
                                      ImgState* __restrict__ st, unsigned* __restrict__ done) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

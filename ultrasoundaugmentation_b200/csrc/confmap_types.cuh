@@ -97,6 +97,11 @@ struct PcgArgs {
   // per = tasks per image and phase = nstrip4 * (tw_m ? 2 : 1)
   int tw_m, per;
   const float *wS2, *wSE2, *wSW2;   // mirrored weight planes (edges towards the row above), read by the lower half
+  // level preconditioner (fused kernel): column-line solve on the aggregates of 1 row x 4 columns, added to z.
+  // h4 = nullptr: disabled.  Planes [B][H][w4p], w4p = W/4 padded to a multiple of 4.
+  float* h4;               // forward-eliminated level residual (written by DOWN, read by UP)
+  const uint32_t* ipc4;    // level line factors, bf16 ip | bf16 c << 16 like ipc
+  int w4p;
   int debug;         // USAUG_CM_DEBUG_TIMING: block 0 prints per-slot wall times of a few steps
 };
 

@@ -97,7 +97,7 @@ def fused_tgc_deform(image, label, d, tgc, taps):
 def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=20000,
                    precond="line", fp64_vectors=False, zero_guess=False, max_wave=None,
                    return_info=False, timing: list | None = None, debug_timing=False, legacy_kernel=False, coarse=True,
-                   twist=None, up_variant=None):
+                   twist=None, up_variant=None, level=True):
     """K2 (A.3).  image f32 [B,H,W] -> cm f32 [B,H,W] (+ iters int32 [B], true relres f64 [B]).
 
     The batch is solved in waves of at most ``max_wave`` images (workspace ~56 B/pixel/image
@@ -109,7 +109,8 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
     library picks them from the size of a launch -- pin them for results that do not depend on the batch size:
     ``coarse``: True (automatic), False, "fine" (2-row aggregates) or "standard" (4-row);
     ``twist``: None (automatic), True / False -- twisted column-line factorisation, two half sweeps per strip;
-    ``up_variant``: None (automatic), "recompute" or "planes" -- edge weights recomputed or read in the UP phase.
+    ``up_variant``: None (automatic), "recompute" or "planes" -- edge weights recomputed or read in the UP phase;
+    ``level``: False switches the level preconditioner (line solve on 1 x 4 pixel aggregates) off (A/B testing).
     """
     lib = _ffi.load()
     image = _need_cuda(image, "image", torch.float32)
@@ -132,6 +133,7 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
     if up_variant not in (None, "recompute", "planes"):
         raise ValueError(f"up_variant must be None (automatic), 'recompute' or 'planes', got {up_variant!r}")
     flags |= {None: 0, "recompute": _ffi.CM_FORCE_RECOMPUTE, "planes": _ffi.CM_FORCE_PLANES}[up_variant]
+    flags |= 0 if level else _ffi.CM_NO_LEVEL
     with torch.cuda.device(dev):
         per_img = lib.usaug_confmap_workspace_bytes(1, H, W, pc, flags)
         if max_wave is None:
