@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define USAUG_VERSION 10100 /* 1.1.0 */
+#define USAUG_VERSION 10200 /* 1.2.0 */
 
 enum {
   USAUG_OK = 0,
@@ -90,7 +90,8 @@ int usaug_fused_tgc_deform_u8(const uint8_t* img, const uint8_t* lab, float* out
  * cm[B,H,W] out (row 0 = 1, row H-1 = 0).  Stops per image when the TRUE residual satisfies
  * ||b - A x||_2 <= rtol*||b||_2 or after maxiter inner iterations.
  * iters[B] (nullable) inner iterations used; relres[B] (nullable) true relative residual reached.
- * Requires H >= 3.
+ * An image the scheduler watchdog gave up on reports iters = -1, relres = NaN and keeps cm = 0.
+ * img and cm must be 16-byte aligned.  Requires H >= 3.
  */
 size_t usaug_confmap_workspace_bytes(int B, int H, int W, int precond, int flags);
 int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int W, float alpha, float beta,

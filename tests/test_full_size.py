@@ -1,10 +1,12 @@
 """BASELINE.json's full-size configurations on the GPU: size-independent properties (the oracle is too
-slow for whole batches at these sizes) plus one oracle-checked image per configuration."""
+slow for whole batches at these sizes) plus one oracle-checked image per configuration -- configs[2] (one 512x512
+confidence map of the batch of 64), configs[3] (one 1024x1024 image of the full chain), configs[4] (the solver variant
+that only the benchmarked batch of 512 selects, pinned here on two 512x512 images)."""
 import numpy as np
 import pytest
 import torch
 
-from oracle import confmap as ocm
+from oracle import chain as ochain, confmap as ocm, deform as odeform
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -50,6 +52,28 @@ def test_config4_full_chain_32x1024(cuda_device):
     # bone keeps its area to within the deformation's stretch (no label mass invented or lost wholesale)
     a0, a1 = lab.sum(dim=(1, 2)).float(), ol.sum(dim=(1, 2)).float()
     assert ((a1 / a0) > 0.7).all() and ((a1 / a0) < 1.4).all()
+    # one image of the batch against the oracle (direct fp64 solve of 1 046 528 unknowns: ~1 min, ~8 GB)
+    j = 7
+    p = {k: v[j].numpy() for k, v in params.items()}
+    ri, rl = ochain.full_chain(img[j].cpu().numpy(), lab[j].cpu().numpy(), p["d"], p["tgc"], p["a_snr"], p["rho"], p["n_ghost"],
+                               odeform.gaussian_taps(0.02 * W), odeform.gaussian_taps(2.0))
+    assert np.array_equal(ol[j].cpu().numpy(), rl)
+    err = np.abs(oi[j].cpu().numpy().astype(np.float64) - ri)
+    assert (err <= 0.4 * util.tol_cm(1e-8) + util.REL_TOL * np.maximum(np.abs(ri), util.REL_DEN_FLOOR)).all(), err.max()
+
+
+def test_config5_benchmarked_solver_variant_512(cuda_device):
+    """configs[4] as bench.py runs it (512 images of 512x512 per launch) selects the weight-recomputing kernel, 2-row
+    aggregates and the plain (untwisted) line factorisation.  Pinned by flags, that exact variant meets the oracle
+    here on two 512x512 images; so do the variants small launches pick."""
+    from ultrasoundaugmentation_b200 import ops, synth
+    img, _ = synth.make_batch(2, 512, 512, seed=2021, device=cuda_device)
+    ref = ocm.confidence_map_batch(img.cpu().numpy())
+    for kw in (dict(up_variant="recompute", coarse="fine", twist=False), dict(up_variant="planes", coarse="standard", twist=True)):
+        cm, it, rr = ops.confidence_map(img, rtol=1e-8, return_info=True, **kw)
+        torch.cuda.synchronize()
+        assert (rr <= 1e-8).all(), kw
+        assert np.abs(cm.cpu().numpy() - ref).max() <= util.tol_cm(1e-8), kw
 
 
 def test_config5_shard_of_dataloader_sweep(cuda_device):

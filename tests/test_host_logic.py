@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol(built_lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in usaug.h but not exported by libusaug.so"
     assert set(_ffi.SYMBOLS) == set(names), "ctypes table and header out of sync"
-    assert _ffi.load().usaug_version() == 10100
+    assert _ffi.load().usaug_version() == 10200
     assert _ffi.load().usaug_last_error() is not None
 
 

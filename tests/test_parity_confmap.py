@@ -126,25 +126,26 @@ def test_cm_monotone_for_constant_columns(cuda_device):
     assert (np.diff(cm[0], axis=0) <= 1e-6).all()
 
 
-@pytest.mark.parametrize("H,W,what", [(1500, 64, "tall: 4-row aggregates, 375 x 2 coarse grid"),
-                                      (3000, 256, "very tall: 8-row aggregates"),
-                                      (72, 1000, "wide: 64-column aggregates"),
-                                      (40, 2016, "too wide for the banded solver: line preconditioner only"),
+@pytest.mark.parametrize("H,W,what", [(1500, 64, "tall: 375 / 750 aggregate rows of two 8-wide blocks"),
+                                      (2100, 128, "very tall: more than 1024 aggregate rows at the smallest height, so it doubles"),
+                                      (72, 1000, "wide: 32 aggregate columns, 32 x 32 blocks"),
+                                      (40, 2016, "64-column aggregates"),
+                                      (40, 4000, "128-column aggregates: one per strip"),
                                       (9, 64, "fewer than 8 unknown rows: coarse grid disabled")])
 def test_cm_coarse_grid_geometries(cuda_device, H, W, what):
-    """Every coarse-grid geometry of the fused kernel against the generic (line-only, grid-synchronous) kernel."""
+    """Every coarse-grid geometry of the fused kernel against the ORACLE, with 4-row and with 2-row aggregates."""
     from ultrasoundaugmentation_b200 import synth
     img, _ = synth.make_batch(2, H, W, seed=H + W, device=cuda_device)
     img = img.cpu().numpy()
-    a, ita, rra = gpu_cm(cuda_device, img, rtol=1e-9, maxiter=100000)
+    ref = ocm.confidence_map_batch(img)
+    for coarse in ("standard", "fine"):
+        a, ita, rra = gpu_cm(cuda_device, img, rtol=1e-9, maxiter=100000, coarse=coarse)
+        assert (rra <= 1e-9).all(), (what, coarse)
+        assert np.abs(a - ref).max() <= util.tol_cm(1e-9), (what, coarse)
+        assert np.all(a[:, 0] == 1.0) and np.all(a[:, -1] == 0.0)
+    # and the generic (line-only, grid-synchronous) kernel on the same systems
     b, itb, rrb = gpu_cm(cuda_device, img, rtol=1e-9, maxiter=100000, legacy_kernel=True)
-    assert (rra <= 1e-9).all() and (rrb <= 1e-9).all(), what
-    assert np.abs(a - b).max() <= 2 * (2e5 * 1e-9) + 1e-6, what
-    assert np.all(a[:, 0] == 1.0) and np.all(a[:, -1] == 0.0)
-    # 2-row aggregates (the choice for large batches), forced here on a small one
-    c, itc, rrc = gpu_cm(cuda_device, img, rtol=1e-9, maxiter=100000, coarse="fine")
-    assert (rrc <= 1e-9).all(), what
-    assert np.abs(c - b).max() <= 2 * (2e5 * 1e-9) + 1e-6, what
+    assert (rrb <= 1e-9).all() and np.abs(b - ref).max() <= util.tol_cm(1e-9), what
 
 
 @pytest.mark.parametrize("B,H,W,what", [(1800, 40, 128, ">= 12 tasks per SM: weight-recomputing kernel, 2-row aggregates"),

@@ -15,9 +15,17 @@ def rel_err(got: np.ndarray, ref: np.ndarray) -> float:
     return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), REL_DEN_FLOOR)))
 
 
-def tol_cm(rtol: float) -> float:
-    """max|dC| <= 5e4 * rtol + 1e-6 (measured K <= 2.9e4 at beta=90)."""
-    return 5e4 * rtol + 1e-6
+# Measured amplification K = max|C_gpu - C_oracle| / (true relative residual) of the shipped solver on B200
+# (profiles/r2g_error_estimate_study.log: 7 shapes x {speckle, white noise, smooth} x rtol 1e-6..1e-9 x 2 pinned solver
+# variants): speckle <= 2.2e4, white noise <= 6.0e4, smooth <= 7.7e3.  The bound below is that measurement with margin.
+# It is NOT derived: DESIGN.md section 4 explains why neither a rigorous bound nor a solver-side estimate is usable
+# (the error sits in near-null modes the residual barely sees).
+K_CM = {"speckle": 5e4, "noise": 1e5}
+
+
+def tol_cm(rtol: float, image_class: str = "speckle") -> float:
+    """max|dC| <= K * rtol + 1e-6, K = 5e4 for speckle / chain images, 1e5 for white noise."""
+    return K_CM[image_class] * rtol + 1e-6
 
 
 def synth_batch(B, H, W, seed0=1234):

@@ -727,6 +727,10 @@ __device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned 
 // iteration count is above the mean over the running images (update_priority), so slowly converging
 // images advance at chain-latency speed while the memory system is kept busy by the rest, and all images
 // finish at about the same time instead of leaving a latency-bound tail of stragglers.
+// Capacity invariant: a ring entry is rewritten only after tail has advanced by qcap.  Unclaimed entries are bounded by
+// the tasks that can be ready at once (<= per * B, every image has one phase in flight), claimed-but-unread tickets by
+// the number of worker warps (<= 8 * 148); qcap = 2 * per * B + 1024 >= per * B + workers for every launch the
+// host makes (launch_fused_aw never starts more worker warps than tasks), so a reader is never lapped.
 // Slot k of a ring holds ((k + 1) << 32 | payload).  qavail[ring] counts entries completely written and not
 // yet claimed: a consumer decrements it and, only if it was positive, takes ticket k = head++ -- fetch-adds
 // throughout, so claims pipeline in L2 (a CAS on the head serialises the pops at one per round trip:
@@ -747,6 +751,20 @@ __device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsi
   }
   __threadfence();
   atomicAdd(a.qavail + ring, (int)n);
+}
+
+// Bail-out of a stalled scheduler (one lane): every image that is not DONE reports iters = -1, relres = NaN; its
+// confidence map stays at the neutral 0 the C entry point initialised it with.  Then every worker is released.
+__device__ __forceinline__ void q_give_up(const PcgArgs<float>& a) {
+  if (atomicExch(a.done + 1, 1u) == 0u) {
+    for (int b = 0; b < a.B; ++b)
+      if ((int)(__ldcg(&a.st[b].fword) & 0xffffffffull) != F_DONE) {
+        if (a.iters_out) a.iters_out[b] = -1;
+        if (a.relres_out) a.relres_out[b] = __longlong_as_double(0x7ff8000000000000ll);
+      }
+    __threadfence();
+  }
+  atomicMax(a.done, (unsigned)a.B);
 }
 
 // Whole warp.  Returns the payload of the next task, or kNoTask when every image is finished.
@@ -775,7 +793,7 @@ __device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {
       unsigned spins = 0;
       while ((unsigned)((v = *slot) >> 32) != stamp) {
         __nanosleep(32);
-        if (++spins > (1u << 26)) { if (lane == 0) { atomicExch(a.done + 1, 1u); atomicMax(a.done, (unsigned)a.B); } return kNoTask; }
+        if (++spins > (1u << 26)) { if (lane == 0) q_give_up(a); return kNoTask; }
       }
       __threadfence();                                       // acquire
       return (unsigned)(v & 0xffffffffull);
@@ -791,15 +809,7 @@ __device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {
     const unsigned long long claimed = *(volatile unsigned long long*)(a.qhead) + *(volatile unsigned long long*)(a.qhead + 1);
     if (t_idle == 0 || claimed != last_claimed) { t_idle = t; last_claimed = claimed; }
     else if (t - t_idle > a.watchdog_ns) {
-      if (lane == 0 && atomicExch(a.done + 1, 1u) == 0u) {
-        for (int b = 0; b < a.B; ++b)
-          if ((int)(__ldcg(&a.st[b].fword) & 0xffffffffull) != F_DONE) {
-            if (a.iters_out) a.iters_out[b] = -1;
-            if (a.relres_out) a.relres_out[b] = __longlong_as_double(0x7ff8000000000000ll);
-          }
-        __threadfence();
-        atomicMax(a.done, (unsigned)a.B);
-      }
+      if (lane == 0) q_give_up(a);
       __syncwarp();
       return kNoTask;
     }

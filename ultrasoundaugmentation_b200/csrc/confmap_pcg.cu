@@ -228,6 +228,9 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
     set_error("usaug_confmap_pcg: bad solver options rtol=%g maxiter=%d precond=%d", rtol, maxiter, precond);
     return USAUG_E_INVALID_ARG;
   }
+  if ((reinterpret_cast<uintptr_t>(img) & 15u) || (reinterpret_cast<uintptr_t>(cm) & 15u) || (reinterpret_cast<uintptr_t>(ws) & 255u)) {
+    set_error("usaug_confmap_pcg: img and cm must be 16-byte aligned, ws 256-byte aligned"); return USAUG_E_INVALID_ARG;
+  }
   const size_t need = usaug_confmap_workspace_bytes(B, H, W, precond, flags);
   if (ws_bytes < need) { set_error("usaug_confmap_pcg: workspace %zu < %zu", ws_bytes, need); return USAUG_E_WORKSPACE_TOO_SMALL; }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -236,6 +239,8 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   g_debug = (flags & USAUG_CM_DEBUG_TIMING) ? 1 : 0;
   g_legacy = (flags & USAUG_CM_LEGACY_KERNEL) ? 1 : 0;
 
+  // neutral result for images the solver could not finish (scheduler watchdog): C = 0 switches the SNR term off
+  USAUG_CUDA(cudaMemsetAsync(cm, 0, (size_t)B * N * sizeof(float), stream));
   cm_depth_kernel<<<(H + 127) / 128, 128, 0, stream>>>(L.depth, H, alpha);
   USAUG_CHECK_LAUNCH("cm_depth_kernel");
   cm_minmax_kernel<<<dim3(kChunks, B), 256, 0, stream>>>(img, N, L.mm1);

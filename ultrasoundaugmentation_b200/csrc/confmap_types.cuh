@@ -25,9 +25,8 @@ struct ImgState {
   int mode, iters, first, outer;
   double rz, alpha, beta, bb, rr_true, rr_prev, rr_target, rr_rec;
   unsigned cnt1, cnt2;
-  // fused kernel: (first interval in which the mode may run) << 32 | mode.  Phases have different
-  // task counts, so a mode published by the last arriver must not be picked up by tasks of the
-  // same image that are still to come in the SAME interval.
+  // fused kernel: the phase (FMode) the image's queued tasks belong to; written by the last arriver of the
+  // previous phase before it publishes the tasks
   unsigned long long fword;
   int pcur, poor;     // pcur: which p plane holds the current search direction; poor: consecutive weak refinement rounds
   double inner2;      // squared residual reduction asked of the next inner solve (adapts to the fp32 drift floor)

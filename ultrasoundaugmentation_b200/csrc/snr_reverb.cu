@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
     const float* __restrict__ sig, const float* __restrict__ sig_scale,
     TOut* __restrict__ out, int H, int W, const float* __restrict__ a_snr,
     const float* __restrict__ rho, const int* __restrict__ nghost, const int* __restrict__ box,
-    const float* __restrict__ taps_g, int R) {
+    const float* __restrict__ taps_g, int R, int vec_ok) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ float taps[kMaxTaps];
   const int TR = kSrRows + 2 * R;              // label / row-pass rows
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
       if (!(ys0 > ybot + R || ys0 + kSrRows - 1 < ytop - R || x0 > xr + R || x0 + kSrCols - 1 < xl - R)) tile_has_ghost = true;
     }
   }
-  if (!tile_has_ghost && (W & 3) == 0) {
+  if (!tile_has_ghost && vec_ok) {             // vec_ok: W % 4 == 0 and every plane 16-byte aligned (host check)
     const int xc = x0 + 4 * (threadIdx.x & 31), yq = ya + 4 * (threadIdx.x >> 5);
     if (xc >= W) return;
 #pragma unroll
@@ -200,8 +200,12 @@ static int snr_reverb_impl(const float* img, const float* cm, const float* sig, 
   const size_t smem = (size_t)(kSrRows + 2 * R) * kSrCols * sizeof(float) + (size_t)(kSrRows + 2 * R) * (kSrCols + 2 * R);
   if (smem > 48 * 1024)
     USAUG_CUDA(cudaFuncSetAttribute(snr_reverb_kernel<TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the 128-bit fast path needs aligned planes: a raw C-ABI caller (or a tensor view with an odd storage offset) may
+  // hand in anything, and a misaligned vector access would poison the CUDA context
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const int vec_ok = (W % 4 == 0) && al16(img) && al16(cm) && al16(sig) && al16(out) ? 1 : 0;
   snr_reverb_kernel<TOut><<<grid, kSrCols, smem, stream>>>(img, cm, lab, sig, sig_scale, out, H, W, a_snr, rho, nghost,
-                                                           box, feather_taps, R);
+                                                           box, feather_taps, R, vec_ok);
   USAUG_CHECK_LAUNCH("snr_reverb_kernel");
   return USAUG_OK;
 }
