@@ -28,6 +28,13 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* libusaug.so is built with -fvisibility=hidden: only the entry points below are exported. */
+#if defined(__GNUC__)
+#define USAUG_API __attribute__((visibility("default")))
+#else
+#define USAUG_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -63,12 +70,25 @@ enum {
      tasks per SM) or read the weight planes.  Pinning the variant makes results independent of the batch size. */
   USAUG_CM_FORCE_RECOMPUTE = 1024,
   USAUG_CM_FORCE_PLANES = 2048,
-  USAUG_CM_NO_LEVEL = 4096 /* A/B testing: without the level preconditioner (line solve on 1 x 4 aggregates) */
+  USAUG_CM_NO_LEVEL = 4096, /* A/B testing: without the level preconditioner (line solve on 1 x 4 aggregates) */
+  USAUG_CM_SINKS = 8192     /* workspace query: room for the sink plane of usaug_confmap_pcg_sinks (sink_mode != bottom row) */
 };
 
-int usaug_version(void);
+/* where the random walks of the confidence map are absorbed (potential 0); the top row is always the source */
+enum {
+  USAUG_SINK_BOTTOM_ROW = 0,       /* A.3: the bottom row */
+  USAUG_SINK_BOTTOM_AND_SIDES = 1, /* ... and the first and the last column (walks may not leave the sector sideways) */
+  USAUG_SINK_MASK = 2              /* ... and every pixel of rows 1..H-2 where the caller's mask is non-zero */
+};
+
+USAUG_API int usaug_version(void);
 /* thread-local message of the last failing call on this thread ("" if none) */
-const char* usaug_last_error(void);
+USAUG_API const char* usaug_last_error(void);
+
+/* One stream-ordered host-to-device copy (cudaMemcpyAsync) of `bytes` bytes: the per-call parameter block.
+ * `host` should be page-locked memory, so that the copy is asynchronous and can be captured as a memcpy node of a
+ * CUDA graph (the node re-reads the host block on every replay). */
+USAUG_API int usaug_upload(const void* host, void* dev, size_t bytes, void* stream);
 
 /* ---- K1: bone-surface scan + fused TGC + deformation + remap ---------
  * d[B]      axial probe displacement in pixels (clamped on device to |d| <= 0.5*min s_hat)
@@ -76,13 +96,13 @@ const char* usaug_last_error(void);
  * taps[2R+1] smoothing taps of the bone-surface profile (host-computed, identical to the oracle's)
  * out_img/out_lab must not alias the inputs.  Requires 1 <= W <= 4096.
  */
-size_t usaug_warp_workspace_bytes(int B, int H, int W);
-int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, float* out_img, uint8_t* out_lab,
+USAUG_API size_t usaug_warp_workspace_bytes(int B, int H, int W);
+USAUG_API int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, float* out_img, uint8_t* out_lab,
                            int B, int H, int W, const float* d, const float* tgc, int K,
                            const float* taps, int R, void* ws, size_t ws_bytes, void* stream);
 /* 8-bit ingest: img holds 8-bit B-mode pixels, read as v / 255 (correctly rounded
  * fp32); everything else as above.  2 B/px less HBM and 3 B/px less host-to-device traffic. */
-int usaug_fused_tgc_deform_u8(const uint8_t* img, const uint8_t* lab, float* out_img, uint8_t* out_lab,
+USAUG_API int usaug_fused_tgc_deform_u8(const uint8_t* img, const uint8_t* lab, float* out_img, uint8_t* out_lab,
                               int B, int H, int W, const float* d, const float* tgc, int K,
                               const float* taps, int R, void* ws, size_t ws_bytes, void* stream);
 
@@ -93,33 +113,40 @@ int usaug_fused_tgc_deform_u8(const uint8_t* img, const uint8_t* lab, float* out
  * An image the scheduler watchdog gave up on reports iters = -1, relres = NaN and keeps cm = 0.
  * img and cm must be 16-byte aligned.  Requires H >= 3.
  */
-size_t usaug_confmap_workspace_bytes(int B, int H, int W, int precond, int flags);
-int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int W, float alpha, float beta,
+USAUG_API size_t usaug_confmap_workspace_bytes(int B, int H, int W, int precond, int flags);
+USAUG_API int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int W, float alpha, float beta,
                       float gamma, double rtol, int maxiter, int precond, int flags, int* iters,
                       double* relres, void* ws, size_t ws_bytes, void* stream);
+
+/* The same solve with further sink pixels.  sink_mask: uint8 [B,H,W], read only for
+ * USAUG_SINK_MASK (NULL otherwise).  A sink pixel is held at potential 0: cm = 0 there.  For sink_mode != bottom row
+ * the workspace must be sized with USAUG_CM_SINKS set in the flags of the workspace query. */
+USAUG_API int usaug_confmap_pcg_sinks(const float* img, float* cm, int B, int H, int W, float alpha, float beta,
+                      float gamma, double rtol, int maxiter, int precond, int flags, int sink_mode,
+                      const uint8_t* sink_mask, int* iters, double* relres, void* ws, size_t ws_bytes, void* stream);
 
 /* Measurement hook (not part of the data path): when set (non-NULL cudaEvent_t handles), the
  * next usaug_confmap_pcg calls made by THIS thread record `start`/`stop` on the launching stream
  * immediately around the persistent PCG kernel.  Pass NULL, NULL to clear. */
-void usaug_confmap_set_timing_events(void* start_event, void* stop_event);
+USAUG_API void usaug_confmap_set_timing_events(void* start_event, void* stop_event);
 
 /* ---- K3: SNR change + reverberation, fused (A.4, A.5) --------------------------------------
  * cm nullable (NULL = no SNR change).  a_snr[B], rho[B], nghost[B] per-sample parameters;
  * feather_taps[2R+1] Gaussian taps of the bone-mask feathering.  out must not alias img.
  */
-size_t usaug_snr_reverb_workspace_bytes(int B, int H, int W);
-int usaug_snr_reverb(const float* img, const float* cm, const uint8_t* lab, float* out, int B,
+USAUG_API size_t usaug_snr_reverb_workspace_bytes(int B, int H, int W);
+USAUG_API int usaug_snr_reverb(const float* img, const float* cm, const uint8_t* lab, float* out, int B,
                      int H, int W, const float* a_snr, const float* rho, const int* nghost,
                      const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream);
 /* 8-bit egress: out = floor(255 * v + 0.5) of the fp32 result v (two individually rounded fp32 operations). */
-int usaug_snr_reverb_u8(const float* img, const float* cm, const uint8_t* lab, uint8_t* out, int B,
+USAUG_API int usaug_snr_reverb_u8(const float* img, const float* cm, const uint8_t* lab, uint8_t* out, int B,
                         int H, int W, const float* a_snr, const float* rho, const int* nghost,
                         const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream);
 
 /* General form of A.4: I1 = clip(I + (a-1) * C * S) with the signal map
  * S = sig * sig_scale[b] instead of S = I (sig, sig_scale nullable together: NULL = the form above).
  * out is float* or, with out_is_u8 != 0, uint8_t*. */
-int usaug_snr_reverb_signal(const float* img, const float* cm, const float* sig, const float* sig_scale,
+USAUG_API int usaug_snr_reverb_signal(const float* img, const float* cm, const float* sig, const float* sig_scale,
                             const uint8_t* lab, void* out, int out_is_u8, int B, int H, int W,
                             const float* a_snr, const float* rho, const int* nghost,
                             const float* feather_taps, int R, void* ws, size_t ws_bytes, void* stream);
@@ -131,8 +158,8 @@ int usaug_snr_reverb_signal(const float* img, const float* cm, const float* sig,
  * so energy * scale is the normalised map in [0,1] that usaug_snr_reverb_signal takes.
  * Hand-written batched 2-D FFT, 4 <= H, W <= 2048: sizes that are not powers of two are mirror-extended
  * (bottom / right) to the next power of two, and the energy is cropped back.  1 <= scales <= 4. */
-size_t usaug_local_energy_workspace_bytes(int B, int H, int W);
-int usaug_local_energy(const float* img, float* energy, float* scale, int B, int H, int W,
+USAUG_API size_t usaug_local_energy_workspace_bytes(int B, int H, int W);
+USAUG_API int usaug_local_energy(const float* img, float* energy, float* scale, int B, int H, int W,
                        float lambda_min, float mult, int scales, float sigma_f, void* ws,
                        size_t ws_bytes, void* stream);
 
@@ -143,7 +170,7 @@ int usaug_local_energy(const float* img, float* energy, float* scale, int B, int
  *              i* = (r - r_min) * inv_dr,  j* = (theta + theta_max) * inv_dtheta  (0 outside the sector).
  * Image 4-tap bilinear (zeros outside), label nearest.  ray_sin / ray_cos [n_rays] are device tables
  * (needed for direction 0 only).  All coordinates are individually rounded fp32 operations. */
-int usaug_scan_convert(const float* img, const uint8_t* lab, float* out_img, uint8_t* out_lab, int B,
+USAUG_API int usaug_scan_convert(const float* img, const uint8_t* lab, float* out_img, uint8_t* out_lab, int B,
                        int H, int W, int n_samples, int n_rays, int direction, float apex_x, float apex_y,
                        float theta_max, float r_min, float dr, float inv_dr, float inv_dtheta,
                        const float* ray_sin, const float* ray_cos, void* stream);
@@ -151,8 +178,8 @@ int usaug_scan_convert(const float* img, const uint8_t* lab, float* out_img, uin
 /* ---- bone bounding box of a label batch (A.1 step 2 / A.5 "bone-surface row") --------------
  * box[B,4] = {y_top, y_bottom, x_left, x_right}; y_top = -1 when the image has no bone.
  */
-size_t usaug_bone_box_workspace_bytes(int B, int H, int W);
-int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box, void* ws, size_t ws_bytes,
+USAUG_API size_t usaug_bone_box_workspace_bytes(int B, int H, int W);
+USAUG_API int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box, void* ws, size_t ws_bytes,
                    void* stream);
 
 #ifdef __cplusplus

@@ -92,24 +92,55 @@ def laplacian(wS, wE, wSE, wSW) -> sp.csr_matrix:
     return (D - Wm).tocsr()
 
 
-def system(wS, wE, wSE, wSW):
-    """A.3 step 6: (L_UU, b) with top row = 1, bottom row = 0, unknown rows 1..H-2."""
+def sink_mask(H: int, W: int, sink="bottom_row", mask=None) -> np.ndarray:
+    """Boolean [H,W] plane of the EXTRA sink pixels (potential 0) among rows 1..H-2.
+
+    The top row is always the source (potential 1) and the bottom row always a sink.
+    ``bottom_row``: nothing else.  ``bottom_and_sides``: also the first and the last column.
+    ``mask``: also every pixel where ``mask`` is non-zero.
+    """
+    m = np.zeros((H, W), bool)
+    if sink == "bottom_and_sides":
+        m[:, 0] = True
+        m[:, -1] = True
+    elif sink == "mask":
+        if mask is None:
+            raise ValueError("sink='mask' needs a mask plane")
+        m |= np.asarray(mask) != 0
+    elif sink != "bottom_row":
+        raise ValueError(f"unknown sink mode {sink!r}")
+    m[0] = False
+    m[-1] = False
+    return m
+
+
+def system(wS, wE, wSE, wSW, sinks=None):
+    """A.3 step 6: (L_UU, b) with top row = 1, bottom row = 0, unknown rows 1..H-2.
+
+    ``sinks`` (bool [H,W], optional): further pixels held at potential 0.  They stay in the vector as decoupled
+    identity rows (solution exactly 0), so the layout is independent of the mask.
+    """
     H, W = wS.shape
     L = laplacian(wS, wE, wSE, wSW)
     lo, hi = W, (H - 1) * W
     A = L[lo:hi, lo:hi].tocsc()
-    b = -(L[lo:hi, 0:W] @ np.ones(W))
-    return A, np.asarray(b).ravel()
+    b = np.asarray(-(L[lo:hi, 0:W] @ np.ones(W))).ravel()
+    if sinks is not None and sinks[1:-1].any():
+        keep = (~sinks[1:-1].ravel()).astype(np.float64)
+        Dk = sp.diags(keep)
+        A = (Dk @ A @ Dk + sp.diags(1.0 - keep)).tocsc()      # couplings to a sink only count on the neighbour's diagonal
+        b = b * keep
+    return A, b
 
 
-def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, return_info=False):
+def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, return_info=False, sink="bottom_row", mask=None):
     """A.3 complete: confidence map C [H,W] in fp64 (seed rows exactly 1 and 0)."""
     image = np.asarray(image, dtype=f32)
     H, W = image.shape
     if H < 3:
         raise ValueError("confidence map needs H >= 3")
     planes = edge_weights(image, alpha, beta, gamma)
-    A, b = system(*planes)
+    A, b = system(*planes, sinks=sink_mask(H, W, sink, mask))
     x = spla.splu(A).solve(b)
     C = np.empty((H, W), np.float64)
     C[0] = 1.0
@@ -121,8 +152,9 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, return_info=False):
     return C
 
 
-def confidence_map_batch(images, alpha=2.0, beta=90.0, gamma=0.05):
-    return np.stack([confidence_map(im, alpha, beta, gamma) for im in images])
+def confidence_map_batch(images, alpha=2.0, beta=90.0, gamma=0.05, sink="bottom_row", masks=None):
+    return np.stack([confidence_map(im, alpha, beta, gamma, sink=sink, mask=None if masks is None else masks[i])
+                     for i, im in enumerate(images)])
 
 
 def pcg_reference(A, b, precond="line", W=None, rtol=1e-8, maxiter=20000):

@@ -35,6 +35,14 @@ def test_library_loads_and_exports_every_declared_symbol(built_lib):
     assert _ffi.load().usaug_last_error() is not None
 
 
+def test_library_exports_nothing_but_the_c_abi(built_lib):
+    """-fvisibility=hidden: the dynamic symbol table holds the usaug_* entry points of the header and no C++ symbol."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", str(built_lib)], capture_output=True, text=True, check=True).stdout
+    defined = sorted(line.split()[-1] for line in out.splitlines() if " T " in line)
+    assert defined == header_functions(), set(defined) ^ set(header_functions())
+
+
 def test_workspace_queries_are_pure_host_functions(built_lib):
     lib = _ffi.load()
     assert lib.usaug_warp_workspace_bytes(4, 64, 64) > 0
@@ -43,6 +51,7 @@ def test_workspace_queries_are_pure_host_functions(built_lib):
     assert lib.usaug_confmap_workspace_bytes(4, 64, 64, 1, 0) > 3 * small // 2
     assert lib.usaug_confmap_workspace_bytes(1, 64, 64, 1, _ffi.CM_FP64_VECTORS) > small
     assert lib.usaug_confmap_workspace_bytes(1, 2, 64, 1, 0) == 0            # H < 3 is invalid
+    assert lib.usaug_confmap_workspace_bytes(1, 64, 64, 1, _ffi.CM_SINKS) >= small + 64 * 64   # room for the sink plane
     assert lib.usaug_snr_reverb_workspace_bytes(2, 32, 32) >= lib.usaug_bone_box_workspace_bytes(2, 32, 32) > 0
 
 
@@ -53,6 +62,7 @@ def test_invalid_arguments_return_error_codes_without_a_gpu(built_lib):
     with pytest.raises(_ffi.UsaugError):
         _ffi.check(rc, "usaug_fused_tgc_deform")
     assert lib.usaug_confmap_pcg(None, None, 1, 8, 8, 2.0, 90.0, 0.05, 1e-6, 10, 1, 0, None, None, None, 0, None) == -1
+    assert lib.usaug_upload(None, None, 16, None) == -1 and lib.usaug_upload(None, None, 0, None) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

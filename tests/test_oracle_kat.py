@@ -199,3 +199,59 @@ def test_scan_conversion_known_answers():
     assert np.abs(back[core] - smooth[core]).max() <= 5e-3
     assert (back_l[core] != lab[core]).mean() <= 0.02          # only pixels on the disc's boundary may flip
     assert np.all(back[~below] == 0)
+
+
+# ---- sink modes of the confidence map --------------------------------------------------------
+def _dense_confidence_map(image, sinks):
+    """Independent restatement for tiny images: dense 8-neighbour Laplacian built edge by edge, Dirichlet rows removed."""
+    H, W = image.shape
+    wS, wE, wSE, wSW = ocm.edge_weights(image)
+    L = np.zeros((H * W, H * W))
+    def edge(i, j, w):
+        L[i, i] += w; L[j, j] += w; L[i, j] -= w; L[j, i] -= w
+    for y in range(H):
+        for x in range(W):
+            i = y * W + x
+            if x + 1 < W: edge(i, i + 1, wE[y, x])
+            if y + 1 < H:
+                edge(i, i + W, wS[y, x])
+                if x + 1 < W: edge(i, i + W + 1, wSE[y, x])
+                if x > 0: edge(i, i + W - 1, wSW[y, x])
+    fixed = np.zeros(H * W, bool); val = np.zeros(H * W)
+    fixed[:W] = True; val[:W] = 1.0
+    fixed[-W:] = True
+    fixed |= sinks.ravel()
+    U = ~fixed
+    x = np.zeros(H * W); x[fixed] = val[fixed]
+    x[U] = np.linalg.solve(L[np.ix_(U, U)], -L[np.ix_(U, fixed)] @ val[fixed])
+    return x.reshape(H, W)
+
+
+@pytest.mark.parametrize("mode", ["bottom_row", "bottom_and_sides", "mask"])
+def test_sink_modes_match_a_dense_dirichlet_solve(mode):
+    img, lab = osynth.make_bmode(14, 11)
+    mask = np.zeros((14, 11), np.uint8); mask[5:8, 3:6] = 1; mask[0, 2] = 1; mask[13, 4] = 1; mask[9, 10] = 1
+    sinks = ocm.sink_mask(14, 11, mode, mask if mode == "mask" else None)
+    C = ocm.confidence_map(img, sink=mode, mask=mask if mode == "mask" else None)
+    assert np.abs(C - _dense_confidence_map(img, sinks)).max() < 1e-9        # two direct solves of a system with cond ~ 1e6
+    assert (C[sinks] == 0).all() and (C[0] == 1).all() and (C[-1] == 0).all()
+    # maximum principle: further sinks can only lower the potential
+    assert (C <= ocm.confidence_map(img) + 1e-13).all()
+
+
+def test_sink_row_gives_a_ramp_above_and_zero_below():
+    """Closed form: constant image, a full interior row r of sinks => C = 1 - y/r above it and 0 below."""
+    H, W, r = 21, 9, 12
+    mask = np.zeros((H, W), np.uint8); mask[r] = 1
+    C = ocm.confidence_map(np.full((H, W), 0.4, f32), sink="mask", mask=mask)
+    ref = np.clip(1.0 - np.arange(H) / r, 0.0, None)[:, None]
+    assert np.abs(C - ref).max() < 1e-12
+
+
+def test_sink_mask_without_sinks_is_the_plain_map():
+    img, _ = osynth.make_bmode(24, 20)
+    assert np.array_equal(ocm.confidence_map(img, sink="mask", mask=np.zeros((24, 20), np.uint8)), ocm.confidence_map(img))
+    with pytest.raises(ValueError):
+        ocm.confidence_map(img, sink="mask")
+    with pytest.raises(ValueError):
+        ocm.confidence_map(img, sink="everywhere")

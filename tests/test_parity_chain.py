@@ -87,3 +87,44 @@ def test_sharded_equals_unsharded(cuda_device):
             oi, ol = chain(util.cuda(img[lo:hi], cuda_device), util.cuda(lab[lo:hi], cuda_device), p)
             parts_i.append(oi); parts_l.append(ol)
         assert torch.equal(torch.cat(parts_i), full_i) and torch.equal(torch.cat(parts_l), full_l)
+
+
+def test_graphed_chain_is_bitwise_the_eager_chain(cuda_device):
+    """PhysicsChain.capture: the whole chain as one CUDA-graph launch (parameter block uploaded from pinned memory by
+    a graph node, cooperative PCG kernel inside the graph).  Replays with new inputs and parameters must reproduce the
+    eager results bit for bit."""
+    B, H, W = 3, 96, 128
+    img, lab = util.synth_batch(B, H, W)
+    img2, lab2 = util.synth_batch(B, H, W, seed0=99)
+    chain = make_chain()
+    g = chain.capture(util.cuda(img, cuda_device), util.cuda(lab, cuda_device))
+    for k, (i_, l_) in enumerate(((img, lab), (img2, lab2), (img, lab))):
+        params = chain.get_params(B, sample_index=np.arange(B) + 10 * k, image_size=(H, W))
+        ti, tl = util.cuda(i_, cuda_device), util.cuda(l_, cuda_device)
+        ei, el = chain(ti, tl, params)
+        gi, gl = g(ti, tl, params)
+        torch.cuda.synchronize()
+        assert torch.equal(gi, ei) and torch.equal(gl, el), k
+    ri, rl = oracle_chain(img, lab, params, W)                   # and the last replay against the oracle
+    assert np.array_equal(gl.cpu().numpy(), rl)
+    err = np.abs(gi.cpu().numpy().astype(np.float64) - ri)
+    assert (err <= 0.4 * util.tol_cm(RTOL) + util.REL_TOL * np.maximum(np.abs(ri), util.REL_DEN_FLOOR)).all(), err.max()
+
+
+@pytest.mark.parametrize("sink", ["bottom_and_sides", "label"])
+def test_full_chain_with_sink_modes(cuda_device, sink):
+    """SURVEY.md 8(f) row 3 through the transform API: the confidence map of the chain absorbs walks at the image sides,
+    or at the bone pixels of the DEFORMED label."""
+    B, H, W = 2, 128, 128
+    img, lab = util.synth_batch(B, H, W)
+    chain = make_chain(sink=sink)
+    params = chain.get_params(B, image_size=(H, W))
+    gi, gl = chain(util.cuda(img, cuda_device), util.cuda(lab, cuda_device), params)
+    torch.cuda.synchronize()
+    p = {k: v.numpy() for k, v in params.items()}
+    ri, rl = ochain.full_chain_batch(img, lab, p, odeform.gaussian_taps(0.02 * W), odeform.gaussian_taps(2.0), sink=sink)
+    assert np.array_equal(gl.cpu().numpy(), rl)
+    err = np.abs(gi.cpu().numpy().astype(np.float64) - ri)
+    assert (err <= 0.4 * util.tol_cm(RTOL) + util.REL_TOL * np.maximum(np.abs(ri), util.REL_DEN_FLOOR)).all(), err.max()
+    plain, _ = make_chain()(util.cuda(img, cuda_device), util.cuda(lab, cuda_device), params)
+    assert not torch.equal(plain, gi)                     # the sink mode does change the result

@@ -179,3 +179,83 @@ def test_cm_watchdog_ignores_starved_workers(cuda_device, monkeypatch):
     assert (it >= 0).all() and np.isfinite(rr).all(), "watchdog fired on a healthy solve"
     assert (rr <= RTOL).all() and it[17] > 100
     assert np.abs(cm[17] - ocm.confidence_map(img[17])).max() <= util.tol_cm(RTOL)
+
+
+# ---- sink modes -------------------------------------------------------------------------------
+def _sink_case(B, H, W, mode, seed0=500):
+    img, lab = util.synth_batch(B, H, W, seed0=seed0)
+    mask = None
+    if mode == "mask":
+        rng = np.random.default_rng(H * W)
+        mask = (lab != 0).astype(np.uint8)                          # the bone arc ...
+        mask |= (rng.random(lab.shape) < 0.01).astype(np.uint8)      # ... and scattered single pixels
+        mask[:, H // 3, : W // 2] = 1                               # ... and half a row (cuts strips and aggregates)
+        mask[:, :, W - 1] = 1                                       # ... and the last column
+    ref = ocm.confidence_map_batch(img, sink=mode, masks=mask)
+    return img, mask, ref
+
+
+@pytest.mark.parametrize("twist", [False, True])
+@pytest.mark.parametrize("up_variant", ["planes", "recompute"])
+@pytest.mark.parametrize("coarse", ["fine", "standard", False])
+@pytest.mark.parametrize("mode", ["bottom_and_sides", "mask"])
+def test_cm_sink_modes_fused_variants(cuda_device, mode, coarse, up_variant, twist):
+    """Sinks other than the bottom row, every pinned variant of the fused kernel against the oracle's direct solve."""
+    for H, W in ((67, 132), (96, 260)):
+        img, mask, ref = _sink_case(2, H, W, mode)
+        cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, coarse=coarse, up_variant=up_variant, twist=twist, sink=mode,
+                            sink_mask=None if mask is None else util.cuda(mask, cuda_device), maxiter=60000)
+        assert (rr <= RTOL).all(), rr
+        assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
+        sinks = np.stack([ocm.sink_mask(H, W, mode, None if mask is None else mask[b]) for b in range(2)])
+        assert (cm[sinks] == 0.0).all() and np.all(cm[:, 0] == 1.0) and np.all(cm[:, -1] == 0.0)
+
+
+@pytest.mark.parametrize("mode", ["bottom_and_sides", "mask"])
+@pytest.mark.parametrize("kw", [dict(legacy_kernel=True), dict(fp64_vectors=True), dict(precond="jacobi"), dict(level=False)])
+def test_cm_sink_modes_other_kernels(cuda_device, mode, kw):
+    """... and the generic kernel (any width, fp64 vectors), Jacobi, and the fused kernel without the level solve."""
+    H, W = (64, 61) if ("legacy_kernel" in kw or "fp64_vectors" in kw) else (64, 64)
+    img, mask, ref = _sink_case(2, H, W, mode, seed0=900)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, sink=mode, maxiter=60000,
+                        sink_mask=None if mask is None else util.cuda(mask, cuda_device), **kw)
+    assert (rr <= RTOL).all(), rr
+    assert np.abs(cm - ref).max() <= util.tol_cm(RTOL)
+
+
+def test_cm_sink_row_ramp_kat(cuda_device):
+    """Closed form: constant image with a full row r of sinks => C = 1 - y/r above the row, 0 from it downwards."""
+    H, W, r = 96, 128, 40
+    img = np.full((2, H, W), 0.3, np.float32)
+    mask = np.zeros((2, H, W), np.uint8); mask[:, r] = 1
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=1e-10, sink="mask", sink_mask=util.cuda(mask, cuda_device), zero_guess=True)
+    ref = np.clip(1.0 - np.arange(H) / r, 0.0, None)[None, :, None]
+    assert np.abs(cm - ref).max() <= 2e-6 and (cm[:, r:] == 0.0).all()
+
+
+def test_cm_sink_256_iterations_and_plain_equivalence(cuda_device):
+    """256 x 256: parity in both modes; an all-zero mask reproduces the plain solve bit for bit; the two-level
+    preconditioner still pays with sinks (fewer iterations than the line preconditioner alone)."""
+    img, mask, ref = _sink_case(2, 256, 256, "mask")
+    dmask = util.cuda(mask, cuda_device)
+    cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, sink="mask", sink_mask=dmask)
+    assert (rr <= RTOL).all() and np.abs(cm - ref).max() <= util.tol_cm(RTOL)
+    _, it_line, _ = gpu_cm(cuda_device, img, rtol=RTOL, sink="mask", sink_mask=dmask, coarse=False, level=False)
+    assert it.max() <= 0.8 * it_line.max(), (it, it_line)
+    plain, itp, _ = gpu_cm(cuda_device, img, rtol=RTOL)
+    zero, itz, _ = gpu_cm(cuda_device, img, rtol=RTOL, sink="mask", sink_mask=torch.zeros_like(dmask))
+    assert np.array_equal(plain, zero) and np.array_equal(itp, itz)
+    _, _, ref_s = _sink_case(2, 256, 256, "bottom_and_sides")
+    cm_s, _, rr_s = gpu_cm(cuda_device, img, rtol=RTOL, sink="bottom_and_sides")
+    assert (rr_s <= RTOL).all() and np.abs(cm_s - ref_s).max() <= util.tol_cm(RTOL)
+
+
+def test_cm_sink_argument_errors(cuda_device):
+    from ultrasoundaugmentation_b200 import ops
+    img = util.cuda(util.synth_batch(1, 32, 32)[0], cuda_device)
+    with pytest.raises(ValueError):
+        ops.confidence_map(img, sink="mask")
+    with pytest.raises(ValueError):
+        ops.confidence_map(img, sink="top")
+    with pytest.raises(ValueError):
+        ops.confidence_map(img, sink="bottom_row", sink_mask=torch.zeros((1, 32, 32), dtype=torch.uint8, device=cuda_device))

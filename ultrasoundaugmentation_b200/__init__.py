@@ -7,9 +7,9 @@ There is no CPU fallback and no other backend.
 """
 from . import geometry, ops, params, sharding, synth  # noqa: F401
 from .geometry import ConvexGeometry
-from .transforms import (ConfidenceSNR, PhysicsChain, ProbePressureDeformation, Reverberation,
+from .transforms import (ConfidenceSNR, GraphedChain, PhysicsChain, ProbePressureDeformation, Reverberation,
                          TimeGainCompensation)
 
 __all__ = ["ProbePressureDeformation", "TimeGainCompensation", "ConfidenceSNR", "Reverberation",
-           "PhysicsChain", "ConvexGeometry", "geometry", "ops", "params", "sharding", "synth"]
-__version__ = "1.1.0"
+           "PhysicsChain", "GraphedChain", "ConvexGeometry", "geometry", "ops", "params", "sharding", "synth"]
+__version__ = "1.2.0"

@@ -24,11 +24,14 @@ CM_TWIST_OFF = 512
 CM_FORCE_RECOMPUTE = 1024
 CM_FORCE_PLANES = 2048
 CM_NO_LEVEL = 4096
+CM_SINKS = 8192
+SINK_MODES = {"bottom_row": 0, "bottom_and_sides": 1, "mask": 2}
 
 # every symbol include/usaug.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "usaug_version": (c_int, []),
     "usaug_last_error": (c_char_p, []),
+    "usaug_upload": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "usaug_warp_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "usaug_fused_tgc_deform": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
@@ -40,6 +43,9 @@ SYMBOLS = {
     "usaug_confmap_pcg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
                                   c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
+    "usaug_confmap_pcg_sinks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
+                                        c_double, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_size_t, c_void_p]),
     "usaug_confmap_set_timing_events": (None, [c_void_p, c_void_p]),
     "usaug_snr_reverb_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "usaug_snr_reverb": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -10,6 +10,7 @@ import hashlib
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -22,7 +23,7 @@ STAMP = LIB_DIR / "libusaug.stamp"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",   # only the USAUG_API entry points are exported
     # no --use_fast_math: the label coordinate path must stay IEEE (bit-exact parity)
 ]
 
@@ -47,23 +48,54 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu into lib/libusaug.so unless an up-to-date build exists."""
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: Path | None = None) -> Path:
+    """Compile csrc/*.cu into lib/libusaug.so unless an up-to-date build exists.
+
+    ``extra_flags`` / ``out_path``: a differently configured library next to the product one (e.g. the bounds-checked
+    debug build ``-DUSAUG_BOUNDS_CHECK`` -> lib/libusaug_dbg.so, selected at run time with USAUG_LIB)."""
     fp = _fingerprint()
-    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == fp:
-        return LIB_PATH
+    out_path = LIB_PATH if out_path is None else Path(out_path)
+    if out_path == LIB_PATH and not extra_flags:
+        if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == fp:
+            return LIB_PATH
+    else:
+        force = True        # objects of another configuration must not be reused
     LIB_DIR.mkdir(parents=True, exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{CSRC}", "-o", str(LIB_PATH)]
+    obj_dir = LIB_DIR / "obj"
+    obj_dir.mkdir(exist_ok=True)
+    nvcc = find_nvcc()
+    extra = list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src: Path):
+        # one translation unit per nvcc process, all in parallel; an object is reused while its own fingerprint
+        # (source + every header + flags) is unchanged
+        obj = obj_dir / (src.stem + ".o")
+        tag = obj_dir / (src.stem + ".stamp")
+        h = hashlib.sha256(src.read_bytes())
+        for p in sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "usaug.h"]:
+            h.update(p.read_bytes())
+        h.update(" ".join(NVCC_FLAGS + extra).encode())
+        if not force and obj.exists() and tag.exists() and tag.read_text() == h.hexdigest():
+            return obj, ""
+        cmd = [nvcc, *NVCC_FLAGS, *extra, f"-I{ROOT / 'include'}", f"-I{CSRC}", "-c", "-o", str(obj), str(src)]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        tag.write_text(h.hexdigest())
+        return obj, proc.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, _sources()))
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in _sources()]
+        print("".join(log for _, log in results))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+           "-o", str(out_path), *[str(o) for o, _ in results]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
-    STAMP.write_text(fp)
-    return LIB_PATH
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if out_path == LIB_PATH:
+        STAMP.write_text(fp)
+    return out_path
 
 
 if __name__ == "__main__":

@@ -26,3 +26,13 @@ int device_sm_count() {
 
 extern "C" int usaug_version(void) { return USAUG_VERSION; }
 extern "C" const char* usaug_last_error(void) { return usaug::g_err; }
+
+extern "C" int usaug_upload(const void* host, void* dev, size_t bytes, void* stream) {
+  if (bytes == 0) return USAUG_OK;
+  if (!host || !dev) {
+    usaug::set_error("usaug_upload: null pointer");
+    return USAUG_E_INVALID_ARG;
+  }
+  USAUG_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return USAUG_OK;
+}

@@ -64,7 +64,7 @@ static inline CoarseGeom coarse_geom(int H, int W, int min_shift, int min_bx_shi
 __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, CoarseGeom g,
                                                               const float* __restrict__ wS, const float* __restrict__ wE,
                                                               const float* __restrict__ wSE, const float* __restrict__ wSW,
-                                                              double* __restrict__ Ab) {
+                                                              double* __restrict__ Ab, const uint8_t* __restrict__ snk) {
   const int lane = threadIdx.x & 31;
   const int agg = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.y;
@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, Coar
   }
   const size_t base = (size_t)b * H * W;
   const float* S = wS + base; const float* E = wE + base; const float* SE = wSE + base; const float* SW = wSW + base;
+  const uint8_t* K = snk ? snk + base : nullptr;   // sink pixels: out of the aggregate; an edge to one counts like an edge to a seed row
   double sum[9];   // sum[(dI+1)*3 + (dJ+1)]: weight to the neighbouring aggregate; [4] collects the seed couplings
 #pragma unroll
   for (int k = 0; k < 9; ++k) sum[k] = 0.0;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, Coar
     if (x >= W) continue;
     const int y0 = I * g.by + 1, y1 = min(y0 + g.by, H - 1);
     for (int y = y0; y < y1; ++y) {
+      if (K && K[(size_t)y * W + x]) continue;
       // the 8 neighbours of (y, x): (dy, dx, weight)
       const float wgt[8] = {
           S[(size_t)(y - 1) * W + x],                                         // N
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, Coar
       for (int k = 0; k < 8; ++k) {
         const int yy = y + dy[k], xx = x + dx[k];
         if (xx < 0 || xx >= W) continue;
-        if (yy == 0 || yy == H - 1) { sum[4] += (double)wgt[k]; continue; }   // seed row: diagonal only
+        if (yy == 0 || yy == H - 1 || (K && K[(size_t)yy * W + xx])) { sum[4] += (double)wgt[k]; continue; }   // seed row / sink: diagonal only
         const int dI = ((yy - 1) >> g.by_shift) - I, dJ = (xx >> g.bx_shift) - J;
         if (dI == 0 && dJ == 0) continue;                                     // inside the aggregate
         sum[(dI + 1) * 3 + (dJ + 1)] += (double)wgt[k];
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, Coar
     double diag = 0.0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) diag += sum[k];
-    out[0] = diag;
+    out[0] = (diag > 0.0) ? diag : 1.0;                                        // an aggregate of sinks only: decoupled identity row
     out[1 * g.nb] = (J > 0) ? -sum[1 * 3 + 0] : 0.0;                          // (I, J-1)
     out[2 * g.nb] = (I > 0) ? -sum[0 * 3 + 1] : 0.0;                          // (I-1, J)
     out[3 * g.nb] = (I > 0 && J > 0) ? -sum[0 * 3 + 0] : 0.0;                 // (I-1, J-1)

@@ -224,6 +224,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   for (int u = 0; u < R; ++u) issue(ys - u);
   twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
   double acc = 0.0;
+  unsigned mu = 15u, mc = 15u;                    // sink masks of the rows u / c: bit j set = column j is an unknown
   int slot_c = 0;                                 // ring slot of the row being consumed
 #pragma unroll 2
   for (int y = ys; y >= 0; --y) {
@@ -247,7 +248,15 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
       ax.at_row(r->halo, lane, zadd, zaddh);
       pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
       pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
-      const float ph = fmaf(beta, hp, zh + zaddh);
+      float ph = fmaf(beta, hp, zh + zaddh);
+      if (a.snk != nullptr) {                       // (uniform) sink pixels carry ip = 0: the search direction stays 0 there
+        mu = ((f.x & 0xffffu) ? 1u : 0u) | ((f.y & 0xffffu) ? 2u : 0u) | ((f.z & 0xffffu) ? 4u : 0u) | ((f.w & 0xffffu) ? 8u : 0u);
+        if (!(mu & 1u)) pu[1] = 0.f;
+        if (!(mu & 2u)) pu[2] = 0.f;
+        if (!(mu & 4u)) pu[3] = 0.f;
+        if (!(mu & 8u)) pu[4] = 0.f;
+        if (!(hf & 0xffffu)) ph = 0.f;
+      }
       const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
       pu[0] = (lane == 0) ? ph : l;
       pu[5] = (lane == 31) ? ph : rt;
@@ -291,6 +300,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
         t = fmaf(wc.sw[j], pcj - pl[j], t);
         t = fmaf(SEu[j], pcj - pu[j], t);
         t = fmaf(SWu[j], pcj - pu[j + 2], t);
+        if (a.snk != nullptr && !((mc >> j) & 1u)) t = 0.f;       // ... and so does A p (decoupled row)
         q[j] = t;
         dot = fmaf(pcj, t, dot);
       }
@@ -302,6 +312,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
 #pragma unroll
     for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[j]; ab[j] = au[j]; }
     wc = wu;
+    mc = mu;
     issue(y - R);
   }
   cp_async_wait<0>();
@@ -378,6 +389,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   for (int u = 0; u < R; ++u) issue(y1 - u);
   twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
   double acc = 0.0;
+  unsigned mu = 15u, mc = 15u;                    // sink masks of the rows u / c: bit j set = column j is an unknown
   int slot_c = 0;                                 // ring slot of the row being consumed
 #pragma unroll 2
   for (int y = y1; y >= 0; --y) {
@@ -402,7 +414,15 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
       ax.at_row(r->halo, lane, zadd, zaddh);
       pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
       pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
-      const float ph = fmaf(beta, hp, zh + zaddh);
+      float ph = fmaf(beta, hp, zh + zaddh);
+      if (a.snk != nullptr) {                       // (uniform) sink pixels carry ip = 0: the search direction stays 0 there
+        mu = ((f.x & 0xffffu) ? 1u : 0u) | ((f.y & 0xffffu) ? 2u : 0u) | ((f.z & 0xffffu) ? 4u : 0u) | ((f.w & 0xffffu) ? 8u : 0u);
+        if (!(mu & 1u)) pu[1] = 0.f;
+        if (!(mu & 2u)) pu[2] = 0.f;
+        if (!(mu & 4u)) pu[3] = 0.f;
+        if (!(mu & 8u)) pu[4] = 0.f;
+        if (!(hf & 0xffffu)) ph = 0.f;
+      }
       const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
       pu[0] = (lane == 0) ? ph : l;
       pu[5] = (lane == 31) ? ph : rt;
@@ -437,6 +457,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
         t = fmaf(SWc[j], pcj - pl[j], t);
         t = fmaf(SEu[j], pcj - pu[j], t);
         t = fmaf(SWu[j], pcj - pu[j + 2], t);
+        if (a.snk != nullptr && !((mc >> j) & 1u)) t = 0.f;       // ... and so does A p (decoupled row)
         q[j] = t;
         dot = fmaf(pcj, t, dot);
       }
@@ -448,6 +469,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
 #pragma unroll
     for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[j]; }
     wc = wu;
+    mc = mu;
     issue(y - R);
   }
   cp_async_wait<0>();

@@ -17,6 +17,7 @@ namespace usaug {
 struct CmLayout {
   float *depth, *mm1, *mm2, *wS, *wE, *wSE, *wSW, *ip, *c, *aplane;
   float *wS2, *wSE2, *wSW2;   // mirrored weight planes (twisted factorisation + weight-reading F_UP only)
+  uint8_t* snk;               // extra sink pixels (USAUG_CM_SINKS), else nullptr
   float* h4; uint32_t* ipc4; int w4p;   // level preconditioner planes (fused kernel, line preconditioner)
   bool fused, recomp;         // fused fp32 kernel; its F_UP recomputes the edge weights
   int tw_m, per;              // twisted line factorisation: meeting row (0 = off); tasks per image and phase
@@ -86,6 +87,8 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   const size_t n4 = (L.fused && !(flags & USAUG_CM_NO_LEVEL)) ? (size_t)B * H * L.w4p : 0;
   L.h4 = cv.take<float>(n4); L.ipc4 = cv.take<uint32_t>(n4);
   if (!n4) { L.h4 = nullptr; L.ipc4 = nullptr; }
+  L.snk = cv.take<uint8_t>((flags & USAUG_CM_SINKS) ? N : 0);
+  if (!(flags & USAUG_CM_SINKS)) L.snk = nullptr;
   L.x64 = cv.take<double>(N);
   L.e = cv.take<char>(N * tsz); L.r = cv.take<char>(N * tsz); L.p = cv.take<char>(N * tsz);
   L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz); L.p2 = cv.take<char>(N * tsz);
@@ -171,6 +174,7 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.nstrip4 = (W + kStrip4 - 1) / kStrip4;
   a.tw_m = L.tw_m; a.per = L.per; a.wS2 = L.wS2; a.wSE2 = L.wSE2; a.wSW2 = L.wSW2;
   a.h4 = L.h4; a.ipc4 = L.ipc4; a.w4p = L.w4p;
+  a.snk = L.snk;
   // every inner iteration is one step; each refinement round adds <= 3 steps and needs >= 1 iteration
   a.max_steps = 4 * maxiter + 16;
   a.debug = g_debug;
@@ -220,7 +224,22 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
                                  float beta, float gamma, double rtol, int maxiter, int precond,
                                  int flags, int* iters, double* relres, void* ws, size_t ws_bytes,
                                  void* stream_) {
+  return usaug_confmap_pcg_sinks(img, cm, B, H, W, alpha, beta, gamma, rtol, maxiter, precond, flags & ~USAUG_CM_SINKS,
+                                 USAUG_SINK_BOTTOM_ROW, nullptr, iters, relres, ws, ws_bytes, stream_);
+}
+
+extern "C" int usaug_confmap_pcg_sinks(const float* img, float* cm, int B, int H, int W, float alpha,
+                                       float beta, float gamma, double rtol, int maxiter, int precond,
+                                       int flags, int sink_mode, const uint8_t* sink_mask, int* iters,
+                                       double* relres, void* ws, size_t ws_bytes, void* stream_) {
   if (!img || !cm || !ws) { set_error("usaug_confmap_pcg: null pointer"); return USAUG_E_INVALID_ARG; }
+  if (sink_mode != USAUG_SINK_BOTTOM_ROW && sink_mode != USAUG_SINK_BOTTOM_AND_SIDES && sink_mode != USAUG_SINK_MASK) {
+    set_error("usaug_confmap_pcg_sinks: unknown sink mode %d", sink_mode); return USAUG_E_INVALID_ARG;
+  }
+  if (sink_mode == USAUG_SINK_MASK && !sink_mask) {
+    set_error("usaug_confmap_pcg_sinks: USAUG_SINK_MASK needs a mask plane"); return USAUG_E_INVALID_ARG;
+  }
+  flags = (sink_mode == USAUG_SINK_BOTTOM_ROW) ? (flags & ~USAUG_CM_SINKS) : (flags | USAUG_CM_SINKS);
   if (B <= 0 || H < 3 || W <= 0 || (long long)H * W > (1ll << 30)) {
     set_error("usaug_confmap_pcg: bad shape B=%d H=%d W=%d (need H>=3)", B, H, W); return USAUG_E_INVALID_ARG;
   }
@@ -252,20 +271,24 @@ extern "C" int usaug_confmap_pcg(const float* img, float* cm, int B, int H, int 
   cm_weights_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(img, H, W, L.depth, L.mm1, L.wk, L.aplane,
                                                                  L.wS, L.wE, L.wSE, L.wSW, L.wS2, L.wSE2, L.wSW2);
   USAUG_CHECK_LAUNCH("cm_weights_kernel");
+  if (L.snk) {
+    cm_sink_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(H, W, sink_mode, sink_mask, L.snk);
+    USAUG_CHECK_LAUNCH("cm_sink_kernel");
+  }
   cm_factor_kernel<<<dim3(L.nblk, B), 128, 0, stream>>>(H, W, L.wS, L.wE, L.wSE, L.wSW, precond,
                                                         (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.tw_m, L.ip, L.c,
-                                                        L.ipc, L.x64, L.bbpart);
+                                                        L.ipc, L.x64, L.bbpart, L.snk);
   USAUG_CHECK_LAUNCH("cm_factor_kernel");
   if (L.h4 && precond != USAUG_PRECOND_LINE) { L.h4 = nullptr; L.ipc4 = nullptr; }   // the level solve belongs to the line preconditioner
   if (L.h4) {
     // padding columns and seed rows of the level planes must read as zero
     USAUG_CUDA(cudaMemsetAsync(L.h4, 0, (size_t)B * H * L.w4p * sizeof(float), stream));
     USAUG_CUDA(cudaMemsetAsync(L.ipc4, 0, (size_t)B * H * L.w4p * sizeof(uint32_t), stream));
-    cm_factor4_kernel<<<dim3(((W >> 2) + 127) / 128, B), 128, 0, stream>>>(H, W, L.w4p, L.wS, L.wE, L.wSE, L.wSW, L.tw_m, L.ipc4);
+    cm_factor4_kernel<<<dim3(((W >> 2) + 127) / 128, B), 128, 0, stream>>>(H, W, L.w4p, L.wS, L.wE, L.wSE, L.wSW, L.tw_m, L.ipc4, L.snk);
     USAUG_CHECK_LAUNCH("cm_factor4_kernel");
   }
   if (L.cg.by) {
-    coarse_assemble_kernel<<<dim3((L.cg.nc + 7) / 8, B), 256, 0, stream>>>(H, W, L.cg, L.wS, L.wE, L.wSE, L.wSW, L.Ab);
+    coarse_assemble_kernel<<<dim3((L.cg.nc + 7) / 8, B), 256, 0, stream>>>(H, W, L.cg, L.wS, L.wE, L.wSE, L.wSW, L.Ab, L.snk);
     USAUG_CHECK_LAUNCH("coarse_assemble_kernel");
     if (L.cg.nb == 8) coarse_factor_kernel<8><<<B, 128, 0, stream>>>(L.cg, L.Ab, L.Wt);
     else if (L.cg.nb == 16) coarse_factor_kernel<16><<<B, 128, 0, stream>>>(L.cg, L.Ab, L.Wt);

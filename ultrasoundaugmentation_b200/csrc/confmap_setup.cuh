@@ -140,6 +140,20 @@ __global__ void __launch_bounds__(256) cm_weights_kernel(
   }
 }
 
+// Extra sink pixels: mode 1 = first and last column, mode 2 = the caller's mask; rows 0 and H-1 are
+// the seed rows and never marked.
+__global__ void __launch_bounds__(256) cm_sink_kernel(int H, int W, int mode, const uint8_t* __restrict__ mask,
+                                                      uint8_t* __restrict__ snk) {
+  const int b = blockIdx.y, N = H * W;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const int y = i / W, x = i - y * W;
+  const size_t o = (size_t)b * N + i;
+  bool s = false;
+  if (y >= 1 && y <= H - 2) s = (mode == USAUG_SINK_BOTTOM_AND_SIDES) ? (x == 0 || x == W - 1) : (mask[o] != 0);
+  snk[o] = s ? 1 : 0;
+}
+
 // Column-line factorisation T = L D L^T (T = vertical couplings + full diagonal of L_UU):
 //   piv[y] = diag[y] - wS[y-1]^2 / piv[y-1],  ip = 1/piv,  c[y] = wS[y] * ip[y].
 // Jacobi: ip = 1/diag, c = 0.  Also writes the initial guess into x64 (seed rows 1 / 0) and the
@@ -148,7 +162,7 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
     int H, int W, const float* __restrict__ wS, const float* __restrict__ wE,
     const float* __restrict__ wSE, const float* __restrict__ wSW, int precond, int zero_guess, int tw_m,
     float* __restrict__ ip, float* __restrict__ c, uint32_t* __restrict__ ipc, double* __restrict__ x64,
-    double* __restrict__ bbpart) {
+    double* __restrict__ bbpart, const uint8_t* __restrict__ snk) {
   __shared__ double s_bb[4];
   const int b = blockIdx.y;
   const int x = blockIdx.x * 128 + threadIdx.x;
@@ -157,10 +171,15 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
   if (x < W) {
     const float* S = wS + base; const float* E = wE + base;
     const float* SE = wSE + base; const float* SW = wSW + base;
+    // sink pixels: decoupled rows (ip = c = 0, x = 0, b = 0); an edge to a sink stays on its neighbour's diagonal only
+    const uint8_t* K = snk ? snk + base + x : nullptr;
+    auto sink = [&](int y) { return K != nullptr && K[(size_t)y * W] != 0; };
+    auto cpl = [&](int y) { return (sink(y) || sink(y + 1)) ? 0.f : S[(size_t)y * W + x]; };   // T's coupling of rows y, y+1
     {
       double bv = (double)S[x];
       if (x > 0) bv += (double)SE[x - 1];
       if (x < W - 1) bv += (double)SW[x + 1];
+      if (sink(1)) bv = 0.0;
       bb = bv * bv;
     }
     x64[base + x] = 1.0;
@@ -178,17 +197,19 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
       if (x > 0) dg += (double)E[o - 1] + (double)SE[o - W - 1];
       if (x < W - 1) dg += (double)SW[o - W + 1];
       double piv = dg;
-      if (precond == USAUG_PRECOND_LINE && y > 1) piv -= (double)s_prev * (double)s_prev * ip_prev;
-      const double ipv = 1.0 / piv;
+      const bool sk = sink(y);
+      const float sc = cpl(y), sc_prev = (y > 1) ? cpl(y - 1) : 0.f;
+      if (precond == USAUG_PRECOND_LINE && y > 1) piv -= (double)sc_prev * (double)sc_prev * ip_prev;
+      const double ipv = sk ? 0.0 : 1.0 / piv;
       const float ipf = (float)ipv;
-      const float cf = (precond == USAUG_PRECOND_LINE && y < H - 2) ? (float)((double)s * ipv) : 0.0f;
+      const float cf = (precond == USAUG_PRECOND_LINE && y < H - 2) ? (float)((double)sc * ipv) : 0.0f;
       ip[base + o] = ipf;
       c[base + o] = cf;
       // fused kernel: both factors as bf16 in one word (low = ip, high = c).  M = L D L^T stays SPD for
       // any positive ip and any c, and the iteration count is unchanged.
-      if (tw_m == 0 || y < tw_m) ipc[base + o] = bf16_bits(ipf) | (bf16_bits(cf) << 16);
+      if (tw_m == 0 || y < tw_m) ipc[base + o] = sk ? 0u : (bf16_bits(ipf) | (bf16_bits(cf) << 16));
       if (y == tw_m - 1) ip_up = (double)(float)ipv;
-      x64[base + o] = zero_guess ? 0.0 : 1.0 - (double)y / (double)(H - 1);
+      x64[base + o] = (zero_guess || sk) ? 0.0 : 1.0 - (double)y / (double)(H - 1);
       // keep the recurrence consistent with the ROUNDED factors the sweeps will use
       ip_prev = (double)(float)ipv;
       s_prev = s;
@@ -200,18 +221,19 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
       double ip_next = 0.0;
       for (int y = H - 2; y >= tw_m; --y) {
         const size_t o = (size_t)y * W + x;
-        const float s = S[o], sa = S[o - W];                     // edges to row y+1 / to row y-1
-        double dg = (double)s + (double)sa + (double)E[o] + (double)SE[o] + (double)SW[o];
+        double dg = (double)S[o] + (double)S[o - W] + (double)E[o] + (double)SE[o] + (double)SW[o];
         if (x > 0) dg += (double)E[o - 1] + (double)SE[o - W - 1];
         if (x < W - 1) dg += (double)SW[o - W + 1];
+        const bool sk = sink(y);
+        const float s = (y < H - 2) ? cpl(y) : 0.f, sa = (y > 1) ? cpl(y - 1) : 0.f;   // couplings to row y+1 / to row y-1
         double piv = dg;
         if (precond == USAUG_PRECOND_LINE) {
           if (y < H - 2) piv -= (double)s * (double)s * ip_next;
           if (y == tw_m && y > 1) piv -= (double)sa * (double)sa * ip_up;
         }
-        const double ipv = 1.0 / piv;
+        const double ipv = sk ? 0.0 : 1.0 / piv;
         const float cf = (precond == USAUG_PRECOND_LINE && y > tw_m) ? (float)((double)sa * ipv) : 0.0f;
-        ipc[base + o] = bf16_bits((float)ipv) | (bf16_bits(cf) << 16);
+        ipc[base + o] = sk ? 0u : (bf16_bits((float)ipv) | (bf16_bits(cf) << 16));
         ip_next = (double)(float)ipv;
       }
     }
@@ -229,7 +251,8 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
 // factorised like the pixel columns (plain or twisted), stored as bf16 ip | bf16 c << 16 in ipc4[B][H][w4p].
 __global__ void __launch_bounds__(128) cm_factor4_kernel(
     int H, int W, int w4p, const float* __restrict__ wS, const float* __restrict__ wE,
-    const float* __restrict__ wSE, const float* __restrict__ wSW, int tw_m, uint32_t* __restrict__ ipc4) {
+    const float* __restrict__ wSE, const float* __restrict__ wSW, int tw_m, uint32_t* __restrict__ ipc4,
+    const uint8_t* __restrict__ snk) {
   const int b = blockIdx.y;
   const int X = blockIdx.x * 128 + threadIdx.x;
   if (X >= (W >> 2)) return;
@@ -237,9 +260,14 @@ __global__ void __launch_bounds__(128) cm_factor4_kernel(
   const float* S = wS + base; const float* E = wE + base; const float* SE = wSE + base; const float* SW = wSW + base;
   uint32_t* out = ipc4 + (size_t)b * H * w4p + X;
   const int x0 = 4 * X;
+  // with sink pixels the aggregate operator is P4^T Dk A Dk P4 (Dk = 0 on sinks): a sink contributes nothing, an edge
+  // to a sink stays on the diagonal of its other end
+  const uint8_t* K = snk ? snk + base : nullptr;
+  auto live = [&](int y, int j) { return K == nullptr || K[(size_t)y * W + x0 + j] == 0; };
   auto diag4 = [&](int y) {
     double dg = 0.0;
     for (int j = 0; j < 4; ++j) {
+      if (!live(y, j)) continue;
       const int x = x0 + j;
       const size_t o = (size_t)y * W + x;
       dg += (double)S[o] + (double)S[o - W] + (double)E[o] + (double)SE[o] + (double)SW[o];
@@ -247,19 +275,28 @@ __global__ void __launch_bounds__(128) cm_factor4_kernel(
       if (x < W - 1) dg += (double)SW[o - W + 1];
     }
     const size_t o = (size_t)y * W + x0;
-    return dg - 2.0 * ((double)E[o] + (double)E[o + 1] + (double)E[o + 2]);
+    for (int j = 0; j < 3; ++j)
+      if (live(y, j) && live(y, j + 1)) dg -= 2.0 * (double)E[o + j];
+    return dg;
   };
   auto s4 = [&](int y) {                         // coupling between rows y and y+1
     const size_t o = (size_t)y * W + x0;
-    return (double)S[o] + (double)S[o + 1] + (double)S[o + 2] + (double)S[o + 3] + (double)SE[o] + (double)SE[o + 1] +
-           (double)SE[o + 2] + (double)SW[o + 1] + (double)SW[o + 2] + (double)SW[o + 3];
+    double s = 0.0;
+    for (int j = 0; j < 4; ++j) {
+      if (!live(y, j)) continue;
+      if (live(y + 1, j)) s += (double)S[o + j];
+      if (j < 3 && live(y + 1, j + 1)) s += (double)SE[o + j];
+      if (j > 0 && live(y + 1, j - 1)) s += (double)SW[o + j];
+    }
+    return s;
   };
+  auto inv = [](double piv) { return piv > 0.0 ? 1.0 / piv : 0.0; };   // an aggregate of sinks only: decoupled, ip = 0
   const int ytop = tw_m ? tw_m - 1 : H - 2;      // rows eliminated from the top
   double ip_prev = 0.0, s_prev = 0.0, ip_up = 0.0, s_up = 0.0;
   for (int y = 1; y <= ytop; ++y) {
     double piv = diag4(y);
     if (y > 1) piv -= s_prev * s_prev * ip_prev;
-    const double ipv = 1.0 / piv;
+    const double ipv = inv(piv);
     const double s = (y < H - 2) ? s4(y) : 0.0;
     const float cf = (y < H - 2) ? (float)(s * ipv) : 0.f;
     out[(size_t)y * w4p] = bf16_bits((float)ipv) | (bf16_bits(cf) << 16);
@@ -273,7 +310,7 @@ __global__ void __launch_bounds__(128) cm_factor4_kernel(
       double piv = diag4(y);
       if (y < H - 2) piv -= s_next * s_next * ip_next;
       if (y == tw_m && y > 1) piv -= s_up * s_up * ip_up;
-      const double ipv = 1.0 / piv;
+      const double ipv = inv(piv);
       const float cf = (y > tw_m) ? (float)(sa * ipv) : 0.f;
       out[(size_t)y * w4p] = bf16_bits((float)ipv) | (bf16_bits(cf) << 16);
       ip_next = (double)(float)ipv; s_next = sa;

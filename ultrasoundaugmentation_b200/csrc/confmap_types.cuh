@@ -101,6 +101,9 @@ struct PcgArgs {
   float* h4;               // forward-eliminated level residual (written by DOWN, read by UP)
   const uint32_t* ipc4;    // level line factors, bf16 ip | bf16 c << 16 like ipc
   int w4p;
+  // extra sink pixels (potential 0) among rows 1..H-2: [B][H][W] bytes, nullptr = bottom row only.  A sink keeps its
+  // place in every vector as a decoupled row: x = p = q = r = 0 there, line factors ip = c = 0 (the sweeps test ip == 0).
+  const uint8_t* snk;
   int debug;         // USAUG_CM_DEBUG_TIMING: block 0 prints per-slot wall times of a few steps
 };
 

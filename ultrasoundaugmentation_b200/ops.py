@@ -49,6 +49,90 @@ def _dev_param(v, B: int, device, dtype, name: str, width: int | None = None) ->
     return t.contiguous().to(device, non_blocking=True)
 
 
+class ParamStager:
+    """Per-call parameters in ONE pinned block and ONE host-to-device copy.
+
+    Every per-sample parameter vector and tap table of a chain call (d, TGC gains, a_snr, rho, n_ghost, both
+    Gaussian tap tables) is packed into one pinned host buffer and uploaded with a single ``cudaMemcpyAsync`` on
+    the current stream; the kernels read 256-byte aligned views of the device copy.  No pageable staging copies
+    (which are neither stream-ordered with respect to PDL launches nor capturable in a CUDA graph).  A small ring of
+    pinned buffers, each guarded by an event, lets several calls be in flight.
+    """
+
+    def __init__(self, device, depth: int = 4):
+        self.device = torch.device(device)
+        self.depth = max(int(depth), 1)
+        self._ring = [None] * self.depth      # [pinned float32 tensor, event]
+        self._next = 0
+
+    @staticmethod
+    def _words(t: torch.Tensor) -> int:
+        return (t.numel() + 63) // 64 * 64          # 256-byte granules of 4-byte words
+
+    @staticmethod
+    def _host(items: dict) -> dict:
+        host = {}
+        for k, v in items.items():
+            t = torch.as_tensor(v)
+            if t.is_cuda:
+                raise ValueError("ParamStager takes host tensors")
+            if t.dtype not in (torch.float32, torch.int32):
+                t = t.to(torch.int32 if not t.dtype.is_floating_point else torch.float32)
+            host[k] = t.contiguous()
+        return host
+
+    def _pack(self, pinned: torch.Tensor, host: dict) -> dict:
+        off, views = 0, {}
+        for k, t in host.items():
+            n = t.numel()
+            dst = pinned[off:off + n]
+            (dst.view(torch.int32) if t.dtype == torch.int32 else dst).copy_(t.reshape(-1))
+            views[k] = (off, n, t.dtype, tuple(t.shape))
+            off += self._words(t)
+        return views
+
+    def rewrite(self, items: dict) -> None:
+        """Host side only: new values into the pinned block of slot 0, same names and shapes as the last ``stage``
+        (a captured CUDA graph re-reads that block on every replay).  The caller orders it after the previous replay."""
+        host = self._host(items)
+        entry = self._ring[0]
+        if entry is None or self._layout != {k: (tuple(t.shape), t.dtype) for k, t in host.items()}:
+            raise ValueError("ParamStager.rewrite: parameter names / shapes differ from the captured call")
+        self._pack(entry[0], host)
+
+    def stage(self, items: dict) -> dict:
+        """items: name -> host tensor (float32 or int32).  Returns name -> device tensor of the same shape / dtype."""
+        host = self._host(items)
+        self._layout = {k: (tuple(t.shape), t.dtype) for k, t in host.items()}
+        total = max(sum(self._words(t) for t in host.values()), 64)
+        slot = self._next
+        self._next = (slot + 1) % self.depth
+        entry = self._ring[slot]
+        if entry is None or entry[0].numel() < total:
+            entry = [torch.empty(max(total, 1024), dtype=torch.float32).pin_memory(), None]
+            self._ring[slot] = entry
+        pinned, ev = entry
+        capturing = torch.cuda.is_current_stream_capturing()
+        if ev is not None and not capturing:         # (event queries are not allowed while a graph is being captured)
+            ev.synchronize()                         # the copy that last read this buffer has completed (normally long ago)
+        views = self._pack(pinned, host)
+        with torch.cuda.device(self.device):
+            dev = torch.empty(total, dtype=torch.float32, device=self.device)
+            # one cudaMemcpyAsync on the current stream, issued by libusaug itself: torch's pinned-copy path also
+            # records host-allocator events, which is not capturable in a CUDA graph
+            _ffi.check(_ffi.load().usaug_upload(pinned.data_ptr(), dev.data_ptr(), total * 4, _stream_ptr(self.device)),
+                       "usaug_upload")
+            if not capturing:
+                ev = torch.cuda.Event()
+                ev.record()
+                entry[1] = ev
+        out = {}
+        for k, (o, n, dt, shp) in views.items():
+            v = dev[o:o + n]
+            out[k] = (v.view(torch.int32) if dt == torch.int32 else v).reshape(shp)
+        return out
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -97,7 +181,7 @@ def fused_tgc_deform(image, label, d, tgc, taps):
 def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=20000,
                    precond="line", fp64_vectors=False, zero_guess=False, max_wave=None,
                    return_info=False, timing: list | None = None, debug_timing=False, legacy_kernel=False, coarse=True,
-                   twist=None, up_variant=None, level=True):
+                   twist=None, up_variant=None, level=True, sink="bottom_row", sink_mask=None):
     """K2 (A.3).  image f32 [B,H,W] -> cm f32 [B,H,W] (+ iters int32 [B], true relres f64 [B]).
 
     The batch is solved in waves of at most ``max_wave`` images (workspace ~56 B/pixel/image
@@ -111,6 +195,10 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
     ``twist``: None (automatic), True / False -- twisted column-line factorisation, two half sweeps per strip;
     ``up_variant``: None (automatic), "recompute" or "planes" -- edge weights recomputed or read in the UP phase;
     ``level``: False switches the level preconditioner (line solve on 1 x 4 pixel aggregates) off (A/B testing).
+
+    ``sink``: where the random walks are absorbed besides the bottom row -- "bottom_row" (A.3),
+    "bottom_and_sides" (also the first and last column) or "mask" (also every pixel of rows 1..H-2 where ``sink_mask``,
+    uint8 [B,H,W], is non-zero).  The confidence map is exactly 0 on sink pixels.
     """
     lib = _ffi.load()
     image = _need_cuda(image, "image", torch.float32)
@@ -134,6 +222,19 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
         raise ValueError(f"up_variant must be None (automatic), 'recompute' or 'planes', got {up_variant!r}")
     flags |= {None: 0, "recompute": _ffi.CM_FORCE_RECOMPUTE, "planes": _ffi.CM_FORCE_PLANES}[up_variant]
     flags |= 0 if level else _ffi.CM_NO_LEVEL
+    if sink not in _ffi.SINK_MODES:
+        raise ValueError(f"sink must be one of {sorted(_ffi.SINK_MODES)}, got {sink!r}")
+    sink_mode = _ffi.SINK_MODES[sink]
+    if sink == "mask":
+        if sink_mask is None:
+            raise ValueError("sink='mask' needs sink_mask (uint8 [B,H,W])")
+        sink_mask = _need_cuda(sink_mask, "sink_mask", torch.uint8)
+        if sink_mask.shape != image.shape or sink_mask.device != dev:
+            raise ValueError("sink_mask must have the image's shape and device")
+    elif sink_mask is not None:
+        raise ValueError("sink_mask is only read with sink='mask'")
+    if sink_mode:
+        flags |= _ffi.CM_SINKS          # workspace query: room for the sink plane
     with torch.cuda.device(dev):
         per_img = lib.usaug_confmap_workspace_bytes(1, H, W, pc, flags)
         if max_wave is None:
@@ -150,11 +251,12 @@ def confidence_map(image, alpha=2.0, beta=90.0, gamma=0.05, rtol=1e-8, maxiter=2
                 ev[0].record(); ev[1].record()        # materialise the underlying cudaEvent_t handles
                 lib.usaug_confmap_set_timing_events(ev[0].cuda_event, ev[1].cuda_event)
                 timing.append((ev[0], ev[1], lo, n))
-            rc = lib.usaug_confmap_pcg(image[lo:lo + n].data_ptr(), cm[lo:lo + n].data_ptr(), n, H, W,
-                                       float(alpha), float(beta), float(gamma), float(rtol),
-                                       int(maxiter), pc, flags, iters[lo:lo + n].data_ptr(),
-                                       relres[lo:lo + n].data_ptr(), ws.data_ptr(), ws.numel(),
-                                       _stream_ptr(dev))
+            rc = lib.usaug_confmap_pcg_sinks(image[lo:lo + n].data_ptr(), cm[lo:lo + n].data_ptr(), n, H, W,
+                                             float(alpha), float(beta), float(gamma), float(rtol),
+                                             int(maxiter), pc, flags, sink_mode,
+                                             sink_mask[lo:lo + n].data_ptr() if sink_mode == 2 else None,
+                                             iters[lo:lo + n].data_ptr(), relres[lo:lo + n].data_ptr(), ws.data_ptr(),
+                                             ws.numel(), _stream_ptr(dev))
             if timing is not None:
                 lib.usaug_confmap_set_timing_events(None, None)
             _ffi.check(rc, "usaug_confmap_pcg")

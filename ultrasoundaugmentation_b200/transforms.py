@@ -24,7 +24,7 @@ from . import ops
 from .params import uniforms
 
 __all__ = ["ProbePressureDeformation", "TimeGainCompensation", "ConfidenceSNR", "Reverberation",
-           "PhysicsChain"]
+           "PhysicsChain", "GraphedChain"]
 
 
 def _to_bhw(image: torch.Tensor, label: torch.Tensor):
@@ -130,7 +130,11 @@ class ConfidenceSNR(_Transform):
     ``signal="intensity"`` (default, the hot path): S = I.  ``signal="local_energy"``:
     S = the image's monogenic-signal local energy, normalised to [0,1] -- sum of ``scales`` log-Gabor band-pass
     filters with wavelengths ``lambda_min * mult**s`` pixels and their Riesz transforms (image sizes 4...2048;
-    the hand-written FFT runs on the next power of two, mirror-extended)."""
+    the hand-written FFT runs on the next power of two, mirror-extended).
+
+    ``sink``: where the random walks of the confidence map are absorbed besides the bottom row:
+    "bottom_row" (A.3), "bottom_and_sides" (also the first and the last scanline) or "label" (also every bone pixel of
+    the label plane the transform is given -- in a chain, the deformed label)."""
 
     _stream = 3
 
@@ -138,8 +142,11 @@ class ConfidenceSNR(_Transform):
                  gamma: float = 0.05, rtol: float = 1e-8, maxiter: int = 20000, precond: str = "line",
                  fp64_vectors: bool = False, max_wave: Optional[int] = None, p: float = 1.0,
                  seed: int = 0, signal: str = "intensity", lambda_min: float = 8.0, mult: float = 2.1,
-                 scales: int = 3, sigma_f: float = 0.55):
+                 scales: int = 3, sigma_f: float = 0.55, sink: str = "bottom_row"):
         super().__init__(p, seed)
+        if sink not in ("bottom_row", "bottom_and_sides", "label"):
+            raise ValueError("sink must be 'bottom_row', 'bottom_and_sides' or 'label'")
+        self.sink = sink
         if precond not in ("line", "jacobi"):
             raise ValueError("precond must be 'line' or 'jacobi'")
         if signal not in ("intensity", "local_energy"):
@@ -162,10 +169,16 @@ class ConfidenceSNR(_Transform):
         a = np.where(apply, lo + (hi - lo) * u[:, 0], 1.0).astype(np.float32)
         return _as_tensor_dict({"a_snr": a})
 
-    def confidence_map(self, image_bhw: torch.Tensor) -> torch.Tensor:
+    def confidence_map(self, image_bhw: torch.Tensor, label_bhw: Optional[torch.Tensor] = None) -> torch.Tensor:
+        sink, mask = self.sink, None
+        if sink == "label":
+            if label_bhw is None:
+                raise ValueError("sink='label' needs the label plane")
+            sink, mask = "mask", label_bhw
         cm, it, rr = ops.confidence_map(image_bhw, self.alpha, self.beta, self.gamma, self.rtol,
                                         self.maxiter, self.precond, self.fp64_vectors,
-                                        max_wave=self.max_wave, return_info=True, timing=self.timing)
+                                        max_wave=self.max_wave, return_info=True, timing=self.timing,
+                                        sink=sink, sink_mask=mask)
         self.last_info = (it, rr)
         return cm
 
@@ -248,6 +261,18 @@ class PhysicsChain:
         self.transforms = [t for t in (self.deform, self.tgc, self.snr, self.reverb) if t is not None]
         if not self.transforms:
             raise ValueError("empty chain")
+        self._stagers = {}         # device -> ops.ParamStager (pinned parameter blocks; never pickled)
+
+    def __getstate__(self):
+        s = dict(self.__dict__)
+        s["_stagers"] = {}
+        return s
+
+    def _stager(self, device) -> "ops.ParamStager":
+        st = self._stagers.get(device)
+        if st is None:
+            st = self._stagers[device] = ops.ParamStager(device)
+        return st
 
     @classmethod
     def full(cls, seed: int = 0, output_dtype=torch.float32, geometry=None, **snr_kwargs) -> "PhysicsChain":
@@ -291,29 +316,55 @@ class PhysicsChain:
             return ops.polar_to_cart(pi, pl, self.geometry, Hc, Wc)
         return self._run_scanlines(img, lab, params)
 
+    def _host_params(self, B, W, params, image_dtype):
+        """(k1, k3, host dict): which fused kernels run and every parameter they need, as host tensors."""
+        u8_out = self.output_dtype == torch.uint8
+        k1 = self.deform is not None or self.tgc is not None or image_dtype == torch.uint8
+        k3 = self.snr is not None or self.reverb is not None or u8_out
+        host = {}
+        if k1:
+            host["d"] = params["d"] if self.deform is not None else torch.zeros(B)
+            host["tgc"] = params["tgc"] if self.tgc is not None else torch.ones(B, 1)
+            host["taps"] = self.deform.taps(W) if self.deform is not None else ops.gaussian_taps(0.0, 0)
+        if k3:
+            host["a_snr"] = params["a_snr"] if self.snr is not None else torch.ones(B)
+            if self.reverb is not None:
+                host["rho"], host["n_ghost"], host["ftaps"] = params["rho"], params["n_ghost"], self.reverb.taps()
+            else:
+                host["rho"], host["n_ghost"], host["ftaps"] = torch.zeros(B), torch.zeros(B, dtype=torch.int32), ops.gaussian_taps(0.0, 0)
+        for k, v in host.items():
+            want = torch.int32 if k == "n_ghost" else torch.float32
+            host[k] = torch.as_tensor(v).to(want)
+            if k in ("d", "a_snr", "rho", "n_ghost") and tuple(host[k].shape) != (B,):
+                raise ValueError(f"{k} must have shape ({B},), got {tuple(host[k].shape)}")
+        return k1, k3, host
+
     def _run_scanlines(self, img, lab, params):
         B, H, W = img.shape
-        u8_out = self.output_dtype == torch.uint8
+        # every parameter of the call in one pinned block, one host-to-device copy (ops.ParamStager)
+        k1, k3, host = self._host_params(B, W, params, img.dtype)
+        if any(v.is_cuda for v in host.values()):
+            dv = {k: v.to(img.device) for k, v in host.items()}     # caller staged the parameters itself
+        else:
+            dv = self._stager(img.device).stage(host)
         # a uint8 image always passes the first kernel (identity warp if need be): that is where it is ingested
-        if self.deform is not None or self.tgc is not None or img.dtype == torch.uint8:
-            d = params["d"] if self.deform is not None else torch.zeros(B)
-            tgc = params["tgc"] if self.tgc is not None else torch.ones(B, 1)
-            taps = self.deform.taps(W) if self.deform is not None else ops.gaussian_taps(0.0, 0)
-            img, lab = ops.fused_tgc_deform(img, lab, d, tgc, taps)
+        if k1:
+            img, lab = ops.fused_tgc_deform(img, lab, dv["d"], dv["tgc"], dv["taps"])
         cm = sig = sig_scale = None
         if self.snr is not None:
-            cm = self.snr.confidence_map(img)
+            cm = self.snr.confidence_map(img, lab)
             sig, sig_scale = self.snr.signal_map(img)
         # ... and a uint8 result always leaves through the last kernel (pass-through if need be)
-        if self.snr is not None or self.reverb is not None or u8_out:
-            a = params["a_snr"] if self.snr is not None else torch.ones(B)
-            if self.reverb is not None:
-                rho, n, taps = params["rho"], params["n_ghost"], self.reverb.taps()
-            else:
-                rho, n, taps = torch.zeros(B), torch.zeros(B, dtype=torch.int32), ops.gaussian_taps(0.0, 0)
-            img = ops.snr_reverb(img, cm, lab, a, rho, n, taps, out_dtype=self.output_dtype, signal=sig,
-                                 signal_scale=sig_scale)
+        if k3:
+            img = ops.snr_reverb(img, cm, lab, dv["a_snr"], dv["rho"], dv["n_ghost"], dv["ftaps"], out_dtype=self.output_dtype,
+                                 signal=sig, signal_scale=sig_scale)
         return img, lab
+
+    # ---- CUDA graph: the whole chain as ONE submission -----------------------------------------
+    def capture(self, image, label) -> "GraphedChain":
+        """Capture the chain for this batch shape into a CUDA graph (one submission per call instead of ~20 launches).
+        ``image`` / ``label`` give shape, dtype and device; see GraphedChain."""
+        return GraphedChain(self, image, label)
 
     # ---- host path: pinned host buffers in, pinned host buffers out ---------------------------
     def augment_host(self, image: torch.Tensor, label: torch.Tensor, params: Optional[dict] = None,
@@ -401,3 +452,67 @@ class PhysicsChain:
                     yield drain_one()
             while pending:
                 yield drain_one()
+
+
+class GraphedChain:
+    """A PhysicsChain captured into a CUDA graph for one batch shape (SURVEY.md 7.2 hard part 5: launch overhead).
+
+    Everything a call enqueues -- the single parameter upload from a pinned block, the fused K1 launch group, the
+    confidence-map setup kernels and its persistent cooperative PCG kernel, the fused K3 launch group -- becomes one
+    graph launch.  ``g(image, label, params=None, sample_index=None)`` copies the inputs into the graph's static
+    buffers, rewrites the pinned parameter block and replays; it returns the graph's static output tensors, which
+    the NEXT call overwrites (clone them to keep them).  Results are bitwise those of the eager chain.
+    """
+
+    def __init__(self, chain: PhysicsChain, image: torch.Tensor, label: torch.Tensor):
+        if chain.geometry is not None:
+            raise ValueError("a chain with a probe geometry cannot be captured (its table uploads are not graph-safe)")
+        img, lab, shp = _to_bhw(image, label)
+        if not img.is_cuda:
+            raise ValueError("capture needs CUDA tensors")
+        B, H, W = img.shape
+        dev = img.device
+        self.chain, self.shape, self.device = chain, shp, dev
+        self.image, self.label = img.contiguous().clone(), lab.contiguous().clone()
+        self._stager = ops.ParamStager(dev, depth=1)
+        self._done = None
+        params = chain.get_params(B, None, None, chain._scanline_grid(H, W))
+        saved = chain._stagers.get(dev)
+        chain._stagers[dev] = self._stager
+        try:
+            with torch.cuda.device(dev):
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(2):                     # warm-up outside the capture: lazy initialisation, allocator
+                        chain._run(self.image, self.label, params)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.out_image, self.out_label = chain._run(self.image, self.label, params)
+                self.info = chain.snr.last_info if chain.snr is not None else None
+        finally:
+            if saved is None:
+                chain._stagers.pop(dev, None)
+            else:
+                chain._stagers[dev] = saved
+
+    def __call__(self, image, label, params: Optional[dict] = None, sample_index=None):
+        img, lab, shp = _to_bhw(image, label)
+        if tuple(img.shape) != tuple(self.image.shape) or img.dtype != self.image.dtype or img.device != self.device:
+            raise ValueError("GraphedChain was captured for another shape, dtype or device")
+        B, H, W = img.shape
+        if params is None:
+            params = self.chain.get_params(B, None, sample_index, self.chain._scanline_grid(H, W))
+        _, _, host = self.chain._host_params(B, W, params, img.dtype)
+        if self._done is not None:
+            self._done.synchronize()                       # the previous replay has read the pinned block
+        self._stager.rewrite(host)
+        with torch.cuda.device(self.device):
+            self.image.copy_(img, non_blocking=True)
+            self.label.copy_(lab, non_blocking=True)
+            self.graph.replay()
+            self._done = torch.cuda.Event()
+            self._done.record()
+        return self.out_image.reshape(shp), self.out_label.reshape(shp)
