@@ -33,6 +33,7 @@ struct CoarseGeom {
   int nb;        // block size: nbx padded to 8, 16 or 32 = row pitch of rc / zc and of the W blocks
   int nc;        // nby * nb: padded coarse vector length per image
   int rec;       // floats per block-row record: nb*nb (W_I) + 4*nb (E_I: centre, left, right, spare)
+  int tw;        // twisted block factorisation: the aggregate row where the two elimination fronts meet; -1 = plain (top-down)
 };
 
 // min_shift: log2 of the smallest aggregate height tried.  Thin aggregates converge faster (CPU prototype at
@@ -51,6 +52,7 @@ static inline CoarseGeom coarse_geom(int H, int W, int min_shift, int min_bx_shi
   g.nby = (hu + g.by - 1) >> sh;
   g.nc = g.nby * g.nb;
   g.rec = g.nb * g.nb + 4 * g.nb;
+  g.tw = -1;
   return g;
 }
 
@@ -126,50 +128,81 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, Coar
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block LDL^T of Ac, one 128-thread block per image, fp64 in shared memory:
-//   Delta_I = D_I - E_I W_{I-1} E_I^T,  W_I = Delta_I^-1 by in-place Gauss-Jordan (SPD, no pivoting).
-// Record I of Wt[b] = { W_I [NB][NB] (symmetrised, fp32, zero in the padding), eC[NB], eL[NB], eR[NB], 0[NB] }.
+// Block LDL^T of Ac, one 128-thread block per image, fp64 in shared memory.
+//   plain   (g.tw < 0):   Delta_I = D_I - E_I W_{I-1} E_I^T                         for I = 0 .. nby-1
+//   twisted (g.tw = M):   the same for I < M;   Delta_I = D_I - E_{I+1}^T W_{I+1} E_{I+1}   for I > M (from the bottom);
+//                         Delta_M = D_M - E_M W_{M-1} E_M^T - E_{M+1}^T W_{M+1} E_{M+1}   where the two fronts meet
+//   W_I = Delta_I^-1 by in-place Gauss-Jordan (SPD, no pivoting).
+// Record I of Wt[b] = { W_I [NB][NB] (symmetrised, fp32, zero in the padding), eC[NB], eL[NB], eR[NB], 0[NB] } with
+// E_I = the coupling of aggregate row I to row I-1 (eC: same column, eL: column J-1, eR: column J+1).
 // ---------------------------------------------------------------------------------------------
 template <int NB>
 __global__ void __launch_bounds__(128) coarse_factor_kernel(CoarseGeom g, const double* __restrict__ Ab,
                                                             float* __restrict__ Wt) {
   constexpr int P = NB + 1;                      // odd pitch: column accesses are conflict-free
-  __shared__ double Wp[NB * P], M[NB * P], X[NB * P];
-  __shared__ double ab[5 * NB], prow[NB], pcol[NB];
+  __shared__ double WpT[NB * P], WpB[NB * P], M[NB * P], X[NB * P];
+  __shared__ double ab[5 * NB], en[3 * NB], prow[NB], pcol[NB];
   const int tid = threadIdx.x, b = blockIdx.x;
-  const int nbx = g.nbx;
-  const double* A = Ab + (size_t)b * g.nby * 5 * NB;
-  float* out = Wt + (size_t)b * g.nby * g.rec;
-  for (int I = 0; I < g.nby; ++I) {
+  const int nbx = g.nbx, nby = g.nby;
+  const int mid = (g.tw >= 0) ? g.tw : nby;      // rows below `mid` are eliminated from the top
+  const double* A = Ab + (size_t)b * nby * 5 * NB;
+  float* out = Wt + (size_t)b * nby * g.rec;
+  // order of elimination: 0 .. mid-1 from the top, nby-1 .. mid+1 from the bottom, then the meeting row
+  for (int step = 0; step < nby; ++step) {
+    const int nt = mid < nby ? mid : nby;
+    const int I = (step < nt) ? step : (step < nby - 1 ? nby - 1 - (step - nt) : mid);
+    const bool from_top = I > 0 && I <= mid;                                         // subtract E_I W_{I-1} E_I^T
+    const bool from_bot = I >= mid && I < nby - 1;                                   // subtract E_{I+1}^T W_{I+1} E_{I+1}
     for (int i = tid; i < 5 * NB; i += 128) ab[i] = A[(size_t)I * 5 * NB + i];
+    if (from_bot) for (int i = tid; i < 3 * NB; i += 128) en[i] = A[(size_t)(I + 1) * 5 * NB + 2 * NB + i];
     __syncthreads();
     const double *dC = ab, *dL = ab + NB, *eC = ab + 2 * NB, *eL = ab + 3 * NB, *eR = ab + 4 * NB;
-    if (I > 0) {                                 // X = E_I W_{I-1}
-      for (int i = tid; i < NB * NB; i += 128) {
-        const int j = i / NB, k = i - j * NB;
-        double v = eC[j] * Wp[j * P + k];
-        if (j > 0) v += eL[j] * Wp[(j - 1) * P + k];
-        if (j < NB - 1) v += eR[j] * Wp[(j + 1) * P + k];
-        X[j * P + k] = v;
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < NB * NB; i += 128) {   // M = D_I - X E_I^T  (identity in the padding)
+    const double *nC = en, *nL = en + NB, *nR = en + 2 * NB;                          // E_{I+1}
+    for (int i = tid; i < NB * NB; i += 128) {   // M = D_I  (identity in the padding)
       const int j = i / NB, k = i - j * NB;
       double v = 0.0;
       if (j >= nbx || k >= nbx) v = (j == k) ? 1.0 : 0.0;
-      else {
-        if (j == k) v = dC[j];
-        else if (k == j - 1) v = dL[j];
-        else if (k == j + 1) v = dL[k];
-        if (I > 0) {
-          double t = X[j * P + k] * eC[k];
-          if (k > 0) t += X[j * P + k - 1] * eL[k];
-          if (k < NB - 1) t += X[j * P + k + 1] * eR[k];
-          v -= t;
-        }
-      }
+      else if (j == k) v = dC[j];
+      else if (k == j - 1) v = dL[j];
+      else if (k == j + 1) v = dL[k];
       M[j * P + k] = v;
+    }
+    if (from_top) {                              // X = E_I W_{I-1};  M -= X E_I^T
+      for (int i = tid; i < NB * NB; i += 128) {
+        const int j = i / NB, k = i - j * NB;
+        double v = eC[j] * WpT[j * P + k];
+        if (j > 0) v += eL[j] * WpT[(j - 1) * P + k];
+        if (j < NB - 1) v += eR[j] * WpT[(j + 1) * P + k];
+        X[j * P + k] = v;
+      }
+      __syncthreads();
+      for (int i = tid; i < NB * NB; i += 128) {
+        const int j = i / NB, k = i - j * NB;
+        if (j >= nbx || k >= nbx) continue;
+        double t = X[j * P + k] * eC[k];
+        if (k > 0) t += X[j * P + k - 1] * eL[k];
+        if (k < NB - 1) t += X[j * P + k + 1] * eR[k];
+        M[j * P + k] -= t;
+      }
+    }
+    __syncthreads();
+    if (from_bot) {                              // X = E_{I+1}^T W_{I+1};  M -= X E_{I+1}
+      for (int i = tid; i < NB * NB; i += 128) {
+        const int j = i / NB, k = i - j * NB;
+        double v = nC[j] * WpB[j * P + k];
+        if (j < NB - 1) v += nL[j + 1] * WpB[(j + 1) * P + k];
+        if (j > 0) v += nR[j - 1] * WpB[(j - 1) * P + k];
+        X[j * P + k] = v;
+      }
+      __syncthreads();
+      for (int i = tid; i < NB * NB; i += 128) {
+        const int j = i / NB, k = i - j * NB;
+        if (j >= nbx || k >= nbx) continue;
+        double t = X[j * P + k] * nC[k];
+        if (k < NB - 1) t += X[j * P + k + 1] * nL[k + 1];
+        if (k > 0) t += X[j * P + k - 1] * nR[k - 1];
+        M[j * P + k] -= t;
+      }
     }
     __syncthreads();
     for (int p = 0; p < nbx; ++p) {              // in-place Gauss-Jordan inversion
@@ -188,12 +221,13 @@ __global__ void __launch_bounds__(128) coarse_factor_kernel(CoarseGeom g, const 
       __syncthreads();
     }
     float* rec = out + (size_t)I * g.rec;
+    double* Wp = (I < mid) ? WpT : WpB;          // the next Schur complement of this front uses the ROUNDED inverse
     for (int i = tid; i < NB * NB; i += 128) {
       const int j = i / NB, k = i - j * NB;
       const bool in = j < nbx && k < nbx;
       const double w = in ? 0.5 * (M[j * P + k] + M[k * P + j]) : 0.0;
       rec[i] = (float)w;
-      Wp[j * P + k] = (double)(float)w;          // the next Schur complement is formed with the ROUNDED inverse
+      Wp[j * P + k] = (double)(float)w;
     }
     for (int i = tid; i < 4 * NB; i += 128) rec[NB * NB + i] = (i < 3 * NB) ? (float)ab[2 * NB + i] : 0.f;
     __syncthreads();

@@ -2,6 +2,14 @@
 #pragma once
 #include "confmap_generic.cuh"
 
+// rows consumed per cp.async wait in the F_UP / F_DOWN sweeps (instruction-level parallelism across rows)
+#ifndef USAUG_UP_G
+#define USAUG_UP_G 2
+#endif
+#ifndef USAUG_DOWN_G
+#define USAUG_DOWN_G 2
+#endif
+
 namespace usaug {
 
 // =============================================================================================
@@ -161,7 +169,7 @@ __device__ __forceinline__ void twist_seed(const PcgArgs<float>& a, const HalfVi
   if ((lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < a.W)) zhn = bf16_lo(__ldcg(IPC + o + hx)) * __ldcg(Hb + o + hx);
 }
 
-template <int R>
+template <int R, bool SINK>
 __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int half, int lane,
                                           float beta, bool first, int pcur) {
   RingU* ring = reinterpret_cast<RingU*>(ringmem);
@@ -197,24 +205,26 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   const bool h_interior = (hrole && k != 3 && !(k == 2 && first)) || ax.on;
 
   int slot_i = 0;                                 // ring slot of the next row to stage
+  ptrdiff_t o_i = (ptrdiff_t)ys * rs;             // element offset of that row (running: no 64-bit multiply per row)
   auto issue = [&](int y) {                       // stage view row y (rows are visited ys .. 0)
     RingU* r = ring + slot_i;
     slot_i = (slot_i + 1 == R) ? 0 : slot_i + 1;
     const bool in = y >= 0;
     const bool interior = y >= 1 && y <= H - 2;
-    const ptrdiff_t o = (ptrdiff_t)(in ? y : 0) * rs;
+    const ptrdiff_t o = in ? o_i : (ptrdiff_t)0;
     cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
     cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
     cp_async16(&r->a[lane], Ap + o + xs, in && valid);
     cp_async16(&r->halo[lane], ax.on ? ax.src(interior ? y : 1) : hsrc + o + hxs, (in && h_in_only) || (interior && h_interior));
     cp_async_commit();
+    o_i -= rs;
   };
   const unsigned full = 0xffffffffu;
   float zn[4] = {0.f, 0.f, 0.f, 0.f}, zhn = 0.f;            // z of the row below (own columns, halo column)
-  float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pu[6];
-  float ab[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, au[6];     // a of the row below / of this row, columns x-1..x+4
-  WRow wc, wu;
+  float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float ab[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};            // a of the row below, columns x-1..x+4
+  WRow wc;
 #pragma unroll
   for (int j = 0; j < 4; ++j) wc.s[j] = wc.e[j] = wc.se[j] = wc.sw[j] = 0.f;
   wc.eL = wc.seL = wc.swR = 0.f;
@@ -224,67 +234,74 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   for (int u = 0; u < R; ++u) issue(ys - u);
   twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
   double acc = 0.0;
-  unsigned mu = 15u, mc = 15u;                    // sink masks of the rows u / c: bit j set = column j is an unknown
+  unsigned mc = 15u;                              // sink mask of row c: bit j set = column j is an unknown
   int slot_c = 0;                                 // ring slot of the row being consumed
-#pragma unroll 2
-  for (int y = ys; y >= 0; --y) {
-    cp_async_wait<R - 1>();
-    __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
-    {
-      const RingU* r = ring + slot_c;
-      slot_c = (slot_c + 1 == R) ? 0 : slot_c + 1;
-      const float4 h = r->h[lane], p = r->p[lane], av = r->a[lane];
-      const uint4 f = r->ipc[lane];
-      // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
-      const float hh = hsel(r->halo[hoff + 0], lane);
-      const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
-      const float hp = hsel(r->halo[hoff + 2], lane);
-      const float ha = hsel(r->halo[hoff + 3], lane);
-      float z[4];     // line part of z (the recurrence runs on it alone); the coarse part is added on top
-      z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
-      z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
-      const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
-      float zadd, zaddh;
-      ax.at_row(r->halo, lane, zadd, zaddh);
-      pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
-      pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
-      float ph = fmaf(beta, hp, zh + zaddh);
-      if (a.snk != nullptr) {                       // (uniform) sink pixels carry ip = 0: the search direction stays 0 there
-        mu = ((f.x & 0xffffu) ? 1u : 0u) | ((f.y & 0xffffu) ? 2u : 0u) | ((f.z & 0xffffu) ? 4u : 0u) | ((f.w & 0xffffu) ? 8u : 0u);
-        if (!(mu & 1u)) pu[1] = 0.f;
-        if (!(mu & 2u)) pu[2] = 0.f;
-        if (!(mu & 4u)) pu[3] = 0.f;
-        if (!(mu & 8u)) pu[4] = 0.f;
-        if (!(hf & 0xffffu)) ph = 0.f;
-      }
-      const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
-      pu[0] = (lane == 0) ? ph : l;
-      pu[5] = (lane == 31) ? ph : rt;
-      zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
-      if (valid && y >= 1 && y <= yown)
-        *reinterpret_cast<float4*>(P + (ptrdiff_t)y * rs + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
-      au[1] = av.x; au[2] = av.y; au[3] = av.z; au[4] = av.w;
-      const float al = __shfl_up_sync(full, av.w, 1), ar = __shfl_down_sync(full, av.x, 1);
-      au[0] = (lane == 0) ? ha : al;
-      au[5] = (lane == 31) ? ha : ar;
+  ptrdiff_t o_c = (ptrdiff_t)ys * rs + x;         // offset of the row being consumed
+  // G rows are consumed per wait: only the one-FMA recurrences (z, z4) and the p / a / weight hand-down tie a row to
+  // the previous one, so the loads, shuffles, ex2 and stores of neighbouring rows overlap in the single warp of a task.
+  constexpr int G = USAUG_UP_G;
+  static_assert(R > G, "UP ring too shallow");
+  float pu[G][6], au[G][6];
+  unsigned mu[G];
+  // part A of a row: everything that reads the staged slot -- z recurrence, p = z + beta p, the row's a values
+  auto rowA = [&](int y, int g) {
+    const RingU* r = ring + slot_c;
+    slot_c = (slot_c + 1 == R) ? 0 : slot_c + 1;
+    const float4 h = r->h[lane], p = r->p[lane], av = r->a[lane];
+    const uint4 f = r->ipc[lane];
+    // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
+    const float hh = hsel(r->halo[hoff + 0], lane);
+    const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
+    const float hp = hsel(r->halo[hoff + 2], lane);
+    const float ha = hsel(r->halo[hoff + 3], lane);
+    float z[4];     // line part of z (the recurrence runs on it alone); the coarse part is added on top
+    z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
+    z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
+    const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
+    float zadd, zaddh;
+    ax.at_row(r->halo, lane, zadd, zaddh);
+    pu[g][1] = fmaf(beta, p.x, z[0] + zadd); pu[g][2] = fmaf(beta, p.y, z[1] + zadd);
+    pu[g][3] = fmaf(beta, p.z, z[2] + zadd); pu[g][4] = fmaf(beta, p.w, z[3] + zadd);
+    float ph = fmaf(beta, hp, zh + zaddh);
+    mu[g] = 15u;
+    if (SINK) {                                     // sink pixels carry ip = 0: the search direction stays 0 there
+      mu[g] = ((f.x & 0xffffu) ? 1u : 0u) | ((f.y & 0xffffu) ? 2u : 0u) | ((f.z & 0xffffu) ? 4u : 0u) | ((f.w & 0xffffu) ? 8u : 0u);
+      if (!(mu[g] & 1u)) pu[g][1] = 0.f;
+      if (!(mu[g] & 2u)) pu[g][2] = 0.f;
+      if (!(mu[g] & 4u)) pu[g][3] = 0.f;
+      if (!(mu[g] & 8u)) pu[g][4] = 0.f;
+      if (!(hf & 0xffffu)) ph = 0.f;
     }
-    __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
-    // weights of row y (edges inside the row and down to row y+1), masked where the edge does not exist
+    const float l = __shfl_up_sync(full, pu[g][4], 1), rt = __shfl_down_sync(full, pu[g][1], 1);
+    pu[g][0] = (lane == 0) ? ph : l;
+    pu[g][5] = (lane == 31) ? ph : rt;
+    zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
+    if (valid && y >= 1 && y <= yown)
+      *reinterpret_cast<float4*>(P + o_c) = make_float4(pu[g][1], pu[g][2], pu[g][3], pu[g][4]);
+    au[g][1] = av.x; au[g][2] = av.y; au[g][3] = av.z; au[g][4] = av.w;
+    const float al = __shfl_up_sync(full, av.w, 1), ar = __shfl_down_sync(full, av.x, 1);
+    au[g][0] = (lane == 0) ? ha : al;
+    au[g][5] = (lane == 31) ? ha : ar;
+    o_c -= rs;
+  };
+  // part B: weights of row y (edges inside the row and down to row y+1), then q = A p of row y+1
+  auto rowB = [&](int y, int g) {
+    WRow wu;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      wu.s[j] = valid ? edge_w_fast(au[j + 1], ab[j + 1], wk.x, wk.y) : 0.f;
-      wu.e[j] = valid ? edge_w_fast(au[j + 1], au[j + 2], wk.x, wk.z) : 0.f;
-      wu.se[j] = valid ? edge_w_fast(au[j + 1], ab[j + 2], wk.x, wk.w) : 0.f;
-      wu.sw[j] = valid ? edge_w_fast(au[j + 1], ab[j], wk.x, wk.w) : 0.f;
+      wu.s[j] = valid ? edge_w_fast(au[g][j + 1], ab[j + 1], wk.x, wk.y) : 0.f;
+      wu.e[j] = valid ? edge_w_fast(au[g][j + 1], au[g][j + 2], wk.x, wk.z) : 0.f;
+      wu.se[j] = valid ? edge_w_fast(au[g][j + 1], ab[j + 2], wk.x, wk.w) : 0.f;
+      wu.sw[j] = valid ? edge_w_fast(au[g][j + 1], ab[j], wk.x, wk.w) : 0.f;
     }
-    wu.eL = hasL ? edge_w_fast(au[0], au[1], wk.x, wk.z) : 0.f;
-    wu.seL = hasL ? edge_w_fast(au[0], ab[1], wk.x, wk.w) : 0.f;
-    wu.swR = hasR ? edge_w_fast(au[5], ab[4], wk.x, wk.w) : 0.f;
+    wu.eL = hasL ? edge_w_fast(au[g][0], au[g][1], wk.x, wk.z) : 0.f;
+    wu.seL = hasL ? edge_w_fast(au[g][0], ab[1], wk.x, wk.w) : 0.f;
+    wu.swR = hasR ? edge_w_fast(au[g][5], ab[4], wk.x, wk.w) : 0.f;
     if (!hasR) { wu.e[3] = 0.f; wu.se[3] = 0.f; }
     if (!hasL) wu.sw[0] = 0.f;
 
     const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
-    if (yc <= yown) {
+    {
       const float E5[5] = {wc.eL, wc.e[0], wc.e[1], wc.e[2], wc.e[3]};
       const float SEu[4] = {wu.seL, wu.se[0], wu.se[1], wu.se[2]};
       const float SWu[4] = {wu.sw[1], wu.sw[2], wu.sw[3], wu.swR};
@@ -293,27 +310,37 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
       for (int j = 0; j < 4; ++j) {
         const float pcj = pc[j + 1];
         float t = wc.s[j] * (pcj - pl[j + 1]);
-        t = fmaf(wu.s[j], pcj - pu[j + 1], t);
+        t = fmaf(wu.s[j], pcj - pu[g][j + 1], t);
         t = fmaf(E5[j + 1], pcj - pc[j + 2], t);
         t = fmaf(E5[j], pcj - pc[j], t);
         t = fmaf(wc.se[j], pcj - pl[j + 2], t);
         t = fmaf(wc.sw[j], pcj - pl[j], t);
-        t = fmaf(SEu[j], pcj - pu[j], t);
-        t = fmaf(SWu[j], pcj - pu[j + 2], t);
-        if (a.snk != nullptr && !((mc >> j) & 1u)) t = 0.f;       // ... and so does A p (decoupled row)
+        t = fmaf(SEu[j], pcj - pu[g][j], t);
+        t = fmaf(SWu[j], pcj - pu[g][j + 2], t);
+        if (SINK && !((mc >> j) & 1u)) t = 0.f;                 // ... and so does A p (decoupled row)
         q[j] = t;
         dot = fmaf(pcj, t, dot);
       }
-      if (valid) {
-        *reinterpret_cast<float4*>(Q + (ptrdiff_t)yc * rs + x) = make_float4(q[0], q[1], q[2], q[3]);
+      if (valid && yc >= 1 && yc <= yown) {
+        *reinterpret_cast<float4*>(Q + o_c + (ptrdiff_t)(G + 1 - g) * rs) = make_float4(q[0], q[1], q[2], q[3]);
         acc += (double)dot;
       }
     }
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[j]; ab[j] = au[j]; }
+    for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[g][j]; ab[j] = au[g][j]; }
     wc = wu;
-    mc = mu;
-    issue(y - R);
+    mc = mu[g];
+  };
+  for (int y = ys; y >= 0; y -= G) {
+    cp_async_wait<R - G>();
+    __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
+#pragma unroll
+    for (int g = 0; g < G; ++g) rowA(y - g, g);
+    __syncwarp();          // every lane has read these slots' halo chunks before any lane refills them (issue below)
+#pragma unroll
+    for (int g = 0; g < G; ++g) rowB(y - g, g);
+#pragma unroll
+    for (int g = 0; g < G; ++g) issue(y - g - R);
   }
   cp_async_wait<0>();
   return warp_sum(acc);
@@ -322,7 +349,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
 // Variant of F_UP that READS the four weight planes (9 plane touches instead of 6, but ~25 % fewer
 // instructions per row): used when there are too few tasks to be bandwidth-bound, where the single-warp
 // instruction latency of a strip, not HBM, sets the pace.
-template <int R>
+template <int R, bool SINK>
 __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsigned char* ringmem, int b, int strip, int half, int lane,
                                           float beta, bool first, int pcur) {
   RingUP* ring = reinterpret_cast<RingUP*>(ringmem);
@@ -360,12 +387,13 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
 
   const int y1 = ys < H - 2 ? ys : H - 2;         // first row of the sweep (the seed row H-1 carries nothing here)
   int slot_i = 0;                                 // ring slot of the next row to stage
+  ptrdiff_t o_i = (ptrdiff_t)y1 * rs;             // element offset of that row (running: no 64-bit multiply per row)
   auto issue = [&](int y) {                       // stage view row y (rows are visited y1 .. 0)
     RingUP* r = ring + slot_i;
     slot_i = (slot_i + 1 == R) ? 0 : slot_i + 1;
     const bool in = y >= 0;
     const bool interior = y >= 1;
-    const ptrdiff_t o = (ptrdiff_t)(in ? y : 0) * rs;
+    const ptrdiff_t o = in ? o_i : (ptrdiff_t)0;
     cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
     cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
@@ -375,13 +403,14 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
     cp_async16(&r->sw[lane], SW + o + xs, in && valid);
     cp_async16(&r->halo[lane], ax.on ? ax.src(interior ? y : 1) : hsrc + o + hxs, (in && h_in_only) || (interior && h_interior));
     cp_async_commit();
+    o_i -= rs;
   };
   const unsigned full = 0xffffffffu;
   struct WRowP { float4 s, e, se, sw; float hw1, hw2; };
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float zn[4] = {0.f, 0.f, 0.f, 0.f}, zhn = 0.f;            // z of the row below (own columns, halo column)
-  float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pu[6];
-  WRowP wc, wu;
+  float pl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  WRowP wc;
   wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
 
@@ -389,88 +418,103 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   for (int u = 0; u < R; ++u) issue(y1 - u);
   twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
   double acc = 0.0;
-  unsigned mu = 15u, mc = 15u;                    // sink masks of the rows u / c: bit j set = column j is an unknown
+  unsigned mc = 15u;                              // sink mask of row c: bit j set = column j is an unknown
   int slot_c = 0;                                 // ring slot of the row being consumed
-#pragma unroll 2
-  for (int y = y1; y >= 0; --y) {
-    cp_async_wait<R - 1>();
-    __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
-    {
-      const RingUP* r = ring + slot_c;
-      slot_c = (slot_c + 1 == R) ? 0 : slot_c + 1;
-      const float4 h = r->h[lane], p = r->p[lane];
-      const uint4 f = r->ipc[lane];
-      wu.s = r->s[lane]; wu.e = r->e[lane]; wu.se = r->se[lane]; wu.sw = r->sw[lane];
-      // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
-      const float hh = hsel(r->halo[hoff + 0], lane);
-      const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
-      const float hp = hsel(r->halo[hoff + 2], lane);
-      wu.hw1 = hsel(r->halo[hoff + 3], lane); wu.hw2 = hsel(r->halo[hoff + 4], lane);
-      float z[4];     // line part of z (the recurrence runs on it alone); the coarse part is added on top
-      z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
-      z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
-      const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
-      float zadd, zaddh;
-      ax.at_row(r->halo, lane, zadd, zaddh);
-      pu[1] = fmaf(beta, p.x, z[0] + zadd); pu[2] = fmaf(beta, p.y, z[1] + zadd);
-      pu[3] = fmaf(beta, p.z, z[2] + zadd); pu[4] = fmaf(beta, p.w, z[3] + zadd);
-      float ph = fmaf(beta, hp, zh + zaddh);
-      if (a.snk != nullptr) {                       // (uniform) sink pixels carry ip = 0: the search direction stays 0 there
-        mu = ((f.x & 0xffffu) ? 1u : 0u) | ((f.y & 0xffffu) ? 2u : 0u) | ((f.z & 0xffffu) ? 4u : 0u) | ((f.w & 0xffffu) ? 8u : 0u);
-        if (!(mu & 1u)) pu[1] = 0.f;
-        if (!(mu & 2u)) pu[2] = 0.f;
-        if (!(mu & 4u)) pu[3] = 0.f;
-        if (!(mu & 8u)) pu[4] = 0.f;
-        if (!(hf & 0xffffu)) ph = 0.f;
-      }
-      const float l = __shfl_up_sync(full, pu[4], 1), rt = __shfl_down_sync(full, pu[1], 1);
-      pu[0] = (lane == 0) ? ph : l;
-      pu[5] = (lane == 31) ? ph : rt;
-      zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
-      if (valid && y >= 1 && y <= yown) *reinterpret_cast<float4*>(P + (ptrdiff_t)y * rs + x) = make_float4(pu[1], pu[2], pu[3], pu[4]);
+  ptrdiff_t o_c = (ptrdiff_t)y1 * rs + x;         // offset of the row being consumed
+  // G rows per wait, as in up_task: the rows' loads, shuffles and stores overlap in the single warp of a task
+  constexpr int G = USAUG_UP_G;
+  static_assert(R > G, "UP ring too shallow");
+  float pu[G][6];
+  WRowP wu[G];
+  unsigned mu[G];
+  auto rowA = [&](int y, int g) {
+    const RingUP* r = ring + slot_c;
+    slot_c = (slot_c + 1 == R) ? 0 : slot_c + 1;
+    const float4 h = r->h[lane], p = r->p[lane];
+    const uint4 f = r->ipc[lane];
+    wu[g].s = r->s[lane]; wu[g].e = r->e[lane]; wu[g].se = r->se[lane]; wu[g].sw = r->sw[lane];
+    // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
+    const float hh = hsel(r->halo[hoff + 0], lane);
+    const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
+    const float hp = hsel(r->halo[hoff + 2], lane);
+    wu[g].hw1 = hsel(r->halo[hoff + 3], lane); wu[g].hw2 = hsel(r->halo[hoff + 4], lane);
+    float z[4];     // line part of z (the recurrence runs on it alone); the coarse part is added on top
+    z[0] = fmaf(bf16_hi(f.x), zn[0], bf16_lo(f.x) * h.x); z[1] = fmaf(bf16_hi(f.y), zn[1], bf16_lo(f.y) * h.y);
+    z[2] = fmaf(bf16_hi(f.z), zn[2], bf16_lo(f.z) * h.z); z[3] = fmaf(bf16_hi(f.w), zn[3], bf16_lo(f.w) * h.w);
+    const float zh = fmaf(bf16_hi(hf), zhn, bf16_lo(hf) * hh);
+    float zadd, zaddh;
+    ax.at_row(r->halo, lane, zadd, zaddh);
+    pu[g][1] = fmaf(beta, p.x, z[0] + zadd); pu[g][2] = fmaf(beta, p.y, z[1] + zadd);
+    pu[g][3] = fmaf(beta, p.z, z[2] + zadd); pu[g][4] = fmaf(beta, p.w, z[3] + zadd);
+    float ph = fmaf(beta, hp, zh + zaddh);
+    mu[g] = 15u;
+    if (SINK) {                                     // sink pixels carry ip = 0: the search direction stays 0 there
+      mu[g] = ((f.x & 0xffffu) ? 1u : 0u) | ((f.y & 0xffffu) ? 2u : 0u) | ((f.z & 0xffffu) ? 4u : 0u) | ((f.w & 0xffffu) ? 8u : 0u);
+      if (!(mu[g] & 1u)) pu[g][1] = 0.f;
+      if (!(mu[g] & 2u)) pu[g][2] = 0.f;
+      if (!(mu[g] & 4u)) pu[g][3] = 0.f;
+      if (!(mu[g] & 8u)) pu[g][4] = 0.f;
+      if (!(hf & 0xffffu)) ph = 0.f;
     }
-    __syncwarp();          // every lane has read this slot's halo before any lane refills it (issue below)
+    const float l = __shfl_up_sync(full, pu[g][4], 1), rt = __shfl_down_sync(full, pu[g][1], 1);
+    pu[g][0] = (lane == 0) ? ph : l;
+    pu[g][5] = (lane == 31) ? ph : rt;
+    zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
+    if (valid && y >= 1 && y <= yown) *reinterpret_cast<float4*>(P + o_c) = make_float4(pu[g][1], pu[g][2], pu[g][3], pu[g][4]);
+    o_c -= rs;
+  };
+  auto rowB = [&](int y, int g) {
     const int yc = y + 1;                          // row whose q is now computable (u = y, c = y+1, l = y+2)
-    if (yc <= yown) {
+    {
       const float eL_s = __shfl_up_sync(full, wc.e.w, 1);
-      const float seL_s = __shfl_up_sync(full, wu.se.w, 1);
-      const float swR_s = __shfl_down_sync(full, wu.sw.x, 1);
+      const float seL_s = __shfl_up_sync(full, wu[g].se.w, 1);
+      const float swR_s = __shfl_down_sync(full, wu[g].sw.x, 1);
       const float eL = (lane == 0) ? wc.hw1 : eL_s;           // wE[c, x-1]
-      const float seL = (lane == 0) ? wu.hw2 : seL_s;         // wSE[u, x-1]
-      const float swR = (lane == 31) ? wu.hw1 : swR_s;        // wSW[u, x+4]
+      const float seL = (lane == 0) ? wu[g].hw2 : seL_s;      // wSE[u, x-1]
+      const float swR = (lane == 31) ? wu[g].hw1 : swR_s;     // wSW[u, x+4]
       const float Sc[4] = {wc.s.x, wc.s.y, wc.s.z, wc.s.w};
-      const float Su[4] = {wu.s.x, wu.s.y, wu.s.z, wu.s.w};
+      const float Su[4] = {wu[g].s.x, wu[g].s.y, wu[g].s.z, wu[g].s.w};
       const float E5[5] = {eL, wc.e.x, wc.e.y, wc.e.z, wc.e.w};
       const float SEc[4] = {wc.se.x, wc.se.y, wc.se.z, wc.se.w};
       const float SWc[4] = {wc.sw.x, wc.sw.y, wc.sw.z, wc.sw.w};
-      const float SEu[4] = {seL, wu.se.x, wu.se.y, wu.se.z};
-      const float SWu[4] = {wu.sw.y, wu.sw.z, wu.sw.w, swR};
+      const float SEu[4] = {seL, wu[g].se.x, wu[g].se.y, wu[g].se.z};
+      const float SWu[4] = {wu[g].sw.y, wu[g].sw.z, wu[g].sw.w, swR};
       float q[4], dot = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float pcj = pc[j + 1];
         float t = Sc[j] * (pcj - pl[j + 1]);
-        t = fmaf(Su[j], pcj - pu[j + 1], t);
+        t = fmaf(Su[j], pcj - pu[g][j + 1], t);
         t = fmaf(E5[j + 1], pcj - pc[j + 2], t);
         t = fmaf(E5[j], pcj - pc[j], t);
         t = fmaf(SEc[j], pcj - pl[j + 2], t);
         t = fmaf(SWc[j], pcj - pl[j], t);
-        t = fmaf(SEu[j], pcj - pu[j], t);
-        t = fmaf(SWu[j], pcj - pu[j + 2], t);
-        if (a.snk != nullptr && !((mc >> j) & 1u)) t = 0.f;       // ... and so does A p (decoupled row)
+        t = fmaf(SEu[j], pcj - pu[g][j], t);
+        t = fmaf(SWu[j], pcj - pu[g][j + 2], t);
+        if (SINK && !((mc >> j) & 1u)) t = 0.f;                 // ... and so does A p (decoupled row)
         q[j] = t;
         dot = fmaf(pcj, t, dot);
       }
-      if (valid) {
-        *reinterpret_cast<float4*>(Q + (ptrdiff_t)yc * rs + x) = make_float4(q[0], q[1], q[2], q[3]);
+      if (valid && yc >= 1 && yc <= yown) {
+        *reinterpret_cast<float4*>(Q + o_c + (ptrdiff_t)(G + 1 - g) * rs) = make_float4(q[0], q[1], q[2], q[3]);
         acc += (double)dot;
       }
     }
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[j]; }
-    wc = wu;
-    mc = mu;
-    issue(y - R);
+    for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[g][j]; }
+    wc = wu[g];
+    mc = mu[g];
+  };
+  for (int y = y1; y >= 0; y -= G) {
+    cp_async_wait<R - G>();
+    __syncwarp();          // the halo chunks were copied by OTHER lanes: their wait_group must have passed too
+#pragma unroll
+    for (int g = 0; g < G; ++g) rowA(y - g, g);
+    __syncwarp();          // every lane has read these slots' halo chunks before any lane refills them (issue below)
+#pragma unroll
+    for (int g = 0; g < G; ++g) rowB(y - g, g);
+#pragma unroll
+    for (int g = 0; g < G; ++g) issue(y - g - R);
   }
   cp_async_wait<0>();
   return warp_sum(acc);
@@ -514,12 +558,13 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   float* __restrict__ H4 = lv ? a.h4 + base4 + (x >> 2) : a.z;
   float h4p = 0.f, c4p = 0.f;
   int slot_i = 0, slot_c = 0;
+  ptrdiff_t o_i = rs + xs, o4_i = rs4;             // element offsets of the next row to stage (running: no 64-bit multiply per row)
   auto issue = [&](int y) {
     RingD* r = ring + slot_i;
     slot_i = (slot_i + 1 == RD) ? 0 : slot_i + 1;
     const bool in = (y <= ylast) && valid;
-    const ptrdiff_t o = (ptrdiff_t)(y <= ylast ? y : 0) * rs + xs;
-    if (lv) cp_async4(&r->ipc4[lane], F4 + (ptrdiff_t)(y <= ylast ? y : 0) * rs4, in);
+    const ptrdiff_t o = (y <= ylast) ? o_i : (ptrdiff_t)xs;
+    if (lv) cp_async4(&r->ipc4[lane], F4 + ((y <= ylast) ? o4_i : (ptrdiff_t)0), in);
     if (KIND == 2) {
       cp_async16(&r->p[lane], P + o, in);
       cp_async16(&r->pp[lane], PP + o, in);
@@ -529,17 +574,20 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
     cp_async16(&r->r[lane], Rv + o, in);
     cp_async16(&r->ipc[lane], IPC + o, in);
     cp_async_commit();
+    o_i += rs; o4_i += rs4;
   };
 #pragma unroll
   for (int u = 0; u < RD; ++u) issue(1 + u);
   float hp[4] = {0.f, 0.f, 0.f, 0.f}, cp[4] = {0.f, 0.f, 0.f, 0.f};
   float racc = 0.f;
   double rr = 0.0, rz = 0.0;
-#pragma unroll 2
-  for (int y = 1; y <= ylast; ++y) {
-    cp_async_wait<RD - 1>();
+  ptrdiff_t o_c = rs + x, o4_c = rs4;              // offsets of the row being consumed
+  // One row.  Only the one-FMA recurrences (h, h4) tie a row to its predecessor; G rows are consumed per wait so that the
+  // loads, updates and stores of neighbouring rows overlap in the instruction stream of the (single) warp of a task.
+  auto row = [&](int y) {
     const RingD* r = ring + slot_c;
     slot_c = (slot_c + 1 == RD) ? 0 : slot_c + 1;
+    const bool live = valid && y <= ylast;         // rows past the end are staged as zeros and store nothing
     const float4 rv = r->r[lane];
     const uint4 f = r->ipc[lane];
     const float4 cv = make_float4(bf16_hi(f.x), bf16_hi(f.y), bf16_hi(f.z), bf16_hi(f.w));
@@ -549,37 +597,37 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
       const float4 qv = r->q[lane];
       rn[0] = fmaf(-alpha, qv.x, rv.x); rn[1] = fmaf(-alpha, qv.y, rv.y);
       rn[2] = fmaf(-alpha, qv.z, rv.z); rn[3] = fmaf(-alpha, qv.w, rv.w);
-      if (valid) *reinterpret_cast<float4*>(Rv + (ptrdiff_t)y * rs + x) = make_float4(rn[0], rn[1], rn[2], rn[3]);
+      if (live) *reinterpret_cast<float4*>(Rv + o_c) = make_float4(rn[0], rn[1], rn[2], rn[3]);
       if (KIND == 2) {
         const float4 pv = r->p[lane], pq = r->pp[lane], ev = r->e[lane];
         const float4 en = make_float4(fmaf(alpha, pv.x, fmaf(alpha_prev, pq.x, ev.x)), fmaf(alpha, pv.y, fmaf(alpha_prev, pq.y, ev.y)),
                                       fmaf(alpha, pv.z, fmaf(alpha_prev, pq.z, ev.z)), fmaf(alpha, pv.w, fmaf(alpha_prev, pq.w, ev.w)));
-        if (valid) *reinterpret_cast<float4*>(Ev + (ptrdiff_t)y * rs + x) = en;
+        if (live) *reinterpret_cast<float4*>(Ev + o_c) = en;
       }
-    } else if (valid) {
-      *reinterpret_cast<float4*>(Ev + (ptrdiff_t)y * rs + x) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (live) {
+      *reinterpret_cast<float4*>(Ev + o_c) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = fmaf(cp[j], hp[j], rn[j]);
-    if (valid) *reinterpret_cast<float4*>(Hb + (ptrdiff_t)y * rs + x) = make_float4(h[0], h[1], h[2], h[3]);
+    if (live) *reinterpret_cast<float4*>(Hb + o_c) = make_float4(h[0], h[1], h[2], h[3]);
     const float srr = fmaf(rn[0], rn[0], fmaf(rn[1], rn[1], fmaf(rn[2], rn[2], rn[3] * rn[3])));
     float srz = fmaf(iv.x * h[0], h[0], fmaf(iv.y * h[1], h[1], fmaf(iv.z * h[2], h[2], iv.w * h[3] * h[3])));
     const float r4 = (rn[0] + rn[1]) + (rn[2] + rn[3]);             // P4^T r: the lane's four columns
     if (lv) {
       const uint32_t f4 = r->ipc4[lane];
       const float h4 = fmaf(c4p, h4p, r4);
-      if (valid) H4[(ptrdiff_t)y * rs4] = h4;
+      if (live) H4[o4_c] = h4;
       srz = fmaf(bf16_lo(f4) * h4, h4, srz);
       h4p = h4; c4p = bf16_hi(f4);
     }
     rr += (double)srr;
-    if (y != ymid) rz += (double)srz;
+    rz += (double)((y != ymid) ? srz : 0.f);
     if (a.cg.by) {                               // restriction rc = P^T r: sum of the new residual over each aggregate
       racc += r4;
       const int ya = hv.flip ? H - 1 - y : y;    // image row
       // the last row of an aggregate row in the order of travel
-      if (hv.flip ? (((ya - 1) & (a.cg.by - 1)) == 0) : ((ya & (a.cg.by - 1)) == 0 || ya == H - 2)) {
+      if (y <= ylast && (hv.flip ? (((ya - 1) & (a.cg.by - 1)) == 0) : ((ya & (a.cg.by - 1)) == 0 || ya == H - 2))) {
         float v = racc;                                      // 4 ... 32 lanes share one aggregate column
         v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
         if (a.cg.bx_shift >= 5) v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -593,7 +641,16 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
 #pragma unroll
     for (int j = 0; j < 4; ++j) hp[j] = h[j];
     cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
-    issue(y + RD);
+    o_c += rs; o4_c += rs4;
+  };
+  constexpr int G = USAUG_DOWN_G;                  // rows per wait
+  static_assert(RD > G, "DOWN ring too shallow");
+  for (int y = 1; y <= ylast; y += G) {
+    cp_async_wait<RD - G>();
+#pragma unroll
+    for (int g = 0; g < G; ++g) row(y + g);
+#pragma unroll
+    for (int g = 0; g < G; ++g) issue(y + g + RD);
   }
   cp_async_wait<0>();
   rr_out = warp_sum(rr); rz_out = warp_sum(rz);
@@ -612,8 +669,11 @@ struct CoarseSlot {
   float vec[NB];       // forward: rc_I; backward: v_I
 };
 
+// (__noinline__ with narrow arguments: the solves get their own register allocation and instruction schedule, and the
+//  sweeps' code no longer changes when this code does -- F_UP was measured 17 % slower after an unrelated edit here)
 template <int NB, int RING_BYTES>
-__device__ __forceinline__ double coarse_task_nb(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane) {
+__device__ __noinline__ double coarse_task_nb(const CoarseGeom g, const float* __restrict__ rec, const float* __restrict__ rc,
+                                              float* __restrict__ zc, unsigned char* ringmem, int lane) {
   using Slot = CoarseSlot<NB>;
   constexpr int Dfit = (RING_BYTES - 2 * NB * (int)sizeof(float)) / (int)sizeof(Slot);
   constexpr int D = Dfit > 16 ? 16 : Dfit;                       // ring depth in block rows
@@ -622,13 +682,9 @@ __device__ __forceinline__ double coarse_task_nb(const PcgArgs<float>& a, unsign
   constexpr int CP = NB / LPR;                                   // columns of W per lane
   constexpr int WCH = NB * NB / 4;                               // 16-byte chunks of W_I
   constexpr int KW = (WCH + 31) / 32;                            // ... per lane
-  const CoarseGeom g = a.cg;
   const int nby = g.nby;
   Slot* ring = reinterpret_cast<Slot*>(ringmem);
   float* vs = reinterpret_cast<float*>(ringmem + (size_t)D * sizeof(Slot));      // [2][NB]
-  const float* rec = a.Wt + (size_t)b * nby * g.rec;
-  const float* rc = a.rc + (size_t)b * g.nc;
-  float* zc = a.zc + (size_t)b * g.nc;
   const int row = lane & (NB - 1), c0 = (lane / NB) * CP;
   const bool owner = lane < NB;
   const unsigned full = 0xffffffffu;
@@ -733,11 +789,178 @@ __device__ __forceinline__ double coarse_task_nb(const PcgArgs<float>& a, unsign
   return warp_sum(dot);
 }
 
+// Twisted form of the same solve (a.cg.tw = M >= 0): the block factorisation runs from both ends towards aggregate row M,
+// so ONE warp advances two independent recurrences per step -- rows I (from the top) and nby-1-I (from the bottom) --
+// whose shuffle -> shared memory -> matrix-vector chains overlap in its instruction stream: half the dependent steps.
+//   inward     top     v_I = rc_I - E_I w_{I-1},              w_I = W_I v_I      I = 0 .. M-1
+//              bottom  v_I = rc_I - E_{I+1}^T w_{I+1},        w_I = W_I v_I      I = nby-1 .. M+1
+//   meeting    v_M = rc_M - E_M w_{M-1} - E_{M+1}^T w_{M+1},  zc_M = W_M v_M
+//   outward    top     zc_I = W_I (v_I - E_{I+1}^T zc_{I+1})                     I = M-1 .. 0
+//              bottom  zc_I = W_I (v_I - E_I zc_{I-1})                           I = M+1 .. nby-1
+//   rc . zc = sum_I v_I . (W_I v_I)
+template <int NB, int RING_BYTES>
+__device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float* __restrict__ rec, const float* __restrict__ rc,
+                                                 float* __restrict__ zc, unsigned char* ringmem, int lane) {
+  using Slot = CoarseSlot<NB>;
+  constexpr int Dfit = (RING_BYTES - 4 * NB * (int)sizeof(float)) / (int)sizeof(Slot) / 2;
+  constexpr int D = Dfit > 8 ? 8 : Dfit;                         // ring depth per front, in block rows
+  static_assert(D >= 3, "coarse ring too shallow for two fronts");
+  constexpr int LPR = 32 / NB;                                   // lanes per row
+  constexpr int CP = NB / LPR;                                   // columns of W per lane
+  constexpr int WCH = NB * NB / 4;                               // 16-byte chunks of W_I
+  constexpr int KW = (WCH + 31) / 32;                            // ... per lane
+  const int nby = g.nby, M = g.tw, nB = nby - 1 - M;             // M rows above the meeting row, nB below (M - 1 or M)
+  Slot* ringT = reinterpret_cast<Slot*>(ringmem);
+  Slot* ringB = ringT + D;
+  float* vsT = reinterpret_cast<float*>(ringmem + (size_t)2 * D * sizeof(Slot));   // [2][NB]
+  float* vsB = vsT + 2 * NB;
+  const int row = lane & (NB - 1), c0 = (lane / NB) * CP;
+  const bool owner = lane < NB;
+  const unsigned full = 0xffffffffu;
+  const bool w_on = (WCH >= 32) || lane < WCH;
+  const int wr = lane / (NB / 4), wq = lane - wr * (NB / 4);
+  const int w_s = wr * (NB + 4) + 4 * wq;
+  const bool e_on = lane < NB;
+  const bool v_on = (NB == 32) ? lane < 8 : (lane >= NB && lane < NB + NB / 4);
+  const int v_q = (NB == 32) ? lane : lane - NB;
+
+  auto stage = [&](Slot* ring, int k, int I, const float* vec) {   // block row I into slot k % D (no commit)
+    if (I < 0 || I >= nby) return;
+    Slot* s = ring + (k % D);
+    const float* src = rec + (size_t)I * g.rec;
+#pragma unroll
+    for (int j = 0; j < KW; ++j)
+      if (w_on) cp_async16(&s->W[w_s + j * (128 / NB) * (NB + 4)], src + 4 * lane + 128 * j, true);
+    if constexpr (NB == 32) {
+      cp_async16(&s->E[4 * lane], src + NB * NB + 4 * lane, true);
+      if (v_on) cp_async16(&s->vec[4 * v_q], vec + (size_t)I * NB + 4 * v_q, true);
+    } else {
+      const float* asrc = e_on ? src + NB * NB + 4 * lane : vec + (size_t)I * NB + 4 * v_q;
+      float* adst = e_on ? &s->E[4 * lane] : &s->vec[4 * v_q];
+      if (e_on || v_on) cp_async16(adst, asrc, true);
+    }
+  };
+  auto matvec = [&](const Slot* s, const float* v) {             // (W_I v)[row], complete in every lane
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (CP >= 4) {
+#pragma unroll
+      for (int q = 0; q < CP / 4; ++q) {
+        const float4 wv = *reinterpret_cast<const float4*>(&s->W[row * (NB + 4) + c0 + 4 * q]);
+        const float4 vv = *reinterpret_cast<const float4*>(&v[c0 + 4 * q]);
+        acc[0] = fmaf(wv.x, vv.x, acc[0]); acc[1] = fmaf(wv.y, vv.y, acc[1]);
+        acc[2] = fmaf(wv.z, vv.z, acc[2]); acc[3] = fmaf(wv.w, vv.w, acc[3]);
+      }
+    } else {
+      const float2 wv = *reinterpret_cast<const float2*>(&s->W[row * (NB + 4) + c0]);
+      const float2 vv = *reinterpret_cast<const float2*>(&v[c0]);
+      acc[0] = wv.x * vv.x; acc[1] = wv.y * vv.y;
+    }
+    float r = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int o = NB; o < 32; o <<= 1) r += __shfl_xor_sync(full, r, o);
+    return r;
+  };
+  // (E n)[row] with E from a staged record; (E^T n)[row] with E held in registers (the record of the previous step)
+  auto e_direct = [&](const Slot* s, float n) {
+    const float nl = __shfl_up_sync(full, n, 1), nr = __shfl_down_sync(full, n, 1);
+    return fmaf(s->E[row], n, fmaf(s->E[NB + row], (row == 0) ? 0.f : nl, s->E[2 * NB + row] * ((row == NB - 1) ? 0.f : nr)));
+  };
+  auto e_transp = [&](float eC, float eL, float eR, float n) {
+    const float tb = eL * n, tc = eR * n;
+    const float tbs = __shfl_down_sync(full, tb, 1), tcs = __shfl_up_sync(full, tc, 1);
+    return fmaf(eC, n, (row == NB - 1) ? 0.f : tbs) + ((row == 0) ? 0.f : tcs);
+  };
+
+  // ---- inward: the top front consumes block rows 0 .. M (round k = row k), the bottom front nby-1 .. M+1 -------------
+  for (int u = 0; u < D - 1; ++u) { stage(ringT, u, (u <= M) ? u : -1, rc); stage(ringB, u, (u < nB) ? nby - 1 - u : -1, rc); cp_async_commit(); }
+  cp_async_wait<D - 2>();
+  __syncwarp();
+  float wT = 0.f, wB = 0.f;                                      // (W v)[row] of the previous row of each front
+  float bC = 0.f, bL = 0.f, bR = 0.f;                            // E of the previous row of the bottom front
+  float pvw = 0.f;
+  double dot = 0.0;
+  // both fronts in ONE basic block (no branch between them, so that their chains interleave); the top front has at
+  // most one row more than the bottom one: that step runs the bottom front on a zero-filled slot and discards it
+  for (int k = 0; k < M; ++k) {
+    const bool hasB = k < nB;
+    const Slot* sT = ringT + (k % D);
+    const Slot* sB = ringB + (k % D);
+    const float vT = sT->vec[row] - e_direct(sT, wT);
+    const float vB = sB->vec[row] - e_transp(bC, bL, bR, wB);
+    dot += (double)pvw;
+    float* vbT = vsT + (k & 1) * NB;
+    float* vbB = vsB + (k & 1) * NB;
+    if (owner) { vbT[row] = vT; vbB[row] = vB; }
+    { const float tC = sB->E[row], tL = sB->E[NB + row], tR = sB->E[2 * NB + row]; bC = hasB ? tC : bC; bL = hasB ? tL : bL; bR = hasB ? tR : bR; }
+    cp_async_wait<D - 3>();                                      // this lane's pieces of round k + 1 have landed
+    __syncwarp();                                                // publishes the vectors and round k + 1; everybody is done with round k - 1
+    wT = matvec(sT, vbT);
+    const float wBn = matvec(sB, vbB);
+    if (owner) { zc[(size_t)k * NB + row] = vT; if (hasB) zc[(size_t)(nby - 1 - k) * NB + row] = vB; }
+    { const int kn = k + D - 1; stage(ringT, kn, (kn <= M) ? kn : -1, rc); stage(ringB, kn, (kn < nB) ? nby - 1 - kn : -1, rc); cp_async_commit(); }
+    pvw = owner ? fmaf(vT, wT, hasB ? vB * wBn : 0.f) : 0.f;
+    if (hasB) wB = wBn;
+  }
+  dot += (double)pvw;
+  // ---- the meeting row ------------------------------------------------------------------------------------------------
+  float zM, mC, mL, mR;
+  {
+    const Slot* sT = ringT + (M % D);
+    float v = sT->vec[row] - e_direct(sT, wT);
+    if (nB > 0) v -= e_transp(bC, bL, bR, wB);
+    float* vb = vsT + (M & 1) * NB;
+    if (owner) vb[row] = v;
+    mC = sT->E[row]; mL = sT->E[NB + row]; mR = sT->E[2 * NB + row];
+    __syncwarp();
+    zM = matvec(sT, vb);
+    if (owner) { zc[(size_t)M * NB + row] = zM; dot += (double)(v * zM); }
+  }
+  cp_async_wait<0>();
+  __threadfence();                                               // the parked v (in zc) are re-read through cp.async below
+  __syncwarp();
+  // ---- outward: top front rows M-1 .. 0, bottom front rows M+1 .. nby-1 -----------------------------------------------
+  for (int u = 0; u < D - 1; ++u) { stage(ringT, u, M - 1 - u, zc); stage(ringB, u, (u < nB) ? M + 1 + u : -1, zc); cp_async_commit(); }
+  cp_async_wait<D - 2>();
+  __syncwarp();
+  float zT = zM, zB = zM;
+  for (int k = 0; k < M; ++k) {
+    const bool hasB = k < nB;
+    const Slot* sT = ringT + (k % D);
+    const Slot* sB = ringB + (k % D);
+    const float uT = sT->vec[row] - e_transp(mC, mL, mR, zT);
+    const float uB = sB->vec[row] - e_direct(sB, zB);
+    float* vbT = vsT + (k & 1) * NB;
+    float* vbB = vsB + (k & 1) * NB;
+    if (owner) { vbT[row] = uT; vbB[row] = uB; }
+    mC = sT->E[row]; mL = sT->E[NB + row]; mR = sT->E[2 * NB + row];
+    cp_async_wait<D - 3>();
+    __syncwarp();
+    zT = matvec(sT, vbT);
+    zB = matvec(sB, vbB);
+    if (owner) { zc[(size_t)(M - 1 - k) * NB + row] = zT; if (hasB) zc[(size_t)(M + 1 + k) * NB + row] = zB; }
+    { const int kn = k + D - 1; stage(ringT, kn, M - 1 - kn, zc); stage(ringB, kn, (kn < nB) ? M + 1 + kn : -1, zc); cp_async_commit(); }
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  return warp_sum(dot);
+}
+
 template <int RING_BYTES>
 __device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane) {
-  if (a.cg.nb == 16) return coarse_task_nb<16, RING_BYTES>(a, ringmem, b, lane);
-  if (a.cg.nb == 32) return coarse_task_nb<32, RING_BYTES>(a, ringmem, b, lane);
-  return coarse_task_nb<8, RING_BYTES>(a, ringmem, b, lane);
+  const CoarseGeom g = a.cg;
+  const float* rec = a.Wt + (size_t)b * g.nby * g.rec;
+  const float* rc = a.rc + (size_t)b * g.nc;
+  float* zc = a.zc + (size_t)b * g.nc;
+  if (g.tw >= 0) {
+    // (32 x 32 blocks need 5 KB per staged block row: two fronts fit only the deeper rings of the 4-warp kernel;
+    //  the host leaves cg.tw = -1 otherwise)
+    if (g.nb == 16) return coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+    if (g.nb == 8) return coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+    if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) return coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+  }
+  if (g.nb == 16) return coarse_task_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+  if (g.nb == 32) return coarse_task_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+  return coarse_task_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
 }
 
 // ---- ready queue (two multi-producer / multi-consumer rings in global memory) ----------------------
@@ -903,20 +1126,51 @@ __device__ __forceinline__ double twist_fix(const PcgArgs<float>& a, int b, int 
   const uint32_t* Fm = a.ipc + o;
   const uint32_t* Fn = a.ipc + o + W;
   double acc = 0.0;
-  for (int x = 4 * lane; x < W; x += 128) {
-    const float4 ht = __ldcg(reinterpret_cast<const float4*>(Hm + x)), hb = __ldcg(reinterpret_cast<const float4*>(Hn + x));
-    const uint4 fm = __ldcg(reinterpret_cast<const uint4*>(Fm + x)), fn = __ldcg(reinterpret_cast<const uint4*>(Fn + x));
-    const float4 h = make_float4(fmaf(bf16_hi(fn.x), hb.x, ht.x), fmaf(bf16_hi(fn.y), hb.y, ht.y),
-                                 fmaf(bf16_hi(fn.z), hb.z, ht.z), fmaf(bf16_hi(fn.w), hb.w, ht.w));
-    *reinterpret_cast<float4*>(Hm + x) = h;
-    acc += (double)fmaf(bf16_lo(fm.x) * h.x, h.x, fmaf(bf16_lo(fm.y) * h.y, h.y, fmaf(bf16_lo(fm.z) * h.z, h.z, bf16_lo(fm.w) * h.w * h.w)));
+  // four chunks per round with all their loads issued first: the warp that runs this is the last arriver of the phase,
+  // i.e. it sits on the image's critical path, and a round costs one L2 round trip instead of four
+  for (int xb = 4 * lane; xb < W; xb += 512) {
+    float4 ht[4], hb[4]; uint4 fm[4], fn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int x = xb + 128 * u;
+      if (x < W) {
+        ht[u] = __ldcg(reinterpret_cast<const float4*>(Hm + x)); hb[u] = __ldcg(reinterpret_cast<const float4*>(Hn + x));
+        fm[u] = __ldcg(reinterpret_cast<const uint4*>(Fm + x)); fn[u] = __ldcg(reinterpret_cast<const uint4*>(Fn + x));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int x = xb + 128 * u;
+      if (x < W) {
+        const float4 h = make_float4(fmaf(bf16_hi(fn[u].x), hb[u].x, ht[u].x), fmaf(bf16_hi(fn[u].y), hb[u].y, ht[u].y),
+                                     fmaf(bf16_hi(fn[u].z), hb[u].z, ht[u].z), fmaf(bf16_hi(fn[u].w), hb[u].w, ht[u].w));
+        *reinterpret_cast<float4*>(Hm + x) = h;
+        acc += (double)fmaf(bf16_lo(fm[u].x) * h.x, h.x, fmaf(bf16_lo(fm[u].y) * h.y, h.y, fmaf(bf16_lo(fm[u].z) * h.z, h.z, bf16_lo(fm[u].w) * h.w * h.w)));
+      }
+    }
   }
   if (a.h4 != nullptr) {                                            // the same for the level preconditioner's plane
     const size_t o4 = ((size_t)b * a.H + m) * a.w4p;
-    for (int X = lane; X < (W >> 2); X += 32) {
-      const float h = fmaf(bf16_hi(__ldcg(a.ipc4 + o4 + a.w4p + X)), __ldcg(a.h4 + o4 + a.w4p + X), __ldcg(a.h4 + o4 + X));
-      a.h4[o4 + X] = h;
-      acc += (double)(bf16_lo(__ldcg(a.ipc4 + o4 + X)) * h * h);
+    const int W4 = W >> 2;
+    for (int Xb = lane; Xb < W4; Xb += 128) {
+      float hn[4], hm[4]; uint32_t gn[4], gm[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int X = Xb + 32 * u;
+        if (X < W4) {
+          gn[u] = __ldcg(a.ipc4 + o4 + a.w4p + X); hn[u] = __ldcg(a.h4 + o4 + a.w4p + X);
+          hm[u] = __ldcg(a.h4 + o4 + X); gm[u] = __ldcg(a.ipc4 + o4 + X);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int X = Xb + 32 * u;
+        if (X < W4) {
+          const float h = fmaf(bf16_hi(gn[u]), hn[u], hm[u]);
+          a.h4[o4 + X] = h;
+          acc += (double)(bf16_lo(gm[u]) * h * h);
+        }
+      }
     }
   }
   return warp_sum(acc);
@@ -924,7 +1178,9 @@ __device__ __forceinline__ double twist_fix(const PcgArgs<float>& a, int b, int 
 
 // AW = active warps per CTA (8 or 4): fewer active warps own deeper rings.
 // RECOMP = F_UP recomputes the edge weights from the `a` plane (bandwidth-bound regime) or reads them.
-template <int AW, bool RECOMP>
+// SINK = the launch has extra sink pixels (a.snk): F_UP masks p and A p there (a separate instantiation, so that the
+// masks cost the default path nothing -- as a run-time branch they lengthened an F_UP task by 8 %).
+template <int AW, bool RECOMP, bool SINK>
 __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> a) {
   constexpr size_t kWarpRing = (kFusedSmem / AW) & ~(size_t)127;  // ring bytes per active warp
   constexpr int R = (int)(kWarpRing / (RECOMP ? sizeof(RingU) : sizeof(RingUP)));   // F_UP ring depth in rows
@@ -952,9 +1208,9 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     double s0 = 0.0, s1 = 0.0;
     if (mode == F_UP) {
       if constexpr (RECOMP)
-        s0 = up_task<R>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+        s0 = up_task<R, SINK>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
       else
-        s0 = up_task_planes<R>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
+        s0 = up_task_planes<R, SINK>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
     } else if (mode == F_DOWN) {
       if (__ldcg(&st->epend))
         down_task<RD, 2>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->alpha), (float)__ldcg(&st->alpha_prev), __ldcg(&st->pcur), s0, s1);

@@ -57,6 +57,9 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   int min_shift = fine ? 1 : 2, min_bx_shift = 5;
   if (const char* e = getenv("USAUG_CM_COARSE_SHIFT")) min_shift = atoi(e);          // development knob
   L.cg = (!L.fused || (flags & USAUG_CM_NO_COARSE)) ? CoarseGeom{} : coarse_geom(H, W, min_shift, min_bx_shift);
+  // Twisted block factorisation of the coarse operator (two fronts per solve, advanced by one warp): everywhere except
+  // for 32 x 32 blocks in the 8-warp kernel, whose rings are too shallow for two fronts
+  if (L.cg.by && !(L.recomp && L.cg.nb == 32) && !getenv("USAUG_CM_COARSE_PLAIN")) L.cg.tw = L.cg.nby / 2;
   // Twisted line factorisation (two half sweeps per strip): halves the dependent UP -> DOWN chain of an image, which
   // is what bounds launches that cannot fill the GPU; deeply bandwidth-bound launches gain nothing from it.
   L.tw_m = 0;
@@ -118,11 +121,11 @@ static thread_local int g_debug = 0;
 
 static thread_local int g_legacy = 0;   // USAUG_CM_LEGACY_KERNEL: force the two-slot kernel (A/B testing)
 
-template <int AW, bool RECOMP>
+template <int AW, bool RECOMP, bool SINK>
 static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t stream) {
   int per_sm = 0;
-  USAUG_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<AW, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
-  USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel<AW, RECOMP>, 256, kFusedSmem));
+  USAUG_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<AW, RECOMP, SINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+  USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel<AW, RECOMP, SINK>, 256, kFusedSmem));
   if (per_sm < 1) { set_error("pcg_fused_kernel cannot be resident"); return USAUG_E_CUDA; }
   const int tasks = a.per * a.B;
   int blocks = tasks;
@@ -137,7 +140,7 @@ static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t s
   void* params[] = {(void*)&a};
   if (g_ev_start) USAUG_CUDA(cudaEventRecord(g_ev_start, stream));
   // cooperative launch only for its co-residency guarantee: workers spin on the ready queue
-  USAUG_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel<AW, RECOMP>, dim3(blocks), dim3(256), params,
+  USAUG_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel<AW, RECOMP, SINK>, dim3(blocks), dim3(256), params,
                                          kFusedSmem, stream));
   if (g_ev_stop) USAUG_CUDA(cudaEventRecord(g_ev_stop, stream));
   return USAUG_OK;
@@ -151,8 +154,12 @@ static int launch_fused(PcgArgs<float>& a, const CmLayout& L, int B, cudaStream_
   // every inner iteration is two phases; a refinement round adds four
   a.max_steps = 6 * a.maxiter + 64;   // worst case: a refinement round (5 phases) after every iteration
   // few tasks (weight-reading F_UP): 4 active warps per CTA with rings twice as deep keep enough bytes in flight
-  if (L.recomp) return launch_fused_aw<8, true>(a, sms, stream);
-  return launch_fused_aw<4, false>(a, sms, stream);
+  if (a.snk != nullptr) {
+    if (L.recomp) return launch_fused_aw<8, true, true>(a, sms, stream);
+    return launch_fused_aw<4, false, true>(a, sms, stream);
+  }
+  if (L.recomp) return launch_fused_aw<8, true, false>(a, sms, stream);
+  return launch_fused_aw<4, false, false>(a, sms, stream);
 }
 
 template <typename T>
