@@ -211,16 +211,32 @@ __global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ su
 // Per output pixel: 2 image taps + 1 label tap gathered along the scanline, TGC gain, clip.
 // 10 algorithmic bytes per pixel (4+1 in, 4+1 out).
 // ---------------------------------------------------------------------------------------------
-constexpr int kWarpRows = 8;
+constexpr int kWarpRows = 8;       // output rows per thread and tile
+#ifndef USAUG_WARP_TILES
+#define USAUG_WARP_TILES 4
+#endif
+#ifndef USAUG_WARP_PREFETCH
+#define USAUG_WARP_PREFETCH 0
+#endif
+constexpr int kWarpTiles = USAUG_WARP_TILES;      // consecutive tiles per block
 
 // TIn = float (image in [0,1]) or uint8_t (8-bit B-mode ingest: v/255 in correctly rounded fp32, from a
 // 256-entry shared-memory table so the gather loop carries no divide).
+// A block walks kWarpTiles tiles of kWarpRows rows down its 128 scanlines: the per-column quantities (s_hat, d_eff,
+// 1/den) and the TGC gains are set up once per block.  With one 8-row tile per block a block lived for two dependent
+// memory round trips (per-image scalars, then the gathers) and the memory pipeline idled during the first.
+// Measured at B = 1024 of 512 x 512 (one box, same run): 1 tile / 48 registers 719 us, 4 tiles / 48 registers 704 us,
+// 4 tiles / 64 registers (8 blocks per SM) 656 us; prefetching tile i+1 before tile i is stored (USAUG_WARP_PREFETCH)
+// was slower (801 us: the loads of both tiles share scoreboards, so waiting for the older tile waits for the newer too).
+#ifndef USAUG_WARP_MINB
+#define USAUG_WARP_MINB 8
+#endif
 template <typename TIn>
-__global__ void __launch_bounds__(128) fused_warp_kernel(
+__global__ void __launch_bounds__(128, USAUG_WARP_MINB) fused_warp_kernel(
     const TIn* __restrict__ img, const uint8_t* __restrict__ lab, float* __restrict__ out_img,
     uint8_t* __restrict__ out_lab, int H, int W, const float* __restrict__ s_hat,
     const WarpInfo* __restrict__ info, const float* __restrict__ tgc, int K, float gscale) {
-  __shared__ float s_gain[kWarpRows];
+  __shared__ float s_gain[kWarpRows * kWarpTiles];
   __shared__ float s_lut[std::is_same<TIn, uint8_t>::value ? 256 : 1];
   if constexpr (std::is_same<TIn, uint8_t>::value) {
     s_lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
@@ -232,10 +248,10 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
   };
   const int b = blockIdx.z;
   const int x = blockIdx.x * 128 + threadIdx.x;
-  const int ya = blockIdx.y * kWarpRows;
-  if (threadIdx.x < kWarpRows) {          // TGC gain is a function of the output row only
+  const int yb = blockIdx.y * (kWarpRows * kWarpTiles);
+  if (threadIdx.x < kWarpRows * kWarpTiles) {          // TGC gain is a function of the output row only
     const float* g = tgc + (size_t)b * K;
-    const float yf = (float)(ya + threadIdx.x);
+    const float yf = (float)(yb + threadIdx.x);
     float gain;
     if (K == 1) {
       gain = g[0];
@@ -248,91 +264,108 @@ __global__ void __launch_bounds__(128) fused_warp_kernel(
     }
     s_gain[threadIdx.x] = gain;
   }
-  __syncthreads();
-  if (x >= W) return;
   const size_t base = (size_t)b * H * W;
-  const TIn* __restrict__ I = img + base + x;            // column pointers; in-image offsets fit 32 bits
-  const uint8_t* __restrict__ L = lab + base + x;
-  float* __restrict__ OI = out_img + base + x;
-  uint8_t* __restrict__ OL = out_lab + base + x;
+  const int xs = x < W ? x : W - 1;                      // (threads beyond the last column compute, but never store)
+  const TIn* __restrict__ I = img + base + xs;           // column pointers; in-image offsets fit 32 bits
+  const uint8_t* __restrict__ L = lab + base + xs;
+  float* __restrict__ OI = out_img + base + xs;
+  uint8_t* __restrict__ OL = out_lab + base + xs;
   const float de = info[b].d_eff;
-  const float den = __fsub_rn(s_hat[(size_t)b * W + x], de);
+  const float den = __fsub_rn(s_hat[(size_t)b * W + xs], de);
   const unsigned uH = (unsigned)H;
-
-  // Phase 1: source coordinates of all 16 rows.  Phase 2: all gathers back-to-back.
   // t = y / den must be the correctly rounded quotient (label picks are bit-exact).  For 1 <= den < 2^16 and
   // integer y < min(den, 8192) it is computed as  q = RN(y r), e = RN(y - q den), t = RN(q + e r)  with
   // r = RN(1 / den) once per column -- proven equal to the IEEE division for EVERY such pair by the exhaustive run
   // of tools/div_check.cu (3.09e11 quotients, 0 mismatches; Markstein's theorem).  No slow-path call, no branch.
-  int i0[kWarpRows], yn[kWarpRows];
-  float fr[kWarpRows];
   const bool fastdiv = (den >= 1.0f) && (den < 65536.0f) && (H <= 8192);
-  if (fastdiv) {
-    const float rden = __frcp_rn(den);
+  const float rden = fastdiv ? __frcp_rn(den) : 0.0f;
+  __syncthreads();                                       // gains (and the 8-bit table) are in shared memory
+
+  struct Tile {
+    int i0[kWarpRows], yn[kWarpRows];
+    float fr[kWarpRows];
+    TIn v0[kWarpRows], v1[kWarpRows];
+    unsigned lv[kWarpRows];                  // (a byte array here would be placed in local memory)
+    bool interior;
+  };
+  // source coordinates of the tile's rows, then all its gathers back-to-back
+  auto fetch = [&](Tile& t, int ya) {
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r) {
       const float yf = (float)(ya + r);
-      const float q = __fmul_rn(yf, rden);
-      const float e = __fmaf_rn(-q, den, yf);
-      const float t = (yf < den) ? __fmaf_rn(e, rden, q) : 1.0f;       // rows at / below the bone surface: t = 1
-      const float ys = __fadd_rn(yf, __fmul_rn(de, t));
-      i0[r] = __float2int_rd(ys);
-      fr[r] = ys - (float)i0[r];
-      yn[r] = __float2int_rd(__fadd_rn(ys, 0.5f));
+      float tq;
+      if (fastdiv) {
+        const float q = __fmul_rn(yf, rden);
+        const float e = __fmaf_rn(-q, den, yf);
+        tq = (yf < den) ? __fmaf_rn(e, rden, q) : 1.0f;     // rows at / below the bone surface: t = 1
+      } else {
+        tq = 1.0f;
+        if (yf < den) tq = __fdiv_rn(yf, den);
+      }
+      const float ys = __fadd_rn(yf, __fmul_rn(de, tq));
+      t.i0[r] = __float2int_rd(ys);
+      t.fr[r] = ys - (float)t.i0[r];
+      t.yn[r] = __float2int_rd(__fadd_rn(ys, 0.5f));
     }
-  } else {
+    // Block-uniform fast path: 0 <= y_src <= y + |d|, so a tile whose last row + |d| + 2 stays inside
+    // the image needs no bounds checks at all (every tile except the bottom few).
+    t.interior = (float)(ya + kWarpRows + 1) + fabsf(de) < (float)(H - 1);
+    if (t.interior) {
+#pragma unroll
+      for (int r = 0; r < kWarpRows; ++r) {
+        const TIn* p0 = I + t.i0[r] * W;
+        t.v0[r] = p0[0];
+        t.v1[r] = p0[W];
+        t.lv[r] = L[t.yn[r] * W];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kWarpRows; ++r) {
+        const bool in = ya + r < H;
+        t.v0[r] = (in && (unsigned)t.i0[r] < uH) ? I[t.i0[r] * W] : (TIn)0;
+        t.v1[r] = (in && (unsigned)(t.i0[r] + 1) < uH) ? I[(t.i0[r] + 1) * W] : (TIn)0;
+        t.lv[r] = (in && (unsigned)t.yn[r] < uH) ? L[t.yn[r] * W] : 0u;
+      }
+    }
+  };
+  auto finish = [&](const Tile& t, int ya, int ti) {
+    if (x >= W) return;
 #pragma unroll
     for (int r = 0; r < kWarpRows; ++r) {
-      const float yf = (float)(ya + r);
-      float t = 1.0f;
-      if (yf < den) t = __fdiv_rn(yf, den);
-      const float ys = __fadd_rn(yf, __fmul_rn(de, t));
-      i0[r] = __float2int_rd(ys);
-      fr[r] = ys - (float)i0[r];
-      yn[r] = __float2int_rd(__fadd_rn(ys, 0.5f));
+      const int y = ya + r;
+      if (t.interior || y < H) {
+        const float a0 = px(t.v0[r]), a1 = px(t.v1[r]);
+        const float v = fmaf(t.fr[r], a1 - a0, a0);
+        OI[y * W] = fminf(fmaxf(s_gain[ti * kWarpRows + r] * v, 0.0f), 1.0f);
+        OL[y * W] = (uint8_t)t.lv[r];
+      }
     }
-  }
-  TIn v0[kWarpRows], v1[kWarpRows];
-  uint8_t lv[kWarpRows];
-  // Block-uniform fast path: 0 <= y_src <= y + |d|, so a tile whose last row + |d| + 2 stays inside
-  // the image needs no bounds checks at all (every tile except the bottom few).
-  const bool interior = (float)(ya + kWarpRows + 1) + fabsf(de) < (float)(H - 1);
-  if (interior) {
+  };
+#if USAUG_WARP_PREFETCH
+  Tile ta, tb;
+  fetch(ta, yb);
 #pragma unroll
-    for (int r = 0; r < kWarpRows; ++r) {
-      const TIn* p0 = I + i0[r] * W;
-      v0[r] = p0[0];
-      v1[r] = p0[W];
-      lv[r] = L[yn[r] * W];
-    }
-    float* po = OI + ya * W;
-    uint8_t* pl = OL + ya * W;
-#pragma unroll
-    for (int r = 0; r < kWarpRows; ++r) {
-      const float a0 = px(v0[r]), a1 = px(v1[r]);
-      const float v = fmaf(fr[r], a1 - a0, a0);
-      po[r * W] = fminf(fmaxf(s_gain[r] * v, 0.0f), 1.0f);
-      pl[r * W] = lv[r];
-    }
-    return;
+  for (int ti = 0; ti < kWarpTiles; ti += 2) {
+    const int ya = yb + ti * kWarpRows;
+    const bool more1 = ti + 1 < kWarpTiles && ya + kWarpRows < H;
+    if (more1) fetch(tb, ya + kWarpRows);
+    finish(ta, ya, ti);
+    if (!more1) break;
+    const bool more2 = ti + 2 < kWarpTiles && ya + 2 * kWarpRows < H;
+    if (more2) fetch(ta, ya + 2 * kWarpRows);
+    finish(tb, ya + kWarpRows, ti + 1);
+    if (!more2) break;
   }
-#pragma unroll
-  for (int r = 0; r < kWarpRows; ++r) {
-    const bool in = ya + r < H;
-    v0[r] = (in && (unsigned)i0[r] < uH) ? I[i0[r] * W] : (TIn)0;
-    v1[r] = (in && (unsigned)(i0[r] + 1) < uH) ? I[(i0[r] + 1) * W] : (TIn)0;
-    lv[r] = (in && (unsigned)yn[r] < uH) ? L[yn[r] * W] : (uint8_t)0;
+#else
+#pragma unroll 1
+  for (int ti = 0; ti < kWarpTiles; ++ti) {
+    const int ya = yb + ti * kWarpRows;
+    if (ya >= H) break;
+    Tile t;
+    fetch(t, ya);
+    finish(t, ya, ti);
   }
-#pragma unroll
-  for (int r = 0; r < kWarpRows; ++r) {
-    const int y = ya + r;
-    if (y < H) {
-      const float a0 = px(v0[r]), a1 = px(v1[r]);
-      const float v = fmaf(fr[r], a1 - a0, a0);
-      OI[y * W] = fminf(fmaxf(s_gain[r] * v, 0.0f), 1.0f);
-      OL[y * W] = lv[r];
-    }
-  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -405,7 +438,7 @@ static int fused_tgc_deform_impl(const TIn* img, const uint8_t* lab, float* out_
   USAUG_CUDA(launch_pdl(profile_kernel, dim3(B), dim3(256), (size_t)W * 8, stream, surf, scan_tiles(H), H, W, d, taps, R,
                         s_hat, info));
   const float gscale = (H > 1 && K > 1) ? (float)((double)(K - 1) / (double)(H - 1)) : 0.0f;
-  dim3 grid((W + 127) / 128, (H + kWarpRows - 1) / kWarpRows, B);
+  dim3 grid((W + 127) / 128, (H + kWarpRows * kWarpTiles - 1) / (kWarpRows * kWarpTiles), B);
   fused_warp_kernel<TIn><<<grid, 128, 0, stream>>>(img, lab, out_img, out_lab, H, W, s_hat, info, tgc,
                                                    (H > 1) ? K : 1, gscale);     // last kernel of the call: normal launch
   USAUG_CHECK_LAUNCH("fused_warp_kernel");
