@@ -45,7 +45,8 @@ enum {
   USAUG_OK = 0,
   USAUG_E_INVALID_ARG = -1,
   USAUG_E_CUDA = -2,
-  USAUG_E_WORKSPACE_TOO_SMALL = -3
+  USAUG_E_WORKSPACE_TOO_SMALL = -3,
+  USAUG_E_BOUNDS = -4 /* bounds-checked debug build only (lib/libusaug_dbg.so): a kernel wrote past one of its workspace planes */
 };
 
 /* preconditioner of the confidence-map PCG */

@@ -58,10 +58,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: 
     if out_path == LIB_PATH and not extra_flags:
         if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == fp:
             return LIB_PATH
-    else:
-        force = True        # objects of another configuration must not be reused
     LIB_DIR.mkdir(parents=True, exist_ok=True)
-    obj_dir = LIB_DIR / "obj"
+    obj_dir = LIB_DIR / ("obj" if out_path == LIB_PATH else "obj_" + out_path.stem)   # one object cache per configuration
     obj_dir.mkdir(exist_ok=True)
     nvcc = find_nvcc()
     extra = list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
@@ -98,6 +96,17 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: 
     return out_path
 
 
+DEBUG_LIB_PATH = LIB_DIR / "libusaug_dbg.so"
+
+
+def build_debug(force: bool = False) -> Path:
+    """The bounds-checked library (csrc/common.cuh: red zones behind every workspace plane, device-side index asserts).
+    Select it at run time with USAUG_LIB=<this path>; it synchronises at the end of every call."""
+    return build(force=force, extra_flags=("-DUSAUG_BOUNDS_CHECK",), out_path=DEBUG_LIB_PATH)
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug(force="--force" in sys.argv))

@@ -32,16 +32,65 @@ void set_error(const char* fmt, ...);
 
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
+// ---- bounds-checked debug build (-DUSAUG_BOUNDS_CHECK -> lib/libusaug_dbg.so) ---------------------------------------
+// compute-sanitizer is not available on the GPU pool, so the library carries its own checks:
+//   * every sub-buffer carved out of a workspace is followed by a 256-byte red zone, filled with a canary before the
+//     kernels of a call run and verified after them (the debug build synchronises at the end of a call; the product build
+//     never does): a kernel that writes past one of its planes turns the call into USAUG_E_BOUNDS;
+//   * USAUG_DEV_ASSERT(cond) guards the index computations of the kernels (row offsets, ring slots, queue slots,
+//     shared-memory tiles, gather rows): a violated one prints file:line and traps, which surfaces as a CUDA error.
+// Both are compiled out of the product library.
+#ifdef USAUG_BOUNDS_CHECK
+constexpr size_t kRedZone = 256;
+#define USAUG_DEV_ASSERT(cond)                                                              \
+  do {                                                                                      \
+    if (!(cond)) {                                                                          \
+      printf("usaug bounds check failed: %s:%d: %s\n", __FILE__, __LINE__, #cond);          \
+      __trap();                                                                             \
+    }                                                                                       \
+  } while (0)
+#else
+constexpr size_t kRedZone = 0;
+#define USAUG_DEV_ASSERT(cond) do { } while (0)
+#endif
+constexpr unsigned char kCanary = 0xA5;
+
 // Carves 256-byte aligned sub-buffers out of the caller's workspace.
 struct Carver {
   char* base;
   size_t off;
-  explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+  size_t zones[64];     // debug build: offsets of the red zones
+  int nzones;
+  explicit Carver(void* p) : base(static_cast<char*>(p)), off(0), nzones(0) {}
   template <typename T>
   T* take(size_t n) {
     T* r = reinterpret_cast<T*>(base + off);
     off += align_up(n * sizeof(T));
+    if (kRedZone && n) {
+      if (nzones < 64) zones[nzones++] = off;
+      off += kRedZone;
+    }
     return r;
+  }
+  // debug build: fill the red zones (before the first kernel of the call) ...
+  int arm(cudaStream_t stream) {
+    for (int i = 0; i < nzones && base; ++i) USAUG_CUDA(cudaMemsetAsync(base + zones[i], kCanary, kRedZone, stream));
+    return USAUG_OK;
+  }
+  // ... and check them after the last one (synchronises; debug build only)
+  int verify(cudaStream_t stream, const char* what) {
+    if (!kRedZone || !base) return USAUG_OK;
+    USAUG_CUDA(cudaStreamSynchronize(stream));
+    unsigned char host[256];
+    for (int i = 0; i < nzones; ++i) {
+      USAUG_CUDA(cudaMemcpy(host, base + zones[i], kRedZone, cudaMemcpyDeviceToHost));
+      for (size_t k = 0; k < kRedZone; ++k)
+        if (host[k] != kCanary) {
+          set_error("%s: red zone %d of the workspace (offset %zu) was overwritten at byte %zu", what, i, zones[i], k);
+          return USAUG_E_BOUNDS;
+        }
+    }
+    return USAUG_OK;
   }
 };
 

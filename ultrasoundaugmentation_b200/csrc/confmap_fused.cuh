@@ -276,8 +276,11 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
     pu[g][0] = (lane == 0) ? ph : l;
     pu[g][5] = (lane == 31) ? ph : rt;
     zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
-    if (valid && y >= 1 && y <= yown)
+    USAUG_DEV_ASSERT(slot_c >= 0 && slot_c < R);
+    if (valid && y >= 1 && y <= yown) {
+      USAUG_DEV_ASSERT(o_c == (ptrdiff_t)y * rs + x && y <= H - 2 && x + 3 < W);
       *reinterpret_cast<float4*>(P + o_c) = make_float4(pu[g][1], pu[g][2], pu[g][3], pu[g][4]);
+    }
     au[g][1] = av.x; au[g][2] = av.y; au[g][3] = av.z; au[g][4] = av.w;
     const float al = __shfl_up_sync(full, av.w, 1), ar = __shfl_down_sync(full, av.x, 1);
     au[g][0] = (lane == 0) ? ha : al;
@@ -322,6 +325,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
         dot = fmaf(pcj, t, dot);
       }
       if (valid && yc >= 1 && yc <= yown) {
+        USAUG_DEV_ASSERT(o_c + (ptrdiff_t)(G + 1 - g) * rs == (ptrdiff_t)yc * rs + x && yc <= H - 2);
         *reinterpret_cast<float4*>(Q + o_c + (ptrdiff_t)(G + 1 - g) * rs) = make_float4(q[0], q[1], q[2], q[3]);
         acc += (double)dot;
       }
@@ -460,7 +464,11 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
     pu[g][0] = (lane == 0) ? ph : l;
     pu[g][5] = (lane == 31) ? ph : rt;
     zn[0] = z[0]; zn[1] = z[1]; zn[2] = z[2]; zn[3] = z[3]; zhn = zh;
-    if (valid && y >= 1 && y <= yown) *reinterpret_cast<float4*>(P + o_c) = make_float4(pu[g][1], pu[g][2], pu[g][3], pu[g][4]);
+    USAUG_DEV_ASSERT(slot_c >= 0 && slot_c < R);
+    if (valid && y >= 1 && y <= yown) {
+      USAUG_DEV_ASSERT(o_c == (ptrdiff_t)y * rs + x && y <= H - 2 && x + 3 < W);
+      *reinterpret_cast<float4*>(P + o_c) = make_float4(pu[g][1], pu[g][2], pu[g][3], pu[g][4]);
+    }
     o_c -= rs;
   };
   auto rowB = [&](int y, int g) {
@@ -496,6 +504,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
         dot = fmaf(pcj, t, dot);
       }
       if (valid && yc >= 1 && yc <= yown) {
+        USAUG_DEV_ASSERT(o_c + (ptrdiff_t)(G + 1 - g) * rs == (ptrdiff_t)yc * rs + x && yc <= H - 2);
         *reinterpret_cast<float4*>(Q + o_c + (ptrdiff_t)(G + 1 - g) * rs) = make_float4(q[0], q[1], q[2], q[3]);
         acc += (double)dot;
       }
@@ -588,6 +597,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
     const RingD* r = ring + slot_c;
     slot_c = (slot_c + 1 == RD) ? 0 : slot_c + 1;
     const bool live = valid && y <= ylast;         // rows past the end are staged as zeros and store nothing
+    USAUG_DEV_ASSERT(!live || (o_c == (ptrdiff_t)y * rs + x && y >= 1 && y <= H - 2 && x + 3 < W && o4_c == (ptrdiff_t)y * rs4));
     const float4 rv = r->r[lane];
     const uint4 f = r->ipc[lane];
     const float4 cv = make_float4(bf16_hi(f.x), bf16_hi(f.y), bf16_hi(f.z), bf16_hi(f.w));
@@ -633,6 +643,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
         if (a.cg.bx_shift >= 5) v += __shfl_xor_sync(0xffffffffu, v, 4);
         if (a.cg.bx_shift >= 6) v += __shfl_xor_sync(0xffffffffu, v, 8);
         if (a.cg.bx_shift == 7) v += __shfl_xor_sync(0xffffffffu, v, 16);
+        USAUG_DEV_ASSERT(((ya - 1) >> a.cg.by_shift) < a.cg.nby && (!valid || (x >> a.cg.bx_shift) < a.cg.nb));
         if ((lane & ((1 << (a.cg.bx_shift - 2)) - 1)) == 0 && valid)
           a.rc[(size_t)b * a.cg.nc + (size_t)((ya - 1) >> a.cg.by_shift) * a.cg.nb + (x >> a.cg.bx_shift)] = v;
         racc = 0.f;
@@ -896,6 +907,7 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
     __syncwarp();                                                // publishes the vectors and round k + 1; everybody is done with round k - 1
     wT = matvec(sT, vbT);
     const float wBn = matvec(sB, vbB);
+    USAUG_DEV_ASSERT(k < nby && nby - 1 - k >= 0 && (k % D) < D);
     if (owner) { zc[(size_t)k * NB + row] = vT; if (hasB) zc[(size_t)(nby - 1 - k) * NB + row] = vB; }
     { const int kn = k + D - 1; stage(ringT, kn, (kn <= M) ? kn : -1, rc); stage(ringB, kn, (kn < nB) ? nby - 1 - kn : -1, rc); cp_async_commit(); }
     pvw = owner ? fmaf(vT, wT, hasB ? vB * wBn : 0.f) : 0.f;
@@ -991,6 +1003,7 @@ __device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsi
   unsigned long long* slots = a.qslots + (size_t)ring * a.qcap;
   for (unsigned i = 0; i < n; ++i) {
     const unsigned long long k = k0 + i;
+    USAUG_DEV_ASSERT(k - __ldcg(a.qhead + ring) < (unsigned long long)a.qcap);      // the ring never laps an unread entry
     volatile unsigned long long* slot = slots + (k % a.qcap);
     *slot = ((k + 1ull) << 32) | (unsigned long long)(payload0 + i * stride);
   }
@@ -1202,6 +1215,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     t_wait += tq1 - tq0;
     if (payload == kNoTask) break;
     const int b = (int)(payload / (unsigned)per), ti = (int)(payload % (unsigned)per);
+    USAUG_DEV_ASSERT(b >= 0 && b < a.B && 2 * ti + 1 < 2 * a.pmax);
     const int strip = ti % a.nstrip4, half = ti / a.nstrip4;      // half = 1: lower half of a twisted factorisation
     ImgState* st = a.st + b;
     const int mode = (int)(__ldcg(&st->fword) & 0xffffffffull);

@@ -80,6 +80,7 @@ __device__ __forceinline__ double stencil_task(const PcgArgs<T>& a, int b, int x
         q += (A)wSWmR * (Pc - PmR);
         if (own) {
           const size_t o = (size_t)y * W + x;
+          USAUG_DEV_ASSERT(y >= 1 && y <= H - 2 && x >= 0 && x < W);
           if (a.snk != nullptr && a.snk[base + o] != 0) q = (A)0;      // sink pixel: decoupled row, r = q = 0
           if (RESID) { const double rr = -(double)q; Rv[o] = (T)rr; acc += rr * rr; }
           else { Q[o] = (T)q; acc += (double)Pc * (double)q; }

@@ -37,6 +37,7 @@ struct CmLayout {
   double* Ab;
   int nblk, nstrip1, nrb, nstrip2, pmax;
   size_t bytes;
+  Carver cv{nullptr};         // (its red zones: bounds-checked debug build)
 };
 
 static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
@@ -111,6 +112,7 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.Wt = cv.take<float>((size_t)B * L.cg.nby * L.cg.rec);
   L.Ab = cv.take<double>((size_t)B * nc * 5);
   L.bytes = cv.off;
+  L.cv = cv;
   return L;
 }
 
@@ -265,6 +267,7 @@ extern "C" int usaug_confmap_pcg_sinks(const float* img, float* cm, int B, int H
   g_debug = (flags & USAUG_CM_DEBUG_TIMING) ? 1 : 0;
   g_legacy = (flags & USAUG_CM_LEGACY_KERNEL) ? 1 : 0;
 
+  if (int zrc = L.cv.arm(stream)) return zrc;
   // neutral result for images the solver could not finish (scheduler watchdog): C = 0 switches the SNR term off
   USAUG_CUDA(cudaMemsetAsync(cm, 0, (size_t)B * N * sizeof(float), stream));
   cm_depth_kernel<<<(H + 127) / 128, 128, 0, stream>>>(L.depth, H, alpha);
@@ -307,7 +310,8 @@ extern "C" int usaug_confmap_pcg_sinks(const float* img, float* cm, int B, int H
   }
   cm_init_state_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, L.nblk, L.bbpart, L.st, L.done);
   USAUG_CHECK_LAUNCH("cm_init_state_kernel");
-  if (flags & USAUG_CM_FP64_VECTORS)
-    return launch_pcg<double>(L, cm, B, H, W, rtol, maxiter, iters, relres, stream);
-  return launch_pcg<float>(L, cm, B, H, W, rtol, maxiter, iters, relres, stream);
+  int rc = (flags & USAUG_CM_FP64_VECTORS) ? launch_pcg<double>(L, cm, B, H, W, rtol, maxiter, iters, relres, stream)
+                                          : launch_pcg<float>(L, cm, B, H, W, rtol, maxiter, iters, relres, stream);
+  if (rc == USAUG_OK) rc = L.cv.verify(stream, "usaug_confmap_pcg");
+  return rc;
 }

@@ -362,6 +362,7 @@ struct LeLayout {
   float* part;
   int rb_fwd, rb_inv, tc, nblk_inv;
   size_t bytes;
+  Carver cv{nullptr};
 };
 
 static int next_pow2_min8(int n) {
@@ -385,6 +386,7 @@ static LeLayout le_layout(void* ws, int B, int H0, int H, int W) {
   L.spec = cv.take<float2>(N); L.odd = cv.take<float2>(N); L.even = cv.take<float2>(N);
   L.part = cv.take<float>((size_t)B * L.nblk_inv);
   L.bytes = cv.off;
+  L.cv = cv;
   return L;
 }
 
@@ -417,7 +419,8 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
     set_error("usaug_local_energy: workspace too small"); return USAUG_E_WORKSPACE_TOO_SMALL;
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const LeLayout L = le_layout(ws, B, H0, H, W);
+  LeLayout L = le_layout(ws, B, H0, H, W);
+  if (int zrc = L.cv.arm(stream)) return zrc;
   const int lgH = ilog2_exact(H), lgW = ilog2_exact(W);
   LeFilter flt{};
   flt.scales = scales;
@@ -443,5 +446,5 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
   USAUG_CHECK_LAUNCH("le_rows_inv");
   le_scale<<<(B + 127) / 128, 128, 0, stream>>>(L.part, L.nblk_inv, scale, B);
   USAUG_CHECK_LAUNCH("le_scale");
-  return USAUG_OK;
+  return L.cv.verify(stream, "usaug_local_energy");
 }

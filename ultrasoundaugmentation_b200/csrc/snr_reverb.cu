@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
       }
       __syncthreads();
       for (int rr = 0; rr < TR; ++rr) {                   // row pass: thread = column
+        USAUG_DEV_ASSERT(rr * TC + (int)threadIdx.x + 2 * R < TR * TC);
         const uint8_t* lr = labs + rr * TC + threadIdx.x;
         float s = 0.0f;
         for (int i = 0; i <= 2 * R; ++i) s += lr[i] ? taps[i] : 0.0f;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(kSrCols) snr_reverb_kernel(
         const int ys = ys0 + r;
         if (ys < 0 || ya + r >= H || !xin) continue;
         float m = 0.0f;
+        USAUG_DEV_ASSERT(r + 2 * R < TR && ys < H);
         for (int j = 0; j <= 2 * R; ++j) m += taps[j] * rowp[(r + j) * kSrCols + threadIdx.x];
         if (m > 0.0f) {
           const size_t so = (size_t)ys * W + x;
@@ -182,7 +184,7 @@ using namespace usaug;
 
 extern "C" size_t usaug_snr_reverb_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return surface_scan_bytes(B, H, W) + align_up((size_t)B * 4 * sizeof(int));
+  return surface_scan_bytes(B, H, W) + align_up((size_t)B * 4 * sizeof(int)) + 2 * kRedZone;
 }
 
 template <typename TOut>
@@ -209,7 +211,9 @@ static int snr_reverb_impl(const float* img, const float* cm, const float* sig, 
   Carver cv(ws);
   int* surf = cv.take<int>((size_t)B * scan_tiles(H) * W * 2);
   int* box = cv.take<int>((size_t)B * 4);
-  int rc = launch_bone_box(lab, B, H, W, box, surf, stream, true);
+  int rc = cv.arm(stream);
+  if (rc) return rc;
+  rc = launch_bone_box(lab, B, H, W, box, surf, stream, true);
   if (rc) return rc;
   dim3 grid((W + kSrCols - 1) / kSrCols, (H + kSrRows - 1) / kSrRows, B);
   const size_t smem = (size_t)(kSrRows + 2 * R) * kSrCols * sizeof(float) + (size_t)(kSrRows + 2 * R) * (kSrCols + 2 * R);
@@ -222,7 +226,7 @@ static int snr_reverb_impl(const float* img, const float* cm, const float* sig, 
   snr_reverb_kernel<TOut><<<grid, kSrCols, smem, stream>>>(img, cm, lab, sig, sig_scale, out, H, W, a_snr, rho, nghost,
                                                            box, feather_taps, R, vec_ok);
   USAUG_CHECK_LAUNCH("snr_reverb_kernel");
-  return USAUG_OK;
+  return cv.verify(stream, "usaug_snr_reverb");
 }
 
 extern "C" int usaug_snr_reverb(const float* img, const float* cm, const uint8_t* lab, float* out,

@@ -2,6 +2,8 @@
 // Implements SURVEY.md Appendix A.1 (steps 1-5) and A.2.  The coordinate path uses explicitly
 // rounded fp32 intrinsics (no FMA contraction) so nearest-neighbour label picks are bit-exact
 // against the oracle (oracle/deform.py).
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) surface_scan_kernel(const uint8_t* __rest
     }
     const int x = blockIdx.x * 32 * VEC + c;
     if (x < W) {   // one partial per (image, row tile, column): no memset, no atomics
+      USAUG_DEV_ASSERT(c + (PITCH - VEC) * (c / VEC) < 32 * PITCH);
       int* dst = surf + (((size_t)b * gridDim.y + blockIdx.y) * W + x) * 2;
       dst[0] = f;
       dst[1] = (l >= 0) ? l : -1;
@@ -186,6 +189,7 @@ __global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ su
     float acc = 0.0f;
     for (int k = -R; k <= R; ++k) {
       const int xi = min(max(x + k, 0), W - 1);
+      USAUG_DEV_ASSERT(k + R >= 0 && k + R <= 2 * R && xi >= 0 && xi < W);
       acc = __fadd_rn(acc, __fmul_rn(taps[k + R], s_fill[xi]));
     }
     s_hat[(size_t)b * W + x] = acc;
@@ -313,6 +317,7 @@ __global__ void __launch_bounds__(128, USAUG_WARP_MINB) fused_warp_kernel(
     if (t.interior) {
 #pragma unroll
       for (int r = 0; r < kWarpRows; ++r) {
+        USAUG_DEV_ASSERT(t.i0[r] >= 0 && t.i0[r] + 1 < H && t.yn[r] >= 0 && t.yn[r] < H);   // "interior": no bounds checks
         const TIn* p0 = I + t.i0[r] * W;
         t.v0[r] = p0[0];
         t.v1[r] = p0[W];
@@ -334,6 +339,7 @@ __global__ void __launch_bounds__(128, USAUG_WARP_MINB) fused_warp_kernel(
     for (int r = 0; r < kWarpRows; ++r) {
       const int y = ya + r;
       if (t.interior || y < H) {
+        USAUG_DEV_ASSERT(y >= 0 && y < H);
         const float a0 = px(t.v0[r]), a1 = px(t.v1[r]);
         const float v = fmaf(t.fr[r], a1 - a0, a0);
         OI[y * W] = fminf(fmaxf(s_gain[ti * kWarpRows + r] * v, 0.0f), 1.0f);
@@ -405,7 +411,7 @@ using namespace usaug;
 extern "C" size_t usaug_warp_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
   return surface_scan_bytes(B, H, W) + align_up((size_t)B * W * sizeof(float)) +
-         align_up((size_t)B * sizeof(WarpInfo));
+         align_up((size_t)B * sizeof(WarpInfo)) + 3 * kRedZone;
 }
 
 template <typename TIn>
@@ -432,8 +438,9 @@ static int fused_tgc_deform_impl(const TIn* img, const uint8_t* lab, float* out_
   int* surf = cv.take<int>((size_t)B * scan_tiles(H) * W * 2);
   float* s_hat = cv.take<float>((size_t)B * W);
   WarpInfo* info = cv.take<WarpInfo>(B);
-
-  int rc = launch_surface_scan(lab, B, H, W, surf, stream);
+  int rc = cv.arm(stream);
+  if (rc) return rc;
+  rc = launch_surface_scan(lab, B, H, W, surf, stream);
   if (rc) return rc;
   USAUG_CUDA(launch_pdl(profile_kernel, dim3(B), dim3(256), (size_t)W * 8, stream, surf, scan_tiles(H), H, W, d, taps, R,
                         s_hat, info));
@@ -442,7 +449,7 @@ static int fused_tgc_deform_impl(const TIn* img, const uint8_t* lab, float* out_
   fused_warp_kernel<TIn><<<grid, 128, 0, stream>>>(img, lab, out_img, out_lab, H, W, s_hat, info, tgc,
                                                    (H > 1) ? K : 1, gscale);     // last kernel of the call: normal launch
   USAUG_CHECK_LAUNCH("fused_warp_kernel");
-  return USAUG_OK;
+  return cv.verify(stream, "usaug_fused_tgc_deform");
 }
 
 extern "C" int usaug_fused_tgc_deform(const float* img, const uint8_t* lab, float* out_img,
@@ -461,7 +468,7 @@ extern "C" int usaug_fused_tgc_deform_u8(const uint8_t* img, const uint8_t* lab,
 
 extern "C" size_t usaug_bone_box_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return surface_scan_bytes(B, H, W);
+  return surface_scan_bytes(B, H, W) + kRedZone;
 }
 
 namespace usaug {
@@ -487,5 +494,16 @@ extern "C" int usaug_bone_box(const uint8_t* lab, int B, int H, int W, int* box,
   if (ws_bytes < usaug_bone_box_workspace_bytes(B, H, W)) {
     set_error("usaug_bone_box: workspace too small"); return USAUG_E_WORKSPACE_TOO_SMALL;
   }
-  return launch_bone_box(lab, B, H, W, box, static_cast<int*>(ws), static_cast<cudaStream_t>(stream_), false);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Carver cv(ws);
+  int* surf = cv.take<int>((size_t)B * scan_tiles(H) * W * 2);
+  int rc = cv.arm(stream);
+  if (rc) return rc;
+  rc = launch_bone_box(lab, B, H, W, box, surf, stream, false);
+  if (rc) return rc;
+#ifdef USAUG_BOUNDS_CHECK
+  // self-test of the red zones (tests/test_bounds_checked_build.py): one stray int right behind the scan partials
+  if (getenv("USAUG_DBG_FAULT")) USAUG_CUDA(cudaMemsetAsync(surf + (size_t)B * scan_tiles(H) * W * 2, 0, sizeof(int), stream));
+#endif
+  return cv.verify(stream, "usaug_bone_box");
 }
