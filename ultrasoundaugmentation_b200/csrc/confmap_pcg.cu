@@ -170,7 +170,8 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   PcgArgs<T> a;
   a.B = B; a.H = H; a.W = W; a.maxiter = maxiter;
   a.rtol2 = rtol * rtol;
-  const double inner_red = std::is_same<T, float>::value ? 1e-4 : 0.0;   // first refinement round; later rounds adapt
+  double inner_red = std::is_same<T, float>::value ? 1e-4 : 0.0;   // first refinement round; later rounds adapt
+  if (const char* e = getenv("USAUG_CM_INNER_RED")) { if (inner_red > 0.0) inner_red = atof(e); }   // development knob
   a.inner_red2 = inner_red * inner_red;
   a.wS = L.wS; a.wE = L.wE; a.wSE = L.wSE; a.wSW = L.wSW; a.ip = L.ip; a.c = L.c; a.ipc = L.ipc; a.aplane = L.aplane; a.wk = L.wk;
   a.x64 = L.x64;
