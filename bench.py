@@ -295,6 +295,20 @@ def run_stages(a, dev, peak):
     Rf = (ftaps.numel() - 1) // 2
     outb = torch.empty_like(img)
     ws3 = torch.empty(lib.usaug_snr_reverb_workspace_bytes(B, Hs, Ws), dtype=torch.uint8, device=dev)
+    # ... and K1 at the same size (at configs[1]'s 168 MB the three launches' fixed costs dominate)
+    dL = ((torch.rand(B, generator=g) * 0.2 - 0.05) * Hs).to(dev)
+    tgcL = (torch.rand(B, 8, generator=g) * 0.8 + 0.6).to(dev)
+    tapsL = ops.gaussian_taps(0.02 * Ws).to(dev)
+    RL = (tapsL.numel() - 1) // 2
+    olL = torch.empty_like(lab)
+    wsL = torch.empty(lib.usaug_warp_workspace_bytes(B, Hs, Ws), dtype=torch.uint8, device=dev)
+
+    def k1_large():
+        _ffi.check(lib.usaug_fused_tgc_deform(img.data_ptr(), lab.data_ptr(), outb.data_ptr(), olL.data_ptr(), B, Hs, Ws, dL.data_ptr(),
+                                              tgcL.data_ptr(), 8, tapsL.data_ptr(), RL, wsL.data_ptr(), wsL.numel(), st), "K1")
+    out.append(entry("K1: fused TGC+deformation+remap, batch 1024 of 512x512", "surface_scan + profile + fused_warp_kernel",
+                     timed(k1_large, 20, False), 10.0 * B * Hs * Ws, B, reps=20, l2="working set 2.7 GB >> L2", bytes_model="10 B/px"))
+    del olL, wsL
 
     def k3():
         _ffi.check(lib.usaug_snr_reverb(img.data_ptr(), cm.data_ptr(), lab.data_ptr(), outb.data_ptr(), B, Hs, Ws, av.data_ptr(),

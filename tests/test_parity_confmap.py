@@ -259,3 +259,23 @@ def test_cm_sink_argument_errors(cuda_device):
         ops.confidence_map(img, sink="top")
     with pytest.raises(ValueError):
         ops.confidence_map(img, sink="bottom_row", sink_mask=torch.zeros((1, 32, 32), dtype=torch.uint8, device=cuda_device))
+
+
+def test_cm_sharding_across_a_variant_threshold(cuda_device):
+    """Sharding a batch can move a launch into another solver class (cm_layout picks aggregates / twist / weight handling
+    from the number of strip tasks): 1800 tiny images in one launch use 2-row aggregates, the same images as two launches
+    of 900 use 4-row aggregates and the twisted factorisation.  Same systems, same stopping rule: the maps agree within the
+    confidence-map tolerance (not bitwise), and pinning the variant makes the shards bitwise equal to the whole."""
+    B, H, W = 1800, 40, 128
+    img = np.stack([util.synth_batch(1, H, W, seed0=5000 + (b % 61))[0][0] for b in range(61)])
+    img = np.concatenate([img] * (B // 61 + 1))[:B]
+    whole, itw, rrw = gpu_cm(cuda_device, img, rtol=RTOL)
+    halves = [gpu_cm(cuda_device, img[lo:lo + 900], rtol=RTOL) for lo in (0, 900)]
+    parts = np.concatenate([h[0] for h in halves])
+    assert (rrw <= RTOL).all() and all((h[2] <= RTOL).all() for h in halves)
+    assert not np.array_equal(itw, np.concatenate([h[1] for h in halves]))      # another preconditioner: other iteration counts
+    assert np.abs(whole - parts).max() <= 2 * util.tol_cm(RTOL)
+    kw = dict(coarse="standard", twist=False, up_variant="recompute")
+    whole_p, _, _ = gpu_cm(cuda_device, img, rtol=RTOL, **kw)
+    parts_p = np.concatenate([gpu_cm(cuda_device, img[lo:lo + 900], rtol=RTOL, **kw)[0] for lo in (0, 900)])
+    assert np.array_equal(whole_p, parts_p)

@@ -1,8 +1,8 @@
 """Host-side parameter sampling.
 
 Parameters of sample i depend only on (seed, global sample index, transform stream), never on
-the batch it travels in or the GPU it lands on -- so a batch sharded over N GPUs reproduces the
-single-GPU result bit for bit.  The generator is a counter-based splitmix64 hash evaluated
+the batch it travels in or the GPU it lands on -- so a batch sharded over N GPUs draws the single-GPU
+run's parameters bit for bit (what that means for the results: sharding.py).  The generator is a counter-based splitmix64 hash evaluated
 with vectorised NumPy uint64 arithmetic (no per-sample Generator construction).
 """
 from __future__ import annotations

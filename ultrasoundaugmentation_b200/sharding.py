@@ -1,7 +1,11 @@
 """Multi-GPU sharding: every image is an independent unit, so a batch splits across ranks with
 NO collective on the data path.  Parameters are keyed by the GLOBAL sample
-index, so the N-rank result equals the 1-rank result bit for bit.  An optional final gather
-(NCCL on GPUs, gloo in CPU tests) is provided for consumers that want the whole batch.
+index, so every rank draws exactly the parameters the 1-rank run draws for its samples: parameters, labels and
+the K1 / K3 images of the N-rank run equal the 1-rank run bit for bit.  Confidence maps (and the chain images
+that depend on them) are bitwise equal when both runs select the same solver variant -- the library picks it
+from the size of a launch (csrc/confmap_pcg.cu: cm_layout) -- and agree within the confidence-map tolerance
+otherwise; pin the variant (ops.confidence_map: coarse / twist / up_variant) for bitwise results at any N.
+An optional final gather (NCCL on GPUs, gloo in CPU tests) is provided for consumers that want the whole batch.
 """
 from __future__ import annotations
 
