@@ -32,7 +32,7 @@ struct CoarseGeom {
   int nbx, nby;  // coarse grid
   int nb;        // block size: nbx padded to 8, 16 or 32 = row pitch of rc / zc and of the W blocks
   int nc;        // nby * nb: padded coarse vector length per image
-  int rec;       // floats per block-row record: nb*nb (W_I) + 4*nb (E_I: centre, left, right, spare)
+  int rec;       // floats per block-row record: nb*(nb+4) (W_I, rows padded like the shared-memory slot) + 4*nb (E_I: centre, left, right, spare)
   int tw;        // twisted block factorisation: the aggregate row where the two elimination fronts meet; -1 = plain (top-down)
 };
 
@@ -51,7 +51,7 @@ static inline CoarseGeom coarse_geom(int H, int W, int min_shift, int min_bx_shi
   g.by = 1 << sh; g.by_shift = sh;
   g.nby = (hu + g.by - 1) >> sh;
   g.nc = g.nby * g.nb;
-  g.rec = g.nb * g.nb + 4 * g.nb;
+  g.rec = g.nb * (g.nb + 4) + 4 * g.nb;
   g.tw = -1;
   return g;
 }
@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(int H, int W, Coar
 //   twisted (g.tw = M):   the same for I < M;   Delta_I = D_I - E_{I+1}^T W_{I+1} E_{I+1}   for I > M (from the bottom);
 //                         Delta_M = D_M - E_M W_{M-1} E_M^T - E_{M+1}^T W_{M+1} E_{M+1}   where the two fronts meet
 //   W_I = Delta_I^-1 by in-place Gauss-Jordan (SPD, no pivoting).
-// Record I of Wt[b] = { W_I [NB][NB] (symmetrised, fp32, zero in the padding), eC[NB], eL[NB], eR[NB], 0[NB] } with
+// Record I of Wt[b] = { W_I [NB][NB + 4] (symmetrised, fp32, zero in the padding; the row pitch of the solver's shared-memory
+// slots, so that a record is staged by straight 16-byte copies), eC[NB], eL[NB], eR[NB], 0[NB] } with
 // E_I = the coupling of aggregate row I to row I-1 (eC: same column, eL: column J-1, eR: column J+1).
 // ---------------------------------------------------------------------------------------------
 template <int NB>
@@ -226,10 +227,11 @@ __global__ void __launch_bounds__(128) coarse_factor_kernel(CoarseGeom g, const 
       const int j = i / NB, k = i - j * NB;
       const bool in = j < nbx && k < nbx;
       const double w = in ? 0.5 * (M[j * P + k] + M[k * P + j]) : 0.0;
-      rec[i] = (float)w;
+      rec[j * (NB + 4) + k] = (float)w;
+      if (k < 4) rec[j * (NB + 4) + NB + k] = 0.f;       // row padding
       Wp[j * P + k] = (double)(float)w;
     }
-    for (int i = tid; i < 4 * NB; i += 128) rec[NB * NB + i] = (i < 3 * NB) ? (float)ab[2 * NB + i] : 0.f;
+    for (int i = tid; i < 4 * NB; i += 128) rec[NB * (NB + 4) + i] = (i < 3 * NB) ? (float)ab[2 * NB + i] : 0.f;
     __syncthreads();
   }
 }

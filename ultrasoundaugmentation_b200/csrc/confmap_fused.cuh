@@ -691,37 +691,24 @@ __device__ __noinline__ double coarse_task_nb(const CoarseGeom g, const float* _
   static_assert(D >= 3, "coarse ring too shallow");
   constexpr int LPR = 32 / NB;                                   // lanes per row
   constexpr int CP = NB / LPR;                                   // columns of W per lane
-  constexpr int WCH = NB * NB / 4;                               // 16-byte chunks of W_I
-  constexpr int KW = (WCH + 31) / 32;                            // ... per lane
   const int nby = g.nby;
   Slot* ring = reinterpret_cast<Slot*>(ringmem);
   float* vs = reinterpret_cast<float*>(ringmem + (size_t)D * sizeof(Slot));      // [2][NB]
   const int row = lane & (NB - 1), c0 = (lane / NB) * CP;
   const bool owner = lane < NB;
   const unsigned full = 0xffffffffu;
-  // copy roles of this lane, fixed for the whole task: KW chunks of W_I, and one chunk of E_I or of the vector
-  const bool w_on = (WCH >= 32) || lane < WCH;
-  const int wr = lane / (NB / 4), wq = lane - wr * (NB / 4);
-  const int w_s = wr * (NB + 4) + 4 * wq;                        // float offset inside Slot::W; + k * (128 / NB) rows
-  const bool e_on = lane < NB;                                   // E_I: NB chunks
-  const bool v_on = (NB == 32) ? lane < 8 : (lane >= NB && lane < NB + NB / 4);
-  const int v_q = (NB == 32) ? lane : lane - NB;
+  constexpr int RCH = (NB * (NB + 4) + 4 * NB) / 128;            // 16-byte chunks of a record per lane: 1, 3 or 10
+  static_assert((NB * (NB + 4) + 4 * NB) % 128 == 0, "a record is a whole number of 512-byte warp copies");
+  const bool v_on = lane < NB / 4;                               // the vector: NB / 4 chunks
 
   auto issue = [&](int k, int I, const float* vec) {             // stage block row I into slot k % D
     if (I >= 0 && I < nby) {
       Slot* s = ring + (k % D);
-      const float* src = rec + (size_t)I * g.rec;
+      const float* src = rec + (size_t)I * g.rec + 4 * lane;      // a record is the image of Slot::W and Slot::E
+      float* dst = s->W + 4 * lane;
 #pragma unroll
-      for (int j = 0; j < KW; ++j)
-        if (w_on) cp_async16(&s->W[w_s + j * (128 / NB) * (NB + 4)], src + 4 * lane + 128 * j, true);
-      if constexpr (NB == 32) {
-        cp_async16(&s->E[4 * lane], src + NB * NB + 4 * lane, true);
-        if (v_on) cp_async16(&s->vec[4 * v_q], vec + (size_t)I * NB + 4 * v_q, true);
-      } else {
-        const float* asrc = e_on ? src + NB * NB + 4 * lane : vec + (size_t)I * NB + 4 * v_q;
-        float* adst = e_on ? &s->E[4 * lane] : &s->vec[4 * v_q];
-        if (e_on || v_on) cp_async16(adst, asrc, true);
-      }
+      for (int j = 0; j < RCH; ++j) cp_async16(dst + 128 * j, src + 128 * j, true);
+      if (v_on) cp_async16(&s->vec[4 * lane], vec + (size_t)I * NB + 4 * lane, true);
     }
     cp_async_commit();
   };
@@ -818,8 +805,6 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
   static_assert(D >= 3, "coarse ring too shallow for two fronts");
   constexpr int LPR = 32 / NB;                                   // lanes per row
   constexpr int CP = NB / LPR;                                   // columns of W per lane
-  constexpr int WCH = NB * NB / 4;                               // 16-byte chunks of W_I
-  constexpr int KW = (WCH + 31) / 32;                            // ... per lane
   const int nby = g.nby, M = g.tw, nB = nby - 1 - M;             // M rows above the meeting row, nB below (M - 1 or M)
   Slot* ringT = reinterpret_cast<Slot*>(ringmem);
   Slot* ringB = ringT + D;
@@ -828,28 +813,20 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
   const int row = lane & (NB - 1), c0 = (lane / NB) * CP;
   const bool owner = lane < NB;
   const unsigned full = 0xffffffffu;
-  const bool w_on = (WCH >= 32) || lane < WCH;
-  const int wr = lane / (NB / 4), wq = lane - wr * (NB / 4);
-  const int w_s = wr * (NB + 4) + 4 * wq;
-  const bool e_on = lane < NB;
-  const bool v_on = (NB == 32) ? lane < 8 : (lane >= NB && lane < NB + NB / 4);
-  const int v_q = (NB == 32) ? lane : lane - NB;
+  constexpr int RCH = (NB * (NB + 4) + 4 * NB) / 128;            // 16-byte chunks of a record per lane: 1, 3 or 10
+  static_assert((NB * (NB + 4) + 4 * NB) % 128 == 0, "a record is a whole number of 512-byte warp copies");
+  const bool v_on = lane < NB / 4;                               // the vector: NB / 4 chunks
+  const size_t rstep = (size_t)g.rec;
 
-  auto stage = [&](Slot* ring, int k, int I, const float* vec) {   // block row I into slot k % D (no commit)
+  // block row I into slot k % D of a ring (no commit).  A record is the image of Slot::W and Slot::E: straight copies.
+  auto stage = [&](Slot* ring, int k, int I, const float* vec) {
     if (I < 0 || I >= nby) return;
     Slot* s = ring + (k % D);
-    const float* src = rec + (size_t)I * g.rec;
+    const float* src = rec + (size_t)I * rstep + 4 * lane;
+    float* dst = s->W + 4 * lane;
 #pragma unroll
-    for (int j = 0; j < KW; ++j)
-      if (w_on) cp_async16(&s->W[w_s + j * (128 / NB) * (NB + 4)], src + 4 * lane + 128 * j, true);
-    if constexpr (NB == 32) {
-      cp_async16(&s->E[4 * lane], src + NB * NB + 4 * lane, true);
-      if (v_on) cp_async16(&s->vec[4 * v_q], vec + (size_t)I * NB + 4 * v_q, true);
-    } else {
-      const float* asrc = e_on ? src + NB * NB + 4 * lane : vec + (size_t)I * NB + 4 * v_q;
-      float* adst = e_on ? &s->E[4 * lane] : &s->vec[4 * v_q];
-      if (e_on || v_on) cp_async16(adst, asrc, true);
-    }
+    for (int j = 0; j < RCH; ++j) cp_async16(dst + 128 * j, src + 128 * j, true);
+    if (v_on) cp_async16(&s->vec[4 * lane], vec + (size_t)I * NB + 4 * lane, true);
   };
   auto matvec = [&](const Slot* s, const float* v) {             // (W_I v)[row], complete in every lane
     float acc[4] = {0.f, 0.f, 0.f, 0.f};

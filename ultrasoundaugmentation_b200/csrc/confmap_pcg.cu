@@ -82,7 +82,9 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.mm1 = cv.take<float>((size_t)B * kChunks * 2);
   L.mm2 = cv.take<float>((size_t)B * kChunks * 2);
   L.wS = cv.take<float>(N); L.wE = cv.take<float>(N); L.wSE = cv.take<float>(N); L.wSW = cv.take<float>(N);
-  L.ip = cv.take<float>(N); L.c = cv.take<float>(N); L.ipc = cv.take<uint32_t>(N);
+  // fp32 line factors: read by the generic kernel only (the fused kernel reads the packed bf16 plane ipc)
+  L.ip = cv.take<float>(L.fused ? 0 : N); L.c = cv.take<float>(L.fused ? 0 : N); L.ipc = cv.take<uint32_t>(N);
+  if (L.fused) { L.ip = nullptr; L.c = nullptr; }
   L.aplane = cv.take<float>(N); L.wk = cv.take<float4>(B);
   const size_t nmir = (L.tw_m && !L.recomp) ? N : 0;
   L.wS2 = cv.take<float>(nmir); L.wSE2 = cv.take<float>(nmir); L.wSW2 = cv.take<float>(nmir);

@@ -184,9 +184,12 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
     }
     x64[base + x] = 1.0;
     x64[base + (size_t)(H - 1) * W + x] = 0.0;
-    ip[base + x] = 0.f; c[base + x] = 0.f; ipc[base + x] = 0u;
-    ip[base + (size_t)(H - 1) * W + x] = 0.f; c[base + (size_t)(H - 1) * W + x] = 0.f;
+    ipc[base + x] = 0u;
     ipc[base + (size_t)(H - 1) * W + x] = 0u;
+    if (ip != nullptr) {          // (fp32 factor planes: generic kernel only)
+      ip[base + x] = 0.f; c[base + x] = 0.f;
+      ip[base + (size_t)(H - 1) * W + x] = 0.f; c[base + (size_t)(H - 1) * W + x] = 0.f;
+    }
     double ip_prev = 0.0;   // row 0 is a seed: not part of T
     double ip_up = 0.0;     // twisted factorisation: 1 / piv[m-1] of the downward front
     float s_prev = S[x];
@@ -203,8 +206,7 @@ __global__ void __launch_bounds__(128) cm_factor_kernel(
       const double ipv = sk ? 0.0 : 1.0 / piv;
       const float ipf = (float)ipv;
       const float cf = (precond == USAUG_PRECOND_LINE && y < H - 2) ? (float)((double)sc * ipv) : 0.0f;
-      ip[base + o] = ipf;
-      c[base + o] = cf;
+      if (ip != nullptr) { ip[base + o] = ipf; c[base + o] = cf; }
       // fused kernel: both factors as bf16 in one word (low = ip, high = c).  M = L D L^T stays SPD for
       // any positive ip and any c, and the iteration count is unchanged.
       if (tw_m == 0 || y < tw_m) ipc[base + o] = sk ? 0u : (bf16_bits(ipf) | (bf16_bits(cf) << 16));
