@@ -119,10 +119,24 @@ struct UpAux {
       if (pl != nullptr && e >= 0 && e < W4) { on = true; base = pl + base4 + e; stride = rs4; }
     }
   }
-  // source of this lane's chunk for view row yv (only meaningful for an interior row)
-  __device__ __forceinline__ const float* src(int yv) const {
+  // Source of this lane's halo-slot chunk, row by row (the sweeps stage rows y0, y0 - 1, ...): `cur` runs down the lane's
+  // plane for every role that is linear in the view row (strip halo columns and level planes; plain = source of a lane
+  // without an auxiliary role); the coarse lanes take aggregate row ((y - 1) >> sh) of zc.  Branch-free: as a two-way
+  // branch on the lane's role this was ~30 instructions per row executed by every warp of an F_UP task.
+  const float* cur;
+  ptrdiff_t cstep;
+  __device__ __forceinline__ void start(const float* plain, ptrdiff_t plain_step, int y0) {
+    const float* b0 = on ? base : plain;
+    cstep = on ? stride : plain_step;
+    cur = isz ? base : b0 + (ptrdiff_t)y0 * cstep;
+    if (isz) cstep = 0;
+  }
+  __device__ __forceinline__ const float* next(int yv, bool interior) {
     const int y = flip ? H - 1 - yv : yv;
-    return base + (isz ? (ptrdiff_t)(((y - 1) >> sh) * nb) : (ptrdiff_t)yv * stride);
+    const int zo = interior ? ((y - 1) >> sh) * nb : 0;          // (only read by the coarse lanes)
+    const float* r = isz ? base + zo : cur;
+    cur -= cstep;
+    return r;
   }
   // additive terms of view row y for the lane's own columns and for its halo column: P zc + level correction
   __device__ __forceinline__ void at_row(const float4* halo, int lane, float& add, float& addh) {
@@ -216,7 +230,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
     cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
     cp_async16(&r->a[lane], Ap + o + xs, in && valid);
-    cp_async16(&r->halo[lane], ax.on ? ax.src(interior ? y : 1) : hsrc + o + hxs, (in && h_in_only) || (interior && h_interior));
+    cp_async16(&r->halo[lane], ax.next(y, interior), (in && h_in_only) || (interior && h_interior));
     cp_async_commit();
     o_i -= rs;
   };
@@ -230,6 +244,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   wc.eL = wc.seL = wc.swR = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
 
+  ax.start(hsrc + hxs, rs, ys);
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(ys - u);
   twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
@@ -405,7 +420,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
     cp_async16(&r->e[lane], E + o + xs, interior && valid);
     cp_async16(&r->se[lane], SE + o + xs, in && valid);
     cp_async16(&r->sw[lane], SW + o + xs, in && valid);
-    cp_async16(&r->halo[lane], ax.on ? ax.src(interior ? y : 1) : hsrc + o + hxs, (in && h_in_only) || (interior && h_interior));
+    cp_async16(&r->halo[lane], ax.next(y, interior), (in && h_in_only) || (interior && h_interior));
     cp_async_commit();
     o_i -= rs;
   };
@@ -418,6 +433,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
 
+  ax.start(hsrc + hxs, rs, y1);
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(y1 - u);
   twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
