@@ -339,11 +339,10 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
         q[j] = t;
         dot = fmaf(pcj, t, dot);
       }
-      if (valid && yc >= 1 && yc <= yown) {
-        USAUG_DEV_ASSERT(o_c + (ptrdiff_t)(G + 1 - g) * rs == (ptrdiff_t)yc * rs + x && yc <= H - 2);
-        *reinterpret_cast<float4*>(Q + o_c + (ptrdiff_t)(G + 1 - g) * rs) = make_float4(q[0], q[1], q[2], q[3]);
-        acc += (double)dot;
-      }
+      const bool stq = valid && yc >= 1 && yc <= yown;
+      USAUG_DEV_ASSERT(!stq || (o_c + (ptrdiff_t)(G + 1 - g) * rs == (ptrdiff_t)yc * rs + x && yc <= H - 2));
+      if (stq) *reinterpret_cast<float4*>(Q + o_c + (ptrdiff_t)(G + 1 - g) * rs) = make_float4(q[0], q[1], q[2], q[3]);
+      acc += (double)(stq ? dot : 0.f);          // (predicated store, unconditional add: no branch between the rows of a pair)
     }
 #pragma unroll
     for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[g][j]; ab[j] = au[g][j]; }
@@ -519,11 +518,10 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
         q[j] = t;
         dot = fmaf(pcj, t, dot);
       }
-      if (valid && yc >= 1 && yc <= yown) {
-        USAUG_DEV_ASSERT(o_c + (ptrdiff_t)(G + 1 - g) * rs == (ptrdiff_t)yc * rs + x && yc <= H - 2);
-        *reinterpret_cast<float4*>(Q + o_c + (ptrdiff_t)(G + 1 - g) * rs) = make_float4(q[0], q[1], q[2], q[3]);
-        acc += (double)dot;
-      }
+      const bool stq = valid && yc >= 1 && yc <= yown;
+      USAUG_DEV_ASSERT(!stq || (o_c + (ptrdiff_t)(G + 1 - g) * rs == (ptrdiff_t)yc * rs + x && yc <= H - 2));
+      if (stq) *reinterpret_cast<float4*>(Q + o_c + (ptrdiff_t)(G + 1 - g) * rs) = make_float4(q[0], q[1], q[2], q[3]);
+      acc += (double)(stq ? dot : 0.f);          // (predicated store, unconditional add: no branch between the rows of a pair)
     }
 #pragma unroll
     for (int j = 0; j < 6; ++j) { pl[j] = pc[j]; pc[j] = pu[g][j]; }
@@ -607,6 +605,15 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   float racc = 0.f;
   double rr = 0.0, rz = 0.0;
   ptrdiff_t o_c = rs + x, o4_c = rs4;              // offsets of the row being consumed
+  // restriction: rows until the first flush, destination of that flush, and whether this lane stores
+  //   upper half / untwisted: image rows 1, 2, ...: an aggregate row ends where (ya & (by - 1)) == 0 (and at row H - 2)
+  //   lower half (flipped):   image rows H-2, H-3, ...: an aggregate row ends where ((ya - 1) & (by - 1)) == 0
+  const int by = a.cg.by ? a.cg.by : 1;
+  int agc = hv.flip ? (((H - 2) - 1) & (by - 1)) + 1 : by;
+  const int ya0 = hv.flip ? H - 2 : 1;
+  const bool rc_st = a.cg.by != 0 && valid && (lane & ((1 << (a.cg.bx_shift - 2)) - 1)) == 0;
+  float* rcp = a.rc + (a.cg.by ? (size_t)b * a.cg.nc + (size_t)((ya0 - 1) >> a.cg.by_shift) * a.cg.nb + (size_t)(x >> a.cg.bx_shift) : 0);
+  const ptrdiff_t rc_step = a.cg.by ? (hv.flip ? -(ptrdiff_t)a.cg.nb : (ptrdiff_t)a.cg.nb) : 0;
   // One row.  Only the one-FMA recurrences (h, h4) tie a row to its predecessor; G rows are consumed per wait so that the
   // loads, updates and stores of neighbouring rows overlap in the instruction stream of the (single) warp of a task.
   auto row = [&](int y) {
@@ -649,21 +656,21 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
     }
     rr += (double)srr;
     rz += (double)((y != ymid) ? srz : 0.f);
-    if (a.cg.by) {                               // restriction rc = P^T r: sum of the new residual over each aggregate
-      racc += r4;
-      const int ya = hv.flip ? H - 1 - y : y;    // image row
-      // the last row of an aggregate row in the order of travel
-      if (y <= ylast && (hv.flip ? (((ya - 1) & (a.cg.by - 1)) == 0) : ((ya & (a.cg.by - 1)) == 0 || ya == H - 2))) {
-        float v = racc;                                      // 4 ... 32 lanes share one aggregate column
-        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (a.cg.bx_shift >= 5) v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if (a.cg.bx_shift >= 6) v += __shfl_xor_sync(0xffffffffu, v, 8);
-        if (a.cg.bx_shift == 7) v += __shfl_xor_sync(0xffffffffu, v, 16);
-        USAUG_DEV_ASSERT(((ya - 1) >> a.cg.by_shift) < a.cg.nby && (!valid || (x >> a.cg.bx_shift) < a.cg.nb));
-        if ((lane & ((1 << (a.cg.bx_shift - 2)) - 1)) == 0 && valid)
-          a.rc[(size_t)b * a.cg.nc + (size_t)((ya - 1) >> a.cg.by_shift) * a.cg.nb + (x >> a.cg.bx_shift)] = v;
-        racc = 0.f;
-      }
+    // restriction rc = P^T r: sum of the new residual over each aggregate, flushed at the last row of an aggregate row in
+    // the order of travel (a countdown and a running destination: the test and the address were ~20 instructions per row)
+    racc += r4;
+    agc -= (y <= ylast) ? 1 : 0;                   // (the zero-filled row past the end of an odd sweep does not count)
+    if (agc == 0) {
+      float v = racc;                                        // 4 ... 32 lanes share one aggregate column
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+      const float t4 = __shfl_xor_sync(0xffffffffu, v, 4); v += (a.cg.bx_shift >= 5) ? t4 : 0.f;
+      const float t8 = __shfl_xor_sync(0xffffffffu, v, 8); v += (a.cg.bx_shift >= 6) ? t8 : 0.f;
+      const float t16 = __shfl_xor_sync(0xffffffffu, v, 16); v += (a.cg.bx_shift == 7) ? t16 : 0.f;
+      USAUG_DEV_ASSERT(!rc_st || (rcp >= a.rc + (size_t)b * a.cg.nc && rcp < a.rc + (size_t)(b + 1) * a.cg.nc));
+      if (rc_st) *rcp = v;
+      rcp += rc_step;
+      racc = 0.f;
+      agc = a.cg.by;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) hp[j] = h[j];
@@ -678,6 +685,14 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
     for (int g = 0; g < G; ++g) row(y + g);
 #pragma unroll
     for (int g = 0; g < G; ++g) issue(y + g + RD);
+  }
+  if (agc != by) {                                   // a partial aggregate row at the end of the sweep (image row H - 2, or row m)
+    float v = racc;
+    v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+    const float t4 = __shfl_xor_sync(0xffffffffu, v, 4); v += (a.cg.bx_shift >= 5) ? t4 : 0.f;
+    const float t8 = __shfl_xor_sync(0xffffffffu, v, 8); v += (a.cg.bx_shift >= 6) ? t8 : 0.f;
+    const float t16 = __shfl_xor_sync(0xffffffffu, v, 16); v += (a.cg.bx_shift == 7) ? t16 : 0.f;
+    if (rc_st) *rcp = v;
   }
   cp_async_wait<0>();
   rr_out = warp_sum(rr); rz_out = warp_sum(rz);
