@@ -1036,8 +1036,10 @@ __device__ __forceinline__ void q_give_up(const PcgArgs<float>& a) {
 // Whole warp.  Returns the payload of the next task, or kNoTask when every image is finished.
 // ALL lanes execute the polling loads (a warp with 31 lanes parked at a convergence barrier while one lane
 // spins was measured to slow the other warps of the SM ~4x); lane 0's values are broadcast and lane 0 claims.
-__device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {
-  unsigned ns = 32;
+// sleep_max: longest back-off of an idle worker between polls (latency-bound launches poll eagerly: every hand-off of an
+// image's phase to the next sits on its critical path, and their idle workers have nothing else to do)
+__device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane, unsigned sleep_max) {
+  unsigned ns = 32, polls = 0;
   unsigned long long t_idle = 0, last_claimed = 0;
   for (;;) {
     int av0, av1;
@@ -1066,7 +1068,8 @@ __device__ __forceinline__ unsigned q_pop(const PcgArgs<float>& a, int lane) {
     }
     if (__ldcg(a.done) >= (unsigned)a.B) return kNoTask;
     __nanosleep(ns);
-    if (ns < kIdleSleepMaxNs) { ns *= 2; continue; }
+    if (ns < sleep_max) { ns *= 2; continue; }
+    if ((++polls & 63u) != 0u) continue;                     // (the watchdog's own loads would halve the polling rate)
     // watchdog: a scheduling bug must not hang the device.  It watches GLOBAL progress (tasks claimed by anybody),
     // not this worker's own luck: with one slowly converging image left, a worker can lose the race for its few
     // tasks for a long time while the solve is perfectly healthy.
@@ -1218,7 +1221,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
   unsigned n_mode[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (;;) {
     const unsigned long long tq0 = a.debug ? now() : 0ull;
-    const unsigned payload = q_pop(a, lane);
+    const unsigned payload = q_pop(a, lane, RECOMP ? kIdleSleepMaxNs : 128u);
     const unsigned long long tq1 = a.debug ? now() : 0ull;
     t_wait += tq1 - tq0;
     if (payload == kNoTask) break;

@@ -56,7 +56,13 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   const bool many = tasks >= 12ll * sms;
   const bool fine = (flags & USAUG_CM_COARSE_FINE) ? true : (flags & USAUG_CM_COARSE_STANDARD) ? false : many;
   int min_shift = fine ? 1 : 2, min_bx_shift = 5;
-  if (const char* e = getenv("USAUG_CM_COARSE_SHIFT")) min_shift = atoi(e);          // development knob
+  // Latency-bound launches of wide images: 64-column aggregates keep the blocks of the coarse operator at 16 x 16 -- the
+  // single-warp solve is on every image's critical path there, and a 32 x 32 block row costs 2.6x a 16 x 16 one
+  // (32 images of 1024 x 1024: solve 219 -> 84 us, 444 -> 462 iterations, 138 -> 160 img/s).  Bandwidth-bound launches keep
+  // the finer grid: their solves overlap with other images' sweeps, and iterations are what they pay for.
+  if (!L.recomp && W > 512 && W <= 1024) min_bx_shift = 6;
+  if (const char* e = getenv("USAUG_CM_COARSE_SHIFT")) min_shift = atoi(e);          // development knobs
+  if (const char* e = getenv("USAUG_CM_COARSE_BXSHIFT")) min_bx_shift = atoi(e);
   L.cg = (!L.fused || (flags & USAUG_CM_NO_COARSE)) ? CoarseGeom{} : coarse_geom(H, W, min_shift, min_bx_shift);
   // Twisted block factorisation of the coarse operator (two fronts per solve, advanced by one warp): everywhere except
   // for 32 x 32 blocks in the 8-warp kernel, whose rings are too shallow for two fronts
