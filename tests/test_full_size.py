@@ -64,12 +64,13 @@ def test_config4_full_chain_32x1024(cuda_device):
 
 def test_config5_benchmarked_solver_variant_512(cuda_device):
     """configs[4] as bench.py runs it (512 images of 512x512 per launch) selects the weight-recomputing kernel, 2-row
-    aggregates and the plain (untwisted) line factorisation.  Pinned by flags, that exact variant meets the oracle
-    here on two 512x512 images; so do the variants small launches pick."""
+    aggregates and the twisted line factorisation.  Pinned by flags, that exact variant meets the oracle
+    here on two 512x512 images; so do the variant small launches pick (weight planes read) and the other combinations."""
     from ultrasoundaugmentation_b200 import ops, synth
     img, _ = synth.make_batch(2, 512, 512, seed=2021, device=cuda_device)
     ref = ocm.confidence_map_batch(img.cpu().numpy())
-    for kw in (dict(up_variant="recompute", coarse="fine", twist=False), dict(up_variant="planes", coarse="standard", twist=True)):
+    for kw in (dict(up_variant="recompute", coarse="fine", twist=True), dict(up_variant="planes", coarse="fine", twist=True),
+               dict(up_variant="recompute", coarse="fine", twist=False), dict(up_variant="planes", coarse="standard", twist=True)):
         cm, it, rr = ops.confidence_map(img, rtol=1e-8, return_info=True, **kw)
         torch.cuda.synchronize()
         assert (rr <= 1e-8).all(), kw

@@ -261,21 +261,30 @@ def test_cm_sink_argument_errors(cuda_device):
         ops.confidence_map(img, sink="bottom_row", sink_mask=torch.zeros((1, 32, 32), dtype=torch.uint8, device=cuda_device))
 
 
-def test_cm_sharding_across_a_variant_threshold(cuda_device):
-    """Sharding a batch can move a launch into another solver class (cm_layout picks aggregates / twist / weight handling
-    from the number of strip tasks): 1800 tiny images in one launch use 2-row aggregates, the same images as two launches
-    of 900 use 4-row aggregates and the twisted factorisation.  Same systems, same stopping rule: the maps agree within the
-    confidence-map tolerance (not bitwise), and pinning the variant makes the shards bitwise equal to the whole."""
-    B, H, W = 1800, 40, 128
-    img = np.stack([util.synth_batch(1, H, W, seed0=5000 + (b % 61))[0][0] for b in range(61)])
-    img = np.concatenate([img] * (B // 61 + 1))[:B]
+def test_cm_sharding_and_solver_variants(cuda_device):
+    """What sharding a batch can change.  The library picks the solver variant from the size of a launch (cm_layout):
+    * F_UP reads the weight planes (few strip tasks) or recomputes the weights (many): the same device function produces
+      the weights either way, so the two are BITWISE equal -- 1000 tiny images in one launch == two launches of 500;
+    * images taller than 514 rows use 2-row aggregates only in deeply bandwidth-bound launches: 1800 images of 600 x 128 in
+      one launch vs two launches of 900 differ in the preconditioner, i.e. in the low bits -- same systems, same stopping
+      rule, so they agree within the confidence-map tolerance, and pinning the variant makes them bitwise equal again."""
+    def batch(B, H, W):
+        img = np.stack([util.synth_batch(1, H, W, seed0=5000 + (b % 61))[0][0] for b in range(61)])
+        return np.concatenate([img] * (B // 61 + 1))[:B]
+    img = batch(1000, 40, 128)
+    whole, itw, rrw = gpu_cm(cuda_device, img, rtol=RTOL)
+    parts = np.concatenate([gpu_cm(cuda_device, img[lo:lo + 500], rtol=RTOL)[0] for lo in (0, 500)])
+    assert (rrw <= RTOL).all() and np.array_equal(whole, parts)
+    a, _, _ = gpu_cm(cuda_device, img[:64], rtol=RTOL, up_variant="planes")
+    b, _, _ = gpu_cm(cuda_device, img[:64], rtol=RTOL, up_variant="recompute")
+    assert np.array_equal(a, b) and np.array_equal(a, whole[:64])
+
+    img = batch(1800, 600, 128)
     whole, itw, rrw = gpu_cm(cuda_device, img, rtol=RTOL)
     halves = [gpu_cm(cuda_device, img[lo:lo + 900], rtol=RTOL) for lo in (0, 900)]
     parts = np.concatenate([h[0] for h in halves])
     assert (rrw <= RTOL).all() and all((h[2] <= RTOL).all() for h in halves)
     assert not np.array_equal(itw, np.concatenate([h[1] for h in halves]))      # another preconditioner: other iteration counts
     assert np.abs(whole - parts).max() <= 2 * util.tol_cm(RTOL)
-    kw = dict(coarse="standard", twist=False, up_variant="recompute")
-    whole_p, _, _ = gpu_cm(cuda_device, img, rtol=RTOL, **kw)
-    parts_p = np.concatenate([gpu_cm(cuda_device, img[lo:lo + 900], rtol=RTOL, **kw)[0] for lo in (0, 900)])
-    assert np.array_equal(whole_p, parts_p)
+    parts_p = np.concatenate([gpu_cm(cuda_device, img[lo:lo + 900], rtol=RTOL, coarse="fine")[0] for lo in (0, 900)])
+    assert np.array_equal(whole, parts_p)

@@ -53,8 +53,12 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   // few tasks: the single-warp instruction latency of a strip sets the pace, so F_UP reads the weight planes
   // (fewer instructions per row); many tasks: HBM sets the pace, so it recomputes them (fewer bytes)
   L.recomp = (flags & USAUG_CM_FORCE_RECOMPUTE) ? true : (flags & USAUG_CM_FORCE_PLANES) ? false : tasks >= 6ll * sms;
+  // Aggregates of 2 rows instead of 4: ~16 % fewer iterations for a coarse solve twice as long.  Since the solve takes
+  // 40 us per 128 aggregate rows (round 2) that pays at every batch size while the image has <= 256 aggregate rows of 2
+  // (profiles/r3g_solver_variants_by_batch.log: +7 % at 64 images of 512 x 512, +12 % at 128 ... 384); taller images keep 4-row
+  // aggregates unless the launch is deeply bandwidth-bound, where the solves hide behind other images' sweeps.
   const bool many = tasks >= 12ll * sms;
-  const bool fine = (flags & USAUG_CM_COARSE_FINE) ? true : (flags & USAUG_CM_COARSE_STANDARD) ? false : many;
+  const bool fine = (flags & USAUG_CM_COARSE_FINE) ? true : (flags & USAUG_CM_COARSE_STANDARD) ? false : (many || H - 2 <= 512);
   int min_shift = fine ? 1 : 2, min_bx_shift = 5;
   // Latency-bound launches of wide images: 64-column aggregates keep the blocks of the coarse operator at 16 x 16 -- the
   // single-warp solve is on every image's critical path there, and a 32 x 32 block row costs 2.6x a 16 x 16 one
@@ -68,9 +72,10 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   // for 32 x 32 blocks in the 8-warp kernel, whose rings are too shallow for two fronts
   if (L.cg.by && !(L.recomp && L.cg.nb == 32) && !getenv("USAUG_CM_COARSE_PLAIN")) L.cg.tw = L.cg.nby / 2;
   // Twisted line factorisation (two half sweeps per strip): halves the dependent UP -> DOWN chain of an image, which
-  // is what bounds launches that cannot fill the GPU; deeply bandwidth-bound launches gain nothing from it.
+  // is what bounds launches that cannot fill the GPU -- and with twice the tasks of half the length the ready queue also
+  // balances bandwidth-bound launches better (512 images of 512 x 512: 848 -> 916 img/s), so it is always on.
   L.tw_m = 0;
-  const bool twist = (flags & USAUG_CM_TWIST_ON) ? true : (flags & USAUG_CM_TWIST_OFF) ? false : !many;
+  const bool twist = (flags & USAUG_CM_TWIST_OFF) ? false : true;
   if (L.fused && twist && H - 2 >= 32) {
     const int by = L.cg.by ? L.cg.by : 1;
     const int m = ((H - 1) / 2) & ~(by - 1);                    // on an aggregate-row boundary: rows 1..m | m+1..H-2
