@@ -241,7 +241,7 @@ def test_cm_sink_256_iterations_and_plain_equivalence(cuda_device):
     cm, it, rr = gpu_cm(cuda_device, img, rtol=RTOL, sink="mask", sink_mask=dmask)
     assert (rr <= RTOL).all() and np.abs(cm - ref).max() <= util.tol_cm(RTOL)
     _, it_line, _ = gpu_cm(cuda_device, img, rtol=RTOL, sink="mask", sink_mask=dmask, coarse=False, level=False)
-    assert it.max() <= 0.8 * it_line.max(), (it, it_line)
+    assert it.max() <= 0.85 * it_line.max(), (it, it_line)
     plain, itp, _ = gpu_cm(cuda_device, img, rtol=RTOL)
     zero, itz, _ = gpu_cm(cuda_device, img, rtol=RTOL, sink="mask", sink_mask=torch.zeros_like(dmask))
     assert np.array_equal(plain, zero) and np.array_equal(itp, itz)

@@ -27,8 +27,9 @@ namespace usaug {
 // =============================================================================================
 enum FMode : int { F_RESID = 0, F_PRECOND = 1, F_UP = 2, F_DOWN = 3, F_FOLD = 4, F_FINAL = 5, F_DONE = 6, F_COARSE = 7 };
 
-struct RingU {   // one staged row of a 128-column strip for F_UP (2560 bytes)
-  float4 h[32], p[32], a[32];
+struct RingU {   // one staged row of a 128-column strip for F_UP (2304 bytes)
+  uint2 hq[32];    // h as bf16: 4 columns per lane (copied 16 bytes at a time by the even lanes)
+  float4 p[32], a[32];
   uint4 ipc[32];
   // 16-byte chunks that contain the strip's halo columns (cp.async.cg = L2, never a stale L1 line):
   // [0..3] columns x0-4..x0-1 of h, ipc, p, a (.w is the left neighbour column);
@@ -45,8 +46,23 @@ constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
 
 __device__ __forceinline__ float hsel(const float4& v, int lane) { return lane == 31 ? v.x : v.w; }
 
-struct RingUP {   // one staged row of a 128-column strip for F_UP, weight planes read from memory (4096 bytes)
-  float4 h[32], p[32], s[32], e[32], se[32], sw[32];
+// The h plane of the fused kernel (h = L^-1 r, written by F_DOWN, read by the next F_UP) is stored as bf16 in the z
+// allocation, row pitch = W rounded up to 8 elements (16-byte copies): 4 of the ~60 bytes an unknown costs per iteration.
+// h only feeds the preconditioner z = L^-T D^-1 h; F_DOWN forms r.z = sum ip h h~ with the rounded h~ that F_UP will see,
+// so the pair (z, r.z) stays consistent, and the recurrences themselves run in fp32.
+__device__ __forceinline__ int h_pitch(int W) { return (W + 7) & ~7; }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {      // round to nearest even, one instruction
+  uint32_t w;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+  return w;
+}
+__device__ __forceinline__ float hq_halo(const float4& v, int lane) {      // column x0-1 of a left chunk / x0+128 of a right one
+  return lane == 31 ? bf16_lo(__float_as_uint(v.x)) : bf16_hi(__float_as_uint(v.w));
+}
+
+struct RingUP {   // one staged row of a 128-column strip for F_UP, weight planes read from memory (3840 bytes)
+  uint2 hq[32];    // h as bf16: 4 columns per lane (copied 16 bytes at a time by the even lanes)
+  float4 p[32], s[32], e[32], se[32], sw[32];
   uint4 ipc[32];
   // 16-byte chunks that contain the strip's halo columns (cp.async.cg = L2, never a stale L1 line):
   // [0..4] columns x0-4..x0-1 of h, ipc, p, wE, wSE (.w is the left neighbour column);
@@ -164,10 +180,10 @@ struct WRow {
 // Twisted factorisation, upper half: its F_UP sweep starts one row beyond row m (the first row of the lower half,
 // which the stencil of row m needs), and that row's recurrence runs the other way: z[m+1] = c[m+1] z[m] + ip[m+1] h[m+1].
 // z[m] = ip[m] h[m] has no recurrence term, so it is formed directly here and seeds the sweep.
-__device__ __forceinline__ void twist_seed(const PcgArgs<float>& a, const HalfView& hv, const float* Hb, const uint32_t* IPC,
+__device__ __forceinline__ void twist_seed(const PcgArgs<float>& a, const HalfView& hv, const uint16_t* HQ, const uint32_t* IPC,
                                            int b, int x, int x0, int lane, bool valid, float (&zn)[4], float& zhn, UpAux& ax) {
   if (a.tw_m == 0 || hv.flip) return;
-  const size_t o = (size_t)a.tw_m * a.W;
+  const size_t o = (size_t)a.tw_m * a.W, oh = (size_t)a.tw_m * h_pitch(a.W);
   if (a.h4 != nullptr) {                                          // the level preconditioner's recurrences, same seed
     const size_t o4 = ((size_t)b * a.H + a.tw_m) * a.w4p;
     const int X = x >> 2, Xh = ((lane == 0) ? x0 - 1 : x0 + kStrip4) >> 2;
@@ -175,12 +191,13 @@ __device__ __forceinline__ void twist_seed(const PcgArgs<float>& a, const HalfVi
     if ((lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < a.W)) ax.z4hn = bf16_lo(__ldcg(a.ipc4 + o4 + Xh)) * __ldcg(a.h4 + o4 + Xh);
   }
   if (valid) {
-    const float4 h = __ldcg(reinterpret_cast<const float4*>(Hb + o + x));
+    const uint2 hw = __ldcg(reinterpret_cast<const uint2*>(HQ + oh + x));
     const uint4 f = __ldcg(reinterpret_cast<const uint4*>(IPC + o + x));
-    zn[0] = bf16_lo(f.x) * h.x; zn[1] = bf16_lo(f.y) * h.y; zn[2] = bf16_lo(f.z) * h.z; zn[3] = bf16_lo(f.w) * h.w;
+    zn[0] = bf16_lo(f.x) * bf16_lo(hw.x); zn[1] = bf16_lo(f.y) * bf16_hi(hw.x);
+    zn[2] = bf16_lo(f.z) * bf16_lo(hw.y); zn[3] = bf16_lo(f.w) * bf16_hi(hw.y);
   }
   const int hx = (lane == 0) ? x0 - 1 : x0 + kStrip4;
-  if ((lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < a.W)) zhn = bf16_lo(__ldcg(IPC + o + hx)) * __ldcg(Hb + o + hx);
+  if ((lane == 0 && x0 > 0) || (lane == 31 && x0 + kStrip4 < a.W)) zhn = bf16_lo(__ldcg(IPC + o + hx)) * __uint_as_float((uint32_t)__ldcg(HQ + oh + hx) << 16);
 }
 
 template <int R, bool SINK>
@@ -201,7 +218,9 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   const float4 wk = a.wk[b];
   // reads: h (z plane), p_old (pin); writes: p_new (pout), q.  Nothing is updated in place, because the
   // halo columns of this strip belong to a neighbouring strip whose warp runs asynchronously.
-  const float* __restrict__ Hb = a.z + base;
+  const int hp = h_pitch(W);                                       // bf16 h plane: its own row pitch and stride
+  const ptrdiff_t rsh = hv.flip ? -(ptrdiff_t)hp : (ptrdiff_t)hp;
+  const uint16_t* __restrict__ HQ = reinterpret_cast<const uint16_t*>(a.z) + (size_t)b * H * hp + (hv.flip ? (size_t)(H - 1) * hp : 0);
   const float* __restrict__ Pin = (pcur ? a.p2 : a.p) + base;
   float* __restrict__ P = (pcur ? a.p : a.p2) + base;
   float* __restrict__ Q = a.q + base;
@@ -211,8 +230,10 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   const int hx = isL ? x0 - 4 : x0 + kStrip4;
   const bool hcol = isL ? (x0 > 0) : (x0 + kStrip4 < W);
   const bool hrole = hcol && k <= 3;
-  const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin : Ap;
-  const int hxs = hrole ? hx : 0;
+  // (k == 0: the h halo chunk holds 8 bf16 columns, x0-8 .. x0-1 or x0+128 .. x0+135, and steps by the bf16 pitch)
+  const float* hsrc = (k == 0) ? reinterpret_cast<const float*>(HQ + (hrole ? (isL ? x0 - 8 : x0 + kStrip4) : 0))
+                      : ((k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin : Ap) + (hrole ? hx : 0);
+  const ptrdiff_t hstep = (k == 0) ? rsh / 2 : rs;
   UpAux ax;
   ax.init(a, hv, b, x, x0, lane, W);
   const bool h_in_only = hrole && k == 3;         // the a plane is also needed from the seed rows
@@ -220,13 +241,15 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
 
   int slot_i = 0;                                 // ring slot of the next row to stage
   ptrdiff_t o_i = (ptrdiff_t)ys * rs;             // element offset of that row (running: no 64-bit multiply per row)
+  ptrdiff_t oh_i = (ptrdiff_t)ys * rsh;           // ... and in the bf16 h plane
   auto issue = [&](int y) {                       // stage view row y (rows are visited ys .. 0)
     RingU* r = ring + slot_i;
     slot_i = (slot_i + 1 == R) ? 0 : slot_i + 1;
     const bool in = y >= 0;
     const bool interior = y >= 1 && y <= H - 2;
     const ptrdiff_t o = in ? o_i : (ptrdiff_t)0;
-    cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
+    if (!(lane & 1)) cp_async16(&r->hq[lane], HQ + (in ? oh_i : (ptrdiff_t)0) + xs, interior && valid);   // 8 columns: this lane's and the next one's
+    oh_i -= rsh;
     cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
     cp_async16(&r->a[lane], Ap + o + xs, in && valid);
@@ -244,10 +267,10 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   wc.eL = wc.seL = wc.swR = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
 
-  ax.start(hsrc + hxs, rs, ys);
+  ax.start(hsrc, hstep, ys);
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(ys - u);
-  twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
+  twist_seed(a, hv, HQ, IPC, b, x, x0, lane, valid, zn, zhn, ax);
   double acc = 0.0;
   unsigned mc = 15u;                              // sink mask of row c: bit j set = column j is an unknown
   int slot_c = 0;                                 // ring slot of the row being consumed
@@ -262,10 +285,12 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   auto rowA = [&](int y, int g) {
     const RingU* r = ring + slot_c;
     slot_c = (slot_c + 1 == R) ? 0 : slot_c + 1;
-    const float4 h = r->h[lane], p = r->p[lane], av = r->a[lane];
+    const uint2 hw = r->hq[lane];
+    const float4 h = make_float4(bf16_lo(hw.x), bf16_hi(hw.x), bf16_lo(hw.y), bf16_hi(hw.y));
+    const float4 p = r->p[lane], av = r->a[lane];
     const uint4 f = r->ipc[lane];
     // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
-    const float hh = hsel(r->halo[hoff + 0], lane);
+    const float hh = hq_halo(r->halo[hoff + 0], lane);
     const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
     const float hp = hsel(r->halo[hoff + 2], lane);
     const float ha = hsel(r->halo[hoff + 3], lane);
@@ -385,7 +410,9 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   const uint32_t* __restrict__ IPC = a.ipc + base;
   // reads: h (z plane), p_old (pin); writes: p_new (pout), q.  Nothing is updated in place, because the
   // halo columns of this strip belong to a neighbouring strip whose warp runs asynchronously.
-  const float* __restrict__ Hb = a.z + base;
+  const int hp = h_pitch(W);                                       // bf16 h plane: its own row pitch and stride
+  const ptrdiff_t rsh = hv.flip ? -(ptrdiff_t)hp : (ptrdiff_t)hp;
+  const uint16_t* __restrict__ HQ = reinterpret_cast<const uint16_t*>(a.z) + (size_t)b * H * hp + (hv.flip ? (size_t)(H - 1) * hp : 0);
   const float* __restrict__ Pin = (pcur ? a.p2 : a.p) + base;
   float* __restrict__ P = (pcur ? a.p : a.p2) + base;
   float* __restrict__ Q = a.q + base;
@@ -395,9 +422,10 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   const int hx = isL ? x0 - 4 : x0 + kStrip4;
   const bool hcol = isL ? (x0 > 0) : (x0 + kStrip4 < W);
   const bool hrole = hcol && (k <= 3 || (k == 4 && isL));
-  const float* hsrc = (k == 0) ? Hb : (k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin
-                      : (k == 3) ? (isL ? E : SW) : SE;
-  const int hxs = hrole ? hx : 0;
+  // (k == 0: the h halo chunk holds 8 bf16 columns, x0-8 .. x0-1 or x0+128 .. x0+135, and steps by the bf16 pitch)
+  const float* hsrc = (k == 0) ? reinterpret_cast<const float*>(HQ + (hrole ? (isL ? x0 - 8 : x0 + kStrip4) : 0))
+                      : ((k == 1) ? reinterpret_cast<const float*>(IPC) : (k == 2) ? Pin : (k == 3) ? (isL ? E : SW) : SE) + (hrole ? hx : 0);
+  const ptrdiff_t hstep = (k == 0) ? rsh / 2 : rs;
   UpAux ax;
   ax.init(a, hv, b, x, x0, lane, W);
   const bool h_in_only = hrole && k >= 3;         // weights are also needed from the seed row 0
@@ -406,13 +434,15 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   const int y1 = ys < H - 2 ? ys : H - 2;         // first row of the sweep (the seed row H-1 carries nothing here)
   int slot_i = 0;                                 // ring slot of the next row to stage
   ptrdiff_t o_i = (ptrdiff_t)y1 * rs;             // element offset of that row (running: no 64-bit multiply per row)
+  ptrdiff_t oh_i = (ptrdiff_t)y1 * rsh;           // ... and in the bf16 h plane
   auto issue = [&](int y) {                       // stage view row y (rows are visited y1 .. 0)
     RingUP* r = ring + slot_i;
     slot_i = (slot_i + 1 == R) ? 0 : slot_i + 1;
     const bool in = y >= 0;
     const bool interior = y >= 1;
     const ptrdiff_t o = in ? o_i : (ptrdiff_t)0;
-    cp_async16(&r->h[lane], Hb + o + xs, interior && valid);
+    if (!(lane & 1)) cp_async16(&r->hq[lane], HQ + (in ? oh_i : (ptrdiff_t)0) + xs, interior && valid);   // 8 columns: this lane's and the next one's
+    oh_i -= rsh;
     cp_async16(&r->ipc[lane], IPC + o + xs, interior && valid);
     cp_async16(&r->p[lane], Pin + o + xs, interior && valid && !first);
     cp_async16(&r->s[lane], S + o + xs, in && valid);
@@ -432,10 +462,10 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   wc.s = wc.e = wc.se = wc.sw = zero4; wc.hw1 = wc.hw2 = 0.f;
   const int hoff = (lane == 31) ? 16 : 0;
 
-  ax.start(hsrc + hxs, rs, y1);
+  ax.start(hsrc, hstep, y1);
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(y1 - u);
-  twist_seed(a, hv, Hb, IPC, b, x, x0, lane, valid, zn, zhn, ax);
+  twist_seed(a, hv, HQ, IPC, b, x, x0, lane, valid, zn, zhn, ax);
   double acc = 0.0;
   unsigned mc = 15u;                              // sink mask of row c: bit j set = column j is an unknown
   int slot_c = 0;                                 // ring slot of the row being consumed
@@ -449,11 +479,13 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   auto rowA = [&](int y, int g) {
     const RingUP* r = ring + slot_c;
     slot_c = (slot_c + 1 == R) ? 0 : slot_c + 1;
-    const float4 h = r->h[lane], p = r->p[lane];
+    const uint2 hw = r->hq[lane];
+    const float4 h = make_float4(bf16_lo(hw.x), bf16_hi(hw.x), bf16_lo(hw.y), bf16_hi(hw.y));
+    const float4 p = r->p[lane];
     const uint4 f = r->ipc[lane];
     wu[g].s = r->s[lane]; wu[g].e = r->e[lane]; wu[g].se = r->se[lane]; wu[g].sw = r->sw[lane];
     // lane 0 uses the left chunks' .w, lane 31 the right chunks' .x; other lanes read but never use them
-    const float hh = hsel(r->halo[hoff + 0], lane);
+    const float hh = hq_halo(r->halo[hoff + 0], lane);
     const uint32_t hf = __float_as_uint(hsel(r->halo[hoff + 1], lane));
     const float hp = hsel(r->halo[hoff + 2], lane);
     wu[g].hw1 = hsel(r->halo[hoff + 3], lane); wu[g].hw2 = hsel(r->halo[hoff + 4], lane);
@@ -569,7 +601,10 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   const float* __restrict__ PP = (pcur ? a.p : a.p2) + base;       // p of the previous iteration
   float* __restrict__ Ev = a.e + base; float* __restrict__ Rv = a.r + base;
   const float* __restrict__ Q = a.q + base;
-  float* __restrict__ Hb = a.z + base;          // h = L^-1 r goes to the z plane (read by the next F_UP)
+  // h = L^-1 r goes to the z allocation as bf16 (read by the next F_UP; see h_pitch)
+  const int hpit = h_pitch(W);
+  const ptrdiff_t rsh = hv.flip ? -(ptrdiff_t)hpit : (ptrdiff_t)hpit;
+  uint16_t* __restrict__ HQ = reinterpret_cast<uint16_t*>(a.z) + (size_t)b * H * hpit + (hv.flip ? (size_t)(H - 1) * hpit : 0);
   // level preconditioner (four-column aggregates = one lane): h4 = L4^-1 (P4^T r), its own plane of pitch w4p
   const bool lv = a.h4 != nullptr;
   const int W4 = a.w4p;
@@ -604,7 +639,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   float hp[4] = {0.f, 0.f, 0.f, 0.f}, cp[4] = {0.f, 0.f, 0.f, 0.f};
   float racc = 0.f;
   double rr = 0.0, rz = 0.0;
-  ptrdiff_t o_c = rs + x, o4_c = rs4;              // offsets of the row being consumed
+  ptrdiff_t o_c = rs + x, o4_c = rs4, oh_c = rsh + x;   // offsets of the row being consumed
   // restriction: rows until the first flush, destination of that flush, and whether this lane stores
   //   upper half / untwisted: image rows 1, 2, ...: an aggregate row ends where (ya & (by - 1)) == 0 (and at row H - 2)
   //   lower half (flipped):   image rows H-2, H-3, ...: an aggregate row ends where ((ya - 1) & (by - 1)) == 0
@@ -643,9 +678,11 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
     float h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = fmaf(cp[j], hp[j], rn[j]);
-    if (live) *reinterpret_cast<float4*>(Hb + o_c) = make_float4(h[0], h[1], h[2], h[3]);
+    const uint32_t hw0 = pack_bf16x2(h[0], h[1]), hw1 = pack_bf16x2(h[2], h[3]);
+    if (live) *reinterpret_cast<uint2*>(HQ + oh_c) = make_uint2(hw0, hw1);
     const float srr = fmaf(rn[0], rn[0], fmaf(rn[1], rn[1], fmaf(rn[2], rn[2], rn[3] * rn[3])));
-    float srz = fmaf(iv.x * h[0], h[0], fmaf(iv.y * h[1], h[1], fmaf(iv.z * h[2], h[2], iv.w * h[3] * h[3])));
+    // r.z = sum ip h h~ with the rounded h~ that F_UP will read: consistent with the z it forms
+    float srz = fmaf(iv.x * h[0], bf16_lo(hw0), fmaf(iv.y * h[1], bf16_hi(hw0), fmaf(iv.z * h[2], bf16_lo(hw1), iv.w * h[3] * bf16_hi(hw1))));
     const float r4 = (rn[0] + rn[1]) + (rn[2] + rn[3]);             // P4^T r: the lane's four columns
     if (lv) {
       const uint32_t f4 = r->ipc4[lane];
@@ -675,7 +712,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
 #pragma unroll
     for (int j = 0; j < 4; ++j) hp[j] = h[j];
     cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
-    o_c += rs; o4_c += rs4;
+    o_c += rs; o4_c += rs4; oh_c += rsh;
   };
   constexpr int G = USAUG_DOWN_G;                  // rows per wait
   static_assert(RD > G, "DOWN ring too shallow");
@@ -1143,22 +1180,22 @@ __device__ __forceinline__ double resid_strip(const PcgArgs<float>& a, int b, in
 // r[m] + c[m-1] h[m-1].  The last arriver of the phase (one warp) adds the lower half's term c[m+1] h[m+1], stores the
 // complete row and returns the row's share of r.z = sum ip h^2.
 __device__ __forceinline__ double twist_fix(const PcgArgs<float>& a, int b, int lane) {
-  const int W = a.W, m = a.tw_m;
+  const int W = a.W, m = a.tw_m, hp = h_pitch(W);
   const size_t o = (size_t)b * a.H * W + (size_t)m * W;
-  float* Hm = a.z + o;
-  const float* Hn = a.z + o + W;
+  uint16_t* Hm = reinterpret_cast<uint16_t*>(a.z) + ((size_t)b * a.H + m) * hp;       // bf16 h plane, rows m and m + 1
+  const uint16_t* Hn = Hm + hp;
   const uint32_t* Fm = a.ipc + o;
   const uint32_t* Fn = a.ipc + o + W;
   double acc = 0.0;
   // four chunks per round with all their loads issued first: the warp that runs this is the last arriver of the phase,
   // i.e. it sits on the image's critical path, and a round costs one L2 round trip instead of four
   for (int xb = 4 * lane; xb < W; xb += 512) {
-    float4 ht[4], hb[4]; uint4 fm[4], fn[4];
+    uint2 ht[4], hb[4]; uint4 fm[4], fn[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int x = xb + 128 * u;
       if (x < W) {
-        ht[u] = __ldcg(reinterpret_cast<const float4*>(Hm + x)); hb[u] = __ldcg(reinterpret_cast<const float4*>(Hn + x));
+        ht[u] = __ldcg(reinterpret_cast<const uint2*>(Hm + x)); hb[u] = __ldcg(reinterpret_cast<const uint2*>(Hn + x));
         fm[u] = __ldcg(reinterpret_cast<const uint4*>(Fm + x)); fn[u] = __ldcg(reinterpret_cast<const uint4*>(Fn + x));
       }
     }
@@ -1166,10 +1203,12 @@ __device__ __forceinline__ double twist_fix(const PcgArgs<float>& a, int b, int 
     for (int u = 0; u < 4; ++u) {
       const int x = xb + 128 * u;
       if (x < W) {
-        const float4 h = make_float4(fmaf(bf16_hi(fn[u].x), hb[u].x, ht[u].x), fmaf(bf16_hi(fn[u].y), hb[u].y, ht[u].y),
-                                     fmaf(bf16_hi(fn[u].z), hb[u].z, ht[u].z), fmaf(bf16_hi(fn[u].w), hb[u].w, ht[u].w));
-        *reinterpret_cast<float4*>(Hm + x) = h;
-        acc += (double)fmaf(bf16_lo(fm[u].x) * h.x, h.x, fmaf(bf16_lo(fm[u].y) * h.y, h.y, fmaf(bf16_lo(fm[u].z) * h.z, h.z, bf16_lo(fm[u].w) * h.w * h.w)));
+        const float h0 = fmaf(bf16_hi(fn[u].x), bf16_lo(hb[u].x), bf16_lo(ht[u].x)), h1 = fmaf(bf16_hi(fn[u].y), bf16_hi(hb[u].x), bf16_hi(ht[u].x));
+        const float h2 = fmaf(bf16_hi(fn[u].z), bf16_lo(hb[u].y), bf16_lo(ht[u].y)), h3 = fmaf(bf16_hi(fn[u].w), bf16_hi(hb[u].y), bf16_hi(ht[u].y));
+        const uint32_t w0 = pack_bf16x2(h0, h1), w1 = pack_bf16x2(h2, h3);
+        *reinterpret_cast<uint2*>(Hm + x) = make_uint2(w0, w1);
+        acc += (double)fmaf(bf16_lo(fm[u].x) * h0, bf16_lo(w0), fmaf(bf16_lo(fm[u].y) * h1, bf16_hi(w0),
+                       fmaf(bf16_lo(fm[u].z) * h2, bf16_lo(w1), bf16_lo(fm[u].w) * h3 * bf16_hi(w1))));
       }
     }
   }

@@ -303,6 +303,9 @@ extern "C" int usaug_confmap_pcg_sinks(const float* img, float* cm, int B, int H
                                                         (flags & USAUG_CM_ZERO_GUESS) ? 1 : 0, L.tw_m, L.ip, L.c,
                                                         L.ipc, L.x64, L.bbpart, L.snk);
   USAUG_CHECK_LAUNCH("cm_factor_kernel");
+  // fused kernel: the bf16 h plane lives in the z allocation with its rows padded to 8 columns; the padding is never
+  // written, but the lanes beyond the last column read it (and pass it on to their neighbour's stencil with weight 0)
+  if (L.fused && (W & 7)) USAUG_CUDA(cudaMemsetAsync(L.z, 0, (size_t)N * B * sizeof(float), stream));
   if (L.h4 && precond != USAUG_PRECOND_LINE) { L.h4 = nullptr; L.ipc4 = nullptr; }   // the level solve belongs to the line preconditioner
   if (L.h4) {
     // padding columns and seed rows of the level planes must read as zero
