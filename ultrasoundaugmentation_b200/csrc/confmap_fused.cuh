@@ -9,6 +9,10 @@
 #ifndef USAUG_DOWN_G
 #define USAUG_DOWN_G 2
 #endif
+// shared memory of a CTA in staged F_UP rows (2304 B each); the worker warps split it into their private rings
+#ifndef USAUG_RING_ROWS
+#define USAUG_RING_ROWS 80
+#endif
 
 namespace usaug {
 
@@ -41,7 +45,7 @@ struct RingD {   // one staged row for F_DOWN / F_PRECOND (3200 bytes)
   uint4 ipc[32];
   uint32_t ipc4[32];   // level preconditioner: line factor of each lane's four-column aggregate
 };
-constexpr int kRingRowsPerCta = 80;                                   // 80 x 2560 B = 200 KB per CTA
+constexpr int kRingRowsPerCta = USAUG_RING_ROWS;                      // x 2304 B per CTA
 constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
 
 __device__ __forceinline__ float hsel(const float4& v, int lane) { return lane == 31 ? v.x : v.w; }
