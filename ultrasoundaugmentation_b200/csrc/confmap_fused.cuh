@@ -105,6 +105,19 @@ struct HalfView {
 // Everything is zero-filled where it does not exist (seed rows, image border, feature disabled), so the consumer adds
 // the terms unconditionally.  (Round 1 fetched zc with plain loads one aggregate row ahead; ncu showed the sweep
 // waiting on exactly those loads at the next warp barrier: 19 % of the F_UP stall samples of a latency-bound launch.)
+constexpr unsigned kCoarseDone = 0x7fffffffu;   // ImgState::zprog: the coarse solve of this iteration is complete
+
+// slow path of UpAux::wait_zc: until more than `k` outward steps of the coarse solve are published (whole warp)
+__device__ __noinline__ unsigned zc_spin(volatile unsigned* prog, unsigned k) {
+  unsigned v, spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(const_cast<const unsigned*>(prog)) : "memory");
+    if (v > k) return v;
+    __nanosleep(64);
+    if (++spins > (1u << 24)) __trap();                    // (~10 s: the producer is a running warp, this cannot happen)
+  }
+}
+
 struct UpAux {
   const float* base;     // this lane's source: view row 0 of a level plane / row 0 of zc, chunk offset included
   ptrdiff_t stride;      // elements per view row (0 for the coarse lanes, whose row comes from the aggregate index)
@@ -113,8 +126,32 @@ struct UpAux {
   int zown, zhal;        // float index inside halo[5..7] of the lane's own / halo aggregate column
   int hoff4;             // 28 (lane 0: left neighbour aggregate) or 30 (lane 31: right one)
   float z4n, z4hn;       // level recurrence: z4 of the previous row (own aggregate, halo aggregate)
+  // the coarse solve may still be producing zc (its outward phase runs behind the publication of this phase's tasks):
+  // zM = the meeting aggregate row (-1: zc is complete before any task starts), zknown = outward steps known to be done
+  volatile unsigned* zprog;
+  int zM;
+  unsigned zknown;
+  // Whole warp, before view row yv is staged: its aggregate row of zc must be final.  Aggregate row I is produced by outward step
+  // |I - M| - 1 (the meeting row itself before the tasks were published); the sweeps move away from the meeting row like the solve
+  // does, about half as fast, so after a short wait at the start this is a register compare per row and a reload every few dozen rows.
+  // Called ONCE per group of staged rows, outside the row bodies (a spin loop inside `issue` split the basic blocks of the
+  // row pair and cost F_UP 30 %): yv = the row of the group that lies furthest from the meeting row.
+  __device__ __forceinline__ int zc_step(int yv) const {     // outward step of the coarse solve that writes view row yv's aggregate row
+    const int yc = min(max(yv, 1), H - 2);
+    const int y = flip ? H - 1 - yc : yc;
+    const int I = (y - 1) >> sh;
+    return (I > zM ? I - zM : zM - I) - 1;
+  }
+  // view rows ya .. yb are about to be staged: the step is a convex function of the row, so its maximum is at one of the ends
+  // (twisted sweeps only ever move away from the meeting row; the plain sweep approaches it first)
+  __device__ __forceinline__ void wait_zc(int ya, int yb) {
+    if (zM < 0) return;
+    const int k = max(zc_step(ya), zc_step(yb));
+    if (k >= (int)zknown) zknown = zc_spin(zprog, (unsigned)k);
+  }
   __device__ __forceinline__ void init(const PcgArgs<float>& a, const HalfView& hv, int b, int x, int x0, int lane, int W) {
     flip = hv.flip; H = a.H; sh = a.cg.by_shift; nb = a.cg.nb;
+    zprog = &a.st[b].zprog; zM = a.cg.by ? a.cg.tw : -1; zknown = 0u;
     on = false; isz = false; base = a.z; stride = 0;
     z4n = z4hn = 0.f;
     hoff4 = (lane == 31) ? 30 : 28;
@@ -272,6 +309,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   const int hoff = (lane == 31) ? 16 : 0;
 
   ax.start(hsrc, hstep, ys);
+  ax.wait_zc(ys, ys - (R - 1));
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(ys - u);
   twist_seed(a, hv, HQ, IPC, b, x, x0, lane, valid, zn, zhn, ax);
@@ -386,6 +424,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
     __syncwarp();          // every lane has read these slots' halo chunks before any lane refills them (issue below)
 #pragma unroll
     for (int g = 0; g < G; ++g) rowB(y - g, g);
+    ax.wait_zc(y - R, y - (G - 1) - R);
 #pragma unroll
     for (int g = 0; g < G; ++g) issue(y - g - R);
   }
@@ -467,6 +506,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   const int hoff = (lane == 31) ? 16 : 0;
 
   ax.start(hsrc, hstep, y1);
+  ax.wait_zc(y1, y1 - (R - 1));
 #pragma unroll
   for (int u = 0; u < R; ++u) issue(y1 - u);
   twist_seed(a, hv, HQ, IPC, b, x, x0, lane, valid, zn, zhn, ax);
@@ -572,6 +612,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
     __syncwarp();          // every lane has read these slots' halo chunks before any lane refills them (issue below)
 #pragma unroll
     for (int g = 0; g < G; ++g) rowB(y - g, g);
+    ax.wait_zc(y - R, y - (G - 1) - R);
 #pragma unroll
     for (int g = 0; g < G; ++g) issue(y - g - R);
   }
@@ -868,9 +909,17 @@ __device__ __noinline__ double coarse_task_nb(const CoarseGeom g, const float* _
 //   outward    top     zc_I = W_I (v_I - E_{I+1}^T zc_{I+1})                     I = M-1 .. 0
 //              bottom  zc_I = W_I (v_I - E_I zc_{I-1})                           I = M+1 .. nby-1
 //   rc . zc = sum_I v_I . (W_I v_I)
+// The solve runs in two calls: phase 0 = inward + meeting row (returns rc . zc, which completes r . z and therefore beta, and
+// leaves the meeting row's z and couplings in `mid`), phase 1 = outward.  Between them the caller publishes the image's F_UP
+// tasks: F_UP consumes the aggregate rows of zc from the meeting row outwards -- the order in which phase 1 produces them -- so
+// the sweeps start behind the outward front instead of after it.  Phase 1 publishes its progress after 8 steps and then every 16
+// (`prog` = outward steps completed, after a fence); up_task waits on it before it stages a row (UpAux::wait_zc).
+struct CoarseMid { float zM, mC, mL, mR; };
+
 template <int NB, int RING_BYTES>
 __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float* __restrict__ rec, const float* __restrict__ rc,
-                                                 float* __restrict__ zc, unsigned char* ringmem, int lane) {
+                                                 float* __restrict__ zc, unsigned char* ringmem, int lane, int phase,
+                                                 CoarseMid* mid, volatile unsigned* prog) {
   using Slot = CoarseSlot<NB>;
   constexpr int Dfit = (RING_BYTES - 4 * NB * (int)sizeof(float)) / (int)sizeof(Slot) / 2;
   constexpr int D = Dfit > 8 ? 8 : Dfit;                         // ring depth per front, in block rows
@@ -931,6 +980,7 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
     return fmaf(eC, n, (row == NB - 1) ? 0.f : tbs) + ((row == 0) ? 0.f : tcs);
   };
 
+  if (phase == 0) {
   // ---- inward: the top front consumes block rows 0 .. M (round k = row k), the bottom front nby-1 .. M+1 -------------
   for (int u = 0; u < D - 1; ++u) { stage(ringT, u, (u <= M) ? u : -1, rc); stage(ringB, u, (u < nB) ? nby - 1 - u : -1, rc); cp_async_commit(); }
   cp_async_wait<D - 2>();
@@ -977,9 +1027,14 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
     if (owner) { zc[(size_t)M * NB + row] = zM; dot += (double)(v * zM); }
   }
   cp_async_wait<0>();
-  __threadfence();                                               // the parked v (in zc) are re-read through cp.async below
-  __syncwarp();
+  __threadfence();                                               // the parked v (in zc) are re-read through cp.async in phase 1;
+  __syncwarp();                                                  // zc of the meeting row is final and visible
+  mid->zM = zM; mid->mC = mC; mid->mL = mL; mid->mR = mR;
+  return warp_sum(dot);
+  }
   // ---- outward: top front rows M-1 .. 0, bottom front rows M+1 .. nby-1 -----------------------------------------------
+  const float zM = mid->zM;
+  float mC = mid->mC, mL = mid->mL, mR = mid->mR;
   for (int u = 0; u < D - 1; ++u) { stage(ringT, u, M - 1 - u, zc); stage(ringB, u, (u < nB) ? M + 1 + u : -1, zc); cp_async_commit(); }
   cp_async_wait<D - 2>();
   __syncwarp();
@@ -1000,28 +1055,69 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
     zB = matvec(sB, vbB);
     if (owner) { zc[(size_t)(M - 1 - k) * NB + row] = zT; if (hasB) zc[(size_t)(M + 1 + k) * NB + row] = zB; }
     { const int kn = k + D - 1; stage(ringT, kn, M - 1 - kn, zc); stage(ringB, kn, (kn < nB) ? M + 1 + kn : -1, zc); cp_async_commit(); }
+#ifndef USAUG_ZPROG_EVERY
+#define USAUG_ZPROG_EVERY 16
+#endif
+    if ((k & (USAUG_ZPROG_EVERY - 1)) == USAUG_ZPROG_EVERY - 1 || k == 7) {                              // the first k + 1 aggregate rows of both fronts are final
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) *prog = (unsigned)(k + 1);
+    }
   }
   cp_async_wait<0>();
+  __threadfence();
   __syncwarp();
-  return warp_sum(dot);
+  if (lane == 0) *prog = kCoarseDone;
+  return 0.0;
 }
 
+// coarse_begin: everything of the solve that r . z needs (the whole solve in the plain form; inward phase + meeting row in the
+// twisted form) -- returns rc . zc.  coarse_finish: the rest (outward phase), after the caller has published the F_UP tasks.
 template <int RING_BYTES>
-__device__ __forceinline__ double coarse_task(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane) {
+__device__ __forceinline__ double coarse_begin(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane, CoarseMid* mid, bool& pending,
+                                               bool overlap) {
   const CoarseGeom g = a.cg;
   const float* rec = a.Wt + (size_t)b * g.nby * g.rec;
   const float* rc = a.rc + (size_t)b * g.nc;
   float* zc = a.zc + (size_t)b * g.nc;
+  volatile unsigned* prog = &a.st[b].zprog;
+  pending = false;
   if (g.tw >= 0) {
     // (32 x 32 blocks need 5 KB per staged block row: two fronts fit only the deeper rings of the 4-warp kernel;
     //  the host leaves cg.tw = -1 otherwise)
-    if (g.nb == 16) return coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
-    if (g.nb == 8) return coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
-    if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) return coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+    if (g.nb == 16 || g.nb == 8 || RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) {
+      if (lane == 0) *prog = 0u;                 // (the F_UP tasks that will read it are published after phase 0)
+      double d = 0.0;
+      if (g.nb == 16) d = coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog);
+      else if (g.nb == 8) d = coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog);
+      else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) d = coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog);
+      // Bandwidth-bound launches finish the solve before anything is published: a sweep that waits for zc would hold a worker
+      // warp other tasks could use (512 images of 512 x 512: 990 -> 917 img/s with the overlap).
+      if (overlap) { pending = true; return d; }
+      if (g.nb == 16) coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
+      else if (g.nb == 8) coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
+      else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
+      return d;
+    }
   }
-  if (g.nb == 16) return coarse_task_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
-  if (g.nb == 32) return coarse_task_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
-  return coarse_task_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+  double d;
+  if (g.nb == 16) d = coarse_task_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+  else if (g.nb == 32) d = coarse_task_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+  else d = coarse_task_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane);
+  if (lane == 0) *prog = kCoarseDone;            // complete before anything is published (the caller fences)
+  return d;
+}
+
+template <int RING_BYTES>
+__device__ __forceinline__ void coarse_finish(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane, CoarseMid* mid) {
+  const CoarseGeom g = a.cg;
+  const float* rec = a.Wt + (size_t)b * g.nby * g.rec;
+  const float* rc = a.rc + (size_t)b * g.nc;
+  float* zc = a.zc + (size_t)b * g.nc;
+  volatile unsigned* prog = &a.st[b].zprog;
+  if (g.nb == 16) coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
+  else if (g.nb == 8) coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
+  else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
 }
 
 // ---- ready queue (two multi-producer / multi-consumer rings in global memory) ----------------------
@@ -1274,6 +1370,8 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     ImgState* st = a.st + b;
     const int mode = (int)(__ldcg(&st->fword) & 0xffffffffull);
     double s0 = 0.0, s1 = 0.0;
+    CoarseMid cmid;                       // a coarse solve this warp has begun in this round and must finish after publishing
+    bool coarse_pending = false;
     if (mode == F_UP) {
       if constexpr (RECOMP)
         s0 = up_task<R, SINK>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
@@ -1289,7 +1387,7 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     } else if (mode == F_RESID) {
       s0 = resid_strip(a, b, strip, half, lane);
     } else if (mode == F_COARSE) {
-      s0 = coarse_task<(int)kWarpRing>(a, ringmem, b, lane);
+      s0 = coarse_begin<(int)kWarpRing>(a, ringmem, b, lane, &cmid, coarse_pending, !RECOMP);
     } else {
       const int x = strip * kStrip4 + 4 * lane;
       // rows of this task: all of them, or one side of row m
@@ -1410,20 +1508,29 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
       // hand-off less on the UP -> DOWN -> COARSE chain (+2 % at B <= 64).  Bandwidth-bound launches keep it in
       // the queue: there it is the two service classes that decide who runs next (inline: -11 % at B = 512).
       const unsigned long long tc0 = a.debug ? now() : 0ull;
-      const double rc_zc = coarse_task<(int)kWarpRing>(a, ringmem, b, lane);
+      const double rc_zc = coarse_begin<(int)kWarpRing>(a, ringmem, b, lane, &cmid, coarse_pending, !RECOMP);
       __threadfence();                                          // every lane publishes its part of zc
       __syncwarp();
       if (a.debug) { t_mode[F_COARSE] += now() - tc0; n_mode[F_COARSE]++; }
       if (lane == 0) next = after_coarse(rc_zc);
       next = __shfl_sync(0xffffffffu, next, 0);
     }
-    if (lane != 0) continue;
-    st->fword = (unsigned long long)next;
-    if (next == F_DONE) {
-      __threadfence();
-      atomicAdd(a.done, 1u);                                       // idle workers leave when done == B
-    } else {
-      q_push_n(a, __ldcg(&st->prio), (unsigned)(b * per), 1u, (next == F_COARSE) ? 1u : (unsigned)per);
+    if (lane == 0) {
+      st->fword = (unsigned long long)next;
+      if (next == F_DONE) {
+        __threadfence();
+        atomicAdd(a.done, 1u);                                     // idle workers leave when done == B
+      } else {
+        q_push_n(a, __ldcg(&st->prio), (unsigned)(b * per), 1u, (next == F_COARSE) ? 1u : (unsigned)per);
+      }
+    }
+    __syncwarp();
+    // a coarse solve begun above: its F_UP tasks are published, now produce the rest of zc behind which they sweep
+    // (next != F_UP: the inner solve has ended -- FOLD does not read zc)
+    if (coarse_pending && next == F_UP) {
+      const unsigned long long tc0 = a.debug ? now() : 0ull;
+      coarse_finish<(int)kWarpRing>(a, ringmem, b, lane, &cmid);
+      if (a.debug) t_mode[F_COARSE] += now() - tc0;
     }
   }
   if ((a.debug & 1) && lane == 0 && warp == 0 && (blockIdx.x % 74) == 0)

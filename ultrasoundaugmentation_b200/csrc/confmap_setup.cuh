@@ -331,7 +331,7 @@ __global__ void cm_init_state_kernel(int B, int nblk, const double* __restrict__
   s.mode = M_RESID; s.iters = 0; s.first = 1; s.outer = 0;
   s.rz = 0; s.alpha = 0; s.beta = 0; s.bb = bb; s.rr_true = 0; s.rr_prev = 1e300; s.rr_target = 0; s.rr_rec = 0;
   s.cnt1 = 0; s.cnt2 = 0; s.fword = 0ull; s.pcur = 0; s.poor = 0; s.inner2 = 0.0; s.alpha_prev = 0.0; s.epend = 0; s.fresh = 0; s.rz_line = 0.0;
-  s.prio = 0; s.counted = 0; s.rem = 0.f;
+  s.prio = 0; s.counted = 0; s.rem = 0.f; s.zprog = 0x7fffffffu;
   st[b] = s;
 }
 

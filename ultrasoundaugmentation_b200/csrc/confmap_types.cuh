@@ -35,6 +35,7 @@ struct ImgState {
   double rz_line;     // line part of r.z of the current iteration (the COARSE task adds rc.zc)
   int prio, counted;  // fused kernel: ready-queue class of this image's tasks (1 = served first); counted in qsum/qcnt
   float rem;          // predicted remaining iterations (the contribution of this image to qsum)
+  unsigned zprog;     // fused kernel: outward steps of the running coarse solve whose rows of zc are final (F_UP waits on it)
 };
 
 constexpr int kStrip4 = 128;
