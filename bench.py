@@ -560,7 +560,7 @@ def run_ours(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if a.strong else "weak", "vs_baseline": None,
-            "dtype": "f32 (fp64 dot products + fp64 residual refinement)", "data": "synthetic",
+            "dtype": "f32 (fp64 dot products + fp64 residual refinement; the preconditioner's line factors and h plane are stored as bf16)", "data": "synthetic",
             "config": {"workload": "configs[4]: full chain (deform+TGC+remap, confidence-map PCG, SNR, reverb), "
                                    f"{nloc} images of {H}x{W} per GPU per step, {world} GPU(s) = batch {a.batch} "
                                    + ("(the literal configs[4] batch, strong scaling)" if a.strong else "(8 GPUs = configs[4]'s 4096)"),

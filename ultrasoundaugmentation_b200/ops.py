@@ -134,6 +134,9 @@ class ParamStager:
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
+    """Caller-owned workspace of a C-ABI call.  Deliberately a fresh ``torch.empty`` per call: torch's caching allocator IS the
+    workspace cache (a repeated size is a free-list hit, no cudaMalloc), and unlike a buffer cached on the chain object it is
+    stream-safe -- ``augment_host_stream`` keeps three calls in flight, and a CUDA graph gets its private pool."""
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
