@@ -107,6 +107,25 @@ struct HalfView {
 // waiting on exactly those loads at the next warp barrier: 19 % of the F_UP stall samples of a latency-bound launch.)
 constexpr unsigned kCoarseDone = 0x7fffffffu;   // ImgState::zprog: the coarse solve of this iteration is complete
 
+// Speculative coarse solve: the restriction rc is consumed while the image's F_DOWN tasks are still writing it.  Every word of
+// rc is self-validating: the solve leaves a sentinel (a NaN no arithmetic produces) in each word it has consumed, the next
+// phase's sweeps overwrite it with plain stores (no fence, no counter in the sweep), and a staged row that still holds a
+// sentinel was simply staged too early -- its words are then polled in global memory.
+constexpr unsigned kRcSentinel = 0x7fffdeadu;
+__device__ __forceinline__ bool rc_pending(float v) { return __float_as_uint(v) == kRcSentinel; }
+// this lane's word of a block row, polled until it is written -- or until every F_DOWN task has arrived (then whatever is
+// there is final: a solve that has broken down must not hang the device)
+__device__ __noinline__ float rc_poll(const float* word, const volatile unsigned* arrived, unsigned per) {
+  unsigned spins = 0;
+  for (;;) {
+    const float v = __ldcg(word);
+    if (!rc_pending(v)) return v;
+    if (*arrived >= per) return __ldcg(word);
+    __nanosleep(100);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
 // slow path of UpAux::wait_zc: until more than `k` outward steps of the coarse solve are published (whole warp)
 __device__ __noinline__ unsigned zc_spin(volatile unsigned* prog, unsigned k) {
   unsigned v, spins = 0;
@@ -694,6 +713,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
   const bool rc_st = a.cg.by != 0 && valid && (lane & ((1 << (a.cg.bx_shift - 2)) - 1)) == 0;
   float* rcp = a.rc + (a.cg.by ? (size_t)b * a.cg.nc + (size_t)((ya0 - 1) >> a.cg.by_shift) * a.cg.nb + (size_t)(x >> a.cg.bx_shift) : 0);
   const ptrdiff_t rc_step = a.cg.by ? (hv.flip ? -(ptrdiff_t)a.cg.nb : (ptrdiff_t)a.cg.nb) : 0;
+
   // One row.  Only the one-FMA recurrences (h, h4) tie a row to its predecessor; G rows are consumed per wait so that the
   // loads, updates and stores of neighbouring rows overlap in the instruction stream of the (single) warp of a task.
   auto row = [&](int y) {
@@ -753,6 +773,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
       rcp += rc_step;
       racc = 0.f;
       agc = a.cg.by;
+
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) hp[j] = h[j];
@@ -917,9 +938,10 @@ __device__ __noinline__ double coarse_task_nb(const CoarseGeom g, const float* _
 struct CoarseMid { float zM, mC, mL, mR; };
 
 template <int NB, int RING_BYTES>
-__device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float* __restrict__ rec, const float* __restrict__ rc,
+__device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float* __restrict__ rec, float* rc,
                                                  float* __restrict__ zc, unsigned char* ringmem, int lane, int phase,
-                                                 CoarseMid* mid, volatile unsigned* prog) {
+                                                 CoarseMid* mid, volatile unsigned* prog, bool spec, int per,
+                                                 const volatile unsigned* arrived) {
   using Slot = CoarseSlot<NB>;
   constexpr int Dfit = (RING_BYTES - 4 * NB * (int)sizeof(float)) / (int)sizeof(Slot) / 2;
   constexpr int D = Dfit > 8 ? 8 : Dfit;                         // ring depth per front, in block rows
@@ -982,7 +1004,11 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
 
   if (phase == 0) {
   // ---- inward: the top front consumes block rows 0 .. M (round k = row k), the bottom front nby-1 .. M+1 -------------
-  for (int u = 0; u < D - 1; ++u) { stage(ringT, u, (u <= M) ? u : -1, rc); stage(ringB, u, (u < nB) ? nby - 1 - u : -1, rc); cp_async_commit(); }
+  // Speculative mode: rc is still being written by the image's F_DOWN tasks, from the outside in -- the order in which the
+  // fronts consume it; see kRcSentinel.  The meeting row is staged after ALL tasks have arrived.
+  const int mlast = spec ? M - 1 : M;                            // last block row the top ring stages inside the pipeline
+  const bool mine = owner && row < g.nbx;                        // this lane owns a real (not padding) word of every block row
+  for (int u = 0; u < D - 1; ++u) { stage(ringT, u, (u <= mlast) ? u : -1, rc); stage(ringB, u, (u < nB) ? nby - 1 - u : -1, rc); cp_async_commit(); }
   cp_async_wait<D - 2>();
   __syncwarp();
   float wT = 0.f, wB = 0.f;                                      // (W v)[row] of the previous row of each front
@@ -995,8 +1021,23 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
     const bool hasB = k < nB;
     const Slot* sT = ringT + (k % D);
     const Slot* sB = ringB + (k % D);
-    const float vT = sT->vec[row] - e_direct(sT, wT);
-    const float vB = sB->vec[row] - e_transp(bC, bL, bR, wB);
+    float rT = sT->vec[row], rB = sB->vec[row];
+    if (spec) {
+      const bool late = mine && (rc_pending(rT) || (hasB && rc_pending(rB)));
+      if (__any_sync(full, late)) {                              // staged before the sweeps had written it: poll the words themselves
+        if (mine) {
+          rT = rc_poll(rc + (size_t)k * NB + row, arrived, (unsigned)per);
+          if (hasB) rB = rc_poll(rc + (size_t)(nby - 1 - k) * NB + row, arrived, (unsigned)per);
+        }
+        rT = __shfl_sync(full, rT, row); rB = __shfl_sync(full, rB, row);     // (the lanes that share a row)
+      }
+      if (mine) {                                                // consumed: leave the sentinel for the next phase
+        rc[(size_t)k * NB + row] = __uint_as_float(kRcSentinel);
+        if (hasB) rc[(size_t)(nby - 1 - k) * NB + row] = __uint_as_float(kRcSentinel);
+      }
+    }
+    const float vT = rT - e_direct(sT, wT);
+    const float vB = rB - e_transp(bC, bL, bR, wB);
     dot += (double)pvw;
     float* vbT = vsT + (k & 1) * NB;
     float* vbB = vsB + (k & 1) * NB;
@@ -1008,11 +1049,22 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
     const float wBn = matvec(sB, vbB);
     USAUG_DEV_ASSERT(k < nby && nby - 1 - k >= 0 && (k % D) < D);
     if (owner) { zc[(size_t)k * NB + row] = vT; if (hasB) zc[(size_t)(nby - 1 - k) * NB + row] = vB; }
-    { const int kn = k + D - 1; stage(ringT, kn, (kn <= M) ? kn : -1, rc); stage(ringB, kn, (kn < nB) ? nby - 1 - kn : -1, rc); cp_async_commit(); }
+    { const int kn = k + D - 1; stage(ringT, kn, (kn <= mlast) ? kn : -1, rc); stage(ringB, kn, (kn < nB) ? nby - 1 - kn : -1, rc); cp_async_commit(); }
     pvw = owner ? fmaf(vT, wT, hasB ? vB * wBn : 0.f) : 0.f;
     if (hasB) wB = wBn;
   }
   dot += (double)pvw;
+  if (spec) {                                                    // every F_DOWN task of the image has arrived: rc is complete
+    unsigned spins = 0;
+    while (*arrived < (unsigned)per) { __nanosleep(100); if (++spins > (1u << 24)) __trap(); }
+    __threadfence();
+    cp_async_wait<0>();
+    __syncwarp();
+    stage(ringT, M, M, rc);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+  }
   // ---- the meeting row ------------------------------------------------------------------------------------------------
   float zM, mC, mL, mR;
   {
@@ -1025,6 +1077,7 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
     __syncwarp();
     zM = matvec(sT, vb);
     if (owner) { zc[(size_t)M * NB + row] = zM; dot += (double)(v * zM); }
+    if (spec && mine) rc[(size_t)M * NB + row] = __uint_as_float(kRcSentinel);
   }
   cp_async_wait<0>();
   __threadfence();                                               // the parked v (in zc) are re-read through cp.async in phase 1;
@@ -1075,12 +1128,15 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
 // twisted form) -- returns rc . zc.  coarse_finish: the rest (outward phase), after the caller has published the F_UP tasks.
 template <int RING_BYTES>
 __device__ __forceinline__ double coarse_begin(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane, CoarseMid* mid, bool& pending,
-                                               bool overlap) {
+                                               bool overlap, bool speculative = false) {
   const CoarseGeom g = a.cg;
   const float* rec = a.Wt + (size_t)b * g.nby * g.rec;
-  const float* rc = a.rc + (size_t)b * g.nc;
+  float* rc = a.rc + (size_t)b * g.nc;
   float* zc = a.zc + (size_t)b * g.nc;
   volatile unsigned* prog = &a.st[b].zprog;
+  // speculative: rc is still being produced by the image's F_DOWN tasks (arr = their arrival counter)
+  const volatile unsigned* arr = &a.st[b].cnt1;
+  const int per = a.per;
   pending = false;
   if (g.tw >= 0) {
     // (32 x 32 blocks need 5 KB per staged block row: two fronts fit only the deeper rings of the 4-warp kernel;
@@ -1088,15 +1144,15 @@ __device__ __forceinline__ double coarse_begin(const PcgArgs<float>& a, unsigned
     if (g.nb == 16 || g.nb == 8 || RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) {
       if (lane == 0) *prog = 0u;                 // (the F_UP tasks that will read it are published after phase 0)
       double d = 0.0;
-      if (g.nb == 16) d = coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog);
-      else if (g.nb == 8) d = coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog);
-      else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) d = coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog);
+      if (g.nb == 16) d = coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog, speculative, per, arr);
+      else if (g.nb == 8) d = coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog, speculative, per, arr);
+      else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) d = coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 0, mid, prog, speculative, per, arr);
       // Bandwidth-bound launches finish the solve before anything is published: a sweep that waits for zc would hold a worker
       // warp other tasks could use (512 images of 512 x 512: 990 -> 917 img/s with the overlap).
       if (overlap) { pending = true; return d; }
-      if (g.nb == 16) coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
-      else if (g.nb == 8) coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
-      else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
+      if (g.nb == 16) coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog, false, per, arr);
+      else if (g.nb == 8) coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog, false, per, arr);
+      else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog, false, per, arr);
       return d;
     }
   }
@@ -1112,12 +1168,12 @@ template <int RING_BYTES>
 __device__ __forceinline__ void coarse_finish(const PcgArgs<float>& a, unsigned char* ringmem, int b, int lane, CoarseMid* mid) {
   const CoarseGeom g = a.cg;
   const float* rec = a.Wt + (size_t)b * g.nby * g.rec;
-  const float* rc = a.rc + (size_t)b * g.nc;
+  float* rc = a.rc + (size_t)b * g.nc;
   float* zc = a.zc + (size_t)b * g.nc;
   volatile unsigned* prog = &a.st[b].zprog;
-  if (g.nb == 16) coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
-  else if (g.nb == 8) coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
-  else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog);
+  if (g.nb == 16) coarse_task_tw_nb<16, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog, false, a.per, prog);
+  else if (g.nb == 8) coarse_task_tw_nb<8, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog, false, a.per, prog);
+  else if constexpr (RING_BYTES >= 6 * (int)sizeof(CoarseSlot<32>) + 512) coarse_task_tw_nb<32, RING_BYTES>(g, rec, rc, zc, ringmem, lane, 1, mid, prog, false, a.per, prog);
 }
 
 // ---- ready queue (two multi-producer / multi-consumer rings in global memory) ----------------------
@@ -1138,12 +1194,16 @@ __device__ __forceinline__ void coarse_finish(const PcgArgs<float>& a, unsigned 
 // throughout, so claims pipeline in L2 (a CAS on the head serialises the pops at one per round trip:
 // measured 1 us per task, 3.5x slower than this at 512 images).
 constexpr unsigned kNoTask = 0xffffffffu;
+constexpr unsigned kSpecTask = 0x80000000u;   // payload flag: the speculative coarse solve of image (payload & ~flag), see pcg_fused_kernel
 constexpr unsigned kIdleSleepMaxNs = 2048;
 constexpr unsigned long long kWatchdogNs = 4000000000ull;   // default: idle workers give up when NOBODY has claimed a task for 4 s
 
 // pushes n entries: payload0, payload0+stride, ...  (one lane)
-__device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsigned payload0, unsigned stride, unsigned n) {
-  const unsigned long long k0 = atomicAdd(a.qtail + ring, (unsigned long long)n);
+// (extra != kNoTask: one more entry with that payload, behind the n others)
+__device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsigned payload0, unsigned stride, unsigned n,
+                                         unsigned extra = kNoTask) {
+  const unsigned nx = n + (extra != kNoTask ? 1u : 0u);
+  const unsigned long long k0 = atomicAdd(a.qtail + ring, (unsigned long long)nx);
   __threadfence();                                          // release: state written before the stamps
   unsigned long long* slots = a.qslots + (size_t)ring * a.qcap;
   for (unsigned i = 0; i < n; ++i) {
@@ -1152,8 +1212,13 @@ __device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsi
     volatile unsigned long long* slot = slots + (k % a.qcap);
     *slot = ((k + 1ull) << 32) | (unsigned long long)(payload0 + i * stride);
   }
+  if (extra != kNoTask) {
+    const unsigned long long k = k0 + n;
+    volatile unsigned long long* slot = slots + (k % a.qcap);
+    *slot = ((k + 1ull) << 32) | (unsigned long long)extra;
+  }
   __threadfence();
-  atomicAdd(a.qavail + ring, (int)n);
+  atomicAdd(a.qavail + ring, (int)nx);
 }
 
 // Bail-out of a stalled scheduler (one lane): every image that is not DONE reports iters = -1, relres = NaN; its
@@ -1364,7 +1429,14 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     const unsigned long long tq1 = a.debug ? now() : 0ull;
     t_wait += tq1 - tq0;
     if (payload == kNoTask) break;
-    const int b = (int)(payload / (unsigned)per), ti = (int)(payload % (unsigned)per);
+    // A speculative coarse task (a.spec) travels with the F_DOWN / F_PRECOND tasks of its image.  It runs the inward phase of the
+    // coarse solve BEHIND those sweeps (they flush the restriction rc from the outside in, the order the two fronts consume
+    // it), waits for all of them to arrive, and then arrives itself as the (per + 1)-th and, by construction, LAST task of the
+    // phase: it reduces their partial sums, advances the image's state and publishes F_UP like any last arriver -- with
+    // rc . zc already in hand, so the ~45 us of the inward phase are off the image's critical path.
+    const bool spec_task = (payload & kSpecTask) != 0u;
+    const int b = spec_task ? (int)(payload & ~kSpecTask) : (int)(payload / (unsigned)per);
+    const int ti = spec_task ? 0 : (int)(payload % (unsigned)per);
     USAUG_DEV_ASSERT(b >= 0 && b < a.B && 2 * ti + 1 < 2 * a.pmax);
     const int strip = ti % a.nstrip4, half = ti / a.nstrip4;      // half = 1: lower half of a twisted factorisation
     ImgState* st = a.st + b;
@@ -1372,7 +1444,11 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     double s0 = 0.0, s1 = 0.0;
     CoarseMid cmid;                       // a coarse solve this warp has begun in this round and must finish after publishing
     bool coarse_pending = false;
-    if (mode == F_UP) {
+    double spec_d = 0.0;                  // rc . zc of a speculative coarse solve
+    if (spec_task) {
+      USAUG_DEV_ASSERT(mode == F_DOWN || mode == F_PRECOND);
+      spec_d = coarse_begin<(int)kWarpRing>(a, ringmem, b, lane, &cmid, coarse_pending, true, true);
+    } else if (mode == F_UP) {
       if constexpr (RECOMP)
         s0 = up_task<R, SINK>(a, ringmem, b, strip, half, lane, (float)__ldcg(&st->beta), __ldcg(&st->first) != 0, __ldcg(&st->pcur));
       else
@@ -1426,18 +1502,23 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     if (a.debug) { t_mode[mode] += tq2 - tq1; n_mode[mode]++; }
     // ---- arrival: every lane publishes its own stores, then lane 0 takes a ticket -------------------
     double* part = a.part + (size_t)b * a.pmax * 2;
-    if (lane == 0) { part[2 * ti] = s0; part[2 * ti + 1] = s1; }
+    if (lane == 0 && !spec_task) { part[2 * ti] = s0; part[2 * ti + 1] = s1; }
     __threadfence();
     __syncwarp();
     unsigned tk = 0;
     if (lane == 0) tk = atomicAdd(&st->cnt1, 1u);
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (a.debug) t_arr += now() - tq2;
-    const int ntask = (mode == F_COARSE) ? 1 : per;               // F_COARSE is a single task per image
+    // F_COARSE is a single task per image; a phase with a speculative coarse task has per + 1 participants, and that task
+    // arrives last (it has waited for the others)
+    const bool spec_phase = a.spec && (mode == F_DOWN || mode == F_PRECOND);
+    const int ntask = (mode == F_COARSE) ? 1 : per + (spec_phase ? 1 : 0);
+    USAUG_DEV_ASSERT(!spec_phase || (tk == (unsigned)per) == spec_task);
     if (tk != (unsigned)ntask - 1) continue;
     // ---- last strip of this image and phase: reduce, advance the state, publish the next phase ------
     __threadfence();
-    reduce_parts(part, ntask, lane, s0, s1);
+    reduce_parts(part, (mode == F_COARSE) ? 1 : per, lane, s0, s1);
+
     if (a.tw_m && (mode == F_DOWN || mode == F_PRECOND)) {
       s1 += twist_fix(a, b, lane);
       __threadfence();                                            // every lane publishes its part of row m
@@ -1502,7 +1583,13 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
     }
     }
     next = __shfl_sync(0xffffffffu, next, 0);
-    if (!RECOMP && next == F_COARSE) {
+    if (!RECOMP && next == F_COARSE && spec_task) {
+      // the inward phase has already run behind the sweeps
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) next = after_coarse(spec_d);
+      next = __shfl_sync(0xffffffffu, next, 0);
+    } else if (!RECOMP && next == F_COARSE) {
       // Latency-bound launches (few tasks, the !RECOMP kernel): the coarse solve is a single-warp task, so the warp
       // that completed the phase runs it right here instead of handing it to another worker through the queue -- one
       // hand-off less on the UP -> DOWN -> COARSE chain (+2 % at B <= 64).  Bandwidth-bound launches keep it in
@@ -1521,7 +1608,8 @@ __global__ void __launch_bounds__(256, 1) pcg_fused_kernel(const PcgArgs<float> 
         __threadfence();
         atomicAdd(a.done, 1u);                                     // idle workers leave when done == B
       } else {
-        q_push_n(a, __ldcg(&st->prio), (unsigned)(b * per), 1u, (next == F_COARSE) ? 1u : (unsigned)per);
+        q_push_n(a, __ldcg(&st->prio), (unsigned)(b * per), 1u, (next == F_COARSE) ? 1u : (unsigned)per,
+                 (a.spec && (next == F_DOWN || next == F_PRECOND)) ? (kSpecTask | (unsigned)b) : kNoTask);
       }
     }
     __syncwarp();

@@ -24,6 +24,7 @@ struct CmLayout {
   uint32_t* ipc;
   float4* wk;
   double *x64, *bbpart, *part;
+  bool spec;                  // the coarse solve runs behind the F_DOWN sweeps (latency-bound launches)
   void *e, *r, *p, *q, *z, *p2;
   ImgState* st;
   unsigned* done;
@@ -111,6 +112,9 @@ static CmLayout cm_layout(void* ws, int B, int H, int W, int flags) {
   L.q = cv.take<char>(N * tsz); L.z = cv.take<char>(N * tsz); L.p2 = cv.take<char>(N * tsz);
   L.bbpart = cv.take<double>((size_t)B * L.nblk);
   L.part = cv.take<double>((size_t)B * L.pmax * 2);
+  // the coarse solve runs behind the F_DOWN sweeps (its inward phase consumes the restriction in the order they flush it) in
+  // latency-bound launches with both twisted factorisations; see confmap_fused.cuh
+  L.spec = L.fused && !L.recomp && L.tw_m > 0 && L.cg.by && L.cg.tw >= 0 && !getenv("USAUG_CM_NO_SPEC");
   L.st = cv.take<ImgState>(B);
   L.done = cv.take<unsigned>(2);
   // two ready rings; every image has at most `per` ready tasks at a time, in one ring or the other
@@ -142,7 +146,7 @@ static int launch_fused_aw(PcgArgs<float>& a, int blocks_cap_sms, cudaStream_t s
   USAUG_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<AW, RECOMP, SINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
   USAUG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel<AW, RECOMP, SINK>, 256, kFusedSmem));
   if (per_sm < 1) { set_error("pcg_fused_kernel cannot be resident"); return USAUG_E_CUDA; }
-  const int tasks = a.per * a.B;
+  const int tasks = (a.per + (a.spec ? 1 : 0)) * a.B;           // (+ one speculative coarse task per image)
   int blocks = tasks;
   if (blocks > blocks_cap_sms) blocks = blocks_cap_sms;
   if (blocks < 1) blocks = 1;
@@ -198,6 +202,7 @@ static int launch_pcg(const CmLayout& L, float* cm, int B, int H, int W, double 
   a.tw_m = L.tw_m; a.per = L.per; a.wS2 = L.wS2; a.wSE2 = L.wSE2; a.wSW2 = L.wSW2;
   a.h4 = L.h4; a.ipc4 = L.ipc4; a.w4p = L.w4p;
   a.snk = L.snk;
+  a.spec = L.spec ? 1 : 0;
   // every inner iteration is one step; each refinement round adds <= 3 steps and needs >= 1 iteration
   a.max_steps = 4 * maxiter + 16;
   a.debug = g_debug;
@@ -324,6 +329,11 @@ extern "C" int usaug_confmap_pcg_sinks(const float* img, float* cm, int B, int H
     // the padding columns of the coarse vectors are never written by the sweeps
     USAUG_CUDA(cudaMemsetAsync(L.rc, 0, (size_t)B * L.cg.nc * sizeof(float), stream));
     USAUG_CUDA(cudaMemsetAsync(L.zc, 0, (size_t)B * L.cg.nc * sizeof(float), stream));
+  }
+  if (L.spec) {
+    const size_t n = (size_t)B * L.cg.nc;
+    cm_rc_poison_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(L.rc, n, L.cg.nb, L.cg.nbx);
+    USAUG_CHECK_LAUNCH("cm_rc_poison_kernel");
   }
   cm_init_state_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, L.nblk, L.bbpart, L.st, L.done);
   USAUG_CHECK_LAUNCH("cm_init_state_kernel");

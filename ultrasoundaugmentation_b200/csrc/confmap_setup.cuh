@@ -320,6 +320,12 @@ __global__ void __launch_bounds__(128) cm_factor4_kernel(
   }
 }
 
+// speculative coarse solve (confmap_fused.cuh: kRcSentinel): every real word of rc starts as "not yet written"; padding columns are 0
+__global__ void cm_rc_poison_kernel(float* __restrict__ rc, size_t n, int nb, int nbx) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rc[i] = ((int)(i % (size_t)nb) < nbx) ? __uint_as_float(0x7fffdeadu) : 0.f;
+}
+
 __global__ void cm_init_state_kernel(int B, int nblk, const double* __restrict__ bbpart,
                                      ImgState* __restrict__ st, unsigned* __restrict__ done) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

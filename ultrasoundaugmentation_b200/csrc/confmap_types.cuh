@@ -105,6 +105,9 @@ struct PcgArgs {
   // extra sink pixels (potential 0) among rows 1..H-2: [B][H][W] bytes, nullptr = bottom row only.  A sink keeps its
   // place in every vector as a decoupled row: x = p = q = r = 0 there, line factors ip = c = 0 (the sweeps test ip == 0).
   const uint8_t* snk;
+  // fused kernel, latency-bound launches: the coarse solve of an iteration is queued WITH the F_DOWN / F_PRECOND tasks and
+  // runs its inward phase behind them (spec = 1; the words of rc are then self-validating, see kRcSentinel)
+  int spec;
   int debug;         // USAUG_CM_DEBUG_TIMING: block 0 prints per-slot wall times of a few steps
 };
 
