@@ -1208,7 +1208,9 @@ __device__ __forceinline__ void q_push_n(const PcgArgs<float>& a, int ring, unsi
   unsigned long long* slots = a.qslots + (size_t)ring * a.qcap;
   for (unsigned i = 0; i < n; ++i) {
     const unsigned long long k = k0 + i;
-    USAUG_DEV_ASSERT(k - __ldcg(a.qhead + ring) < (unsigned long long)a.qcap);      // the ring never laps an unread entry
+    // the ring never laps an unread entry (signed: another producer's count may already have let consumers claim tickets
+    // beyond this one, they then wait for this entry's stamp)
+    USAUG_DEV_ASSERT((long long)(k - __ldcg(a.qhead + ring)) < (long long)a.qcap);
     volatile unsigned long long* slot = slots + (k % a.qcap);
     *slot = ((k + 1ull) << 32) | (unsigned long long)(payload0 + i * stride);
   }
