@@ -2,17 +2,10 @@
 #pragma once
 #include "confmap_generic.cuh"
 
-// rows consumed per cp.async wait in the F_UP / F_DOWN sweeps (instruction-level parallelism across rows)
-#ifndef USAUG_UP_G
-#define USAUG_UP_G 2
-#endif
-#ifndef USAUG_DOWN_G
-#define USAUG_DOWN_G 2
-#endif
-// shared memory of a CTA in staged F_UP rows (2304 B each); the worker warps split it into their private rings
-#ifndef USAUG_RING_ROWS
-#define USAUG_RING_ROWS 80
-#endif
+// rows consumed per cp.async wait in the F_UP / F_DOWN sweeps (instruction-level parallelism across rows; 3 and 4 were measured
+// slower: fewer rows in flight), and the shared memory of a CTA in staged F_UP rows of 2304 B (the worker warps split it into
+// their private rings; 88 and 96 rows were not faster)
+constexpr int kRowsPerWaitUp = 2, kRowsPerWaitDown = 2;
 
 namespace usaug {
 
@@ -45,7 +38,7 @@ struct RingD {   // one staged row for F_DOWN / F_PRECOND (3200 bytes)
   uint4 ipc[32];
   uint32_t ipc4[32];   // level preconditioner: line factor of each lane's four-column aggregate
 };
-constexpr int kRingRowsPerCta = USAUG_RING_ROWS;                      // x 2304 B per CTA
+constexpr int kRingRowsPerCta = 80;                                   // x 2304 B = 180 KB per CTA
 constexpr size_t kFusedSmem = sizeof(RingU) * kRingRowsPerCta;
 
 __device__ __forceinline__ float hsel(const float4& v, int lane) { return lane == 31 ? v.x : v.w; }
@@ -338,7 +331,7 @@ __device__ __forceinline__ double up_task(const PcgArgs<float>& a, unsigned char
   ptrdiff_t o_c = (ptrdiff_t)ys * rs + x;         // offset of the row being consumed
   // G rows are consumed per wait: only the one-FMA recurrences (z, z4) and the p / a / weight hand-down tie a row to
   // the previous one, so the loads, shuffles, ex2 and stores of neighbouring rows overlap in the single warp of a task.
-  constexpr int G = USAUG_UP_G;
+  constexpr int G = kRowsPerWaitUp;
   static_assert(R > G, "UP ring too shallow");
   float pu[G][6], au[G][6];
   unsigned mu[G];
@@ -534,7 +527,7 @@ __device__ __forceinline__ double up_task_planes(const PcgArgs<float>& a, unsign
   int slot_c = 0;                                 // ring slot of the row being consumed
   ptrdiff_t o_c = (ptrdiff_t)y1 * rs + x;         // offset of the row being consumed
   // G rows per wait, as in up_task: the rows' loads, shuffles and stores overlap in the single warp of a task
-  constexpr int G = USAUG_UP_G;
+  constexpr int G = kRowsPerWaitUp;
   static_assert(R > G, "UP ring too shallow");
   float pu[G][6];
   WRowP wu[G];
@@ -780,7 +773,7 @@ __device__ __forceinline__ void down_task(const PcgArgs<float>& a, unsigned char
     cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
     o_c += rs; o4_c += rs4; oh_c += rsh;
   };
-  constexpr int G = USAUG_DOWN_G;                  // rows per wait
+  constexpr int G = kRowsPerWaitDown;              // rows per wait
   static_assert(RD > G, "DOWN ring too shallow");
   for (int y = 1; y <= ylast; y += G) {
     cp_async_wait<RD - G>();
@@ -1108,10 +1101,7 @@ __device__ __noinline__ double coarse_task_tw_nb(const CoarseGeom g, const float
     zB = matvec(sB, vbB);
     if (owner) { zc[(size_t)(M - 1 - k) * NB + row] = zT; if (hasB) zc[(size_t)(M + 1 + k) * NB + row] = zB; }
     { const int kn = k + D - 1; stage(ringT, kn, M - 1 - kn, zc); stage(ringB, kn, (kn < nB) ? M + 1 + kn : -1, zc); cp_async_commit(); }
-#ifndef USAUG_ZPROG_EVERY
-#define USAUG_ZPROG_EVERY 16
-#endif
-    if ((k & (USAUG_ZPROG_EVERY - 1)) == USAUG_ZPROG_EVERY - 1 || k == 7) {                              // the first k + 1 aggregate rows of both fronts are final
+    if ((k & 15) == 15 || k == 7) {                              // the first k + 1 aggregate rows of both fronts are final
       __threadfence();
       __syncwarp();
       if (lane == 0) *prog = (unsigned)(k + 1);

@@ -78,16 +78,10 @@ __device__ __forceinline__ void apply_plan(const ScPlan& p, const float* __restr
 }
 
 constexpr int kScRows = 4;      // output rows per thread
-#ifndef USAUG_SC_IMGS
-#define USAUG_SC_IMGS 16
-#endif
-constexpr int kScImgs = USAUG_SC_IMGS;      // images per block (blockIdx.z = chunk of images)
+constexpr int kScImgs = 16;      // images per block (blockIdx.z = chunk of images)
 
 // output = polar [n_s, n_r]; thread = ray, kScRows samples
-#ifndef USAUG_SC_MINB
-#define USAUG_SC_MINB 8
-#endif
-__global__ void __launch_bounds__(128, USAUG_SC_MINB) sc_cart_to_polar(const float* __restrict__ img, const uint8_t* __restrict__ lab,
+__global__ void __launch_bounds__(128, 8) sc_cart_to_polar(const float* __restrict__ img, const uint8_t* __restrict__ lab,
                                                         float* __restrict__ out_img, uint8_t* __restrict__ out_lab,
                                                         int B, int H, int W, int ns, int nr, ScGeom g,
                                                         const float* __restrict__ sin_t, const float* __restrict__ cos_t) {
@@ -121,7 +115,7 @@ __global__ void __launch_bounds__(128, USAUG_SC_MINB) sc_cart_to_polar(const flo
 }
 
 // output = Cartesian [H, W]; thread = column, kScRows rows
-__global__ void __launch_bounds__(128, USAUG_SC_MINB) sc_polar_to_cart(const float* __restrict__ img, const uint8_t* __restrict__ lab,
+__global__ void __launch_bounds__(128, 8) sc_polar_to_cart(const float* __restrict__ img, const uint8_t* __restrict__ lab,
                                                         float* __restrict__ out_img, uint8_t* __restrict__ out_lab,
                                                         int B, int H, int W, int ns, int nr, ScGeom g) {
   const int x = blockIdx.x * 128 + threadIdx.x;

@@ -216,13 +216,7 @@ __global__ void __launch_bounds__(256) profile_kernel(const int* __restrict__ su
 // 10 algorithmic bytes per pixel (4+1 in, 4+1 out).
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarpRows = 8;       // output rows per thread and tile
-#ifndef USAUG_WARP_TILES
-#define USAUG_WARP_TILES 4
-#endif
-#ifndef USAUG_WARP_PREFETCH
-#define USAUG_WARP_PREFETCH 0
-#endif
-constexpr int kWarpTiles = USAUG_WARP_TILES;      // consecutive tiles per block
+constexpr int kWarpTiles = 4;       // consecutive tiles per block
 
 // TIn = float (image in [0,1]) or uint8_t (8-bit B-mode ingest: v/255 in correctly rounded fp32, from a
 // 256-entry shared-memory table so the gather loop carries no divide).
@@ -230,13 +224,10 @@ constexpr int kWarpTiles = USAUG_WARP_TILES;      // consecutive tiles per block
 // 1/den) and the TGC gains are set up once per block.  With one 8-row tile per block a block lived for two dependent
 // memory round trips (per-image scalars, then the gathers) and the memory pipeline idled during the first.
 // Measured at B = 1024 of 512 x 512 (one box, same run): 1 tile / 48 registers 719 us, 4 tiles / 48 registers 704 us,
-// 4 tiles / 64 registers (8 blocks per SM) 656 us; prefetching tile i+1 before tile i is stored (USAUG_WARP_PREFETCH)
+// 4 tiles / 64 registers (8 blocks per SM) 656 us; prefetching tile i+1 before tile i is stored
 // was slower (801 us: the loads of both tiles share scoreboards, so waiting for the older tile waits for the newer too).
-#ifndef USAUG_WARP_MINB
-#define USAUG_WARP_MINB 8
-#endif
 template <typename TIn>
-__global__ void __launch_bounds__(128, USAUG_WARP_MINB) fused_warp_kernel(
+__global__ void __launch_bounds__(128, 8) fused_warp_kernel(
     const TIn* __restrict__ img, const uint8_t* __restrict__ lab, float* __restrict__ out_img,
     uint8_t* __restrict__ out_lab, int H, int W, const float* __restrict__ s_hat,
     const WarpInfo* __restrict__ info, const float* __restrict__ tgc, int K, float gscale) {
@@ -347,22 +338,6 @@ __global__ void __launch_bounds__(128, USAUG_WARP_MINB) fused_warp_kernel(
       }
     }
   };
-#if USAUG_WARP_PREFETCH
-  Tile ta, tb;
-  fetch(ta, yb);
-#pragma unroll
-  for (int ti = 0; ti < kWarpTiles; ti += 2) {
-    const int ya = yb + ti * kWarpRows;
-    const bool more1 = ti + 1 < kWarpTiles && ya + kWarpRows < H;
-    if (more1) fetch(tb, ya + kWarpRows);
-    finish(ta, ya, ti);
-    if (!more1) break;
-    const bool more2 = ti + 2 < kWarpTiles && ya + 2 * kWarpRows < H;
-    if (more2) fetch(ta, ya + 2 * kWarpRows);
-    finish(tb, ya + kWarpRows, ti + 1);
-    if (!more2) break;
-  }
-#else
 #pragma unroll 1
   for (int ti = 0; ti < kWarpTiles; ++ti) {
     const int ya = yb + ti * kWarpRows;
@@ -371,7 +346,6 @@ __global__ void __launch_bounds__(128, USAUG_WARP_MINB) fused_warp_kernel(
     fetch(t, ya);
     finish(t, ya, ti);
   }
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
