@@ -315,7 +315,32 @@ def run_stages(a, dev, peak):
                                         rho.data_ptr(), ng.data_ptr(), ftaps.data_ptr(), Rf, ws3.data_ptr(), ws3.numel(), st), "K3")
     out.append(entry("K3: SNR + reverb, batch 1024 of 512x512", "surface_scan + bone_box + snr_reverb_kernel",
                      timed(k3, 20, False), 13.0 * B * Hs * Ws, B, reps=20, l2="working set 3.5 GB >> L2", bytes_model="13 B/px"))
-    del img, lab, cm, outb
+    # SURVEY 8(f) rows at the same size: scan conversion both ways (10 B/px) ...
+    geo = us.ConvexGeometry.default(Hs, Ws, theta_max=0.4)
+    gax, gay, gth, grmin, gdr, ginv_dr, ginv_dth = (float(v) for v in geo.scalars())
+    s_, c_ = geo.tables()
+    sin_t, cos_t = torch.from_numpy(s_).to(dev), torch.from_numpy(c_).to(dev)
+    pl, cl = torch.empty_like(lab), torch.empty_like(lab)
+    for direction, name, (si, sl, di, dl) in ((0, "Cartesian -> polar", (img, lab, outb, pl)), (1, "polar -> Cartesian", (outb, pl, cm, cl))):
+        def scv():
+            _ffi.check(lib.usaug_scan_convert(si.data_ptr(), sl.data_ptr(), di.data_ptr(), dl.data_ptr(), B, Hs, Ws, Hs, Ws, direction,
+                                              gax, gay, gth, grmin, gdr, ginv_dr, ginv_dth, sin_t.data_ptr(), cos_t.data_ptr(), st),
+                       "scan conversion")
+        out.append(entry(f"8(f): scan conversion {name}, batch 1024 of 512x512", "scan_convert_kernel", timed(scv, 20, False),
+                         10.0 * B * Hs * Ws, B, reps=20, l2="working set 2.7 GB >> L2", bytes_model="10 B/px"))
+    del pl, cl, cm, outb, lab
+    # ... and local energy (monogenic signal, separable DFTs: 56 B/px), batch 512 of 512x512
+    B = 512
+    img = img[:B].contiguous()
+    energy, scale = torch.empty_like(img), torch.empty(B, device=dev)
+    wsE = torch.empty(lib.usaug_local_energy_workspace_bytes(B, Hs, Ws), dtype=torch.uint8, device=dev)
+
+    def le():
+        _ffi.check(lib.usaug_local_energy(img.data_ptr(), energy.data_ptr(), scale.data_ptr(), B, Hs, Ws, 8.0, 2.1, 3, 0.55,
+                                          wsE.data_ptr(), wsE.numel(), st), "local energy")
+    out.append(entry("8(f): local energy, batch 512 of 512x512", "rows fwd + cols + rows inv + scale", timed(le, 10, False),
+                     56.0 * B * Hs * Ws, B, reps=10, l2="working set >> L2", bytes_model="56 B/px"))
+    del img, energy, wsE
     torch.cuda.empty_cache()
     # configs[2]: confidence-map PCG, batch 64 of 512x512 (64 B x unknowns x iterations)
     B, Hs, Ws = 64, 512, 512

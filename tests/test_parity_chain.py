@@ -111,6 +111,22 @@ def test_graphed_chain_is_bitwise_the_eager_chain(cuda_device):
     assert (err <= 0.4 * util.tol_cm(RTOL) + util.REL_TOL * np.maximum(np.abs(ri), util.REL_DEN_FLOOR)).all(), err.max()
 
 
+def test_graphed_chain_with_label_sinks(cuda_device):
+    """The captured chain with the bone pixels of the deformed label as sinks: the sink mask is produced inside the
+    graph (K1 writes the label the PCG setup reads), so a replay with other labels must follow them."""
+    B, H, W = 2, 96, 128
+    chain = make_chain(sink="label")
+    batches = [util.synth_batch(B, H, W), util.synth_batch(B, H, W, seed0=7)]
+    g = chain.capture(util.cuda(batches[0][0], cuda_device), util.cuda(batches[0][1], cuda_device))
+    for k, (i_, l_) in enumerate(batches + batches[:1]):
+        params = chain.get_params(B, sample_index=np.arange(B) + 5 * k, image_size=(H, W))
+        ti, tl = util.cuda(i_, cuda_device), util.cuda(l_, cuda_device)
+        ei, el = chain(ti, tl, params)
+        gi, gl = g(ti, tl, params)
+        torch.cuda.synchronize()
+        assert torch.equal(gi, ei) and torch.equal(gl, el), k
+
+
 @pytest.mark.parametrize("sink", ["bottom_and_sides", "label"])
 def test_full_chain_with_sink_modes(cuda_device, sink):
     """SURVEY.md 8(f) row 3 through the transform API: the confidence map of the chain absorbs walks at the image sides,
