@@ -1,24 +1,27 @@
 // Monogenic-signal local energy (oracle/local_energy.py):
 //   F = FFT2(I);  even = Re IFFT2(G F);  q = IFFT2(G (v' - i u')/rho F);  E = sqrt(even^2 + |q|^2)
-// with G = sum of log-Gabor band-pass filters.  Hand-written batched 2-D FFT for power-of-two sizes:
+// with G = sum of log-Gabor band-pass filters.  Hand-written batched 2-D FFT for power-of-two sizes on the block-level
+// mixed-radix Stockham transform of fft_stockham.cuh (register radix-8 passes, swizzled shared memory, natural order
+// in and out):
 //
-//   le_rows_fwd   per image row: real -> complex radix-2 DIF FFT in shared memory (natural in, BIT-REVERSED out)
-//   le_cols       per tile of columns: DIF FFT along y, filter multiply (frequencies from the bit-reversed
-//                 positions), two radix-2 DIT inverse FFTs along y (bit-reversed in, natural out)
-//   le_rows_inv   per image row: DIT inverse FFT of both planes along x, energy, per-block maxima
+//   le_twiddles   the twiddle tables of the two transform lengths, once per call (2 blocks)
+//   le_rows_fwd   per group of image rows: real -> complex FFT along x
+//   le_cols       per tile of columns: FFT along y, filter multiply, two inverse FFTs along y
+//   le_rows_inv   per group of image rows: inverse FFT of both planes along x, energy, per-block maxima
 //   le_scale      per image: 1 / max E (0 for an image without band-pass content)
 //
-// Pairing a DIF forward with a DIT inverse transform means no bit-reversal permutation is ever executed.
 // Sizes that are not powers of two are mirror-extended (bottom / right, edge included) to the next power of two
 // (Hp x Wp) on the way into le_rows_fwd; rows and columns beyond H x W are never written back.
 // HBM traffic: 4 + 8 | 8 + 16 | 16 + 4 = 56 B/px; everything else stays in shared memory.
+#include "fft_stockham.cuh"
 #include "kernels.cuh"
 
 namespace usaug {
 
-constexpr int kLeThreads = 256;
+constexpr int kLeThreads = 256;       // fft::block_fft needs blockDim.x * 8 to be a multiple of the transform length
 constexpr int kLeMaxScales = 4;
 constexpr int kLeMaxN = 2048;
+constexpr int kLeColPad = 2;          // column sequences are H + 2 apart: the transposing copies of a tile spread over the banks
 
 struct LeFilter {
   int scales;
@@ -26,313 +29,186 @@ struct LeFilter {
   float inv_den;     // 1 / (2 ln^2 sigma_f)
 };
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
-
-// tw[k] = exp(-2 pi i k / n), k < n/2
-__device__ __forceinline__ void make_twiddles(float2* tw, int n) {
-  for (int k = threadIdx.x; k < n / 2; k += blockDim.x) {
-    float s, c;
-    sincospif(2.0f * (float)k / (float)n, &s, &c);
-    tw[k] = make_float2(c, -s);
-  }
-}
-
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-
-// ---- in-place radix-2 FFT of nseq sequences of n = 1 << lg points (sequence q at data + q * pitch) ----------
-// Stage s pairs elements half = 2^s apart; its twiddle for position pos (< half) is tw[pos << (lg - 1 - s)].
-//   * stages with half >= 128 run through shared memory, two stages per pass (a thread owns a quad): the four
-//     accesses of a quad are >= 64 elements apart and consecutive threads touch consecutive elements -> no bank
-//     conflicts;
-//   * all stages with half <= 64 run INSIDE A WARP: a warp loads a 128-point block with contiguous accesses into four
-//     registers per lane (elements lane, lane + 32, lane + 64, lane + 96), does half = 64 and 32 in-thread and
-//     half = 16 .. 1 with shuffles, and writes the block back.  An n = 512 transform is 2 conflict-free
-//     shared-memory round trips instead of 5 passes whose small strides replayed ~57 % of the wavefronts (ncu).
-// fft_dif: decimation in frequency, natural order in, bit-reversed order out.  ifft_dit: inverse transform
-// (conjugate twiddles, unscaled), decimation in time, bit-reversed order in, natural order out.
-
-__device__ __forceinline__ void smem_radix2_stage(float2* data, int pitch, int nseq, int lg, int s, const float2* tw,
-                                                  bool inverse) {
-  const int half = 1 << s, half_n = 1 << (lg - 1);
-  for (int idx = threadIdx.x; idx < nseq * half_n; idx += blockDim.x) {
-    const int q = idx >> (lg - 1), j = idx & (half_n - 1);
-    const int pos = j & (half - 1);
-    float2* x = data + q * pitch + (((j >> s) << (s + 1)) | pos);
-    float2 w = tw[pos << (lg - 1 - s)];
-    if (inverse) {
-      w.y = -w.y;
-      const float2 a = x[0], t = cmul(x[half], w);
-      x[0] = cadd(a, t); x[half] = csub(a, t);
-    } else {
-      const float2 a = x[0], c = x[half];
-      x[0] = cadd(a, c); x[half] = cmul(csub(a, c), w);
-    }
-  }
-  __syncthreads();
-}
-
-// stages s (half = 2^s) and s-1 of the forward transform in one pass
-__device__ __forceinline__ void smem_radix4_dif(float2* data, int pitch, int nseq, int lg, int s, const float2* tw) {
-  const int quarter = 1 << (s - 1), nquad = 1 << (lg - 2);
-  for (int idx = threadIdx.x; idx < nseq * nquad; idx += blockDim.x) {
-    const int q = idx >> (lg - 2), j = idx & (nquad - 1);
-    const int pos = j & (quarter - 1);
-    float2* x = data + q * pitch + (((j >> (s - 1)) << (s + 1)) | pos);
-    const float2 a0 = x[0], a1 = x[quarter], a2 = x[2 * quarter], a3 = x[3 * quarter];
-    const float2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), tw[pos << (lg - 1 - s)]);
-    const float2 b1 = cadd(a1, a3), b3 = cmul(csub(a1, a3), tw[(pos + quarter) << (lg - 1 - s)]);
-    const float2 w = tw[pos << (lg - s)];
-    x[0] = cadd(b0, b1); x[quarter] = cmul(csub(b0, b1), w);
-    x[2 * quarter] = cadd(b2, b3); x[3 * quarter] = cmul(csub(b2, b3), w);
-  }
-  __syncthreads();
-}
-
-// stages s (half = 2^s) and s+1 of the inverse transform in one pass
-__device__ __forceinline__ void smem_radix4_dit(float2* data, int pitch, int nseq, int lg, int s, const float2* tw) {
-  const int half = 1 << s, nquad = 1 << (lg - 2);
-  for (int idx = threadIdx.x; idx < nseq * nquad; idx += blockDim.x) {
-    const int q = idx >> (lg - 2), j = idx & (nquad - 1);
-    const int pos = j & (half - 1);
-    float2* x = data + q * pitch + (((j >> s) << (s + 2)) | pos);
-    const float2 w = cconj(tw[pos << (lg - 1 - s)]);
-    const float2 a0 = x[0], t1 = cmul(x[half], w), a2 = x[2 * half], t3 = cmul(x[3 * half], w);
-    const float2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
-    const float2 u2 = cmul(b2, cconj(tw[pos << (lg - 2 - s)]));
-    const float2 u3 = cmul(b3, cconj(tw[(pos + half) << (lg - 2 - s)]));
-    x[0] = cadd(b0, u2); x[2 * half] = csub(b0, u2);
-    x[half] = cadd(b1, u3); x[3 * half] = csub(b1, u3);
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
-  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
-}
-
-// All stages with half <= 16 * RPL of the blocks of 32 * RPL points, in registers (RPL = 1, 2 or 4 values per lane).
-template <int RPL, bool INVERSE>
-__device__ __forceinline__ void warp_stages(float2* data, int pitch, int nseq, int lg, const float2* tw) {
-  constexpr int BS = 32 * RPL;                    // block size; the transform has n >= BS points
-  constexpr int LB = (RPL == 4) ? 7 : (RPL == 2) ? 6 : 5;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int nblk = nseq << (lg - LB);             // blocks in all sequences
-  // The twiddles of the register stages depend on the lane only: fetched once per call.  (Read per block, the
-  // strided table reads of the shuffle stages were 16-way bank conflicts.)
-  float2 wsh[5], w5 = make_float2(1.f, 0.f), w6a = w5, w6b = w5;
-#pragma unroll
-  for (int s = 0; s <= 4; ++s) wsh[s] = tw[(lane & ((1 << s) - 1)) << (lg - 1 - s)];
-  if (RPL >= 2) w5 = tw[lane << (lg - 6)];
-  if (RPL == 4) { w6a = tw[lane << (lg - 7)]; w6b = tw[(lane + 32) << (lg - 7)]; }
-  if (INVERSE) {
-#pragma unroll
-    for (int s = 0; s <= 4; ++s) wsh[s].y = -wsh[s].y;
-    w5.y = -w5.y; w6a.y = -w6a.y; w6b.y = -w6b.y;
-  }
-  for (int blk = warp; blk < nblk; blk += nwarp) {
-    const int q = blk >> (lg - LB);
-    float2* x = data + q * pitch + ((blk & ((1 << (lg - LB)) - 1)) << LB);
-    float2 v[RPL];
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) v[k] = x[k * 32 + lane];
-    if (!INVERSE) {
-      // half = 64: (0,2) (1,3); half = 32: (0,1) (2,3); element index inside the block = k * 32 + lane
-      if (RPL == 4) {
-        const float2 a0 = v[0], a1 = v[1];
-        v[0] = cadd(a0, v[2]); v[2] = cmul(csub(a0, v[2]), w6a);
-        v[1] = cadd(a1, v[3]); v[3] = cmul(csub(a1, v[3]), w6b);
-      }
-      if (RPL >= 2) {
-#pragma unroll
-        for (int k = 0; k < RPL; k += 2) {
-          const float2 a = v[k];
-          v[k] = cadd(a, v[k + 1]); v[k + 1] = cmul(csub(a, v[k + 1]), w5);
-        }
-      }
-#pragma unroll
-      for (int s = 4; s >= 0; --s) {              // half = 16 .. 1 across lanes
-        const int h = 1 << s;
-        const bool up = lane & h;
-#pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-          const float2 o = shfl_xor2(v[k], h);
-          v[k] = up ? cmul(csub(o, v[k]), wsh[s]) : cadd(v[k], o);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int s = 0; s <= 4; ++s) {              // half = 1 .. 16 across lanes
-        const int h = 1 << s;
-        const bool up = lane & h;
-#pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-          const float2 t = up ? cmul(v[k], wsh[s]) : v[k];  // the upper element is twiddled before the exchange
-          const float2 o = shfl_xor2(t, h);
-          v[k] = up ? csub(o, t) : cadd(t, o);
-        }
-      }
-      if (RPL >= 2) {
-#pragma unroll
-        for (int k = 0; k < RPL; k += 2) {
-          const float2 t = cmul(v[k + 1], w5), a = v[k];
-          v[k] = cadd(a, t); v[k + 1] = csub(a, t);
-        }
-      }
-      if (RPL == 4) {
-        const float2 t2 = cmul(v[2], w6a), t3 = cmul(v[3], w6b);
-        const float2 a0 = v[0], a1 = v[1];
-        v[0] = cadd(a0, t2); v[2] = csub(a0, t2);
-        v[1] = cadd(a1, t3); v[3] = csub(a1, t3);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) x[k * 32 + lane] = v[k];
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ void fft_dif(float2* data, int pitch, int nseq, int lg, const float2* tw) {
-  if (lg < 5) {                                   // n = 8, 16: plain shared-memory stages
-    for (int s = lg - 1; s >= 0; --s) smem_radix2_stage(data, pitch, nseq, lg, s, tw, false);
-    return;
-  }
-  const int lb = lg < 7 ? lg : 7;                 // stages below lb run in registers
-  int s = lg - 1;
-  if ((lg - lb) & 1) { smem_radix2_stage(data, pitch, nseq, lg, s, tw, false); --s; }
-  for (; s >= lb; s -= 2) smem_radix4_dif(data, pitch, nseq, lg, s, tw);
-  if (lb == 7) warp_stages<4, false>(data, pitch, nseq, lg, tw);
-  else if (lb == 6) warp_stages<2, false>(data, pitch, nseq, lg, tw);
-  else warp_stages<1, false>(data, pitch, nseq, lg, tw);
-}
-
-__device__ __forceinline__ void ifft_dit(float2* data, int pitch, int nseq, int lg, const float2* tw) {
-  if (lg < 5) {
-    for (int s = 0; s < lg; ++s) smem_radix2_stage(data, pitch, nseq, lg, s, tw, true);
-    return;
-  }
-  const int lb = lg < 7 ? lg : 7;
-  if (lb == 7) warp_stages<4, true>(data, pitch, nseq, lg, tw);
-  else if (lb == 6) warp_stages<2, true>(data, pitch, nseq, lg, tw);
-  else warp_stages<1, true>(data, pitch, nseq, lg, tw);
-  int s = lb;
-  for (; s + 1 < lg; s += 2) smem_radix4_dit(data, pitch, nseq, lg, s, tw);
-  if (s < lg) smem_radix2_stage(data, pitch, nseq, lg, s, tw, true);
-}
-
 // signed DFT frequency index of bin k (numpy.fft.fftfreq * n): the Nyquist bin is -n/2
 __device__ __forceinline__ int signed_bin(int k, int n) { return (k < n / 2) ? k : k - n; }
 
-// ---- rows, forward: block = rb rows ---------------------------------------------------------------
-// img is [B][H0][W0]; spec is [B][H][W] with H, W the padded (power-of-two) sizes
-__global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restrict__ img, float2* __restrict__ spec,
-                                                          int H0, int W0, int H, int W, int lgW, int rb, size_t nrows) {
-  extern __shared__ __align__(16) unsigned char le_smem[];
-  float2* tw = reinterpret_cast<float2*>(le_smem);          // [W/2]
-  float2* data = tw + W / 2;                                // [rb][W]
-  const size_t row0 = (size_t)blockIdx.x * rb;
-  make_twiddles(tw, W);
-  for (int i = threadIdx.x; i < rb * W; i += blockDim.x) {
-    const size_t r = row0 + i / W;
-    float v = 0.f;
-    if (r < nrows) {
-      const int b = (int)(r / H), yp = (int)(r % H), xp = i % W;
-      const int y = (yp < H0) ? yp : 2 * H0 - 1 - yp, x = (xp < W0) ? xp : 2 * W0 - 1 - xp;   // mirror extension
-      v = img[((size_t)b * H0 + y) * W0 + x];
+__device__ __forceinline__ void load_twiddles(float2* tw, const float2* __restrict__ twg, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = twg[i];
+}
+
+__global__ void __launch_bounds__(kLeThreads) le_twiddles(fft::Plan pw, fft::Plan ph, float2* __restrict__ tww,
+                                                          float2* __restrict__ twh) {
+  if (blockIdx.x == 0) fft::fill_twiddles(pw, tww, threadIdx.x, blockDim.x);
+  else fft::fill_twiddles(ph, twh, threadIdx.x, blockDim.x);
+}
+
+// The filter of frequency (ky, kx), the same for every image of the call: filt[kx * H + ky] = (G, G u'/rho, G v'/rho, 0)
+// with the odd multipliers zero at the Nyquist bins (column-major: le_cols walks ky fastest).
+__global__ void __launch_bounds__(kLeThreads) le_filter(float4* __restrict__ filt, int H, int W, int lgH, LeFilter flt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const int kv = signed_bin(i & (H - 1), H), ku = signed_bin(i >> lgH, W);
+  const float u = (float)ku / (float)W, v = (float)kv / (float)H;
+  const float rho2 = fmaf(u, u, v * v);
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rho2 > 0.f) {
+    const float lr = 0.5f * logf(rho2);
+    float g = 0.f;
+    for (int s = 0; s < flt.scales; ++s) {
+      const float t = lr + flt.ln_lambda[s];
+      g += expf(-t * t * flt.inv_den);
     }
-    data[i] = make_float2(v, 0.f);
+    const float gr = g * rsqrtf(rho2);
+    f = make_float4(g, (2 * ku == -W) ? 0.f : u * gr, (2 * kv == -H) ? 0.f : v * gr, 0.f);
+  }
+  filt[i] = f;
+}
+
+// ---- rows, forward: block = rb rows ---------------------------------------------------------------
+// img is [B][H0][W0]; spec is [B][H][W] with H, W the padded (power-of-two) sizes.  The copies move two points per
+// thread and step: x and x + 1 (x even) live at the shared-memory slots s and s ^ 1.
+__global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restrict__ img, float2* __restrict__ spec,
+                                                          int H0, int W0, int H, int W, int lgH, fft::Plan pw,
+                                                          const float2* __restrict__ twg, int rb, size_t nrows) {
+  extern __shared__ __align__(16) unsigned char le_smem[];
+  float2* tw = reinterpret_cast<float2*>(le_smem);          // [W]  (pw.tw_total <= W entries used)
+  float2* data = tw + W;                                    // [rb][W], element x of a row at slot swz(x)
+  const size_t row0 = (size_t)blockIdx.x * rb;
+  const int lgW = pw.lg;
+  // no mirror extension: rows are pairs of 8 bytes (if the caller's pointer is that aligned)
+  const bool exact = (H0 == H) && (W0 == W) && (reinterpret_cast<size_t>(img) & 7) == 0;
+  load_twiddles(tw, twg, pw.tw_total);
+  for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
+    const int q = i >> lgW, xp = i & (W - 1);
+    const size_t r = row0 + q;
+    float v0 = 0.f, v1 = 0.f;
+    if (r < nrows) {
+      if (exact) {
+        const float2 t = *reinterpret_cast<const float2*>(img + r * W + xp);
+        v0 = t.x; v1 = t.y;
+      } else {
+        const int b = (int)(r >> lgH), yp = (int)(r & (size_t)(H - 1));
+        const int y = (yp < H0) ? yp : 2 * H0 - 1 - yp;                                        // mirror extension
+        const int xa = (xp < W0) ? xp : 2 * W0 - 1 - xp, xb = (xp + 1 < W0) ? xp + 1 : 2 * W0 - 2 - xp;
+        const float* row = img + ((size_t)b * H0 + y) * W0;
+        v0 = row[xa]; v1 = row[xb];
+      }
+    }
+    const int s = (q << lgW) + fft::swz(xp);
+    data[s] = make_float2(v0, 0.f);
+    data[s ^ 1] = make_float2(v1, 0.f);
   }
   __syncthreads();
-  fft_dif(data, W, rb, lgW, tw);
-  for (int i = threadIdx.x; i < rb * W; i += blockDim.x) {
-    const size_t r = row0 + i / W;
-    if (r < nrows) spec[r * W + (i % W)] = data[i];
+  fft::block_fft<false>(data, W, rb, pw, tw);
+  for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
+    const int q = i >> lgW, xp = i & (W - 1);
+    const size_t r = row0 + q;
+    if (r < nrows) {
+      const int s = (q << lgW) + fft::swz(xp);
+      const float2 a = data[s], c = data[s ^ 1];
+      *reinterpret_cast<float4*>(spec + r * W + xp) = make_float4(a.x, a.y, c.x, c.y);
+    }
   }
 }
 
 // ---- columns: block = tc columns of one image ---------------------------------------------------------
 __global__ void __launch_bounds__(kLeThreads) le_cols(const float2* __restrict__ spec, float2* __restrict__ odd,
-                                                      float2* __restrict__ even, int H0, int H, int W, int lgH, int lgW,
-                                                      int tc, LeFilter flt) {
+                                                      float2* __restrict__ even, const float4* __restrict__ filt,
+                                                      int H0, int H, int W, fft::Plan ph,
+                                                      const float2* __restrict__ twg, int tc, int lg_tc) {
   extern __shared__ __align__(16) unsigned char le_smem[];
-  const int pitch = H + 1;                                  // odd pitch: the tc columns of one row hit different banks
-  float2* tw = reinterpret_cast<float2*>(le_smem);          // [H/2]
-  float2* A = tw + H / 2;                                   // [tc][H+1]  spectrum, then the Riesz (odd) pair
-  float2* Bv = A + tc * pitch;                              // [tc][H+1]  the even part
+  const int pitch = H + kLeColPad, lgH = ph.lg;
+  float2* tw = reinterpret_cast<float2*>(le_smem);          // [H]
+  float2* A = tw + H;                                       // [tc][pitch]  spectrum, then the Riesz (odd) pair
+  float2* Bv = A + tc * pitch;                              // [tc][pitch]  the even part
   const int b = blockIdx.y, x0 = blockIdx.x * tc;
   const size_t base = (size_t)b * H * W;
-  make_twiddles(tw, H);
-  for (int i = threadIdx.x; i < tc * H; i += blockDim.x) {
-    const int c = i % tc, y = i / tc;
-    A[c * pitch + y] = spec[base + (size_t)y * W + x0 + c];
-  }
-  __syncthreads();
-  fft_dif(A, pitch, tc, lgH, tw);
-  // position (py, px) holds frequency (rev(py), rev(px)): the row pass left x in bit-reversed order too
-  for (int i = threadIdx.x; i < tc * H; i += blockDim.x) {
-    const int c = i / H, py = i % H;
-    const int kv = signed_bin((int)(__brev((unsigned)py) >> (32 - lgH)), H);
-    const int ku = signed_bin((int)(__brev((unsigned)(x0 + c)) >> (32 - lgW)), W);
-    const float u = (float)ku / (float)W, v = (float)kv / (float)H;
-    const float rho2 = fmaf(u, u, v * v);
-    float2 fo = make_float2(0.f, 0.f), fe = make_float2(0.f, 0.f);
-    if (rho2 > 0.f) {
-      const float lr = 0.5f * logf(rho2);
-      float g = 0.f;
-      for (int s = 0; s < flt.scales; ++s) {
-        const float t = lr + flt.ln_lambda[s];
-        g += expf(-t * t * flt.inv_den);
-      }
-      const float2 F = A[c * pitch + py];
-      fe = make_float2(g * F.x, g * F.y);
-      // (v' - i u') / rho * G * F, odd multipliers zero at the Nyquist bins
-      const float gr = g * rsqrtf(rho2);
-      const float uo = (2 * ku == -W) ? 0.f : u * gr, vo = (2 * kv == -H) ? 0.f : v * gr;
-      fo = make_float2(fmaf(vo, F.x, uo * F.y), fmaf(vo, F.y, -uo * F.x));
+  load_twiddles(tw, twg, ph.tw_total);
+  if (tc >= 2) {                                            // two columns per thread and step: 16-byte accesses
+    for (int i = 2 * threadIdx.x; i < tc * H; i += 2 * blockDim.x) {
+      const int c = i & (tc - 1), y = i >> lg_tc;
+      const float4 t = *reinterpret_cast<const float4*>(spec + base + (size_t)y * W + x0 + c);
+      const int s = c * pitch + fft::swz(y);
+      A[s] = make_float2(t.x, t.y);
+      A[s + pitch] = make_float2(t.z, t.w);
     }
-    A[c * pitch + py] = fo;
-    Bv[c * pitch + py] = fe;
+  } else {
+    for (int y = threadIdx.x; y < H; y += blockDim.x) A[fft::swz(y)] = spec[base + (size_t)y * W + x0];
   }
   __syncthreads();
-  ifft_dit(A, pitch, 2 * tc, lgH, tw);                      // A and Bv are contiguous: 2 tc sequences
-  for (int i = threadIdx.x; i < tc * H0; i += blockDim.x) {   // rows of the mirror extension are not needed again
-    const int c = i % tc, y = i / tc;
-    const size_t o = base + (size_t)y * W + x0 + c;
-    odd[o] = A[c * pitch + y];
-    even[o] = Bv[c * pitch + y];
+  fft::block_fft<false>(A, pitch, tc, ph, tw);
+  const float4* fcol = filt + (size_t)x0 * H;               // the tile's filter columns are contiguous
+  for (int i = threadIdx.x; i < tc * H; i += blockDim.x) {
+    const int c = i >> lgH, py = i & (H - 1);
+    const int slot = c * pitch + fft::swz(py);
+    const float4 f = fcol[i];                               // (G, G u'/rho, G v'/rho): zero at DC
+    const float2 F = A[slot];
+    // even: G F;  odd: (v' - i u') / rho * G * F
+    Bv[slot] = make_float2(f.x * F.x, f.x * F.y);
+    A[slot] = make_float2(fmaf(f.z, F.x, f.y * F.y), fmaf(f.z, F.y, -f.y * F.x));
+  }
+  __syncthreads();
+  fft::block_fft<true>(A, pitch, 2 * tc, ph, tw);           // A and Bv are contiguous: 2 tc sequences
+  // rows of the mirror extension are not needed again
+  if (tc >= 2) {
+    for (int i = 2 * threadIdx.x; i < tc * H0; i += 2 * blockDim.x) {
+      const int c = i & (tc - 1), y = i >> lg_tc;
+      const size_t o = base + (size_t)y * W + x0 + c;
+      const int s = c * pitch + fft::swz(y);
+      const float2 a0 = A[s], a1 = A[s + pitch], e0 = Bv[s], e1 = Bv[s + pitch];
+      *reinterpret_cast<float4*>(odd + o) = make_float4(a0.x, a0.y, a1.x, a1.y);
+      *reinterpret_cast<float4*>(even + o) = make_float4(e0.x, e0.y, e1.x, e1.y);
+    }
+  } else {
+    for (int y = threadIdx.x; y < H0; y += blockDim.x) {
+      const size_t o = base + (size_t)y * W + x0;
+      odd[o] = A[fft::swz(y)];
+      even[o] = Bv[fft::swz(y)];
+    }
   }
 }
 
 // ---- rows, inverse + energy: block = rb rows -----------------------------------------------------------
 __global__ void __launch_bounds__(kLeThreads) le_rows_inv(const float2* __restrict__ odd, const float2* __restrict__ even,
                                                           float* __restrict__ energy, float* __restrict__ part,
-                                                          int H0, int W0, int H, int W, int lgW, int rb, float norm) {
+                                                          int H0, int W0, int H, int W, fft::Plan pw,
+                                                          const float2* __restrict__ twg, int rb, float norm) {
   extern __shared__ __align__(16) unsigned char le_smem[];
   __shared__ float s_max[kLeThreads / 32];
-  float2* tw = reinterpret_cast<float2*>(le_smem);          // [W/2]
-  float2* data = tw + W / 2;                                // [2 rb][W]: odd rows, then even rows
-  const int b = blockIdx.y;
+  float2* tw = reinterpret_cast<float2*>(le_smem);          // [W]
+  float2* data = tw + W;                                    // [2 rb][W]: odd rows, then even rows
+  const int b = blockIdx.y, lgW = pw.lg;
   const int row0 = blockIdx.x * rb;                         // H % rb == 0; only blocks with row0 < H0 are launched
   const size_t base = ((size_t)b * H + row0) * W;
-  make_twiddles(tw, W);
-  for (int i = threadIdx.x; i < rb * W; i += blockDim.x) {
-    data[i] = odd[base + i];
-    data[rb * W + i] = even[base + i];
+  load_twiddles(tw, twg, pw.tw_total);
+  for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
+    const int s = (i & ~(W - 1)) + fft::swz(i & (W - 1));
+    const float4 o = *reinterpret_cast<const float4*>(odd + base + i);
+    const float4 e = *reinterpret_cast<const float4*>(even + base + i);
+    data[s] = make_float2(o.x, o.y); data[s ^ 1] = make_float2(o.z, o.w);
+    data[rb * W + s] = make_float2(e.x, e.y); data[rb * W + (s ^ 1)] = make_float2(e.z, e.w);
   }
   __syncthreads();
-  ifft_dit(data, W, 2 * rb, lgW, tw);
+  fft::block_fft<true>(data, W, 2 * rb, pw, tw);
   float m = 0.f;
-  for (int i = threadIdx.x; i < rb * W; i += blockDim.x) {
-    const int y = row0 + i / W, x = i % W;
+  // even row length: x and x + 1 as one 8-byte store
+  const bool pairs = (W0 & 1) == 0 && (reinterpret_cast<size_t>(energy) & 7) == 0;
+  for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
+    const int y = row0 + (i >> lgW), x = i & (W - 1);
     if (y >= H0 || x >= W0) continue;                       // mirror extension: not part of the result
-    const float2 q = data[i];
-    const float e = data[rb * W + i].x;
-    const float en = sqrtf(fmaf(e, e, fmaf(q.x, q.x, q.y * q.y))) * norm;
-    energy[((size_t)b * H0 + y) * W0 + x] = en;
-    m = fmaxf(m, en);
+    const int s = (i & ~(W - 1)) + fft::swz(x);
+    const float2 q0 = data[s], q1 = data[s ^ 1];
+    const float e0 = data[rb * W + s].x, e1 = data[rb * W + (s ^ 1)].x;
+    const float en0 = sqrtf(fmaf(e0, e0, fmaf(q0.x, q0.x, q0.y * q0.y))) * norm;
+    const float en1 = sqrtf(fmaf(e1, e1, fmaf(q1.x, q1.x, q1.y * q1.y))) * norm;
+    float* dst = energy + ((size_t)b * H0 + y) * W0 + x;
+    if (pairs) {
+      *reinterpret_cast<float2*>(dst) = make_float2(en0, en1);
+      m = fmaxf(m, fmaxf(en0, en1));
+    } else {
+      dst[0] = en0; m = fmaxf(m, en0);
+      if (x + 1 < W0) { dst[1] = en1; m = fmaxf(m, en1); }
+    }
   }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
@@ -358,7 +234,8 @@ static int ilog2_exact(int n) {
 }
 
 struct LeLayout {
-  float2 *spec, *odd, *even;
+  float2 *spec, *odd, *even, *tww, *twh;
+  float4* filt;       // [W][H] filter multipliers, shared by all images of the call
   float* part;
   int rb_fwd, rb_inv, tc, nblk_inv;
   size_t bytes;
@@ -384,6 +261,8 @@ static LeLayout le_layout(void* ws, int B, int H0, int H, int W) {
   L.nblk_inv = (H0 + L.rb_inv - 1) / L.rb_inv;
   Carver cv(ws);
   L.spec = cv.take<float2>(N); L.odd = cv.take<float2>(N); L.even = cv.take<float2>(N);
+  L.tww = cv.take<float2>(kLeMaxN); L.twh = cv.take<float2>(kLeMaxN);
+  L.filt = cv.take<float4>((size_t)H * W);
   L.part = cv.take<float>((size_t)B * L.nblk_inv);
   L.bytes = cv.off;
   L.cv = cv;
@@ -429,19 +308,26 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
   flt.inv_den = (float)(1.0 / (2.0 * lsf * lsf));
 
   const size_t nrows = (size_t)B * H;
-  const size_t sm_fwd = (size_t)(W / 2 + L.rb_fwd * W) * sizeof(float2);
-  const size_t sm_col = (size_t)(H / 2 + 2 * L.tc * (H + 1)) * sizeof(float2);
-  const size_t sm_inv = (size_t)(W / 2 + 2 * L.rb_inv * W) * sizeof(float2);
+  const fft::Plan pw = fft::make_plan(lgW), ph = fft::make_plan(lgH);
+  // twiddle table + the sequences, rounded up to whole transform steps (fft::padded_seqs)
+  const size_t sm_fwd = (size_t)(W + fft::padded_seqs(L.rb_fwd, lgW, kLeThreads) * W) * sizeof(float2);
+  const size_t sm_col = (size_t)(H + fft::padded_seqs(2 * L.tc, lgH, kLeThreads) * (H + kLeColPad)) * sizeof(float2);
+  const size_t sm_inv = (size_t)(W + fft::padded_seqs(2 * L.rb_inv, lgW, kLeThreads) * W) * sizeof(float2);
   if (sm_fwd > 48 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
   if (sm_col > 48 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_col));
   if (sm_inv > 48 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv));
 
-  le_rows_fwd<<<(unsigned)((nrows + L.rb_fwd - 1) / L.rb_fwd), kLeThreads, sm_fwd, stream>>>(img, L.spec, H0, W0, H, W, lgW,
-                                                                                            L.rb_fwd, nrows);
+  le_twiddles<<<2, kLeThreads, 0, stream>>>(pw, ph, L.tww, L.twh);
+  USAUG_CHECK_LAUNCH("le_twiddles");
+  le_filter<<<(unsigned)(((size_t)H * W + kLeThreads - 1) / kLeThreads), kLeThreads, 0, stream>>>(L.filt, H, W, lgH, flt);
+  USAUG_CHECK_LAUNCH("le_filter");
+  le_rows_fwd<<<(unsigned)((nrows + L.rb_fwd - 1) / L.rb_fwd), kLeThreads, sm_fwd, stream>>>(img, L.spec, H0, W0, H, W, lgH, pw,
+                                                                                            L.tww, L.rb_fwd, nrows);
   USAUG_CHECK_LAUNCH("le_rows_fwd");
-  le_cols<<<dim3(W / L.tc, B), kLeThreads, sm_col, stream>>>(L.spec, L.odd, L.even, H0, H, W, lgH, lgW, L.tc, flt);
+  le_cols<<<dim3(W / L.tc, B), kLeThreads, sm_col, stream>>>(L.spec, L.odd, L.even, L.filt, H0, H, W, ph, L.twh, L.tc,
+                                                             ilog2_exact(L.tc));
   USAUG_CHECK_LAUNCH("le_cols");
-  le_rows_inv<<<dim3(L.nblk_inv, B), kLeThreads, sm_inv, stream>>>(L.odd, L.even, energy, L.part, H0, W0, H, W, lgW,
+  le_rows_inv<<<dim3(L.nblk_inv, B), kLeThreads, sm_inv, stream>>>(L.odd, L.even, energy, L.part, H0, W0, H, W, pw, L.tww,
                                                                   L.rb_inv, (float)(1.0 / ((double)H * (double)W)));
   USAUG_CHECK_LAUNCH("le_rows_inv");
   le_scale<<<(B + 127) / 128, 128, 0, stream>>>(L.part, L.nblk_inv, scale, B);
