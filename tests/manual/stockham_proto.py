@@ -70,3 +70,32 @@ if __name__ == "__main__":
         print("pad", name)
         for n in (512, 1024, 256):
             conflict_model(n, pad)
+
+
+def seqfast_conflicts():
+    """le_cols: first pass writes / last pass reads with the sequence index fastest across lanes (global accesses of a
+    tile of columns are then contiguous).  Which pitch (H + pad) keeps those shared-memory accesses conflict-free?"""
+    swz = lambda i: i ^ ((i >> 3) & 15)
+    for n in (64, 256, 512, 1024, 2048):
+        lg = n.bit_length() - 1
+        spp = 2048 // n
+        rs = radices(lg)
+        R0, RL = rs[0], rs[-1]
+        NsL = n // RL
+        for pad in (0, 1, 2, 4, 6, 8, 10):
+            pitch = n + pad
+            w = r_ = cnt = 0
+            for w0 in range(0, 2048 // R0, 32):
+                lanes = [((w0 + l) & (spp - 1), (w0 + l) // spp) for l in range(32)]
+                for r in range(R0):      # first pass (Ns = 1) writes d + r, d = j * R0
+                    w += wavefronts([q * pitch + swz(j * R0 + r) for q, j in lanes]); cnt += 2
+            cnt2 = 0
+            for w0 in range(0, 2048 // RL, 32):
+                lanes = [((w0 + l) & (spp - 1), (w0 + l) // spp) for l in range(32)]
+                for r in range(RL):      # last pass reads j + r n / RL
+                    r_ += wavefronts([q * pitch + swz(j + r * NsL) for q, j in lanes]); cnt2 += 2
+            print(f"  n={n} spp={spp} pad={pad}: first-pass writes {w / cnt:.2f}x  last-pass reads {r_ / cnt2:.2f}x")
+
+
+if __name__ == "__main__":
+    seqfast_conflicts()

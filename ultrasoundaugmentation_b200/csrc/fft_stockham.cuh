@@ -99,15 +99,10 @@ template <int R> USAUG_HD void swz_basis(int sh, int* bs) {
   for (int k = 0; (1 << k) < R; ++k) bs[k] = swz(1 << (sh + k));
 }
 
-// One butterfly of a pass: sequence `seq` (n points from its slot 0), butterfly j < n / R.  Reads (rbs = swz_basis of
-// lg - log2 R), twiddles and transforms into v; returns the element index d the r-th result goes to as d + (r << ns_lg).
-template <int R, bool INV>
-USAUG_HD int butterfly_read(const float2* seq, int j, int ns_lg, const float2* tw, const int* rbs, float2* v) {
+// Butterfly j (< n / R) of a pass on the R elements v[r] = x[j + r n/R]: twiddles and transforms them in place and
+// returns the element index d the r-th result goes to as d + (r << ns_lg).
+template <int R, bool INV> USAUG_HD int butterfly(int j, int ns_lg, const float2* tw, float2* v) {
   constexpr int RLG = (R == 8) ? 3 : (R == 4) ? 2 : 1;
-  int idx[R];
-  xor_fan<R>(swz(j), rbs, idx);            // j < n/R shares no bit with r n/R
-#pragma unroll
-  for (int r = 0; r < R; ++r) v[r] = seq[idx[r]];
   const int m = j & ((1 << ns_lg) - 1);
   if (ns_lg > 0) {
 #pragma unroll
@@ -119,6 +114,16 @@ USAUG_HD int butterfly_read(const float2* seq, int j, int ns_lg, const float2* t
   }
   dft<R, INV>(v);
   return ((j >> ns_lg) << (ns_lg + RLG)) | m;
+}
+
+// The same from a sequence in (swizzled) shared memory; rbs = swz_basis of lg - log2 R.
+template <int R, bool INV>
+USAUG_HD int butterfly_read(const float2* seq, int j, int ns_lg, const float2* tw, const int* rbs, float2* v) {
+  int idx[R];
+  xor_fan<R>(swz(j), rbs, idx);            // j < n/R shares no bit with r n/R
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = seq[idx[r]];
+  return butterfly<R, INV>(j, ns_lg, tw, v);
 }
 
 // wbs = swz_basis of ns_lg
@@ -138,14 +143,32 @@ inline int padded_seqs(int nseq, int lg, int threads) {
 }
 
 #ifdef __CUDACC__
+// I/O policy of the first / last pass of a block transform: SmemIO = the swizzled sequences in shared memory.  Any
+// other type is a functor on NATURAL element indices, called once per butterfly --
+//   In:   template <int R> void load(int q, int i0, int stride, float2* v) const    v[r] = element i0 + r stride of sequence q
+//   Out:  template <int R> void store(int q, int i0, int stride, const float2* v) const
+//         static constexpr bool kWritesSmem    true if store() writes the sequences the pass reads (needs the barrier)
+// -- so that a transform reads its input from and writes its result to global memory directly, without staging
+// copies (and without their barriers), or applies a pointwise operation on the way out.
+struct SmemIO { static constexpr bool kWritesSmem = true; };
+template <class T> struct is_smem { static constexpr bool value = false; };
+template <> struct is_smem<SmemIO> { static constexpr bool value = true; };
+
+constexpr int kBlockLg = 8;            // block_fft is written for 256 threads
+
 // One pass over nseq sequences (sequence q at data + q * pitch).  The block walks the butterflies in steps of
-// blockDim.x * 8 points; blockDim.x * 8 is a multiple of n, so a step covers whole sequences: the reads of a step are
-// separated from its writes by one barrier, and steps touch different sequences.
-template <int R, bool INV>
-__device__ __forceinline__ void block_pass(float2* data, int pitch, int nseq, int lg, int ns_lg, const float2* tw) {
+// 256 * 8 points; that is a multiple of n, so a step covers whole sequences: the shared-memory reads of a step are
+// separated from its shared-memory writes by one barrier, and steps touch different sequences.  SEQ_FAST: consecutive
+// lanes take the same butterfly of consecutive sequences (a functor then sees consecutive q per warp: contiguous
+// global accesses for sequences that are the columns of an image).
+template <int R, bool INV, bool SEQ_FAST, class In, class Out>
+__device__ __forceinline__ void block_pass(float2* data, int pitch, int nseq, int lg, int ns_lg, const float2* tw,
+                                           const In& in, const Out& out) {
   constexpr int RLG = (R == 8) ? 3 : (R == 4) ? 2 : 1;
   constexpr int U = kPointsPerThread / R;
+  constexpr bool GIN = !is_smem<In>::value, GOUT = !is_smem<Out>::value;
   const int nb_lg = lg - RLG, total = nseq << nb_lg;
+  const int spp_lg = kBlockLg + 3 - lg;                      // sequences per step (log2)
   int rbs[RLG], wbs[RLG];
   swz_basis<R>(nb_lg, rbs);
   swz_basis<R>(ns_lg, wbs);
@@ -154,36 +177,69 @@ __device__ __forceinline__ void block_pass(float2* data, int pitch, int nseq, in
     asm("" : "+r"(rbs[k]));
     asm("" : "+r"(wbs[k]));
   }
-  for (int base = 0; base < total; base += (int)blockDim.x * U) {
+  int step = 0;
+  for (int base = 0; base < total; base += (1 << kBlockLg) * U, ++step) {
     float2 v[U][R];
-    float2* seq[U];
-    int dst[U];
+    int q[U], dst[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int b = base + u * (int)blockDim.x + (int)threadIdx.x;
-      seq[u] = data + (b >> nb_lg) * pitch;
-      dst[u] = butterfly_read<R, INV>(seq[u], b & ((1 << nb_lg) - 1), ns_lg, tw, rbs, v[u]);
-    }
-    __syncthreads();
+      const int t = (u << kBlockLg) + (int)threadIdx.x;     // butterfly inside the step
+      int j;
+      if (SEQ_FAST) { q[u] = (step << spp_lg) + (t & ((1 << spp_lg) - 1)); j = t >> spp_lg; }
+      else { q[u] = (base + t) >> nb_lg; j = (base + t) & ((1 << nb_lg) - 1); }
+      if constexpr (GIN) {
+        in.template load<R>(q[u], j, 1 << nb_lg, v[u]);
+      } else {
+        int idx[R];
+        xor_fan<R>(swz(j), rbs, idx);      // j < n/R shares no bit with r n/R
+        const float2* seq = data + q[u] * pitch;
 #pragma unroll
-    for (int u = 0; u < U; ++u) butterfly_write<R>(seq[u], dst[u], wbs, v[u]);
+        for (int r = 0; r < R; ++r) v[u][r] = seq[idx[r]];
+      }
+      dst[u] = butterfly<R, INV>(j, ns_lg, tw, v[u]);
+    }
+    if (!GIN && Out::kWritesSmem) __syncthreads();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if constexpr (GOUT) {
+        out.template store<R>(q[u], dst[u], 1 << ns_lg, v[u]);
+      } else {
+        butterfly_write<R>(data + q[u] * pitch, dst[u], wbs, v[u]);
+      }
+    }
   }
-  __syncthreads();
+  if (Out::kWritesSmem) __syncthreads();
 }
 
-// Forward (INV = false) or unscaled inverse transform of nseq sequences of n = 1 << pl.lg points each, in place.
-// tw: the plan's twiddle tables (shared memory).  Requires blockDim.x * 8 % n == 0 and room for
-// padded_seqs(nseq, lg, blockDim.x) sequences.
-template <bool INV>
-__device__ __forceinline__ void block_fft(float2* data, int pitch, int nseq, const Plan& pl, const float2* tw) {
+// Forward (INV = false) or unscaled inverse transform of nseq sequences of n = 1 << pl.lg points each.
+// tw: the plan's twiddle tables (shared memory).  256 threads; room for padded_seqs(nseq, lg, 256) sequences.
+// in / out: SmemIO (in place in shared memory) or functors (see above) used by the first / last pass;
+// SEQ_FAST_IN / _OUT: lane order of that pass (see block_pass).  A single-pass transform uses SEQ_FAST_IN.
+template <bool INV, bool SEQ_FAST_IN, bool SEQ_FAST_OUT, class In, class Out>
+__device__ __forceinline__ void block_fft(float2* data, int pitch, int nseq, const Plan& pl, const float2* tw,
+                                          const In& in, const Out& out) {
+  const SmemIO sm{};
 #pragma unroll
   for (int p = 0; p < kMaxPasses; ++p) {            // unrolled: the plan stays in the kernel's parameter space
     if (p >= pl.npass) break;
     const float2* t = tw + pl.tw_off[p];
-    if (pl.rlg[p] == 3) block_pass<8, INV>(data, pitch, nseq, pl.lg, pl.ns_lg[p], t);
-    else if (pl.rlg[p] == 2) block_pass<4, INV>(data, pitch, nseq, pl.lg, pl.ns_lg[p], t);
-    else block_pass<2, INV>(data, pitch, nseq, pl.lg, pl.ns_lg[p], t);
+    const int lg = pl.lg, ns_lg = pl.ns_lg[p];
+    const bool last = (p == pl.npass - 1);
+    // the input functor belongs to pass 0, the output functor to the last pass
+#define USAUG_FFT_PASS(R)                                                                                    \
+    if (p == 0 && last) block_pass<R, INV, SEQ_FAST_IN>(data, pitch, nseq, lg, ns_lg, t, in, out);            \
+    else if (p == 0) block_pass<R, INV, SEQ_FAST_IN>(data, pitch, nseq, lg, ns_lg, t, in, sm);                \
+    else if (last) block_pass<R, INV, SEQ_FAST_OUT>(data, pitch, nseq, lg, ns_lg, t, sm, out);                \
+    else block_pass<R, INV, false>(data, pitch, nseq, lg, ns_lg, t, sm, sm);
+    if (pl.rlg[p] == 3) { USAUG_FFT_PASS(8) }
+    else if (pl.rlg[p] == 2) { USAUG_FFT_PASS(4) }
+    else { USAUG_FFT_PASS(2) }
+#undef USAUG_FFT_PASS
   }
+}
+template <bool INV>
+__device__ __forceinline__ void block_fft(float2* data, int pitch, int nseq, const Plan& pl, const float2* tw) {
+  block_fft<INV, false, false>(data, pitch, nseq, pl, tw, SmemIO{}, SmemIO{});
 }
 
 // twiddle tables of a plan (global or shared memory), filled by `nthreads` cooperating threads

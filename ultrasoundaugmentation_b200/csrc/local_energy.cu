@@ -21,7 +21,9 @@ namespace usaug {
 constexpr int kLeThreads = 256;       // fft::block_fft needs blockDim.x * 8 to be a multiple of the transform length
 constexpr int kLeMaxScales = 4;
 constexpr int kLeMaxN = 2048;
-constexpr int kLeColPad = 2;          // column sequences are H + 2 apart: the transposing copies of a tile spread over the banks
+// column sequences are H + max(1, H / 128) apart: with the sequence-fastest lane order of le_cols' global passes the
+// shared-memory accesses of a warp then fall into different banks (tests/manual/stockham_proto.py, seqfast_conflicts)
+static inline int le_col_pitch(int H) { return H + ((H >> 7) > 1 ? (H >> 7) : 1); }
 
 struct LeFilter {
   int scales;
@@ -65,8 +67,48 @@ __global__ void __launch_bounds__(kLeThreads) le_filter(float4* __restrict__ fil
 }
 
 // ---- rows, forward: block = rb rows ---------------------------------------------------------------
-// img is [B][H0][W0]; spec is [B][H][W] with H, W the padded (power-of-two) sizes.  The copies move two points per
-// thread and step: x and x + 1 (x even) live at the shared-memory slots s and s ^ 1.
+// img is [B][H0][W0]; spec is [B][H][W] with H, W the padded (power-of-two) sizes.  The first pass of the transform
+// reads the image rows, the last one writes the spectrum rows: shared memory only carries the exchanges in between.
+struct RowsFwdIn {
+  const float* __restrict__ img;
+  size_t row0, nrows;
+  int H0, W0, H, W, lgH;
+  bool exact;                                               // no mirror extension
+  template <int R> __device__ __forceinline__ void load(int q, int x0, int stride, float2* v) const {
+    const size_t r = row0 + q;
+#pragma unroll
+    for (int k = 0; k < R; ++k) v[k] = make_float2(0.f, 0.f);
+    if (r >= nrows) return;
+    if (exact) {
+      const float* p = img + r * W + x0;
+#pragma unroll
+      for (int k = 0; k < R; ++k) v[k].x = p[k * stride];
+    } else {
+      const int b = (int)(r >> lgH), yp = (int)(r & (size_t)(H - 1));
+      const int y = (yp < H0) ? yp : 2 * H0 - 1 - yp;                                           // mirror extension
+      const float* p = img + ((size_t)b * H0 + y) * W0;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int xp = x0 + k * stride;
+        v[k].x = p[(xp < W0) ? xp : 2 * W0 - 1 - xp];
+      }
+    }
+  }
+};
+struct RowsFwdOut {
+  static constexpr bool kWritesSmem = false;
+  float2* __restrict__ spec;
+  size_t row0, nrows;
+  int W;
+  template <int R> __device__ __forceinline__ void store(int q, int x0, int stride, const float2* v) const {
+    const size_t r = row0 + q;
+    if (r >= nrows) return;
+    float2* p = spec + r * W + x0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) p[k * stride] = v[k];
+  }
+};
+
 __global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restrict__ img, float2* __restrict__ spec,
                                                           int H0, int W0, int H, int W, int lgH, fft::Plan pw,
                                                           const float2* __restrict__ twg, int rb, size_t nrows) {
@@ -74,101 +116,103 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restric
   float2* tw = reinterpret_cast<float2*>(le_smem);          // [W]  (pw.tw_total <= W entries used)
   float2* data = tw + W;                                    // [rb][W], element x of a row at slot swz(x)
   const size_t row0 = (size_t)blockIdx.x * rb;
-  const int lgW = pw.lg;
-  // no mirror extension: rows are pairs of 8 bytes (if the caller's pointer is that aligned)
-  const bool exact = (H0 == H) && (W0 == W) && (reinterpret_cast<size_t>(img) & 7) == 0;
   load_twiddles(tw, twg, pw.tw_total);
-  for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
-    const int q = i >> lgW, xp = i & (W - 1);
-    const size_t r = row0 + q;
-    float v0 = 0.f, v1 = 0.f;
-    if (r < nrows) {
-      if (exact) {
-        const float2 t = *reinterpret_cast<const float2*>(img + r * W + xp);
-        v0 = t.x; v1 = t.y;
-      } else {
-        const int b = (int)(r >> lgH), yp = (int)(r & (size_t)(H - 1));
-        const int y = (yp < H0) ? yp : 2 * H0 - 1 - yp;                                        // mirror extension
-        const int xa = (xp < W0) ? xp : 2 * W0 - 1 - xp, xb = (xp + 1 < W0) ? xp + 1 : 2 * W0 - 2 - xp;
-        const float* row = img + ((size_t)b * H0 + y) * W0;
-        v0 = row[xa]; v1 = row[xb];
-      }
-    }
-    const int s = (q << lgW) + fft::swz(xp);
-    data[s] = make_float2(v0, 0.f);
-    data[s ^ 1] = make_float2(v1, 0.f);
-  }
   __syncthreads();
-  fft::block_fft<false>(data, W, rb, pw, tw);
-  for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
-    const int q = i >> lgW, xp = i & (W - 1);
-    const size_t r = row0 + q;
-    if (r < nrows) {
-      const int s = (q << lgW) + fft::swz(xp);
-      const float2 a = data[s], c = data[s ^ 1];
-      *reinterpret_cast<float4*>(spec + r * W + xp) = make_float4(a.x, a.y, c.x, c.y);
-    }
-  }
+  const RowsFwdIn in{img, row0, nrows, H0, W0, H, W, lgH, (H0 == H) && (W0 == W)};
+  const RowsFwdOut out{spec, row0, nrows, W};
+  fft::block_fft<false, false, false>(data, W, rb, pw, tw, in, out);
 }
 
 // ---- columns: block = tc columns of one image ---------------------------------------------------------
+// sequence q < tc = column x0 + q.  The forward transform reads the spectrum columns in its first pass; the inverse
+// transform of the 2 tc sequences (odd pair, then even part) writes the two planes in its last pass.  Both use the
+// sequence-fastest lane order, so a warp touches tc-wide contiguous pieces of consecutive rows.
+struct ColsIn {
+  const float2* __restrict__ src;                           // spec + image base + x0
+  int W, tc;
+  template <int R> __device__ __forceinline__ void load(int q, int y0, int stride, float2* v) const {
+    if (q >= tc) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) v[k] = make_float2(0.f, 0.f);
+      return;
+    }
+    const float2* p = src + (size_t)y0 * W + q;
+    const size_t step = (size_t)stride * W;
+#pragma unroll
+    for (int k = 0; k < R; ++k, p += step) v[k] = *p;
+  }
+};
+// last pass of the forward transform: the filter multiply on the way back into shared memory.
+//   even: G F -> Bv;   odd: (v' - i u') / rho * G * F -> A (in place)
+struct ColsFilterOut {
+  static constexpr bool kWritesSmem = true;
+  float2* A;
+  float2* Bv;
+  const float4* __restrict__ fcol;                          // filt + x0 * H: (G, G u'/rho, G v'/rho), zero at DC
+  int H, pitch, tc;
+  template <int R> __device__ __forceinline__ void store(int q, int y0, int stride, const float2* v) const {
+    if (q >= tc) return;
+    const float4* f = fcol + (size_t)q * H + y0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float4 g = f[k * stride];
+      const float2 F = v[k];
+      const int slot = q * pitch + fft::swz(y0 + k * stride);
+      Bv[slot] = make_float2(g.x * F.x, g.x * F.y);
+      A[slot] = make_float2(fmaf(g.z, F.x, g.y * F.y), fmaf(g.z, F.y, -g.y * F.x));
+    }
+  }
+};
+struct ColsOut {
+  static constexpr bool kWritesSmem = false;
+  float2* __restrict__ odd;                                 // + image base + x0
+  float2* __restrict__ even;
+  int W, tc, H0;
+  template <int R> __device__ __forceinline__ void store(int q, int y0, int stride, const float2* v) const {
+    if (q >= 2 * tc) return;
+    float2* p = ((q < tc) ? odd + q : even + (q - tc)) + (size_t)y0 * W;
+    const size_t step = (size_t)stride * W;
+#pragma unroll
+    for (int k = 0; k < R; ++k, p += step)
+      if (y0 + k * stride < H0) *p = v[k];                  // rows of the mirror extension are not needed again
+  }
+};
+
 __global__ void __launch_bounds__(kLeThreads) le_cols(const float2* __restrict__ spec, float2* __restrict__ odd,
                                                       float2* __restrict__ even, const float4* __restrict__ filt,
                                                       int H0, int H, int W, fft::Plan ph,
-                                                      const float2* __restrict__ twg, int tc, int lg_tc) {
+                                                      const float2* __restrict__ twg, int tc, int pitch) {
   extern __shared__ __align__(16) unsigned char le_smem[];
-  const int pitch = H + kLeColPad, lgH = ph.lg;
   float2* tw = reinterpret_cast<float2*>(le_smem);          // [H]
   float2* A = tw + H;                                       // [tc][pitch]  spectrum, then the Riesz (odd) pair
   float2* Bv = A + tc * pitch;                              // [tc][pitch]  the even part
   const int b = blockIdx.y, x0 = blockIdx.x * tc;
-  const size_t base = (size_t)b * H * W;
+  const size_t base = (size_t)b * H * W + x0;
   load_twiddles(tw, twg, ph.tw_total);
-  if (tc >= 2) {                                            // two columns per thread and step: 16-byte accesses
-    for (int i = 2 * threadIdx.x; i < tc * H; i += 2 * blockDim.x) {
-      const int c = i & (tc - 1), y = i >> lg_tc;
-      const float4 t = *reinterpret_cast<const float4*>(spec + base + (size_t)y * W + x0 + c);
-      const int s = c * pitch + fft::swz(y);
-      A[s] = make_float2(t.x, t.y);
-      A[s + pitch] = make_float2(t.z, t.w);
-    }
-  } else {
-    for (int y = threadIdx.x; y < H; y += blockDim.x) A[fft::swz(y)] = spec[base + (size_t)y * W + x0];
-  }
   __syncthreads();
-  fft::block_fft<false>(A, pitch, tc, ph, tw);
-  const float4* fcol = filt + (size_t)x0 * H;               // the tile's filter columns are contiguous
-  for (int i = threadIdx.x; i < tc * H; i += blockDim.x) {
-    const int c = i >> lgH, py = i & (H - 1);
-    const int slot = c * pitch + fft::swz(py);
-    const float4 f = fcol[i];                               // (G, G u'/rho, G v'/rho): zero at DC
-    const float2 F = A[slot];
-    // even: G F;  odd: (v' - i u') / rho * G * F
-    Bv[slot] = make_float2(f.x * F.x, f.x * F.y);
-    A[slot] = make_float2(fmaf(f.z, F.x, f.y * F.y), fmaf(f.z, F.y, -f.y * F.x));
-  }
-  __syncthreads();
-  fft::block_fft<true>(A, pitch, 2 * tc, ph, tw);           // A and Bv are contiguous: 2 tc sequences
-  // rows of the mirror extension are not needed again
-  if (tc >= 2) {
-    for (int i = 2 * threadIdx.x; i < tc * H0; i += 2 * blockDim.x) {
-      const int c = i & (tc - 1), y = i >> lg_tc;
-      const size_t o = base + (size_t)y * W + x0 + c;
-      const int s = c * pitch + fft::swz(y);
-      const float2 a0 = A[s], a1 = A[s + pitch], e0 = Bv[s], e1 = Bv[s + pitch];
-      *reinterpret_cast<float4*>(odd + o) = make_float4(a0.x, a0.y, a1.x, a1.y);
-      *reinterpret_cast<float4*>(even + o) = make_float4(e0.x, e0.y, e1.x, e1.y);
-    }
-  } else {
-    for (int y = threadIdx.x; y < H0; y += blockDim.x) {
-      const size_t o = base + (size_t)y * W + x0;
-      odd[o] = A[fft::swz(y)];
-      even[o] = Bv[fft::swz(y)];
-    }
-  }
+  // forward: columns from global memory (sequence-fastest lanes), filter applied by the last pass
+  fft::block_fft<false, true, false>(A, pitch, tc, ph, tw, ColsIn{spec + base, W, tc},
+                                     ColsFilterOut{A, Bv, filt + (size_t)x0 * H, H, pitch, tc});
+  fft::block_fft<true, false, true>(A, pitch, 2 * tc, ph, tw, fft::SmemIO{}, ColsOut{odd + base, even + base, W, tc, H0});
 }
 
 // ---- rows, inverse + energy: block = rb rows -----------------------------------------------------------
+struct RowsInvIn {
+  const float2* __restrict__ odd;                           // + base of the block's first row
+  const float2* __restrict__ even;
+  int W, rb;
+  template <int R> __device__ __forceinline__ void load(int q, int x0, int stride, float2* v) const {
+    if (q >= 2 * rb) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) v[k] = make_float2(0.f, 0.f);
+      return;
+    }
+    const float2* p = ((q < rb) ? odd + (size_t)q * W : even + (size_t)(q - rb) * W) + x0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) v[k] = p[k * stride];
+  }
+};
+
 __global__ void __launch_bounds__(kLeThreads) le_rows_inv(const float2* __restrict__ odd, const float2* __restrict__ even,
                                                           float* __restrict__ energy, float* __restrict__ part,
                                                           int H0, int W0, int H, int W, fft::Plan pw,
@@ -181,15 +225,8 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_inv(const float2* __restri
   const int row0 = blockIdx.x * rb;                         // H % rb == 0; only blocks with row0 < H0 are launched
   const size_t base = ((size_t)b * H + row0) * W;
   load_twiddles(tw, twg, pw.tw_total);
-  for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
-    const int s = (i & ~(W - 1)) + fft::swz(i & (W - 1));
-    const float4 o = *reinterpret_cast<const float4*>(odd + base + i);
-    const float4 e = *reinterpret_cast<const float4*>(even + base + i);
-    data[s] = make_float2(o.x, o.y); data[s ^ 1] = make_float2(o.z, o.w);
-    data[rb * W + s] = make_float2(e.x, e.y); data[rb * W + (s ^ 1)] = make_float2(e.z, e.w);
-  }
   __syncthreads();
-  fft::block_fft<true>(data, W, 2 * rb, pw, tw);
+  fft::block_fft<true, false, false>(data, W, 2 * rb, pw, tw, RowsInvIn{odd + base, even + base, W, rb}, fft::SmemIO{});
   float m = 0.f;
   // even row length: x and x + 1 as one 8-byte store
   const bool pairs = (W0 & 1) == 0 && (reinterpret_cast<size_t>(energy) & 7) == 0;
@@ -252,9 +289,9 @@ static int next_pow2_min8(int n) {
 static LeLayout le_layout(void* ws, int B, int H0, int H, int W) {
   LeLayout L;
   const size_t N = (size_t)B * H * W;
-  // rows per block: 32 KB of sequences (forward) / 64 KB (inverse: two planes), at least 1, at most 16
+  // rows per block: 32 KB of sequences (forward, and inverse: two planes), at least 1, at most 16
   L.rb_fwd = 4096 / W; if (L.rb_fwd < 1) L.rb_fwd = 1; if (L.rb_fwd > 16) L.rb_fwd = 16;
-  L.rb_inv = 4096 / W; if (L.rb_inv < 1) L.rb_inv = 1; if (L.rb_inv > 16) L.rb_inv = 16;
+  L.rb_inv = 2048 / W; if (L.rb_inv < 1) L.rb_inv = 1; if (L.rb_inv > 16) L.rb_inv = 16;
   while (H % L.rb_inv) L.rb_inv >>= 1;
   // columns per block: 64 KB of sequences (two buffers) so that three blocks share an SM
   L.tc = 4096 / H; if (L.tc < 1) L.tc = 1; if (L.tc > 16) L.tc = 16; if (L.tc > W) L.tc = W;
@@ -311,11 +348,11 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
   const fft::Plan pw = fft::make_plan(lgW), ph = fft::make_plan(lgH);
   // twiddle table + the sequences, rounded up to whole transform steps (fft::padded_seqs)
   const size_t sm_fwd = (size_t)(W + fft::padded_seqs(L.rb_fwd, lgW, kLeThreads) * W) * sizeof(float2);
-  const size_t sm_col = (size_t)(H + fft::padded_seqs(2 * L.tc, lgH, kLeThreads) * (H + kLeColPad)) * sizeof(float2);
+  const size_t sm_col = (size_t)(H + fft::padded_seqs(2 * L.tc, lgH, kLeThreads) * le_col_pitch(H)) * sizeof(float2);
   const size_t sm_inv = (size_t)(W + fft::padded_seqs(2 * L.rb_inv, lgW, kLeThreads) * W) * sizeof(float2);
-  if (sm_fwd > 48 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
-  if (sm_col > 48 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_col));
-  if (sm_inv > 48 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv));
+  if (sm_fwd > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+  if (sm_col > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_col));
+  if (sm_inv > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv));
 
   le_twiddles<<<2, kLeThreads, 0, stream>>>(pw, ph, L.tww, L.twh);
   USAUG_CHECK_LAUNCH("le_twiddles");
@@ -325,7 +362,7 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
                                                                                             L.tww, L.rb_fwd, nrows);
   USAUG_CHECK_LAUNCH("le_rows_fwd");
   le_cols<<<dim3(W / L.tc, B), kLeThreads, sm_col, stream>>>(L.spec, L.odd, L.even, L.filt, H0, H, W, ph, L.twh, L.tc,
-                                                             ilog2_exact(L.tc));
+                                                             le_col_pitch(H));
   USAUG_CHECK_LAUNCH("le_cols");
   le_rows_inv<<<dim3(L.nblk_inv, B), kLeThreads, sm_inv, stream>>>(L.odd, L.even, energy, L.part, H0, W0, H, W, pw, L.tww,
                                                                   L.rb_inv, (float)(1.0 / ((double)H * (double)W)));
