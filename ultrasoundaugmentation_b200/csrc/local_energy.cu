@@ -13,6 +13,7 @@
 // Sizes that are not powers of two are mirror-extended (bottom / right, edge included) to the next power of two
 // (Hp x Wp) on the way into le_rows_fwd; rows and columns beyond H x W are never written back.
 // HBM traffic: 4 + 8 | 8 + 16 | 16 + 4 = 56 B/px; everything else stays in shared memory.
+#include <cstdlib>
 #include "fft_stockham.cuh"
 #include "kernels.cuh"
 
@@ -150,6 +151,7 @@ struct ColsFilterOut {
   float2* Bv;
   const float4* __restrict__ fcol;                          // filt + x0 * H: (G, G u'/rho, G v'/rho), zero at DC
   int H, pitch, tc;
+  bool with_even;
   template <int R> __device__ __forceinline__ void store(int q, int y0, int stride, const float2* v) const {
     if (q >= tc) return;
     const float4* f = fcol + (size_t)q * H + y0;
@@ -158,7 +160,7 @@ struct ColsFilterOut {
       const float4 g = f[k * stride];
       const float2 F = v[k];
       const int slot = q * pitch + fft::swz(y0 + k * stride);
-      Bv[slot] = make_float2(g.x * F.x, g.x * F.y);
+      if (with_even) Bv[slot] = make_float2(g.x * F.x, g.x * F.y);
       A[slot] = make_float2(fmaf(g.z, F.x, g.y * F.y), fmaf(g.z, F.y, -g.y * F.x));
     }
   }
@@ -167,9 +169,9 @@ struct ColsOut {
   static constexpr bool kWritesSmem = false;
   float2* __restrict__ odd;                                 // + image base + x0
   float2* __restrict__ even;
-  int W, tc, H0;
+  int W, tc, H0, nseq;
   template <int R> __device__ __forceinline__ void store(int q, int y0, int stride, const float2* v) const {
-    if (q >= 2 * tc) return;
+    if (q >= nseq) return;
     float2* p = ((q < tc) ? odd + q : even + (q - tc)) + (size_t)y0 * W;
     const size_t step = (size_t)stride * W;
 #pragma unroll
@@ -190,26 +192,46 @@ __global__ void __launch_bounds__(kLeThreads) le_cols(const float2* __restrict__
   const size_t base = (size_t)b * H * W + x0;
   load_twiddles(tw, twg, ph.tw_total);
   __syncthreads();
+  // The even part is real, so its row spectrum after this kernel is Hermitian along x: columns beyond W / 2 are the
+  // conjugates of their mirror images and are neither transformed back nor stored (le_rows_inv rebuilds them).
+  const bool with_even = x0 <= W / 2;
+  const int nseq = with_even ? 2 * tc : tc;
   // forward: columns from global memory (sequence-fastest lanes), filter applied by the last pass
   fft::block_fft<false, true, false>(A, pitch, tc, ph, tw, ColsIn{spec + base, W, tc},
-                                     ColsFilterOut{A, Bv, filt + (size_t)x0 * H, H, pitch, tc});
-  fft::block_fft<true, false, true>(A, pitch, 2 * tc, ph, tw, fft::SmemIO{}, ColsOut{odd + base, even + base, W, tc, H0});
+                                     ColsFilterOut{A, Bv, filt + (size_t)x0 * H, H, pitch, tc, with_even});
+  fft::block_fft<true, false, true>(A, pitch, nseq, ph, tw, fft::SmemIO{}, ColsOut{odd + base, even + base, W, tc, H0, nseq});
 }
 
 // ---- rows, inverse + energy: block = rb rows -----------------------------------------------------------
+// sequence q < rb: the odd (Riesz) row q.  The even part of every row is real, so two of its rows share one
+// transform: sequence rb + k carries even row 2k + i * even row 2k+1, and the inverse transform returns the two real
+// rows as its real and imaginary parts.
 struct RowsInvIn {
   const float2* __restrict__ odd;                           // + base of the block's first row
   const float2* __restrict__ even;
-  int W, rb;
+  int W, rb, rows_left;                                     // rows_left = H0 - row0: rows below it were never written
   template <int R> __device__ __forceinline__ void load(int q, int x0, int stride, float2* v) const {
-    if (q >= 2 * rb) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) v[k] = make_float2(0.f, 0.f);
-      return;
+    for (int k = 0; k < R; ++k) v[k] = make_float2(0.f, 0.f);
+    if (q < rb) {
+      const float2* p = odd + (size_t)q * W + x0;
+#pragma unroll
+      for (int k = 0; k < R; ++k) v[k] = p[k * stride];
+    } else if (2 * (q - rb) < rb) {
+      // even rows: stored for x <= W / 2 only, e(W - x) = conj e(x)
+      const float2* p = even + (size_t)(2 * (q - rb)) * W;
+      const bool two = 2 * (q - rb) + 1 < min(rb, rows_left);
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int x = x0 + k * stride;
+        const bool mir = x > W / 2;
+        const int xs = mir ? W - x : x;
+        float2 a = p[xs];
+        float2 c = two ? p[W + xs] : make_float2(0.f, 0.f);
+        if (mir) { a.y = -a.y; c.y = -c.y; }
+        v[k] = make_float2(a.x - c.y, a.y + c.x);
+      }
     }
-    const float2* p = ((q < rb) ? odd + (size_t)q * W : even + (size_t)(q - rb) * W) + x0;
-#pragma unroll
-    for (int k = 0; k < R; ++k) v[k] = p[k * stride];
   }
 };
 
@@ -220,22 +242,23 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_inv(const float2* __restri
   extern __shared__ __align__(16) unsigned char le_smem[];
   __shared__ float s_max[kLeThreads / 32];
   float2* tw = reinterpret_cast<float2*>(le_smem);          // [W]
-  float2* data = tw + W;                                    // [2 rb][W]: odd rows, then even rows
+  float2* data = tw + W;                                    // [rb + (rb + 1) / 2][W]: odd rows, then pairs of even rows
   const int b = blockIdx.y, lgW = pw.lg;
   const int row0 = blockIdx.x * rb;                         // H % rb == 0; only blocks with row0 < H0 are launched
   const size_t base = ((size_t)b * H + row0) * W;
   load_twiddles(tw, twg, pw.tw_total);
   __syncthreads();
-  fft::block_fft<true, false, false>(data, W, 2 * rb, pw, tw, RowsInvIn{odd + base, even + base, W, rb}, fft::SmemIO{});
+  fft::block_fft<true, false, false>(data, W, rb + (rb + 1) / 2, pw, tw, RowsInvIn{odd + base, even + base, W, rb, H0 - row0}, fft::SmemIO{});
   float m = 0.f;
   // even row length: x and x + 1 as one 8-byte store
   const bool pairs = (W0 & 1) == 0 && (reinterpret_cast<size_t>(energy) & 7) == 0;
   for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
     const int y = row0 + (i >> lgW), x = i & (W - 1);
     if (y >= H0 || x >= W0) continue;                       // mirror extension: not part of the result
-    const int s = (i & ~(W - 1)) + fft::swz(x);
-    const float2 q0 = data[s], q1 = data[s ^ 1];
-    const float e0 = data[rb * W + s].x, e1 = data[rb * W + (s ^ 1)].x;
+    const int yl = i >> lgW, sx = fft::swz(x);
+    const int s = (yl << lgW) + sx, se = ((rb + (yl >> 1)) << lgW) + sx;
+    const float2 q0 = data[s], q1 = data[s ^ 1], p0 = data[se], p1 = data[se ^ 1];
+    const float e0 = (yl & 1) ? p0.y : p0.x, e1 = (yl & 1) ? p1.y : p1.x;
     const float en0 = sqrtf(fmaf(e0, e0, fmaf(q0.x, q0.x, q0.y * q0.y))) * norm;
     const float en1 = sqrtf(fmaf(e1, e1, fmaf(q1.x, q1.x, q1.y * q1.y))) * norm;
     float* dst = energy + ((size_t)b * H0 + y) * W0 + x;
@@ -289,12 +312,15 @@ static int next_pow2_min8(int n) {
 static LeLayout le_layout(void* ws, int B, int H0, int H, int W) {
   LeLayout L;
   const size_t N = (size_t)B * H * W;
-  // rows per block: 32 KB of sequences (forward, and inverse: two planes), at least 1, at most 16
+  // rows per block: 32 KB of sequences forward, 48 KB inverse (odd rows + pairs of even rows), at least 1, at most 16
   L.rb_fwd = 4096 / W; if (L.rb_fwd < 1) L.rb_fwd = 1; if (L.rb_fwd > 16) L.rb_fwd = 16;
-  L.rb_inv = 2048 / W; if (L.rb_inv < 1) L.rb_inv = 1; if (L.rb_inv > 16) L.rb_inv = 16;
+  L.rb_inv = 4096 / W; if (L.rb_inv < 1) L.rb_inv = 1; if (L.rb_inv > 16) L.rb_inv = 16;
   while (H % L.rb_inv) L.rb_inv >>= 1;
-  // columns per block: 64 KB of sequences (two buffers) so that three blocks share an SM
-  L.tc = 4096 / H; if (L.tc < 1) L.tc = 1; if (L.tc > 16) L.tc = 16; if (L.tc > W) L.tc = W;
+  // columns per block: one transform step (2048 points) forward, two for the inverse pair: 32 KB of sequences, so that
+  // six blocks share an SM (measured: 8 columns of 512 rows are 6 % slower, 8 of 1024 rows 25 %)
+  L.tc = 2048 / H; if (L.tc < 2) L.tc = 2; if (L.tc > 16) L.tc = 16; if (L.tc > W) L.tc = W;
+  if (const char* e = getenv("USAUG_LE_TC")) { L.tc = atoi(e); }
+  if (const char* e = getenv("USAUG_LE_RBI")) { L.rb_inv = atoi(e); }
   L.nblk_inv = (H0 + L.rb_inv - 1) / L.rb_inv;
   Carver cv(ws);
   L.spec = cv.take<float2>(N); L.odd = cv.take<float2>(N); L.even = cv.take<float2>(N);
@@ -349,7 +375,7 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
   // twiddle table + the sequences, rounded up to whole transform steps (fft::padded_seqs)
   const size_t sm_fwd = (size_t)(W + fft::padded_seqs(L.rb_fwd, lgW, kLeThreads) * W) * sizeof(float2);
   const size_t sm_col = (size_t)(H + fft::padded_seqs(2 * L.tc, lgH, kLeThreads) * le_col_pitch(H)) * sizeof(float2);
-  const size_t sm_inv = (size_t)(W + fft::padded_seqs(2 * L.rb_inv, lgW, kLeThreads) * W) * sizeof(float2);
+  const size_t sm_inv = (size_t)(W + fft::padded_seqs(L.rb_inv + (L.rb_inv + 1) / 2, lgW, kLeThreads) * W) * sizeof(float2);
   if (sm_fwd > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
   if (sm_col > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_col));
   if (sm_inv > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv));
