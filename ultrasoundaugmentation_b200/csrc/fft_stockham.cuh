@@ -52,9 +52,48 @@ inline Plan make_plan(int lg) {
 
 USAUG_HD int swz(int i) { return i ^ ((i >> 3) & 15); }
 
-USAUG_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-USAUG_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-USAUG_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic.  On the device it uses the packed fp32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: one
+// issue slot for both components; the transforms are issue-bound): a complex add is one instruction, a complex
+// multiply three.  The host versions (tests/manual/fft_host_check.cu) are the plain formulas.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long pk(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 upk(unsigned long long r) {
+  float2 a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+  return upk(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+  return upk(r);
+}
+// a * b = a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  unsigned long long t, r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk(make_float2(a.x, a.x))), "l"(pk(b)));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(make_float2(a.y, a.y))), "l"(pk(make_float2(-b.y, b.x))), "l"(t));
+  return upk(r);
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(make_float2(s, s))));
+  return upk(r);
+}
+#else
+inline float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+inline float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+inline float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+#endif
 // a * (-i) for the forward transform, a * (+i) for the inverse
 template <bool INV> USAUG_HD float2 rot(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
 
@@ -75,8 +114,9 @@ template <int R, bool INV> USAUG_HD void dft(float2* v) {
     float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
     float2 a4 = csub(v[0], v[4]), d5 = csub(v[1], v[5]), a6 = rot<INV>(csub(v[2], v[6])), d7 = csub(v[3], v[7]);
     // w8 = (1 -+ i) / sqrt 2 and w8^3 = (-1 -+ i) / sqrt 2
-    float2 a5 = INV ? make_float2(h * (d5.x - d5.y), h * (d5.x + d5.y)) : make_float2(h * (d5.x + d5.y), h * (d5.y - d5.x));
-    float2 a7 = INV ? make_float2(-h * (d7.x + d7.y), h * (d7.x - d7.y)) : make_float2(h * (d7.y - d7.x), -h * (d7.x + d7.y));
+    // w8 = (1 -+ i) / sqrt 2 and w8^3 = (-1 -+ i) / sqrt 2, with rot(d) = -+ i d
+    float2 a5 = cscale(cadd(d5, rot<INV>(d5)), h);
+    float2 a7 = cscale(csub(rot<INV>(d7), d7), h);
     dft4<INV>(a0, a1, a2, a3);      // X0 X2 X4 X6
     dft4<INV>(a4, a5, a6, a7);      // X1 X3 X5 X7
     v[0] = a0; v[1] = a4; v[2] = a1; v[3] = a5; v[4] = a2; v[5] = a6; v[6] = a3; v[7] = a7;

@@ -5,15 +5,21 @@
 // in and out):
 //
 //   le_twiddles   the twiddle tables of the two transform lengths, once per call (2 blocks)
-//   le_rows_fwd   per group of image rows: real -> complex FFT along x
-//   le_cols       per tile of columns: FFT along y, filter multiply, two inverse FFTs along y
-//   le_rows_inv   per group of image rows: inverse FFT of both planes along x, energy, per-block maxima
+//   le_filter     the filter multipliers (G, G u'/rho, G v'/rho) per frequency, once per call: the same for every image
+//   le_rows_fwd   per group of image rows: real -> complex FFT along x; the first pass reads the image, the last one
+//                 writes the spectrum (no staging copies)
+//   le_cols       per tile of columns: FFT along y (first pass reads the columns, last pass applies the filter on the
+//                 way back into shared memory), then the inverse FFT along y of the odd (Riesz) pair and of the even
+//                 part, whose last pass writes the two planes.  The even part is real: its columns beyond W/2 are
+//                 conjugate mirrors and are neither transformed back nor stored.
+//   le_rows_inv   per group of image rows: inverse FFT along x of the odd rows and of PAIRS of even rows (two real rows
+//                 as real and imaginary part of one transform), energy, per-block maxima
 //   le_scale      per image: 1 / max E (0 for an image without band-pass content)
 //
 // Sizes that are not powers of two are mirror-extended (bottom / right, edge included) to the next power of two
 // (Hp x Wp) on the way into le_rows_fwd; rows and columns beyond H x W are never written back.
-// HBM traffic: 4 + 8 | 8 + 16 | 16 + 4 = 56 B/px; everything else stays in shared memory.
-#include <cstdlib>
+// HBM traffic: 4 + 8 | 8 + 8 + 4 | 8 + 4 + 4 = 48 B/px (the stage model in bench.py still counts the 56 B/px of the
+// version that stored the whole even plane); everything else stays in shared memory.
 #include "fft_stockham.cuh"
 #include "kernels.cuh"
 
@@ -34,6 +40,13 @@ struct LeFilter {
 
 // signed DFT frequency index of bin k (numpy.fft.fftfreq * n): the Nyquist bin is -n/2
 __device__ __forceinline__ int signed_bin(int k, int n) { return (k < n / 2) ? k : k - n; }
+
+// sqrt.approx: one MUFU instruction, relative error 2^-23 (the energy is compared at 2e-5 of its maximum)
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 __device__ __forceinline__ void load_twiddles(float2* tw, const float2* __restrict__ twg, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = twg[i];
@@ -180,7 +193,7 @@ struct ColsOut {
   }
 };
 
-__global__ void __launch_bounds__(kLeThreads) le_cols(const float2* __restrict__ spec, float2* __restrict__ odd,
+__global__ void __launch_bounds__(kLeThreads, 4) le_cols(const float2* __restrict__ spec, float2* __restrict__ odd,
                                                       float2* __restrict__ even, const float4* __restrict__ filt,
                                                       int H0, int H, int W, fft::Plan ph,
                                                       const float2* __restrict__ twg, int tc, int pitch) {
@@ -252,22 +265,32 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_inv(const float2* __restri
   float m = 0.f;
   // even row length: x and x + 1 as one 8-byte store
   const bool pairs = (W0 & 1) == 0 && (reinterpret_cast<size_t>(energy) & 7) == 0;
-  for (int i = 2 * threadIdx.x; i < rb * W; i += 2 * blockDim.x) {
-    const int y = row0 + (i >> lgW), x = i & (W - 1);
+  // one item = two pixels (x, x + 1) of the two rows that share an even sequence
+  const int npair = (rb + 1) >> 1;
+  for (int i = threadIdx.x; i < npair << (lgW - 1); i += blockDim.x) {
+    const int k = i >> (lgW - 1), x = (i & (W / 2 - 1)) << 1;
+    const int y = row0 + 2 * k;
     if (y >= H0 || x >= W0) continue;                       // mirror extension: not part of the result
-    const int yl = i >> lgW, sx = fft::swz(x);
-    const int s = (yl << lgW) + sx, se = ((rb + (yl >> 1)) << lgW) + sx;
-    const float2 q0 = data[s], q1 = data[s ^ 1], p0 = data[se], p1 = data[se ^ 1];
-    const float e0 = (yl & 1) ? p0.y : p0.x, e1 = (yl & 1) ? p1.y : p1.x;
-    const float en0 = sqrtf(fmaf(e0, e0, fmaf(q0.x, q0.x, q0.y * q0.y))) * norm;
-    const float en1 = sqrtf(fmaf(e1, e1, fmaf(q1.x, q1.x, q1.y * q1.y))) * norm;
+    const int sx = fft::swz(x);
+    const float2* po = data + ((2 * k) << lgW) + sx;        // odd row 2k; row 2k + 1 follows W slots later
+    const float2* pe = data + ((rb + k) << lgW) + sx;       // (even row 2k) + i (even row 2k + 1)
+    const float2 e0 = pe[0], e1 = (pe - sx)[sx ^ 1];
     float* dst = energy + ((size_t)b * H0 + y) * W0 + x;
-    if (pairs) {
-      *reinterpret_cast<float2*>(dst) = make_float2(en0, en1);
-      m = fmaxf(m, fmaxf(en0, en1));
-    } else {
-      dst[0] = en0; m = fmaxf(m, en0);
-      if (x + 1 < W0) { dst[1] = en1; m = fmaxf(m, en1); }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && (2 * k + 1 >= rb || y + 1 >= H0)) break;
+      const float2 q0 = po[h << lgW], q1 = (po - sx)[(h << lgW) + (sx ^ 1)];
+      const float a0 = h ? e0.y : e0.x, a1 = h ? e1.y : e1.x;
+      const float en0 = fast_sqrt(fmaf(a0, a0, fmaf(q0.x, q0.x, q0.y * q0.y))) * norm;
+      const float en1 = fast_sqrt(fmaf(a1, a1, fmaf(q1.x, q1.x, q1.y * q1.y))) * norm;
+      float* d = dst + (size_t)h * W0;
+      if (pairs) {
+        *reinterpret_cast<float2*>(d) = make_float2(en0, en1);
+        m = fmaxf(m, fmaxf(en0, en1));
+      } else {
+        d[0] = en0; m = fmaxf(m, en0);
+        if (x + 1 < W0) { d[1] = en1; m = fmaxf(m, en1); }
+      }
     }
   }
   m = warp_max(m);
@@ -319,8 +342,6 @@ static LeLayout le_layout(void* ws, int B, int H0, int H, int W) {
   // columns per block: one transform step (2048 points) forward, two for the inverse pair: 32 KB of sequences, so that
   // six blocks share an SM (measured: 8 columns of 512 rows are 6 % slower, 8 of 1024 rows 25 %)
   L.tc = 2048 / H; if (L.tc < 2) L.tc = 2; if (L.tc > 16) L.tc = 16; if (L.tc > W) L.tc = W;
-  if (const char* e = getenv("USAUG_LE_TC")) { L.tc = atoi(e); }
-  if (const char* e = getenv("USAUG_LE_RBI")) { L.rb_inv = atoi(e); }
   L.nblk_inv = (H0 + L.rb_inv - 1) / L.rb_inv;
   Carver cv(ws);
   L.spec = cv.take<float2>(N); L.odd = cv.take<float2>(N); L.even = cv.take<float2>(N);
