@@ -338,7 +338,7 @@ def run_stages(a, dev, peak):
     def le():
         _ffi.check(lib.usaug_local_energy(img.data_ptr(), energy.data_ptr(), scale.data_ptr(), B, Hs, Ws, 8.0, 2.1, 3, 0.55,
                                           wsE.data_ptr(), wsE.numel(), st), "local energy")
-    out.append(entry("8(f): local energy, batch 512 of 512x512", "rows fwd + cols + rows inv + scale", timed(le, 10, False),
+    out.append(entry("8(f): local energy, batch 512 of 512x512", "le_rows_fwd + le_cols + le_rows_inv (Stockham radix-8 FFT)", timed(le, 10, False),
                      56.0 * B * Hs * Ws, B, reps=10, l2="working set >> L2", bytes_model="56 B/px"))
     del img, energy, wsE
     torch.cuda.empty_cache()
