@@ -7,7 +7,7 @@
 //   le_twiddles   the twiddle tables of the two transform lengths, once per call (2 blocks)
 //   le_filter     the filter multipliers (G, G u'/rho, G v'/rho) per frequency, once per call: the same for every image
 //   le_rows_fwd   per group of image rows: real -> complex FFT along x; the first pass reads the image, the last one
-//                 writes the spectrum (no staging copies)
+//                 writes the bins 0 .. W/2 of the spectrum (no staging copies; the other bins are conjugate mirrors)
 //   le_cols       per tile of columns: FFT along y (first pass reads the columns, last pass applies the filter on the
 //                 way back into shared memory), then the inverse FFT along y of the odd (Riesz) pair and of the even
 //                 part, whose last pass writes the two planes.  The even part is real: its columns beyond W/2 are
@@ -18,7 +18,7 @@
 //
 // Sizes that are not powers of two are mirror-extended (bottom / right, edge included) to the next power of two
 // (Hp x Wp) on the way into le_rows_fwd; rows and columns beyond H x W are never written back.
-// HBM traffic: 4 + 8 | 8 + 8 + 4 | 8 + 4 + 4 = 48 B/px (the stage model in bench.py still counts the 56 B/px of the
+// HBM traffic: 4 + 4 | 4 + 8 + 4 | 8 + 4 + 4 = 40 B/px (the stage model in bench.py still counts the 56 B/px of the
 // version that stored the whole even plane); everything else stays in shared memory.
 #include "fft_stockham.cuh"
 #include "kernels.cuh"
@@ -119,7 +119,9 @@ struct RowsFwdOut {
     if (r >= nrows) return;
     float2* p = spec + r * W + x0;
 #pragma unroll
-    for (int k = 0; k < R; ++k) p[k * stride] = v[k];
+    for (int k = 0; k < R; ++k)
+      if (x0 + k * stride <= W / 2) p[k * stride] = v[k];     // the rows are real: bins beyond W / 2 are conjugate mirrors
+
   }
 };
 
@@ -142,18 +144,24 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restric
 // transform of the 2 tc sequences (odd pair, then even part) writes the two planes in its last pass.  Both use the
 // sequence-fastest lane order, so a warp touches tc-wide contiguous pieces of consecutive rows.
 struct ColsIn {
-  const float2* __restrict__ src;                           // spec + image base + x0
-  int W, tc;
+  const float2* __restrict__ src;                           // spec + image base
+  int W, tc, x0;
   template <int R> __device__ __forceinline__ void load(int q, int y0, int stride, float2* v) const {
     if (q >= tc) {
 #pragma unroll
       for (int k = 0; k < R; ++k) v[k] = make_float2(0.f, 0.f);
       return;
     }
-    const float2* p = src + (size_t)y0 * W + q;
+    // le_rows_fwd stores the bins 0 .. W / 2 of every (real) row; the others are their conjugate mirrors
+    const int c = x0 + q;
+    const bool mir = c > W / 2;
+    const float2* p = src + (size_t)y0 * W + (mir ? W - c : c);
     const size_t step = (size_t)stride * W;
 #pragma unroll
-    for (int k = 0; k < R; ++k, p += step) v[k] = *p;
+    for (int k = 0; k < R; ++k, p += step) {
+      v[k] = *p;
+      if (mir) v[k].y = -v[k].y;
+    }
   }
 };
 // last pass of the forward transform: the filter multiply on the way back into shared memory.
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(kLeThreads, 4) le_cols(const float2* __restric
   const bool with_even = x0 <= W / 2;
   const int nseq = with_even ? 2 * tc : tc;
   // forward: columns from global memory (sequence-fastest lanes), filter applied by the last pass
-  fft::block_fft<false, true, false>(A, pitch, tc, ph, tw, ColsIn{spec + base, W, tc},
+  fft::block_fft<false, true, false>(A, pitch, tc, ph, tw, ColsIn{spec + base - x0, W, tc, x0},
                                      ColsFilterOut{A, Bv, filt + (size_t)x0 * H, H, pitch, tc, with_even});
   fft::block_fft<true, false, true>(A, pitch, nseq, ph, tw, fft::SmemIO{}, ColsOut{odd + base, even + base, W, tc, H0, nseq});
 }
