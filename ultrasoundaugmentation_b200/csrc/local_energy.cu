@@ -83,45 +83,33 @@ __global__ void __launch_bounds__(kLeThreads) le_filter(float4* __restrict__ fil
 // ---- rows, forward: block = rb rows ---------------------------------------------------------------
 // img is [B][H0][W0]; spec is [B][H][W] with H, W the padded (power-of-two) sizes.  The first pass of the transform
 // reads the image rows, the last one writes the spectrum rows: shared memory only carries the exchanges in between.
+// Two real rows share one complex transform: sequence q carries z = row 2q + i * row 2q+1.  With Z = FFT(z) the two
+// (Hermitian) row spectra are A(k) = (Z(k) + conj Z(W - k)) / 2 and B(k) = (Z(k) - conj Z(W - k)) / 2i.
 struct RowsFwdIn {
   const float* __restrict__ img;
-  size_t row0, nrows;
+  size_t row0, nrows;                                       // nrows = B * H and the rows per block are even
   int H0, W0, H, W, lgH;
   bool exact;                                               // no mirror extension
   template <int R> __device__ __forceinline__ void load(int q, int x0, int stride, float2* v) const {
-    const size_t r = row0 + q;
+    const size_t r = row0 + 2 * (size_t)q;
 #pragma unroll
     for (int k = 0; k < R; ++k) v[k] = make_float2(0.f, 0.f);
     if (r >= nrows) return;
     if (exact) {
       const float* p = img + r * W + x0;
 #pragma unroll
-      for (int k = 0; k < R; ++k) v[k].x = p[k * stride];
+      for (int k = 0; k < R; ++k) v[k] = make_float2(p[k * stride], p[W + k * stride]);
     } else {
-      const int b = (int)(r >> lgH), yp = (int)(r & (size_t)(H - 1));
-      const int y = (yp < H0) ? yp : 2 * H0 - 1 - yp;                                           // mirror extension
-      const float* p = img + ((size_t)b * H0 + y) * W0;
+      const int b = (int)(r >> lgH), yp = (int)(r & (size_t)(H - 1));                           // yp even, yp + 1 < H
+      const int ya = (yp < H0) ? yp : 2 * H0 - 1 - yp, yb = (yp + 1 < H0) ? yp + 1 : 2 * H0 - 2 - yp;   // mirror extension
+      const float* pa = img + ((size_t)b * H0 + ya) * W0;
+      const float* pb = img + ((size_t)b * H0 + yb) * W0;
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        const int xp = x0 + k * stride;
-        v[k].x = p[(xp < W0) ? xp : 2 * W0 - 1 - xp];
+        const int xp = x0 + k * stride, x = (xp < W0) ? xp : 2 * W0 - 1 - xp;
+        v[k] = make_float2(pa[x], pb[x]);
       }
     }
-  }
-};
-struct RowsFwdOut {
-  static constexpr bool kWritesSmem = false;
-  float2* __restrict__ spec;
-  size_t row0, nrows;
-  int W;
-  template <int R> __device__ __forceinline__ void store(int q, int x0, int stride, const float2* v) const {
-    const size_t r = row0 + q;
-    if (r >= nrows) return;
-    float2* p = spec + r * W + x0;
-#pragma unroll
-    for (int k = 0; k < R; ++k)
-      if (x0 + k * stride <= W / 2) p[k * stride] = v[k];     // the rows are real: bins beyond W / 2 are conjugate mirrors
-
   }
 };
 
@@ -130,13 +118,29 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restric
                                                           const float2* __restrict__ twg, int rb, size_t nrows) {
   extern __shared__ __align__(16) unsigned char le_smem[];
   float2* tw = reinterpret_cast<float2*>(le_smem);          // [W]  (pw.tw_total <= W entries used)
-  float2* data = tw + W;                                    // [rb][W], element x of a row at slot swz(x)
+  float2* data = tw + W;                                    // [rb / 2][W], element x of a sequence at slot swz(x)
   const size_t row0 = (size_t)blockIdx.x * rb;
+  const int lgW = pw.lg, np = rb >> 1;
   load_twiddles(tw, twg, pw.tw_total);
   __syncthreads();
   const RowsFwdIn in{img, row0, nrows, H0, W0, H, W, lgH, (H0 == H) && (W0 == W)};
-  const RowsFwdOut out{spec, row0, nrows, W};
-  fft::block_fft<false, false, false>(data, W, rb, pw, tw, in, out);
+  fft::block_fft<false, false, false>(data, W, np, pw, tw, in, fft::SmemIO{});
+  // separate the two spectra; only the bins 0 .. W / 2 are stored (the rows are real: the others are conjugate mirrors)
+  for (int i = threadIdx.x; i < np << (lgW - 1); i += blockDim.x) {
+    const int q = i >> (lgW - 1), k = i & (W / 2 - 1);
+    const size_t r = row0 + 2 * (size_t)q;
+    if (r >= nrows) break;
+    const float2* z = data + (q << lgW);
+    const float2 zk = z[fft::swz(k)], zm = z[fft::swz((W - k) & (W - 1))];
+    float2* pa = spec + r * W + k;
+    pa[0] = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    pa[W] = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+    if (k == 0) {                                           // ... and the Nyquist bin, its own mirror
+      const float2 zn = z[fft::swz(W / 2)];
+      pa[W / 2] = make_float2(zn.x, 0.f);
+      pa[W + W / 2] = make_float2(zn.y, 0.f);
+    }
+  }
 }
 
 // ---- columns: block = tc columns of one image ---------------------------------------------------------
@@ -344,7 +348,7 @@ static LeLayout le_layout(void* ws, int B, int H0, int H, int W) {
   LeLayout L;
   const size_t N = (size_t)B * H * W;
   // rows per block: 32 KB of sequences forward, 48 KB inverse (odd rows + pairs of even rows), at least 1, at most 16
-  L.rb_fwd = 4096 / W; if (L.rb_fwd < 1) L.rb_fwd = 1; if (L.rb_fwd > 16) L.rb_fwd = 16;
+  L.rb_fwd = 8192 / W; if (L.rb_fwd < 2) L.rb_fwd = 2; if (L.rb_fwd > 16) L.rb_fwd = 16;     // even: rows are transformed in pairs
   L.rb_inv = 4096 / W; if (L.rb_inv < 1) L.rb_inv = 1; if (L.rb_inv > 16) L.rb_inv = 16;
   while (H % L.rb_inv) L.rb_inv >>= 1;
   // columns per block: one transform step (2048 points) forward, two for the inverse pair: 32 KB of sequences, so that
@@ -402,7 +406,7 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
   const size_t nrows = (size_t)B * H;
   const fft::Plan pw = fft::make_plan(lgW), ph = fft::make_plan(lgH);
   // twiddle table + the sequences, rounded up to whole transform steps (fft::padded_seqs)
-  const size_t sm_fwd = (size_t)(W + fft::padded_seqs(L.rb_fwd, lgW, kLeThreads) * W) * sizeof(float2);
+  const size_t sm_fwd = (size_t)(W + fft::padded_seqs(L.rb_fwd / 2, lgW, kLeThreads) * W) * sizeof(float2);
   const size_t sm_col = (size_t)(H + fft::padded_seqs(2 * L.tc, lgH, kLeThreads) * le_col_pitch(H)) * sizeof(float2);
   const size_t sm_inv = (size_t)(W + fft::padded_seqs(L.rb_inv + (L.rb_inv + 1) / 2, lgW, kLeThreads) * W) * sizeof(float2);
   if (sm_fwd > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
