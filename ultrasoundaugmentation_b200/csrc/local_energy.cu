@@ -143,61 +143,68 @@ __global__ void __launch_bounds__(kLeThreads) le_rows_fwd(const float* __restric
   }
 }
 
-// ---- columns: block = tc columns of one image ---------------------------------------------------------
-// sequence q < tc = column x0 + q.  The forward transform reads the spectrum columns in its first pass; the inverse
-// transform of the 2 tc sequences (odd pair, then even part) writes the two planes in its last pass.  Both use the
-// sequence-fastest lane order, so a warp touches tc-wide contiguous pieces of consecutive rows.
+// ---- columns: block = tc columns of one image AND their mirror columns ---------------------------------
+// The image is real: F(ky, W - kx) = conj F(-ky, kx).  A block therefore transforms the tc columns x0 .. x0 + tc - 1
+// (x0 < W / 2) forward once, and takes the spectrum of the mirror columns W - x0 - q from it by index reversal.
+// Back go three groups of tc sequences: the odd (Riesz) pair and the even part of the tile, and the odd pair of the
+// mirror tile (the even part is real, so le_rows_inv rebuilds its columns beyond W / 2 as conjugate mirrors; the odd
+// pair has no such symmetry).  Five column transforms per (column, mirror column) instead of six.  The Nyquist column
+// W / 2 is its own mirror: one extra block per image handles it alone.
+// The first pass of the forward transform reads the spectrum columns, the last pass of the inverse transform writes
+// the planes, both with the sequence-fastest lane order: a warp touches tc-wide contiguous pieces of consecutive rows.
 struct ColsIn {
-  const float2* __restrict__ src;                           // spec + image base
-  int W, tc, x0;
+  const float2* __restrict__ src;                           // spec + image base + x0
+  int W, tc;
   template <int R> __device__ __forceinline__ void load(int q, int y0, int stride, float2* v) const {
     if (q >= tc) {
 #pragma unroll
       for (int k = 0; k < R; ++k) v[k] = make_float2(0.f, 0.f);
       return;
     }
-    // le_rows_fwd stores the bins 0 .. W / 2 of every (real) row; the others are their conjugate mirrors
-    const int c = x0 + q;
-    const bool mir = c > W / 2;
-    const float2* p = src + (size_t)y0 * W + (mir ? W - c : c);
+    const float2* p = src + (size_t)y0 * W + q;
     const size_t step = (size_t)stride * W;
 #pragma unroll
-    for (int k = 0; k < R; ++k, p += step) {
-      v[k] = *p;
-      if (mir) v[k].y = -v[k].y;
-    }
+    for (int k = 0; k < R; ++k, p += step) v[k] = *p;
   }
 };
-// last pass of the forward transform: the filter multiply on the way back into shared memory.
-//   even: G F -> Bv;   odd: (v' - i u') / rho * G * F -> A (in place)
+// even: G F;   odd: (v' - i u') / rho * G * F;   f = (G, G u'/rho, G v'/rho), zero at DC
+__device__ __forceinline__ float2 le_even(float4 f, float2 F) { return make_float2(f.x * F.x, f.x * F.y); }
+__device__ __forceinline__ float2 le_odd(float4 f, float2 F) {
+  return make_float2(fmaf(f.z, F.x, f.y * F.y), fmaf(f.z, F.y, -f.y * F.x));
+}
+// Nyquist column: the filter multiply as the last pass of the forward transform, on the way back into shared memory
 struct ColsFilterOut {
   static constexpr bool kWritesSmem = true;
   float2* A;
   float2* Bv;
-  const float4* __restrict__ fcol;                          // filt + x0 * H: (G, G u'/rho, G v'/rho), zero at DC
+  const float4* __restrict__ fcol;                          // filt + x0 * H
   int H, pitch, tc;
-  bool with_even;
   template <int R> __device__ __forceinline__ void store(int q, int y0, int stride, const float2* v) const {
     if (q >= tc) return;
     const float4* f = fcol + (size_t)q * H + y0;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const float4 g = f[k * stride];
-      const float2 F = v[k];
       const int slot = q * pitch + fft::swz(y0 + k * stride);
-      if (with_even) Bv[slot] = make_float2(g.x * F.x, g.x * F.y);
-      A[slot] = make_float2(fmaf(g.z, F.x, g.y * F.y), fmaf(g.z, F.y, -g.y * F.x));
+      Bv[slot] = le_even(f[k * stride], v[k]);
+      A[slot] = le_odd(f[k * stride], v[k]);
     }
   }
 };
+// sequences [0, tc): odd pair of column x0 + q; [tc, 2 tc): even part of column x0 + q - tc; [2 tc, 3 tc) (if
+// `mirror`): odd pair of the mirror column W - (x0 + q - 2 tc), which does not exist for column 0.
 struct ColsOut {
   static constexpr bool kWritesSmem = false;
-  float2* __restrict__ odd;                                 // + image base + x0
+  float2* __restrict__ odd;                                 // + image base
   float2* __restrict__ even;
-  int W, tc, H0, nseq;
+  int W, tc, H0, x0;
+  bool mirror;
   template <int R> __device__ __forceinline__ void store(int q, int y0, int stride, const float2* v) const {
-    if (q >= nseq) return;
-    float2* p = ((q < tc) ? odd + q : even + (q - tc)) + (size_t)y0 * W;
+    float2* p;
+    if (q < tc) p = odd + x0 + q;
+    else if (q < 2 * tc) p = even + x0 + (q - tc);
+    else if (mirror && q < 3 * tc && x0 + (q - 2 * tc) != 0) p = odd + W - (x0 + (q - 2 * tc));
+    else return;
+    p += (size_t)y0 * W;
     const size_t step = (size_t)stride * W;
 #pragma unroll
     for (int k = 0; k < R; ++k, p += step)
@@ -210,21 +217,52 @@ __global__ void __launch_bounds__(kLeThreads, 4) le_cols(const float2* __restric
                                                       int H0, int H, int W, fft::Plan ph,
                                                       const float2* __restrict__ twg, int tc, int pitch) {
   extern __shared__ __align__(16) unsigned char le_smem[];
+  const int lgH = ph.lg;
   float2* tw = reinterpret_cast<float2*>(le_smem);          // [H]
-  float2* A = tw + H;                                       // [tc][pitch]  spectrum, then the Riesz (odd) pair
-  float2* Bv = A + tc * pitch;                              // [tc][pitch]  the even part
-  const int b = blockIdx.y, x0 = blockIdx.x * tc;
-  const size_t base = (size_t)b * H * W + x0;
+  float2* A = tw + H;                                       // [tc][pitch]  spectrum, then the odd pair of the tile
+  const int b = blockIdx.y;
+  const size_t ibase = (size_t)b * H * W;
   load_twiddles(tw, twg, ph.tw_total);
   __syncthreads();
-  // The even part is real, so its row spectrum after this kernel is Hermitian along x: columns beyond W / 2 are the
-  // conjugates of their mirror images and are neither transformed back nor stored (le_rows_inv rebuilds them).
-  const bool with_even = x0 <= W / 2;
-  const int nseq = with_even ? 2 * tc : tc;
-  // forward: columns from global memory (sequence-fastest lanes), filter applied by the last pass
-  fft::block_fft<false, true, false>(A, pitch, tc, ph, tw, ColsIn{spec + base - x0, W, tc, x0},
-                                     ColsFilterOut{A, Bv, filt + (size_t)x0 * H, H, pitch, tc, with_even});
-  fft::block_fft<true, false, true>(A, pitch, nseq, ph, tw, fft::SmemIO{}, ColsOut{odd + base, even + base, W, tc, H0, nseq});
+  if ((int)blockIdx.x * tc >= W / 2) {                      // the Nyquist column alone: [odd][even]
+    const int x0 = W / 2;
+    fft::block_fft<false, true, false>(A, pitch, 1, ph, tw, ColsIn{spec + ibase + x0, W, 1},
+                                       ColsFilterOut{A, A + pitch, filt + (size_t)x0 * H, H, pitch, 1});
+    fft::block_fft<true, false, true>(A, pitch, 2, ph, tw, fft::SmemIO{}, ColsOut{odd + ibase, even + ibase, W, 1, H0, x0, false});
+    return;
+  }
+  float2* Bv = A + tc * pitch;                              // [tc][pitch]  the even part of the tile
+  float2* Am = Bv + tc * pitch;                             // [tc][pitch]  the odd pair of the mirror tile
+  const int x0 = blockIdx.x * tc;
+  fft::block_fft<false, true, false>(A, pitch, tc, ph, tw, ColsIn{spec + ibase + x0, W, tc}, fft::SmemIO{});
+  // filter: a thread takes the bins ky and H - ky of a column together, F'(ky) = conj F(H - ky) being the mirror
+  // column's spectrum (the bins 0 and H / 2 are their own partners)
+  for (int i = threadIdx.x; i < tc << (lgH - 1); i += blockDim.x) {
+    const int c = i >> (lgH - 1), k1 = i & (H / 2 - 1);
+    const float4* f = filt + (size_t)(x0 + c) * H;          // column x0 + c
+    const float4* g = filt + (size_t)((W - x0 - c) & (W - 1)) * H;   // its mirror column
+    float2* a = A + c * pitch;
+    float2* e = Bv + c * pitch;
+    float2* m = Am + c * pitch;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // h = 0: the pair (k1, H - k1), or bin 0 alone; h = 1: bin H / 2 alone, done by the thread of bin 0
+      if (h == 1 && k1 != 0) break;
+      const int ka = h ? H / 2 : k1, kb = (H - ka) & (H - 1);
+      const int sa = fft::swz(ka), sb = fft::swz(kb);
+      const float2 Fa = a[sa], Fb = a[sb];
+      e[sa] = le_even(f[ka], Fa);
+      a[sa] = le_odd(f[ka], Fa);
+      m[sa] = le_odd(g[ka], make_float2(Fb.x, -Fb.y));
+      if (kb != ka) {
+        e[sb] = le_even(f[kb], Fb);
+        a[sb] = le_odd(f[kb], Fb);
+        m[sb] = le_odd(g[kb], make_float2(Fa.x, -Fa.y));
+      }
+    }
+  }
+  __syncthreads();
+  fft::block_fft<true, false, true>(A, pitch, 3 * tc, ph, tw, fft::SmemIO{}, ColsOut{odd + ibase, even + ibase, W, tc, H0, x0, true});
 }
 
 // ---- rows, inverse + energy: block = rb rows -----------------------------------------------------------
@@ -353,7 +391,7 @@ static LeLayout le_layout(void* ws, int B, int H0, int H, int W) {
   while (H % L.rb_inv) L.rb_inv >>= 1;
   // columns per block: one transform step (2048 points) forward, two for the inverse pair: 32 KB of sequences, so that
   // six blocks share an SM (measured: 8 columns of 512 rows are 6 % slower, 8 of 1024 rows 25 %)
-  L.tc = 2048 / H; if (L.tc < 2) L.tc = 2; if (L.tc > 16) L.tc = 16; if (L.tc > W) L.tc = W;
+  L.tc = 2048 / H; if (L.tc < 2) L.tc = 2; if (L.tc > 16) L.tc = 16; if (L.tc > W / 2) L.tc = W / 2;
   L.nblk_inv = (H0 + L.rb_inv - 1) / L.rb_inv;
   Carver cv(ws);
   L.spec = cv.take<float2>(N); L.odd = cv.take<float2>(N); L.even = cv.take<float2>(N);
@@ -407,7 +445,7 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
   const fft::Plan pw = fft::make_plan(lgW), ph = fft::make_plan(lgH);
   // twiddle table + the sequences, rounded up to whole transform steps (fft::padded_seqs)
   const size_t sm_fwd = (size_t)(W + fft::padded_seqs(L.rb_fwd / 2, lgW, kLeThreads) * W) * sizeof(float2);
-  const size_t sm_col = (size_t)(H + fft::padded_seqs(2 * L.tc, lgH, kLeThreads) * le_col_pitch(H)) * sizeof(float2);
+  const size_t sm_col = (size_t)(H + fft::padded_seqs(3 * L.tc, lgH, kLeThreads) * le_col_pitch(H)) * sizeof(float2);
   const size_t sm_inv = (size_t)(W + fft::padded_seqs(L.rb_inv + (L.rb_inv + 1) / 2, lgW, kLeThreads) * W) * sizeof(float2);
   if (sm_fwd > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
   if (sm_col > 32 * 1024) USAUG_CUDA(cudaFuncSetAttribute(le_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_col));
@@ -420,7 +458,7 @@ extern "C" int usaug_local_energy(const float* img, float* energy, float* scale,
   le_rows_fwd<<<(unsigned)((nrows + L.rb_fwd - 1) / L.rb_fwd), kLeThreads, sm_fwd, stream>>>(img, L.spec, H0, W0, H, W, lgH, pw,
                                                                                             L.tww, L.rb_fwd, nrows);
   USAUG_CHECK_LAUNCH("le_rows_fwd");
-  le_cols<<<dim3(W / L.tc, B), kLeThreads, sm_col, stream>>>(L.spec, L.odd, L.even, L.filt, H0, H, W, ph, L.twh, L.tc,
+  le_cols<<<dim3(W / (2 * L.tc) + 1, B), kLeThreads, sm_col, stream>>>(L.spec, L.odd, L.even, L.filt, H0, H, W, ph, L.twh, L.tc,
                                                              le_col_pitch(H));
   USAUG_CHECK_LAUNCH("le_cols");
   le_rows_inv<<<dim3(L.nblk_inv, B), kLeThreads, sm_inv, stream>>>(L.odd, L.even, energy, L.part, H0, W0, H, W, pw, L.tww,
