@@ -6,11 +6,11 @@
 //
 //   le_twiddles   the twiddle tables of the two transform lengths, once per call (2 blocks)
 //   le_filter     the filter multipliers (G, G u'/rho, G v'/rho) per frequency, once per call: the same for every image
-//   le_rows_fwd   per group of image rows: real -> complex FFT along x; the first pass reads the image, the last one
-//                 writes the bins 0 .. W/2 of the spectrum (no staging copies; the other bins are conjugate mirrors)
-//   le_cols       per tile of columns: FFT along y (first pass reads the columns, last pass applies the filter on the
-//                 way back into shared memory), then the inverse FFT along y of the odd (Riesz) pair and of the even
-//                 part, whose last pass writes the two planes.  The even part is real: its columns beyond W/2 are
+//   le_rows_fwd   per group of image rows: FFT along x, two real rows per complex transform (first pass reads the
+//                 image); the two spectra are separated and their bins 0 .. W/2 stored (the others are conjugate mirrors)
+//   le_cols       per tile of columns and its mirror tile: one forward FFT along y (first pass reads the columns), the
+//                 filter, then the inverse FFT along y of the tile's odd (Riesz) pair and even part and of the mirror
+//                 tile's odd pair, whose last pass writes the planes.  The even part is real: its columns beyond W/2 are
 //                 conjugate mirrors and are neither transformed back nor stored.
 //   le_rows_inv   per group of image rows: inverse FFT along x of the odd rows and of PAIRS of even rows (two real rows
 //                 as real and imaginary part of one transform), energy, per-block maxima
