@@ -30,7 +30,9 @@ def gpu_energy(dev, img, **kw):
 @pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 128, 256), (2, 512, 512), (1, 1024, 1024), (2, 8, 8), (1, 2048, 16),
                                     (1, 16, 2048),
                                     # not powers of two: mirror-extended to the next one
-                                    (2, 97, 131), (2, 100, 64), (1, 480, 640), (2, 5, 9), (1, 4, 4), (1, 1030, 33)])
+                                    (2, 97, 131), (2, 100, 64), (1, 480, 640), (2, 5, 9), (1, 4, 4), (1, 1030, 33),
+                                    # largest transform, odd batch, long thin shapes in both directions
+                                    (1, 2048, 2048), (1, 1500, 700), (3, 260, 8), (2, 8, 260), (1, 4, 2048), (5, 32, 32)])
 def test_local_energy_parity(cuda_device, B, H, W):
     img, _ = util.synth_batch(B, H, W)
     e, s = gpu_energy(cuda_device, img)
