@@ -239,8 +239,7 @@ __global__ void __launch_bounds__(kLeThreads, 4) le_cols(const float2* __restric
   // column's spectrum (the bins 0 and H / 2 are their own partners)
   for (int i = threadIdx.x; i < tc << (lgH - 1); i += blockDim.x) {
     const int c = i >> (lgH - 1), k1 = i & (H / 2 - 1);
-    const float4* f = filt + (size_t)(x0 + c) * H;          // column x0 + c
-    const float4* g = filt + (size_t)((W - x0 - c) & (W - 1)) * H;   // its mirror column
+    const float4* f = filt + (size_t)(x0 + c) * H;          // column x0 + c; its mirror column has u' -> -u'
     float2* a = A + c * pitch;
     float2* e = Bv + c * pitch;
     float2* m = Am + c * pitch;
@@ -251,13 +250,15 @@ __global__ void __launch_bounds__(kLeThreads, 4) le_cols(const float2* __restric
       const int ka = h ? H / 2 : k1, kb = (H - ka) & (H - 1);
       const int sa = fft::swz(ka), sb = fft::swz(kb);
       const float2 Fa = a[sa], Fb = a[sb];
-      e[sa] = le_even(f[ka], Fa);
-      a[sa] = le_odd(f[ka], Fa);
-      m[sa] = le_odd(g[ka], make_float2(Fb.x, -Fb.y));
+      const float4 fa = f[ka];
+      e[sa] = le_even(fa, Fa);
+      a[sa] = le_odd(fa, Fa);
+      m[sa] = le_odd(make_float4(fa.x, -fa.y, fa.z, 0.f), make_float2(Fb.x, -Fb.y));
       if (kb != ka) {
-        e[sb] = le_even(f[kb], Fb);
-        a[sb] = le_odd(f[kb], Fb);
-        m[sb] = le_odd(g[kb], make_float2(Fa.x, -Fa.y));
+        const float4 fb = f[kb];
+        e[sb] = le_even(fb, Fb);
+        a[sb] = le_odd(fb, Fb);
+        m[sb] = le_odd(make_float4(fb.x, -fb.y, fb.z, 0.f), make_float2(Fa.x, -Fa.y));
       }
     }
   }
