@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kLeThreads, 4) le_cols(const float2* __restric
       a[sa] = le_odd(fa, Fa);
       m[sa] = le_odd(make_float4(fa.x, -fa.y, fa.z, 0.f), make_float2(Fb.x, -Fb.y));
       if (kb != ka) {
-        const float4 fb = f[kb];
+        const float4 fb = make_float4(fa.x, fa.y, -fa.z, 0.f);    // bin H - ka: v' -> -v'
         e[sb] = le_even(fb, Fb);
         a[sb] = le_odd(fb, Fb);
         m[sb] = le_odd(make_float4(fb.x, -fb.y, fb.z, 0.f), make_float2(Fa.x, -Fa.y));
